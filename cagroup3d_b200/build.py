@@ -1,0 +1,67 @@
+"""Builds cagroup3d_b200/libcagroup3d_b200.so in-tree with nvcc for sm_100a (no torch, no pybind).
+
+    python -m cagroup3d_b200.build [--force]
+
+The library is the C ABI declared in include/cagroup3d_b200.h.  Objects are cached under
+cagroup3d_b200/csrc/_obj (git-ignored) and rebuilt when a source or header is newer.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libcagroup3d_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+# -fmad=false: no implicit FMA contraction, so coordinate / IoU arithmetic is the reference's fp32
+# operation sequence bit for bit; the GEMM inner loops use explicit fmaf()/tcgen05 and are unaffected.
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "cagroup3d_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src: str, force: bool) -> str:
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    sp = os.path.join(CSRC, src)
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), _deps_mtime()):
+        return obj
+    cmd = [NVCC, *ARCH, *FLAGS, "-c", sp, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(OBJ, src[:-3] + ".ptxas.log")
+    with open(log, "w") as f:
+        f.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed for {src}")
+    return obj
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force), srcs))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

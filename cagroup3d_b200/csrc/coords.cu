@@ -1,0 +1,347 @@
+// Coordinate management: quantisation, hash-unique with first-occurrence winner, strided maps and
+// rule-map (neighbour table) generation.  Integer work, HBM/latency bound; every kernel is a flat
+// grid-stride map over rows with coalesced int4 row accesses.
+//
+// Replaces the MinkowskiEngine coordinate manager used at cagroup3d.py:24, biresnet.py (every
+// strided conv), cagroup_head.py:257-271 and cagroup_roi_head.py:62-69.
+#include "common.cuh"
+#include "../../include/cagroup3d_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// quantisation: (b, x, y, z) float rows -> int32 voxel rows, floor(x / vs) with IEEE division
+// ---------------------------------------------------------------------------------------------
+__global__ void quantize_kernel(const float* __restrict__ pts, int ld, int n, float vx, float vy, float vz,
+                                int mul, int4* __restrict__ out, int* __restrict__ err) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* p = pts + (size_t)i * ld;
+        int b = (int)p[0];
+        int x = (int)floorf(__fdiv_rn(p[1], vx)) * mul;
+        int y = (int)floorf(__fdiv_rn(p[2], vy)) * mul;
+        int z = (int)floorf(__fdiv_rn(p[3], vz)) * mul;
+        if (!cg3d_in_range(x, y, z) || b < 0 || b > 0xFFFF) atomicAdd(err, 1);
+        out[i] = make_int4(b, x, y, z);
+    }
+}
+
+__global__ void stride_kernel(const int4* __restrict__ in, int n, int ts, int4* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = in[i];
+        out[i] = make_int4(c.x, cg3d_floordiv(c.y, ts) * ts, cg3d_floordiv(c.z, ts) * ts, cg3d_floordiv(c.w, ts) * ts);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash insert: slot claimed by CAS on the key, winner row = atomicMin over rows with that key
+// ---------------------------------------------------------------------------------------------
+__global__ void hash_insert_kernel(const int4* __restrict__ coords, int n, unsigned long long* keys, int* vals,
+                                   unsigned mask, int* __restrict__ slot_of_row) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = coords[i];
+        unsigned long long key = cg3d_pack(c.x, c.y, c.z, c.w);
+        unsigned slot = cg3d_hash(key) & mask;
+        while (true) {
+            unsigned long long prev = atomicCAS(keys + slot, CG3D_EMPTY_KEY, key);
+            if (prev == CG3D_EMPTY_KEY || prev == key) break;
+            slot = (slot + 1) & mask;
+        }
+        atomicMin(vals + slot, i);
+        if (slot_of_row) slot_of_row[i] = (int)slot;
+    }
+}
+
+__global__ void flag_winner_kernel(const int* __restrict__ slot_of_row, const int* __restrict__ vals, int n,
+                                   int* __restrict__ flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flag[i] = (vals[slot_of_row[i]] == i) ? 1 : 0;
+}
+
+// ---- exclusive scan of int32 (three small kernels; n up to a few million) ---------------------
+constexpr int kScanBlock = 1024;
+
+__global__ void scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ sums) {
+    __shared__ int warp_sum[32];
+    int i = blockIdx.x * kScanBlock + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = warp_sum[threadIdx.x];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = s;
+    }
+}
+
+__global__ void scan_sums_inplace(int* sums, int nb, int* total) {
+    // single block: sequential over chunks of 1024 with a block-wide inclusive scan each
+    __shared__ int sh[kScanBlock];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += kScanBlock) {
+        int i = base + threadIdx.x;
+        int v = i < nb ? sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < kScanBlock; o <<= 1) {
+            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        int incl = sh[threadIdx.x];
+        if (i < nb) sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void scan_apply(const int* __restrict__ in, int n, const int* __restrict__ sums, int* __restrict__ out) {
+    __shared__ int warp_off[32];
+    int i = blockIdx.x * kScanBlock + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_off[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = warp_off[lane];
+        int si = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        warp_off[lane] = si - s;
+    }
+    __syncthreads();
+    if (i < n) out[i] = sums[blockIdx.x] + warp_off[w] + incl - v;
+}
+
+__global__ void unique_emit_kernel(const int4* __restrict__ coords, const int* __restrict__ slot_of_row,
+                                   const int* __restrict__ vals, const int* __restrict__ excl, int n,
+                                   int4* __restrict__ out_coords, int* __restrict__ first_row,
+                                   int* __restrict__ inverse) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int w = vals[slot_of_row[i]];
+        int u = excl[w];
+        if (inverse) inverse[i] = u;
+        if (w == i) {
+            out_coords[u] = coords[i];
+            if (first_row) first_row[u] = i;
+        }
+    }
+}
+
+__global__ void unique_relabel_kernel(const int* __restrict__ slot_of_row, int* vals, const int* __restrict__ excl,
+                                      const int* __restrict__ flag, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) vals[slot_of_row[i]] = excl[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// rule map as a dense neighbour table: nbr[tap][out_row] = in_row or -1
+// ---------------------------------------------------------------------------------------------
+__global__ void neighbor_table_kernel(const int4* __restrict__ out_coords, int n_out,
+                                      const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                      unsigned mask, int ksize, int step, int* __restrict__ nbr) {
+    int K = ksize * ksize * ksize;
+    long long total = (long long)K * n_out;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int tap = (int)(t / n_out), o = (int)(t % n_out);
+        int4 c = __ldg(out_coords + o);
+        int ox, oy, oz;
+        cg3d_tap_offset(tap, ksize, ox, oy, oz);
+        int x = c.y + ox * step, y = c.z + oy * step, z = c.w + oz * step;
+        int r = -1;
+        if (cg3d_in_range(x, y, z)) r = cg3d_lookup(keys, vals, mask, cg3d_pack(c.x, x, y, z));
+        nbr[t] = r;
+    }
+}
+
+// transposed k=2,s=2 conv onto an existing finer map (A8): one parent, tap from the child offset
+__global__ void transpose_k2s2_table_kernel(const int4* __restrict__ fine, int n_fine,
+                                            const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                            unsigned mask, int ts_coarse, int* __restrict__ nbr) {
+    int ts_f = ts_coarse / 2;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_fine; o += gridDim.x * blockDim.x) {
+        int4 c = fine[o];
+        int px = cg3d_floordiv(c.y, ts_coarse) * ts_coarse, py = cg3d_floordiv(c.z, ts_coarse) * ts_coarse,
+            pz = cg3d_floordiv(c.w, ts_coarse) * ts_coarse;
+        int tap = (c.y - px) / ts_f + 2 * ((c.z - py) / ts_f + 2 * ((c.w - pz) / ts_f));
+        int r = cg3d_lookup(keys, vals, mask, cg3d_pack(c.x, px, py, pz));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nbr[(size_t)k * n_fine + o] = (k == tap) ? r : -1;
+    }
+}
+
+// generative transposed k=3,s=3 onto given fine coordinates (A13)
+__global__ void transpose_k3s3_table_kernel(const int4* __restrict__ fine, int n_fine,
+                                            const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                            unsigned mask, int* __restrict__ nbr) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_fine; o += gridDim.x * blockDim.x) {
+        int4 c = fine[o];
+        int f[3] = {c.y, c.z, c.w}, off[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int r = f[a] - cg3d_floordiv(f[a], 3) * 3;
+            off[a] = r == 0 ? 0 : (r == 1 ? 1 : -1);
+        }
+        int tap = (off[0] + 1) + 3 * ((off[1] + 1) + 3 * (off[2] + 1));
+        int r = cg3d_lookup(keys, vals, mask, cg3d_pack(c.x, f[0] - off[0], f[1] - off[1], f[2] - off[2]));
+        for (int k = 0; k < 27; ++k) nbr[(size_t)k * n_fine + o] = (k == tap) ? r : -1;
+    }
+}
+
+__global__ void lookup_kernel(const int4* __restrict__ q, int n, const unsigned long long* __restrict__ keys,
+                              const int* __restrict__ vals, unsigned mask, int* __restrict__ rows) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = q[i];
+        rows[i] = cg3d_in_range(c.y, c.z, c.w) ? cg3d_lookup(keys, vals, mask, cg3d_pack(c.x, c.y, c.z, c.w)) : -1;
+    }
+}
+
+__global__ void count_valid_kernel(const int* __restrict__ nbr, long long total, unsigned long long* count) {
+    unsigned long long c = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x)
+        c += nbr[t] >= 0;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+inline int grid_for(long long n) {
+    long long b = (n + kThreads - 1) / kThreads;
+    const long long cap = 148LL * 16;   // 148 SMs x 16 resident CTAs of 256 threads
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg3d_hash_capacity(int n) {
+    long long c = 1024;
+    while (c < 2LL * n) c <<= 1;
+    return (int)c;
+}
+
+int cg3d_quantize(const float* pts, int ld, int n, float vx, float vy, float vz, int mul, int* out_coords,
+                  int* err_count, void* stream) {
+    if (n == 0) return 0;
+    quantize_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(pts, ld, n, vx, vy, vz, mul,
+                                                                         (int4*)out_coords, err_count);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_stride_coords(const int* coords, int n, int ts, int* out, void* stream) {
+    if (n == 0) return 0;
+    stride_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const int4*)coords, n, ts, (int4*)out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_exclusive_scan_i32(const int* in, int n, int* out, int* block_sums, int* total, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int nb = cg3d_div_up(n > 0 ? n : 1, kScanBlock);
+    scan_block_sums<<<nb, kScanBlock, 0, s>>>(in, n, block_sums);
+    scan_sums_inplace<<<1, kScanBlock, 0, s>>>(block_sums, nb, total);
+    scan_apply<<<nb, kScanBlock, 0, s>>>(in, n, block_sums, out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_scan_workspace_ints(int n) { return cg3d_div_up(n > 0 ? n : 1, kScanBlock) + 8; }
+
+int cg3d_unique_first(const int* coords, int n, unsigned long long* keys, int* vals, int capacity,
+                      int* out_coords, int* first_row, int* inverse, int* n_unique, int* workspace, void* stream) {
+    // workspace: 3*n + cg3d_scan_workspace_ints(n) ints  (slot_of_row | flag | excl | block sums)
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * (size_t)capacity, s);
+    cudaMemsetAsync(vals, 0x7F, sizeof(int) * (size_t)capacity, s);
+    if (n == 0) { cudaMemsetAsync(n_unique, 0, sizeof(int), s); return 0; }
+    int* slot = workspace;
+    int* flag = workspace + n;
+    int* excl = workspace + 2 * (size_t)n;
+    int* sums = workspace + 3 * (size_t)n;
+    unsigned mask = (unsigned)capacity - 1;
+    int g = grid_for(n);
+    hash_insert_kernel<<<g, kThreads, 0, s>>>((const int4*)coords, n, keys, vals, mask, slot);
+    flag_winner_kernel<<<g, kThreads, 0, s>>>(slot, vals, n, flag);
+    int rc = cg3d_exclusive_scan_i32(flag, n, excl, sums, n_unique, stream);
+    if (rc) return rc;
+    unique_emit_kernel<<<g, kThreads, 0, s>>>((const int4*)coords, slot, vals, excl, n, (int4*)out_coords,
+                                              first_row, inverse);
+    unique_relabel_kernel<<<g, kThreads, 0, s>>>(slot, vals, excl, flag, n);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_hash_build(const int* coords, int n, unsigned long long* keys, int* vals, int capacity, void* stream) {
+    // coords must already be unique: value stored = row index
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * (size_t)capacity, s);
+    cudaMemsetAsync(vals, 0x7F, sizeof(int) * (size_t)capacity, s);
+    if (n == 0) return 0;
+    hash_insert_kernel<<<grid_for(n), kThreads, 0, s>>>((const int4*)coords, n, keys, vals, (unsigned)capacity - 1,
+                                                        nullptr);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_hash_lookup(const int* query, int n, const unsigned long long* keys, const int* vals, int capacity,
+                     int* rows, void* stream) {
+    if (n == 0) return 0;
+    lookup_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const int4*)query, n, keys, vals,
+                                                                      (unsigned)capacity - 1, rows);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_neighbor_table(const int* out_coords, int n_out, const unsigned long long* keys, const int* vals,
+                        int capacity, int ksize, int step, int* nbr, void* stream) {
+    if (n_out == 0) return 0;
+    long long total = (long long)ksize * ksize * ksize * n_out;
+    neighbor_table_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(
+        (const int4*)out_coords, n_out, keys, vals, (unsigned)capacity - 1, ksize, step, nbr);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_transpose_table(const int* fine_coords, int n_fine, const unsigned long long* keys, const int* vals,
+                         int capacity, int ksize, int ts_coarse, int* nbr, void* stream) {
+    if (n_fine == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ksize == 2)
+        transpose_k2s2_table_kernel<<<grid_for(n_fine), kThreads, 0, s>>>((const int4*)fine_coords, n_fine, keys, vals,
+                                                                          (unsigned)capacity - 1, ts_coarse, nbr);
+    else if (ksize == 3)
+        transpose_k3s3_table_kernel<<<grid_for(n_fine), kThreads, 0, s>>>((const int4*)fine_coords, n_fine, keys, vals,
+                                                                          (unsigned)capacity - 1, nbr);
+    else
+        return -1;
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_count_rules(const int* nbr, long long total, unsigned long long* count, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(count, 0, sizeof(unsigned long long), s);
+    if (total == 0) return 0;
+    count_valid_kernel<<<grid_for(total), kThreads, 0, s>>>(nbr, total, count);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// BEV IoU (axis-aligned and rotated) and device-resident greedy NMS.
+//
+// Replaces pcdet/ops/iou3d_nms: nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-186,
+// iou3d_nms_kernel.cu:267-372), boxes_overlap_bev_gpu / boxes_iou_bev_gpu (:236-265).
+// Same decision rule: boxes pre-sorted by descending score, a kept box suppresses every later box
+// whose BEV IoU is > thr; z extent ignored; EPS = 1e-8; corner-in-box margin 1e-2.
+// Unlike the reference there is no N x N/64 bitmask in HBM, no cudaMalloc, no D2H copy and no host
+// loop: one CTA per NMS instance (segment) keeps the alive bitset in shared memory, and all
+// instances of a batch ((sample, class) pairs) run in ONE launch.
+// This translation unit is built with -fmad=false: every + - * / is a separately rounded fp32 op,
+// which makes the axis-aligned path bit-identical to the C oracle.
+#include "common.cuh"
+#include "../../include/cagroup3d_b200.h"
+
+namespace {
+
+#define NMS_EPS 1e-8f
+
+struct P2 { float x, y; };
+
+__device__ __forceinline__ float cross2(P2 a, P2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float cross3(P2 p1, P2 p2, P2 p0) {
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+__device__ __forceinline__ bool rect_cross(P2 p1, P2 p2, P2 q1, P2 q2) {
+    return fminf(p1.x, p2.x) <= fmaxf(q1.x, q2.x) && fminf(q1.x, q2.x) <= fmaxf(p1.x, p2.x) &&
+           fminf(p1.y, p2.y) <= fmaxf(q1.y, q2.y) && fminf(q1.y, q2.y) <= fmaxf(p1.y, p2.y);
+}
+__device__ __forceinline__ bool in_box2d(const float* box, P2 p) {
+    float c = cosf(-box[6]), s = sinf(-box[6]);
+    float rx = (p.x - box[0]) * c + (p.y - box[1]) * (-s);
+    float ry = (p.x - box[0]) * s + (p.y - box[1]) * c;
+    return fabsf(rx) < box[3] / 2 + 1e-2f && fabsf(ry) < box[4] / 2 + 1e-2f;
+}
+__device__ bool seg_isect(P2 p1, P2 p0, P2 q1, P2 q0, P2& ans) {
+    if (!rect_cross(p0, p1, q0, q1)) return false;
+    float s1 = cross3(q0, p1, p0), s2 = cross3(p1, q1, p0), s3 = cross3(p0, q1, q0), s4 = cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return false;
+    float s5 = cross3(q1, p1, p0);
+    if (fabsf(s5 - s1) > NMS_EPS) {
+        ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        float D = a0 * b1 - a1 * b0;
+        ans.x = (b0 * c1 - b1 * c0) / D;
+        ans.y = (a1 * c0 - a0 * c1) / D;
+    }
+    return true;
+}
+__device__ __forceinline__ P2 rot_about(P2 c, float co, float si, P2 p) {
+    P2 r;
+    r.x = (p.x - c.x) * co + (p.y - c.y) * (-si) + c.x;
+    r.y = (p.x - c.x) * si + (p.y - c.y) * co + c.y;
+    return r;
+}
+
+__device__ float overlap_rotated(const float* a, const float* b) {
+    float ahx = a[3] / 2, bhx = b[3] / 2, ahy = a[4] / 2, bhy = b[4] / 2;
+    P2 ca{a[0], a[1]}, cb{b[0], b[1]};
+    P2 A[5] = {{a[0] - ahx, a[1] - ahy}, {a[0] + ahx, a[1] - ahy}, {a[0] + ahx, a[1] + ahy}, {a[0] - ahx, a[1] + ahy}, {0, 0}};
+    P2 B[5] = {{b[0] - bhx, b[1] - bhy}, {b[0] + bhx, b[1] - bhy}, {b[0] + bhx, b[1] + bhy}, {b[0] - bhx, b[1] + bhy}, {0, 0}};
+    float aco = cosf(a[6]), asi = sinf(a[6]), bco = cosf(b[6]), bsi = sinf(b[6]);
+    for (int k = 0; k < 4; ++k) { A[k] = rot_about(ca, aco, asi, A[k]); B[k] = rot_about(cb, bco, bsi, B[k]); }
+    A[4] = A[0]; B[4] = B[0];
+    P2 cp[16], ctr{0.f, 0.f};
+    int cnt = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (seg_isect(A[i + 1], A[i], B[j + 1], B[j], cp[cnt])) { ctr.x = ctr.x + cp[cnt].x; ctr.y = ctr.y + cp[cnt].y; ++cnt; }
+    for (int k = 0; k < 4; ++k) {
+        if (in_box2d(a, B[k])) { ctr.x = ctr.x + B[k].x; ctr.y = ctr.y + B[k].y; cp[cnt++] = B[k]; }
+        if (in_box2d(b, A[k])) { ctr.x = ctr.x + A[k].x; ctr.y = ctr.y + A[k].y; cp[cnt++] = A[k]; }
+    }
+    ctr.x /= cnt; ctr.y /= cnt;
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(cp[i].y - ctr.y, cp[i].x - ctr.x) > atan2f(cp[i + 1].y - ctr.y, cp[i + 1].x - ctr.x)) {
+                P2 t = cp[i]; cp[i] = cp[i + 1]; cp[i + 1] = t;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        P2 u{cp[k].x - cp[0].x, cp[k].y - cp[0].y}, v{cp[k + 1].x - cp[0].x, cp[k + 1].y - cp[0].y};
+        area += cross2(u, v);
+    }
+    return fabsf(area) / 2.0f;
+}
+
+__device__ __forceinline__ float iou_rotated(const float* a, const float* b) {
+    float sa = a[3] * a[4], sb = b[3] * b[4];
+    float so = overlap_rotated(a, b);
+    return so / fmaxf(sa + sb - so, NMS_EPS);
+}
+
+__device__ __forceinline__ float iou_normal(const float* a, const float* b) {
+    float left = fmaxf(a[0] - a[3] / 2, b[0] - b[3] / 2), right = fminf(a[0] + a[3] / 2, b[0] + b[3] / 2);
+    float top = fmaxf(a[1] - a[4] / 2, b[1] - b[4] / 2), bottom = fminf(a[1] + a[4] / 2, b[1] + b[4] / 2);
+    float w = fmaxf(right - left, 0.f), h = fmaxf(bottom - top, 0.f);
+    float inter = w * h;
+    return inter / fmaxf(a[3] * a[4] + b[3] * b[4] - inter, NMS_EPS);
+}
+
+// mode 0: overlap area, 1: rotated IoU, 2: axis-aligned IoU
+__global__ void pairwise_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb, int mode,
+                                float* __restrict__ out) {
+    long long total = (long long)na * nb;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        float a[7], b[7];
+        int i = (int)(t / nb), j = (int)(t % nb);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { a[k] = __ldg(A + (size_t)i * 7 + k); b[k] = __ldg(B + (size_t)j * 7 + k); }
+        out[t] = mode == 0 ? overlap_rotated(a, b) : (mode == 1 ? iou_rotated(a, b) : iou_normal(a, b));
+    }
+}
+
+// One CTA per instance.  boxes: concatenated, each instance's slice sorted by descending score.
+// keep[i] = 1 for survivors; kept_count[inst] = number of survivors.
+__global__ void __launch_bounds__(256) greedy_nms_kernel(const float* __restrict__ boxes, const int* __restrict__ seg,
+                                                         float thr, int rotated, unsigned char* __restrict__ keep,
+                                                         int* __restrict__ kept_count) {
+    extern __shared__ unsigned dead[];
+    const int beg = seg[blockIdx.x], n = seg[blockIdx.x + 1] - beg;
+    const float* bx = boxes + (size_t)beg * 7;
+    for (int w = threadIdx.x; w < (n + 31) / 32; w += blockDim.x) dead[w] = 0u;
+    __syncthreads();
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        if (dead[i >> 5] & (1u << (i & 31))) {           // uniform: every thread reads the same word
+            if (threadIdx.x == 0) keep[beg + i] = 0;
+            continue;
+        }
+        ++nk;
+        if (threadIdx.x == 0) keep[beg + i] = 1;
+        float a[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a[k] = __ldg(bx + (size_t)i * 7 + k);
+        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            if (dead[j >> 5] & (1u << (j & 31))) continue;
+            float b[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) b[k] = __ldg(bx + (size_t)j * 7 + k);
+            float v = rotated ? iou_rotated(a, b) : iou_normal(a, b);
+            if (v > thr) atomicOr(&dead[j >> 5], 1u << (j & 31));
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && kept_count) kept_count[blockIdx.x] = nk;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg3d_boxes_pairwise_bev(const float* boxes_a, int na, const float* boxes_b, int nb, int mode, float* out,
+                            void* stream) {
+    long long total = (long long)na * nb;
+    if (total == 0) return 0;
+    long long b = (total + 127) / 128;
+    pairwise_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 128, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, mode,
+                                                                                          out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_nms_segments(const float* sorted_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
+                      float thr, int rotated, unsigned char* keep, int* kept_count, void* stream) {
+    if (n_segments == 0) return 0;
+    size_t smem = sizeof(unsigned) * (size_t)((max_segment_len + 31) / 32 + 1);
+    if (smem > 200 * 1024) return -2;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(greedy_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    greedy_nms_kernel<<<n_segments, 256, smem, (cudaStream_t)stream>>>(sorted_boxes, seg_offsets, thr, rotated, keep,
+                                                                       kept_count);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+"""Device-resident sparse tensors and the functional sparse ops, all through the C ABI.
+
+Host-side mirror of the slice of the MinkowskiEngine API the reference uses:
+coordinate maps with hash tables, cached strided maps and rule maps (neighbour tables), and
+conv / transposed conv / conv-at-coordinates / avg-pool / trilinear / quantise-average.  torch is
+used for device memory and streams only; every computation is a call into libcagroup3d_b200.so.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
+
+# which conv kernel the engine uses: "simt" (exact fp32) or "tc" (tcgen05 3xTF32); see engine.py
+_CONV_IMPL = {"name": "simt"}
+
+
+def set_conv_impl(name: str) -> None:
+    assert name in ("simt", "tc")
+    _CONV_IMPL["name"] = name
+
+
+def get_conv_impl() -> str:
+    return _CONV_IMPL["name"]
+
+
+class LaunchCounter:
+    """Counts C-ABI calls that launch kernels (bench.py reports it as gpu_launches)."""
+    n = 0
+
+
+def _call(name, *args):
+    LaunchCounter.n += 1
+    _lib.call(name, *args)
+
+
+def _i32(*shape, device):
+    return torch.empty(shape, dtype=torch.int32, device=device)
+
+
+def _f32(*shape, device):
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+@dataclass
+class CoordMap:
+    """Unique int32 (b,x,y,z) rows + their hash table (key -> row)."""
+    coords: torch.Tensor          # [n, 4] int32
+    stride: int
+    keys: torch.Tensor            # [capacity] int64 (u64 bit pattern)
+    vals: torch.Tensor            # [capacity] int32
+    uid: int = field(default=0)
+
+    @property
+    def n(self) -> int:
+        return self.coords.shape[0]
+
+    @property
+    def capacity(self) -> int:
+        return self.keys.shape[0]
+
+
+class Manager:
+    """Caches strided maps by tensor stride (ME semantics A6) and rule maps by (in, out, kind)."""
+
+    def __init__(self):
+        self.by_stride: Dict[int, CoordMap] = {}
+        self.tables: Dict[Tuple, torch.Tensor] = {}
+        self.rule_counts: Dict[Tuple, int] = {}
+        self._uid = 0
+
+    def new_uid(self) -> int:
+        self._uid += 1
+        return self._uid
+
+
+@dataclass
+class SparseTensor:
+    F: torch.Tensor
+    cmap: CoordMap
+    mgr: Manager
+
+    @property
+    def C(self) -> torch.Tensor:
+        return self.cmap.coords
+
+    def with_F(self, F: torch.Tensor) -> "SparseTensor":
+        return SparseTensor(F, self.cmap, self.mgr)
+
+
+# ---- coordinate maps --------------------------------------------------------------------------
+def unique_first(coords: torch.Tensor, stride: int, mgr: Optional[Manager] = None, want_first=False,
+                 want_inverse=False):
+    """Hash-unique in first-occurrence order.  One host sync (reads the unique count)."""
+    dev = coords.device
+    n = coords.shape[0]
+    cap = _lib.hash_capacity(n)
+    keys = torch.empty((cap,), dtype=torch.int64, device=dev)
+    vals = _i32(cap, device=dev)
+    out = _i32(max(n, 1), 4, device=dev)
+    first = _i32(max(n, 1), device=dev) if want_first else None
+    inv = _i32(max(n, 1), device=dev) if want_inverse else None
+    nu = _i32(1, device=dev)
+    ws = _i32(3 * n + _lib.scan_workspace_ints(n), device=dev)
+    _call("cg3d_unique_first", coords, n, keys, vals, cap, out, first, inv, nu, ws)
+    u = int(nu.item())
+    cm = CoordMap(out[:u], stride, keys, vals, mgr.new_uid() if mgr else 0)
+    return cm, (first[:u] if want_first else None), (inv[:n] if want_inverse else None)
+
+
+def build_map(coords: torch.Tensor, stride: int, mgr: Optional[Manager] = None) -> CoordMap:
+    """Hash table over rows that are already unique (conv(x, coordinates=...), A12)."""
+    dev = coords.device
+    n = coords.shape[0]
+    cap = _lib.hash_capacity(n)
+    keys = torch.empty((cap,), dtype=torch.int64, device=dev)
+    vals = _i32(cap, device=dev)
+    _call("cg3d_hash_build", coords, n, keys, vals, cap)
+    return CoordMap(coords, stride, keys, vals, mgr.new_uid() if mgr else 0)
+
+
+def quantize(points4: torch.Tensor, ld: int, n: int, vs, mul: int = 1) -> torch.Tensor:
+    """rows (b,x,y,z) fp32 -> int32 voxel rows; raises if a voxel index overflows the key range."""
+    dev = points4.device
+    out = _i32(max(n, 1), 4, device=dev)
+    err = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _call("cg3d_quantize", points4, ld, n, float(vs[0]), float(vs[1]), float(vs[2]), mul, out, err)
+    return out[:n], err
+
+
+def strided_map(x_map: CoordMap, mgr: Manager, s: int) -> CoordMap:
+    ts = x_map.stride * s
+    if ts not in mgr.by_stride:
+        c = _i32(max(x_map.n, 1), 4, device=x_map.coords.device)
+        _call("cg3d_stride_coords", x_map.coords, x_map.n, ts, c)
+        cm, _, _ = unique_first(c[:x_map.n], ts, mgr)
+        mgr.by_stride[ts] = cm
+    return mgr.by_stride[ts]
+
+
+def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager]) -> torch.Tensor:
+    key = ("conv", in_map.uid, out_map.uid, k)
+    if mgr is not None and key in mgr.tables:
+        return mgr.tables[key]
+    nbr = _i32(k ** 3, max(out_map.n, 1), device=in_map.coords.device)
+    _call("cg3d_neighbor_table", out_map.coords, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k,
+          in_map.stride, nbr)
+    if mgr is not None:
+        mgr.tables[key] = nbr
+    return nbr
+
+
+def transpose_table(in_map: CoordMap, fine_map: CoordMap, k: int, mgr: Optional[Manager]) -> torch.Tensor:
+    key = ("convT", in_map.uid, fine_map.uid, k)
+    if mgr is not None and key in mgr.tables:
+        return mgr.tables[key]
+    nbr = _i32(k ** 3, max(fine_map.n, 1), device=in_map.coords.device)
+    _call("cg3d_transpose_table", fine_map.coords, fine_map.n, in_map.keys, in_map.vals, in_map.capacity, k,
+          in_map.stride, nbr)
+    if mgr is not None:
+        mgr.tables[key] = nbr
+    return nbr
+
+
+def count_rules(nbr: torch.Tensor) -> int:
+    cnt = torch.zeros((1,), dtype=torch.int64, device=nbr.device)
+    _call("cg3d_count_rules", nbr, nbr.numel(), cnt)
+    return int(cnt.item())
+
+
+# ---- compute ----------------------------------------------------------------------------------
+@dataclass
+class Tiles:
+    """Grouped-conv tiling: rows [row0, row0+rows) of tile t use weight group `group`."""
+    row0: torch.Tensor
+    rows: torch.Tensor
+    group: torch.Tensor
+    n: int
+
+
+def make_tiles(seg_offsets, device, tile=64) -> Tiles:
+    """seg_offsets: python list [g0_start, g1_start, ..., total] of contiguous per-group row ranges."""
+    r0, rn, gg = [], [], []
+    for g in range(len(seg_offsets) - 1):
+        a, b = seg_offsets[g], seg_offsets[g + 1]
+        for s in range(a, b, tile):
+            r0.append(s); rn.append(min(tile, b - s)); gg.append(g)
+    t = torch.tensor([r0, rn, gg], dtype=torch.int32).to(device, non_blocking=True)
+    return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), len(r0))
+
+
+def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
+              scale=None, shift=None, residual=None, act=None, tiles: Optional[Tiles] = None,
+              impl: Optional[str] = None) -> torch.Tensor:
+    """out = act((sum_k Fin[nbr[k]] @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout]."""
+    Cin, Cout = W.shape[-2], W.shape[-1]
+    assert Fin.is_contiguous() and W.is_contiguous() and Fin.shape[1] == Cin
+    out = _f32(n_out, Cout, device=Fin.device)
+    if n_out == 0:
+        return out
+    name = impl or _CONV_IMPL["name"]
+    fn = "cg3d_spconv_tc" if (name == "tc" and Cin % 32 == 0 and Cout % 32 == 0) else "cg3d_spconv_simt"
+    _call(fn, Fin, nbr, W, out, n_out, Cin, Cout, K, scale, shift, residual, ACT[act],
+          tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
+          tiles.n if tiles else 0)
+    return out
+
+
+def conv(x: SparseTensor, W: torch.Tensor, k: int, stride: int = 1, **ep) -> SparseTensor:
+    """MinkowskiConvolution forward with a fused epilogue (scale/shift/residual/act)."""
+    if k == 1 and stride == 1:
+        return x.with_F(gemm_rows(x.F, None, W, x.cmap.n, 1, **ep))
+    omap = x.cmap if stride == 1 else strided_map(x.cmap, x.mgr, stride)
+    nbr = neighbor_table(x.cmap, omap, k, x.mgr)
+    return SparseTensor(gemm_rows(x.F, nbr, W, omap.n, k ** 3, **ep), omap, x.mgr)
+
+
+def conv_transpose_k2s2(x: SparseTensor, W: torch.Tensor, **ep) -> SparseTensor:
+    fmap = x.mgr.by_stride[x.cmap.stride // 2]
+    nbr = transpose_table(x.cmap, fmap, 2, x.mgr)
+    return SparseTensor(gemm_rows(x.F, nbr, W, fmap.n, 8, **ep), fmap, x.mgr)
+
+
+def affine_act(x: torch.Tensor, scale=None, shift=None, add=None, act=None, out=None) -> torch.Tensor:
+    out = torch.empty_like(x) if out is None else out
+    _call("cg3d_affine_act", x, scale, shift, add, out, x.shape[0], x.shape[1], ACT[act])
+    return out
+
+
+def interp(x: SparseTensor, query: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """base + x.features_at_coordinates(query) for integer query rows."""
+    nq, C = query.shape[0], x.F.shape[1]
+    out = _f32(nq, C, device=x.F.device)
+    _call("cg3d_interp_trilinear", query, nq, x.cmap.keys, x.cmap.vals, x.cmap.capacity, x.cmap.stride, x.F, C,
+          base, out)
+    return out
+
+
+def avg_pool(x: SparseTensor, k: int, stride: int) -> SparseTensor:
+    omap = strided_map(x.cmap, x.mgr, stride)
+    C = x.F.shape[1]
+    out = _f32(omap.n, C, device=x.F.device)
+    _call("cg3d_avgpool_window", omap.coords, omap.n, x.cmap.coords, x.cmap.n, (k // 2) * x.cmap.stride, x.F, C, out)
+    return SparseTensor(out, omap, x.mgr)
+
+
+def segment_mean(srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C) -> torch.Tensor:
+    dev = inverse.device
+    out = _f32(n_unique, C, device=dev)
+    cnt = _f32(max(n_unique, 1), device=dev)
+    _call("cg3d_segment_mean", srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C, out, cnt)
+    return out
+
+
+def gather_rows(src: torch.Tensor, col0: int, rows: Optional[torch.Tensor], n: int, C: int, divisor: float = 1.0):
+    out = _f32(n, C, device=src.device)
+    _call("cg3d_gather_rows", src, src.shape[1], col0, rows, n, C, divisor, out)
+    return out
+
+
+def exclusive_scan(flags: torch.Tensor):
+    """returns (positions, total as device int tensor)."""
+    n = flags.numel()
+    out = _i32(max(n, 1), device=flags.device)
+    ws = _i32(_lib.scan_workspace_ints(n), device=flags.device)
+    total = _i32(1, device=flags.device)
+    _call("cg3d_exclusive_scan_i32", flags, n, out, ws, total)
+    return out[:n], total

@@ -1,0 +1,177 @@
+/* cagroup3d_b200 -- C ABI of the B200-native CAGroup3D inference hot path.
+ *
+ * One shared library (cagroup3d_b200/libcagroup3d_b200.so), plain pointers and sizes, no torch
+ * types.  Every pointer is a DEVICE pointer unless its name starts with `h_`; `stream` is a
+ * cudaStream_t passed as void*.  Every function returns 0 on success, a cudaError_t (> 0) when a
+ * launch failed, or a negative value for an argument it refuses.  Nothing allocates, nothing
+ * synchronises, nothing calls exit(): the caller owns all buffers (sizes stated per function).
+ *
+ * The reference interface each entry point replaces is cited as file:line relative to
+ * /root/reference (Haiyang-W/CAGroup3D).  "ME" = MinkowskiEngine v0.5.4, the un-vendored
+ * dependency whose coordinate manager and convolution the reference calls from Python; SURVEY.md
+ * Appendix A (A1..A20) is the statement of its semantics these functions implement.
+ *
+ * Coordinates are int32 rows (b, x, y, z), 16 bytes, |x|,|y|,|z| < 32768, 0 <= b < 65536.
+ * Feature matrices are row-major fp32 [rows, channels].
+ * A hash table is (keys: u64[capacity], vals: i32[capacity]), capacity = cg3d_hash_capacity(n).
+ * A rule map is a neighbour table nbr: i32[K][n_out] (tap-major), entry = input row or -1; its
+ * rule pairs {(tap, in, out)} are exactly ME's kernel map.
+ */
+#ifndef CAGROUP3D_B200_H
+#define CAGROUP3D_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- coordinate manager (ME coordinate maps: cagroup3d.py:24, biresnet.py strided convs,
+ *      cagroup_head.py:257-271, cagroup_roi_head.py:62-69) -------------------------------------- */
+
+/* smallest power of two >= 2n (>= 1024). host-only helper. */
+int cg3d_hash_capacity(int n);
+
+/* ints of scratch cg3d_exclusive_scan_i32 needs in `block_sums`. host-only helper. */
+int cg3d_scan_workspace_ints(int n);
+
+/* out[i] = (b, floor(x/vx)*mul, floor(y/vy)*mul, floor(z/vz)*mul) from rows pts[i*ld + 0..3] = (b,x,y,z).
+ * IEEE fp32 division then floor, i.e. ME's float->int coordinate conversion (A1) after the
+ * reference's `coordinates[:, 1:] /= voxel_size` (cagroup3d.py:21-22).  *err_count += rows whose
+ * voxel index does not fit the 16-bit key fields. */
+int cg3d_quantize(const float* pts, int ld, int n, float vx, float vy, float vz, int mul, int* out_coords,
+                  int* err_count, void* stream);
+
+/* out = (b, floor(c/ts)*ts) : coordinates of the stride-`ts` map (A6). */
+int cg3d_stride_coords(const int* coords, int n, int ts, int* out, void* stream);
+
+/* exclusive prefix sum; *total = sum.  block_sums: cg3d_scan_workspace_ints(n) ints. */
+int cg3d_exclusive_scan_i32(const int* in, int n, int* out, int* block_sums, int* total, void* stream);
+
+/* Hash-unique with the first-occurrence (min row index) winner == ME CPU insert order (A2).
+ *   out_coords[u]  unique rows in order of first occurrence          (capacity n rows)
+ *   first_row[u]   input row that won                (may be NULL)
+ *   inverse[i]     unique row of input row i         (may be NULL)
+ *   *n_unique      number of unique rows (device int)
+ * On return the table maps key -> unique row.  workspace: 3*n + cg3d_scan_workspace_ints(n) ints. */
+int cg3d_unique_first(const int* coords, int n, unsigned long long* keys, int* vals, int capacity, int* out_coords,
+                      int* first_row, int* inverse, int* n_unique, int* workspace, void* stream);
+
+/* table over already-unique rows: key -> row index. */
+int cg3d_hash_build(const int* coords, int n, unsigned long long* keys, int* vals, int capacity, void* stream);
+
+/* rows[i] = row of query[i] in the table or -1. */
+int cg3d_hash_lookup(const int* query, int n, const unsigned long long* keys, const int* vals, int capacity, int* rows,
+                     void* stream);
+
+/* ME kernel map of a (possibly strided) convolution or of conv(x, coordinates) (A5-A7, A12):
+ * nbr[tap][o] = row of (out_coords[o] + offset(tap) * step) in the input table.  Taps are x-fastest,
+ * centred for odd ksize and 0..k-1 for even ksize; step = the input's tensor stride. */
+int cg3d_neighbor_table(const int* out_coords, int n_out, const unsigned long long* keys, const int* vals,
+                        int capacity, int ksize, int step, int* nbr, void* stream);
+
+/* transposed-convolution kernel maps onto existing fine coordinates:
+ *   ksize 2: MinkowskiConvolutionTranspose(k=2,s=2) (biresnet.py:309; A8), ts_coarse = input stride
+ *   ksize 3: MinkowskiGenerativeConvolutionTranspose(k=3,s=3)(E, coordinates=A.C) (cagroup_head.py:274; A13)
+ * nbr: i32[ksize^3][n_fine], one valid tap per row. */
+int cg3d_transpose_table(const int* fine_coords, int n_fine, const unsigned long long* keys, const int* vals,
+                         int capacity, int ksize, int ts_coarse, int* nbr, void* stream);
+
+/* *count = number of entries >= 0 (rule pairs P of SURVEY.md section 8d). */
+int cg3d_count_rules(const int* nbr, long long total, unsigned long long* count, void* stream);
+
+/* ---- sparse convolution (ME MinkowskiConvolution / ConvolutionTranspose forward, A4-A8, A19) ---- */
+
+/* out[o, :] = act( (sum_k in[nbr[k][o], :] @ W[g][k]) * scale[g] + shift[g] + residual[o, :] )
+ * W: [G][K][Cin][Cout] (ME's `kernel` layout).  nbr == NULL means K == 1 on identical rows (1x1 conv,
+ * nn.Linear).  scale/shift/residual may be NULL (folded eval-mode BatchNorm / bias / block residual).
+ * act: 0 none, 1 ReLU, 2 ELU.  Grouped mode (tile_row0 != NULL): tile t covers rows
+ * [tile_row0[t], +tile_rows[t]) (<= 64) with weight/scale/shift group tile_group[t] -- used to run
+ * all per-class convolutions of cagroup_head.py:227-282 in one launch.
+ * cg3d_spconv_simt: exact fp32 FFMA path.  cg3d_spconv_tc: tcgen05 tensor-core path (3xTF32). */
+int cg3d_spconv_simt(const float* in, const int* nbr, const float* W, float* out, int n_out, int Cin, int Cout, int K,
+                     const float* scale, const float* shift, const float* residual, int act, const int* tile_row0,
+                     const int* tile_rows, const int* tile_group, int n_tiles, void* stream);
+
+/* out = act(x * scale + shift + add) on an [n, C] matrix; scale, shift, add may be NULL. */
+int cg3d_affine_act(const float* x, const float* scale, const float* shift, const float* add, float* out, long long n,
+                    int C, int act, void* stream);
+
+/* ---- pooling / interpolation / quantisation ---------------------------------------------------- */
+
+/* SparseTensor.features_at_coordinates (biresnet.py:182-197,376,389,394; A9):
+ * out[q] = base[q] + trilinear sample of the stride-`ts` tensor (feats, table) at integer query rows. */
+int cg3d_interp_trilinear(const int* query, int nq, const unsigned long long* keys, const int* vals, int capacity,
+                          int ts, const float* feats, int C, const float* base, float* out, void* stream);
+
+/* MinkowskiAvgPooling (biresnet.py:109-127; A10): out[o] = mean of input rows of the same batch
+ * index with |dx|,|dy|,|dz| <= half. */
+int cg3d_avgpool_window(const int* out_coords, int n_out, const int* in_coords, int n_in, int half, const float* feats,
+                        int C, float* out, void* stream);
+
+/* UNWEIGHTED_AVERAGE quantisation (cagroup_head.py:257-271; A3): out[u] = mean over points p with
+ * inverse[p] == u of feat(p); ref == NULL: feat(p) = srcA[p*ldA ..]; else ref[p] = (row, kind):
+ * kind >= 0 -> srcA[row*ldA + kind*C ..], kind < 0 -> srcB[row*ldB ..].  counts: n_unique floats. */
+int cg3d_segment_mean(const float* srcA, int ldA, const float* srcB, int ldB, const int* ref, const int* inverse,
+                      int n, int n_unique, int C, float* out, float* counts, void* stream);
+
+/* out[r, :] = src[rows[r]*ld + col0 .. +C] / divisor  (rows == NULL: identity). */
+int cg3d_gather_rows(const float* src, int ld, int col0, const int* rows, int n, int C, float divisor, float* out,
+                     void* stream);
+
+/* ---- detection head (cagroup_head.py) ---------------------------------------------------------- */
+
+/* minmax6 = (min x,y,z, max x,y,z) over all rows (cagroup_head.py:209-211). */
+int cg3d_coord_bounds(const int* coords, int n, int* minmax6, void* stream);
+
+/* voted[i, v, :] = clamp(coords[i]*voxel_size + offsets[i, v, :], bounds -+ tensor_stride) (:216-225). */
+int cg3d_vote_points(const int* coords, const float* offsets, int n, int nv, float voxel_size, int tensor_stride,
+                     const int* minmax6, float* voted, void* stream);
+
+/* flags[c*n + i] = sigmoid(sem[i, c]) > thr (:229-230), class-major. */
+int cg3d_semantic_flags(const float* sem, int n, int ncls, float thr, int* flags, void* stream);
+
+/* sel_rows[pos[t]] = t % n for every set flag (pos = exclusive scan of flags). */
+int cg3d_compact_rows(const int* flags, const int* pos, int n, int ncls, int* sel_rows, void* stream);
+
+/* All classes at once (:231-271): fused point p of class c -> coordsA (class voxel size),
+ * coordsE (expand * class voxel size, multiplied back by expand), ref = (source row, vote index or -1).
+ * Batch index of the emitted rows is c*B + b. */
+int cg3d_class_points(const int* coords, const float* voted, const int* sel_rows, const int* sel_off,
+                      const int* fused_off, const int* pad_rows, const float* vsA, const float* vsE, int ncls, int B,
+                      int nv, int expand, int total, float voxel_size, int* coordsA, int* coordsE, int* ref,
+                      void* stream);
+
+/* pred rows = [centerness | cls logits (ncls) | reg (nreg)]; scores = sigmoid(cls)*sigmoid(ctr),
+ * boxes per _bbox_pred_to_bbox (:590-593, 636-649, 654-703). */
+int cg3d_head_decode(const float* pred, int ld, const int* coords, int n, int ncls, int nreg, int B, const float* vsA,
+                     const float* scales, float* scores, float* maxscore, float* boxes, int box_dim, void* stream);
+
+/* ---- NMS / IoU (pcdet/ops/iou3d_nms) ----------------------------------------------------------- */
+
+/* mode 0: boxes_overlap_bev_gpu (iou3d_nms.cpp:44-66), 1: boxes_iou_bev_gpu (:68-88),
+ * 2: axis-aligned BEV IoU (iou3d_nms_kernel.cu:314-325).  out: [na, nb]. */
+int cg3d_boxes_pairwise_bev(const float* boxes_a, int na, const float* boxes_b, int nb, int mode, float* out,
+                            void* stream);
+
+/* nms_gpu (rotated=1, iou3d_nms.cpp:90-136) / nms_normal_gpu (rotated=0, :139-186) for n_segments
+ * independent instances in one launch.  Instance s owns rows [seg_offsets[s], seg_offsets[s+1]) of
+ * sorted_boxes, already in descending-score order.  keep[i] in {0,1}; kept_count[s] (may be NULL). */
+int cg3d_nms_segments(const float* sorted_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
+                      float thr, int rotated, unsigned char* keep, int* kept_count, void* stream);
+
+/* ---- RoI head (cagroup_roi_head.py) ------------------------------------------------------------ */
+
+/* 7^3 grid points per RoI -> voxel rows at coord_key * clamp(floor(p / voxel_size)) (:54-68, :199-224). */
+int cg3d_roi_grid_coords(const float* rois, int n_rois, int rois_per_sample, int grid, int with_yaw, float voxel_size,
+                         int half_extent, int coord_key, int* out_coords, void* stream);
+
+/* rule map of the 7^3 "pooling conv" evaluated at RoI centres (:72-90; A20) on top of the
+ * unique-inverse of the grid voxels: nbr: i32[grid^3][n_rois]. */
+int cg3d_roi_pool_table(const int* inverse, int n_rois, int grid, int* nbr, void* stream);
+
+/* CAGroupResidualCoder.decode_torch + rotate + add centre (:477-510, cagroup_utils.py:147-197). */
+int cg3d_roi_decode(const float* rois, const float* reg, int n, int code_size, int sincos, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
