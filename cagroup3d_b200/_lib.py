@@ -1,52 +1,48 @@
 """ctypes binding of libcagroup3d_b200.so (the C ABI in include/cagroup3d_b200.h).
 
-There is no fallback: if the library is missing or a call fails, this raises.
+The argument types of every entry point are parsed from the header itself, so the binding cannot
+drift from the declared ABI.  There is no fallback: if the library is missing, a declared symbol is
+not exported, or a call returns a non-zero status, this raises.
 """
 from __future__ import annotations
 
 import ctypes
 import os
+import re
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcagroup3d_b200.so")
-
-# signature spec: p = device/host pointer, i = int, f = float, l = long long
-SIGNATURES = {
-    "cg3d_hash_capacity": "i",
-    "cg3d_scan_workspace_ints": "i",
-    "cg3d_quantize": "piifffippp",
-    "cg3d_stride_coords": "piipp",
-    "cg3d_exclusive_scan_i32": "pipppp",
-    "cg3d_unique_first": "pippippppp" + "p",
-    "cg3d_hash_build": "pippip",
-    "cg3d_hash_lookup": "pippipp",
-    "cg3d_neighbor_table": "pippiiipp",
-    "cg3d_transpose_table": "pippiiipp",
-    "cg3d_count_rules": "plpp",
-    "cg3d_spconv_simt": "ppppiiiipppipppip",
-    "cg3d_spconv_tc": "ppppiiiipppipppip",
-    "cg3d_affine_act": "ppppplii" + "p",
-    "cg3d_interp_trilinear": "pippiipippp",
-    "cg3d_avgpool_window": "pipiipipp",
-    "cg3d_segment_mean": "pipippiiippp",
-    "cg3d_gather_rows": "piipiifpp",
-    "cg3d_coord_bounds": "pipp",
-    "cg3d_vote_points": "ppiifippp",
-    "cg3d_semantic_flags": "piifpp",
-    "cg3d_compact_rows": "ppiipp",
-    "cg3d_class_points": "pppppppp" + "iiiii" + "f" + "pppp",
-    "cg3d_head_decode": "pipiiiippppp" + "ip",
-    "cg3d_boxes_pairwise_bev": "pipiipp",
-    "cg3d_nms_segments": "ppiifippp",
-    "cg3d_roi_grid_coords": "piiiifiipp",
-    "cg3d_roi_pool_table": "piipp",
-    "cg3d_roi_decode": "ppiiipp",
-}
-_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_longlong}
+HEADER_PATH = os.path.join(_HERE, "..", "include", "cagroup3d_b200.h")
 
 _lib = None
+_host_only = set()          # entry points without a trailing `void* stream`
+
+
+def parse_header(path: str = HEADER_PATH):
+    """-> {name: [ctypes types]} for every `int cg3d_*(...)` prototype."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(cg3d_\w+)\s*\(([^)]*)\)\s*;", src):
+        name, args = m.group(1), m.group(2)
+        types = []
+        for a in [x.strip() for x in args.split(",") if x.strip()]:
+            if "*" in a:
+                types.append(ctypes.c_void_p)
+            elif a.startswith("float"):
+                types.append(ctypes.c_float)
+            elif a.startswith("long long"):
+                types.append(ctypes.c_longlong)
+            elif a.startswith("int"):
+                types.append(ctypes.c_int)
+            else:
+                raise RuntimeError(f"unparsed parameter '{a}' of {name}")
+        protos[name] = types
+        if not args.strip().endswith("stream"):
+            _host_only.add(name)
+    return protos
 
 
 def load() -> ctypes.CDLL:
@@ -57,12 +53,9 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -m cagroup3d_b200.build` "
                 "(there is no CPU or PyTorch fallback for the CUDA path)")
         lib = ctypes.CDLL(LIB_PATH)
-        for name, sig in SIGNATURES.items():
-            if not hasattr(lib, name):
-                continue                      # optional symbol (checked by exported_symbols test)
-            fn = getattr(lib, name)
-            fn.argtypes = [_CT[c] for c in sig] if name not in ("cg3d_hash_capacity", "cg3d_scan_workspace_ints") \
-                else [ctypes.c_int]
+        for name, types in parse_header().items():
+            fn = getattr(lib, name)           # AttributeError if the library lacks a declared symbol
+            fn.argtypes = types
             fn.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -88,9 +81,18 @@ def call(name: str, *args) -> None:
         raise RuntimeError(f"{name} failed with status {rc}")
 
 
+def host(name: str, *args) -> int:
+    """Host-only helper entry points (sizes of workspaces); returns the int result."""
+    return getattr(load(), name)(*args)
+
+
 def hash_capacity(n: int) -> int:
-    return load().cg3d_hash_capacity(int(n))
+    return host("cg3d_hash_capacity", int(n))
 
 
 def scan_workspace_ints(n: int) -> int:
-    return load().cg3d_scan_workspace_ints(int(n))
+    return host("cg3d_scan_workspace_ints", int(n))
+
+
+def sort_workspace_ints(n: int) -> int:
+    return host("cg3d_sort_workspace_ints", int(n))

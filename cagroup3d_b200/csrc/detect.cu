@@ -32,6 +32,14 @@ __global__ void bounds_kernel(const int4* __restrict__ c, int n, int* __restrict
     }
 }
 
+// first[b] = smallest row index whose batch index is b (decomposition_permutations[b][0], cagroup_head.py:207)
+__global__ void first_rows_kernel(const int4* __restrict__ c, int n, int B, int* __restrict__ first) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int b = c[i].x;
+        if (b >= 0 && b < B) atomicMin(first + b, i);
+    }
+}
+
 __global__ void vote_kernel(const int4* __restrict__ c, const float* __restrict__ off, int n, int nv, float vs,
                             int ts, const int* __restrict__ mm, float* __restrict__ voted) {
     float lo[3], hi[3];
@@ -235,6 +243,15 @@ int cg3d_coord_bounds(const int* coords, int n, int* minmax6, void* stream) {
     cudaMemcpyAsync(minmax6, init, sizeof(init), cudaMemcpyHostToDevice, s);
     if (n == 0) return 0;
     bounds_kernel<<<flat_grid(n), 256, 0, s>>>((const int4*)coords, n, minmax6);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_first_rows(const int* coords, int n, int B, int* first, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(first, 0x7F, sizeof(int) * (size_t)B, s);
+    if (n == 0) return 0;
+    first_rows_kernel<<<flat_grid(n), 256, 0, s>>>((const int4*)coords, n, B, first);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

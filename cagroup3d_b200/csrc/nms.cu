@@ -118,7 +118,7 @@ __global__ void pairwise_kernel(const float* __restrict__ A, int na, const float
 // One CTA per instance.  boxes: concatenated, each instance's slice sorted by descending score.
 // keep[i] = 1 for survivors; kept_count[inst] = number of survivors.
 __global__ void __launch_bounds__(256) greedy_nms_kernel(const float* __restrict__ boxes, const int* __restrict__ seg,
-                                                         float thr, int rotated, unsigned char* __restrict__ keep,
+                                                         float thr, int rotated, int* __restrict__ keep,
                                                          int* __restrict__ kept_count) {
     extern __shared__ unsigned dead[];
     const int beg = seg[blockIdx.x], n = seg[blockIdx.x + 1] - beg;
@@ -165,7 +165,7 @@ int cg3d_boxes_pairwise_bev(const float* boxes_a, int na, const float* boxes_b, 
 }
 
 int cg3d_nms_segments(const float* sorted_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
-                      float thr, int rotated, unsigned char* keep, int* kept_count, void* stream) {
+                      float thr, int rotated, int* keep, int* kept_count, void* stream) {
     if (n_segments == 0) return 0;
     size_t smem = sizeof(unsigned) * (size_t)((max_segment_len + 31) / 32 + 1);
     if (smem > 200 * 1024) return -2;

@@ -29,6 +29,7 @@ struct ConvArgs {
     const int* tile_rows;
     const int* tile_group;
     int n_out, Cin, Cout, K, act;
+    int ldi, ldo, in_act;  // row strides (floats) of in / out; in_act: activation applied to gathered rows
 };
 
 __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
 
     const int a_row = t / 4, a_c = (t % 4) * 4;      // A tile: 64 rows x 16 ch, one float4 per thread
     const int b_k = t / 16, b_n = (t % 16) * 4;      // B tile: 16 x 64, one float4 per thread
-    const bool vecA = (a.Cin % 4) == 0, vecB = (a.Cout % 4) == 0;
+    const bool vecA = (a.Cin % 4) == 0 && (a.ldi % 4) == 0, vecB = (a.Cout % 4) == 0;
 
     for (int k = 0; k < a.K; ++k) {
         int r = -1;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
         for (int c0 = 0; c0 < a.Cin; c0 += TK) {
             float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
             if (my_row >= 0) {
-                const float* src = a.in + (size_t)my_row * a.Cin + c0 + a_c;
+                const float* src = a.in + (size_t)my_row * a.ldi + c0 + a_c;
                 if (vecA && c0 + a_c + 3 < a.Cin) {
                     av = __ldg(reinterpret_cast<const float4*>(src));
                 } else {
@@ -80,6 +81,9 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
                     if (c0 + a_c + 1 < a.Cin) av.y = __ldg(src + 1);
                     if (c0 + a_c + 2 < a.Cin) av.z = __ldg(src + 2);
                     if (c0 + a_c + 3 < a.Cin) av.w = __ldg(src + 3);
+                }
+                if (a.in_act == CG3D_ACT_RELU) {
+                    av.x = fmaxf(av.x, 0.f); av.y = fmaxf(av.y, 0.f); av.z = fmaxf(av.z, 0.f); av.w = fmaxf(av.w, 0.f);
                 }
             }
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
     for (int i = 0; i < 4; ++i) {
         int rr = ty * 4 + i;
         if (rr >= nrows) continue;
-        size_t orow = (size_t)(row0 + rr) * a.Cout;
+        size_t orow = (size_t)(row0 + rr) * a.ldo, rrow = (size_t)(row0 + rr) * a.Cout;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int c = n0 + tx * 4 + j;
@@ -127,24 +131,25 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
             float v = acc[i][j];
             if (a.scale) v *= __ldg(a.scale + (size_t)g * a.Cout + c);
             if (a.shift) v += __ldg(a.shift + (size_t)g * a.Cout + c);
-            if (a.residual) v += __ldg(a.residual + orow + c);
+            if (a.residual) v += __ldg(a.residual + rrow + c);
             a.out[orow + c] = cg3d_act(v, a.act);
         }
     }
 }
 
 // out = act(x * scale + shift (+ add)) over an [n, C] matrix; scale/shift may be null
-__global__ void affine_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+__global__ void affine_act_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ add, float* __restrict__ out,
-                                  long long total, int C, int act) {
+                                  int ldo, long long total, int C, int act) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % C);
-        float v = x[i];
+        long long r = i / C;
+        float v = x[r * ldx + c];
         if (scale) v *= __ldg(scale + c);
         if (shift) v += __ldg(shift + c);
         if (add) v += add[i];
-        out[i] = cg3d_act(v, act);
+        out[r * ldo + c] = cg3d_act(v, act);
     }
 }
 
@@ -152,12 +157,13 @@ __global__ void affine_act_kernel(const float* __restrict__ x, const float* __re
 
 extern "C" {
 
-int cg3d_spconv_simt(const float* in, const int* nbr, const float* W, float* out, int n_out, int Cin, int Cout, int K,
-                     const float* scale, const float* shift, const float* residual, int act, const int* tile_row0,
-                     const int* tile_rows, const int* tile_group, int n_tiles, void* stream) {
+int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const float* W, float* out, int ldo, int n_out,
+                     int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
+                     const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream) {
     if (n_out == 0) return 0;
     if (!nbr && K != 1) return -1;
-    ConvArgs a{in, nbr, W, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act};
+    ConvArgs a{in, nbr, W, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act,
+               ldi, ldo, in_act};
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     dim3 grid(tiles, cg3d_div_up(Cout, TN));
@@ -166,13 +172,13 @@ int cg3d_spconv_simt(const float* in, const int* nbr, const float* W, float* out
     return 0;
 }
 
-int cg3d_affine_act(const float* x, const float* scale, const float* shift, const float* add, float* out, long long n,
-                    int C, int act, void* stream) {
+int cg3d_affine_act(const float* x, int ldx, const float* scale, const float* shift, const float* add, float* out,
+                    int ldo, long long n, int C, int act, void* stream) {
     long long total = n * C;
     if (total == 0) return 0;
     long long b = (total + 255) / 256;
     int grid = (int)(b > 148 * 16 ? 148 * 16 : b);
-    affine_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, add, out, total, C, act);
+    affine_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, add, out, ldo, total, C, act);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

@@ -34,9 +34,23 @@ class LaunchCounter:
     n = 0
 
 
-def _call(name, *args):
+class Profile:
+    """Optional per-call CUDA-event timing (bench.py roofline accounting).  `active` is a list that
+    receives (name, meta, start_event, end_event); None disables it."""
+    active = None
+    stage = ""
+
+
+def _call(name, *args, meta=None):
     LaunchCounter.n += 1
+    if Profile.active is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _lib.call(name, *args)
+    e1.record()
+    Profile.active.append((name, Profile.stage, meta, e0, e1))
 
 
 def _i32(*shape, device):
@@ -196,19 +210,34 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
 
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
               scale=None, shift=None, residual=None, act=None, tiles: Optional[Tiles] = None,
-              impl: Optional[str] = None) -> torch.Tensor:
-    """out = act((sum_k Fin[nbr[k]] @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout]."""
+              impl: Optional[str] = None, in_act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act((sum_k in_act(Fin[nbr[k]]) @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout].
+
+    Fin / out may be column slices of wider row-major matrices (unit column stride)."""
     Cin, Cout = W.shape[-2], W.shape[-1]
-    assert Fin.is_contiguous() and W.is_contiguous() and Fin.shape[1] == Cin
-    out = _f32(n_out, Cout, device=Fin.device)
+    assert Fin.stride(1) == 1 and W.is_contiguous() and Fin.shape[1] == Cin
+    if out is None:
+        out = _f32(n_out, Cout, device=Fin.device)
+    assert out.stride(1) == 1 and out.shape[0] == n_out and out.shape[1] == Cout
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == (n_out, Cout)
     if n_out == 0:
         return out
     name = impl or _CONV_IMPL["name"]
-    fn = "cg3d_spconv_tc" if (name == "tc" and Cin % 32 == 0 and Cout % 32 == 0) else "cg3d_spconv_simt"
-    _call(fn, Fin, nbr, W, out, n_out, Cin, Cout, K, scale, shift, residual, ACT[act],
-          tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
-          tiles.n if tiles else 0)
+    use_tc = name == "tc" and tc_supported(Cin, Cout)
+    fn = "cg3d_spconv_tc" if use_tc else "cg3d_spconv_simt"
+    meta = None
+    if Profile.active is not None:
+        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4,
+                    residual=residual is not None)
+    _call(fn, Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K, scale, shift, residual,
+          ACT[act], tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
+          tiles.n if tiles else 0, meta=meta)
     return out
+
+
+def tc_supported(Cin: int, Cout: int) -> bool:
+    return hasattr(_lib.load(), "cg3d_spconv_tc") and Cin % 32 == 0 and Cout % 32 == 0 and Cout <= 512
 
 
 def conv(x: SparseTensor, W: torch.Tensor, k: int, stride: int = 1, **ep) -> SparseTensor:
@@ -227,8 +256,13 @@ def conv_transpose_k2s2(x: SparseTensor, W: torch.Tensor, **ep) -> SparseTensor:
 
 
 def affine_act(x: torch.Tensor, scale=None, shift=None, add=None, act=None, out=None) -> torch.Tensor:
-    out = torch.empty_like(x) if out is None else out
-    _call("cg3d_affine_act", x, scale, shift, add, out, x.shape[0], x.shape[1], ACT[act])
+    """act(x * scale + shift + add); x / out may be column slices (unit column stride)."""
+    if out is None:
+        out = torch.empty((x.shape[0], x.shape[1]), dtype=torch.float32, device=x.device)
+    assert x.stride(1) == 1 and out.stride(1) == 1
+    if add is not None:
+        assert add.is_contiguous()
+    _call("cg3d_affine_act", x, x.stride(0), scale, shift, add, out, out.stride(0), x.shape[0], x.shape[1], ACT[act])
     return out
 
 

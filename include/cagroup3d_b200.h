@@ -80,20 +80,26 @@ int cg3d_count_rules(const int* nbr, long long total, unsigned long long* count,
 
 /* ---- sparse convolution (ME MinkowskiConvolution / ConvolutionTranspose forward, A4-A8, A19) ---- */
 
-/* out[o, :] = act( (sum_k in[nbr[k][o], :] @ W[g][k]) * scale[g] + shift[g] + residual[o, :] )
+/* out[o, :] = act( (sum_k in_act(in[nbr[k][o], :]) @ W[g][k]) * scale[g] + shift[g] + residual[o, :] )
  * W: [G][K][Cin][Cout] (ME's `kernel` layout).  nbr == NULL means K == 1 on identical rows (1x1 conv,
  * nn.Linear).  scale/shift/residual may be NULL (folded eval-mode BatchNorm / bias / block residual).
- * act: 0 none, 1 ReLU, 2 ELU.  Grouped mode (tile_row0 != NULL): tile t covers rows
- * [tile_row0[t], +tile_rows[t]) (<= 64) with weight/scale/shift group tile_group[t] -- used to run
- * all per-class convolutions of cagroup_head.py:227-282 in one launch.
- * cg3d_spconv_simt: exact fp32 FFMA path.  cg3d_spconv_tc: tcgen05 tensor-core path (3xTF32). */
-int cg3d_spconv_simt(const float* in, const int* nbr, const float* W, float* out, int n_out, int Cin, int Cout, int K,
-                     const float* scale, const float* shift, const float* residual, int act, const int* tile_row0,
-                     const int* tile_rows, const int* tile_group, int n_tiles, void* stream);
+ * ldi / ldo: row strides (floats) of `in` / `out` (a conv may read a column slice of a wider matrix and
+ * write into a slice of a concat buffer); residual rows are dense [n_out, Cout].
+ * in_act: activation applied to gathered input rows (1 = the `self.relu(x)` in front of every BiResNet
+ * stage, biresnet.py:366-394); act: activation of the result.  0 none, 1 ReLU, 2 ELU.
+ * Grouped mode (tile_row0 != NULL): tile t covers rows [tile_row0[t], +tile_rows[t]) (<= 64 for simt,
+ * <= 128 for tc) with weight/scale/shift group tile_group[t] -- used to run all per-class convolutions
+ * of cagroup_head.py:227-282 in one launch.
+ * cg3d_spconv_simt: exact fp32 FFMA path (any Cin/Cout). */
+int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const float* W, float* out, int ldo,
+                     int n_out, int Cin, int Cout, int K, const float* scale, const float* shift,
+                     const float* residual, int act, const int* tile_row0, const int* tile_rows,
+                     const int* tile_group, int n_tiles, void* stream);
 
-/* out = act(x * scale + shift + add) on an [n, C] matrix; scale, shift, add may be NULL. */
-int cg3d_affine_act(const float* x, const float* scale, const float* shift, const float* add, float* out, long long n,
-                    int C, int act, void* stream);
+/* out = act(x * scale + shift + add) on an [n, C] matrix with row strides ldx / ldo; scale, shift, add
+ * ([n, C] dense) may be NULL.  Pre-activation BatchNorm+ReLU of DAPPM (biresnet.py:109-174). */
+int cg3d_affine_act(const float* x, int ldx, const float* scale, const float* shift, const float* add, float* out,
+                    int ldo, long long n, int C, int act, void* stream);
 
 /* ---- pooling / interpolation / quantisation ---------------------------------------------------- */
 
@@ -121,6 +127,9 @@ int cg3d_gather_rows(const float* src, int ld, int col0, const int* rows, int n,
 
 /* minmax6 = (min x,y,z, max x,y,z) over all rows (cagroup_head.py:209-211). */
 int cg3d_coord_bounds(const int* coords, int n, int* minmax6, void* stream);
+
+/* first[b] = first row of sample b (pad_id, cagroup_head.py:207); 0x7F7F7F7F where a sample is empty. */
+int cg3d_first_rows(const int* coords, int n, int B, int* first, void* stream);
 
 /* voted[i, v, :] = clamp(coords[i]*voxel_size + offsets[i, v, :], bounds -+ tensor_stride) (:216-225). */
 int cg3d_vote_points(const int* coords, const float* offsets, int n, int nv, float voxel_size, int tensor_stride,
@@ -154,9 +163,68 @@ int cg3d_boxes_pairwise_bev(const float* boxes_a, int na, const float* boxes_b, 
 
 /* nms_gpu (rotated=1, iou3d_nms.cpp:90-136) / nms_normal_gpu (rotated=0, :139-186) for n_segments
  * independent instances in one launch.  Instance s owns rows [seg_offsets[s], seg_offsets[s+1]) of
- * sorted_boxes, already in descending-score order.  keep[i] in {0,1}; kept_count[s] (may be NULL). */
+ * sorted_boxes, already in descending-score order.  keep[i] in {0,1}; kept_count[s] (may be NULL).
+ * The reference returns keep indices through a CPU tensor after a blocking D2H of an N x N/64 bitmask;
+ * here the flags stay on the device and all (sample, class) instances run in one launch. */
 int cg3d_nms_segments(const float* sorted_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
-                      float thr, int rotated, unsigned char* keep, int* kept_count, void* stream);
+                      float thr, int rotated, int* keep, int* kept_count, void* stream);
+
+/* ---- selection primitives (torch.sort / topk / nonzero / boolean masks on the path) ---- */
+
+/* ints of scratch cg3d_sort_pairs needs. host-only helper. */
+int cg3d_sort_workspace_ints(int n);
+
+/* stable LSD radix sort of (u64 key, i32 value) pairs on key bits [begin_bit, end_bit), ascending,
+ * in place (keys_tmp / vals_tmp: n elements of scratch each).  Replaces scores.sort(descending=True)
+ * (iou3d_nms_utils.py:92,110) and max_scores.topk (cagroup_head.py:596) with keys built by the
+ * functions below: (segment << 32 | ~ordered(score)), ties keep the lower index first. */
+int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, int end_bit,
+                    unsigned long long* keys_tmp, int* vals_tmp, int* workspace, void* stream);
+
+/* counts[s] = #{i : ids[i] == s}, s in [0, nseg). */
+int cg3d_histogram_i32(const int* ids, int n, int nseg, int* counts, void* stream);
+
+/* out[pos[i]] = payload ? payload[i] : i for every set flag (torch.nonzero / boolean-mask gather). */
+int cg3d_compact_i32(const int* flags, const int* pos, int n, const int* payload, int* out, void* stream);
+
+/* seg[i] = b * ncls + c for class-map voxel rows whose batch index is c * B + b. */
+int cg3d_map_segments(const int* coords, int n, int B, int ncls, int* seg, void* stream);
+
+/* top NMS_PRE per (sample, class map) (cagroup_head.py:595-599): key = (seg, ~maxscore) for segments
+ * longer than nms_pre, (seg, 0) otherwise (keeps row order); vals = row. */
+int cg3d_topk_keys(const int* seg, const float* maxscore, int n, const int* seg_counts, int nms_pre,
+                   unsigned long long* keys, int* vals, void* stream);
+
+/* flags[i] = rank of sorted element i inside its segment < nms_pre. */
+int cg3d_rank_filter(const unsigned long long* keys, int n, const int* seg_off, int nms_pre, int* flags, void* stream);
+
+/* flags[j * ncls + i] = scores[cand[j], i] > thr (cagroup_head.py:753). */
+int cg3d_pair_flags(const float* scores, const int* cand, int nc, int ncls, float thr, int* flags, void* stream);
+
+/* compacted (key, source row) of every flagged pair; key = ((b * ncls + i) << 32 | ~score). */
+int cg3d_pair_keys(const float* scores, const int* cand, const int* seg_of_row, int nc, int ncls, const int* flags,
+                   const int* pos, unsigned long long* keys, int* src_row, void* stream);
+
+/* RoI-stage equivalents (cagroup_roi_head.py:437-446): one pair per RoI, class = roi_labels. */
+int cg3d_roi_flags(const float* roi_scores, int n, float thr, int* flags, void* stream);
+int cg3d_roi_keys(const float* roi_scores, const int* roi_labels, int n, int rois_per_sample, int ncls,
+                  const int* flags, const int* pos, unsigned long long* keys, int* src_row, void* stream);
+
+/* seg[i] = keys[i] >> 32. */
+int cg3d_key_segments(const unsigned long long* keys, int n, int* seg, void* stream);
+
+/* out[p] = 7-wide box of row src_row[p] (yaw 0 if box_dim == 6; negated if flip) = boxes[order]. */
+int cg3d_gather_boxes(const float* boxes, int box_dim, const int* src_row, int n, int flip, float* out, void* stream);
+
+/* pack survivors in (sample, class, descending score) order: boxes, scores, labels, sample index
+ * (cagroup_head.py:773-797, cagroup_roi_head.py:455-475). */
+int cg3d_emit_detections(const float* sorted_boxes, const unsigned long long* keys, const int* keep, const int* pos,
+                         int n, int ncls, int with_yaw, int flip, float* out_boxes, float* out_scores, int* out_labels,
+                         int* out_sample, void* stream);
+
+/* reoder_rois_for_refining (cagroup_roi_head.py:328-362): zero-padded (B, rmax, 7) RoIs, yaw negated. */
+int cg3d_pad_rois(const float* det_boxes, const float* det_scores, const int* det_labels, const int* sample_off, int B,
+                  int rmax, float* rois, float* roi_scores, int* roi_labels, void* stream);
 
 /* ---- RoI head (cagroup_roi_head.py) ------------------------------------------------------------ */
 

@@ -204,7 +204,7 @@ class Oracle:
             pts = [torch.from_numpy(O.C[r, 1:]).to(f32) * vsz for r in rows]
             per_class.append(([ctr[r] for r in rows], [bbox[r] for r in rows],
                               [cls_score[r] for r in rows], pts))
-            maps.append(dict(coords=O.C, ctr=ctr, bbox=bbox, cls=cls_score, feat=O.F,
+            maps.append(dict(coords=O.C, ctr=ctr, bbox=bbox, cls=cls_score, reg=reg, feat=O.F,
                              n_sel=int(len(sel))))
         # get_bboxes (cagroup_head.py:557-624)
         results = []
