@@ -1,0 +1,408 @@
+// Sparse convolution as an output-stationary implicit GEMM on the 5th-gen tensor cores (tcgen05).
+//
+//   out[o, :] = epilogue( sum_k in_act(in[nbr[k][o], :]) @ W[g][k] )
+//
+// One CTA owns 128 output rows x NT output channels (NT = 64 / 128 / 256); the accumulator lives in
+// TMEM (128 lanes x NT fp32 columns).  The K loop walks (active tap, 64-channel chunk) stages through a
+// ring of shared-memory buffers:
+//   warps 0-3  gather the 128 feature rows of the stage (rows nbr < 0 are zero-filled): coalesced 32-byte
+//              pieces per lane, 8 lanes per row, split fp32 -> bf16 hi + bf16 lo in registers and written
+//              in the 128B-swizzled K-major UMMA layout; after the K loop they run the epilogue
+//              (tcgen05.ld -> folded BN / bias / residual / ReLU|ELU -> global);
+//   warp 4     streams the stage's weight tile: the weights are pre-split and pre-swizzled once into the
+//              exact shared-memory image, so a stage is ONE linear bulk async copy (cp.async.bulk, TMA
+//              engine, mbarrier complete_tx);
+//   warp 5     one elected lane issues the tcgen05.mma's: per 16-wide k-step three bf16 products
+//              A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulated in fp32 ("bf16x3": the dropped terms are
+//              <= 2^-16 relative, fp32-class accuracy at 1/3 of the bf16 tensor rate), then tcgen05.commit
+//              releases the stage.
+// Taps for which no row of the tile has a neighbour are skipped (found by a prologue scan of the rule
+// map).  No atomics; the accumulation order is fixed (taps ascending), so results are deterministic.
+//
+// Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 64 == 0 and
+// Cout % 64 == 0; the Cin = 3 stem and the narrow prediction
+// heads stay on the exact-fp32 SIMT kernel (spconv_simt.cu).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/cagroup3d_b200.h"
+
+namespace {
+
+constexpr int TM = 128;            // output rows per CTA (UMMA M)
+constexpr int KC = 64;             // channels per stage (128 bytes of bf16 = one swizzle row)
+constexpr int NPROD = 128;         // gather / epilogue threads (warps 0-3)
+constexpr int NTHREADS = 192;
+constexpr int A_PART = TM * 128;   // bytes of one A part (hi or lo) per stage
+constexpr int MAX_TAPS = 729;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000LL) __trap();     // ~4 s watchdog: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row atoms of 1024 bytes (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+    d |= (uint64_t)1 << 46;                    // descriptor version
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 8 fp32 -> 8 bf16 hi (16 bytes) + 8 bf16 lo (16 bytes)
+__device__ __forceinline__ void split8(const float4& a, const float4& b, int relu, uint4& hi, uint4& lo) {
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float x0 = v[2 * i], x1 = v[2 * i + 1];
+        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+        float r0 = x0 - __bfloat162float(hh.x), r1 = x1 - __bfloat162float(hh.y);
+        __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+        h[i] = *reinterpret_cast<uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct TcArgs {
+    const float* in;
+    const int* nbr;
+    const unsigned char* wimg;
+    float* out;
+    const float* scale;
+    const float* shift;
+    const float* residual;
+    const int* tile_row0;
+    const int* tile_rows;
+    const int* tile_group;
+    int n_out, Cin, Cout, K, act, ldi, ldo, in_act;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
+    constexpr int B_PART = NT * 128;                      // bytes of one B part (hi or lo) per stage
+    constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_slot;
+    __shared__ unsigned short taps[MAX_TAPS + 1];
+    __shared__ unsigned char active[MAX_TAPS + 3];
+    __shared__ int n_active_s;
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    int row0, nrows, g = 0;
+    if (a.tile_row0) {
+        row0 = a.tile_row0[blockIdx.x];
+        nrows = a.tile_rows[blockIdx.x];
+        g = a.tile_group[blockIdx.x];
+    } else {
+        row0 = blockIdx.x * TM;
+        nrows = min(TM, a.n_out - row0);
+    }
+    const int n0 = blockIdx.y * NT;
+    const int nchunks = a.Cin / KC;
+    const int ntn = a.Cout / NT;
+
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+
+    // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, NPROD + 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (a.nbr) {
+        for (int k = warp; k < a.K; k += NTHREADS / 32) {
+            bool any = false;
+            for (int r = lane; r < nrows; r += 32) any |= __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) >= 0;
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0) active[k] = any ? 1 : 0;
+        }
+    } else {
+        if (t == 0) active[0] = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        int cnt = 0;
+        for (int b0 = 0; b0 < a.K; b0 += 32) {
+            int k = b0 + lane;
+            bool f = k < a.K && active[k];
+            unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) taps[cnt + __popc(m & ((1u << lane) - 1))] = (unsigned short)k;
+            cnt += __popc(m);
+        }
+        if (lane == 0) n_active_s = cnt;
+    }
+    __syncthreads();
+    const int n_active = n_active_s;
+    const int n_iters = n_active * nchunks;
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp < 4) {
+        // ================= gather producers =================
+        const int piece = t & 7;                       // which 8-float piece of the 64-channel chunk
+        const int rbase = t >> 3;                      // rows rbase + 16 j
+        const uint32_t sw_off = (uint32_t)((rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
+        int it = 0;
+        for (int ai = 0; ai < n_active; ++ai) {
+            const int k = taps[ai];
+            int rows[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int r = rbase + 16 * j;
+                rows[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) : row0 + r) : -1;
+            }
+            for (int c = 0; c < nchunks; ++c, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                float4 v0[8], v1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (rows[j] >= 0) {
+                        const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)rows[j] * a.ldi + c * KC + piece * 8);
+                        v0[j] = __ldg(src);
+                        v1[j] = __ldg(src + 1);
+                    } else {
+                        v0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v1[j] = v0[j];
+                    }
+                }
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                unsigned char* As = base_ptr + (size_t)s * STAGE_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 hi, lo;
+                    split8(v0[j], v1[j], a.in_act == CG3D_ACT_RELU, hi, lo);
+                    uint32_t off = (uint32_t)(((rbase >> 3) + 2 * j) * 1024) + sw_off;
+                    *reinterpret_cast<uint4*>(As + off) = hi;
+                    *reinterpret_cast<uint4*>(As + A_PART + off) = lo;
+                }
+                fence_async_smem();
+                mbar_arrive(full0 + 8 * s);
+            }
+        }
+        // ================= epilogue =================
+        if (n_iters > 0) {
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+        }
+        const int r = warp * 32 + lane;
+        const bool live = r < nrows;
+        const size_t orow = (size_t)(row0 + r) * a.ldo, rrow = (size_t)(row0 + r) * a.Cout;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t v[16];
+            if (n_iters > 0) {
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int col = n0 + c0 + q * 4 + i;
+                        float x = __uint_as_float(v[q * 4 + i]);
+                        if (a.scale) x *= __ldg(a.scale + (size_t)g * a.Cout + col);
+                        if (a.shift) x += __ldg(a.shift + (size_t)g * a.Cout + col);
+                        if (a.residual) x += __ldg(a.residual + rrow + col);
+                        o[i] = cg3d_act(x, a.act);
+                    }
+                    *reinterpret_cast<float4*>(a.out + orow + n0 + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ================= weight-tile loader (bulk async copy) =================
+        if (lane == 0) {
+            int it = 0;
+            for (int ai = 0; ai < n_active; ++ai) {
+                const int k = taps[ai];
+                for (int c = 0; c < nchunks; ++c, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const size_t blk = (((size_t)g * a.K + k) * nchunks + c) * ntn + blockIdx.y;
+                    mbar_expect_tx(full0 + 8 * s, 2 * B_PART);
+                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + 2 * A_PART), a.wimg + blk * (size_t)(2 * B_PART),
+                                  2 * B_PART, full0 + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
+                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART);
+                const uint64_t b_hi = make_desc(sa + 2 * A_PART), b_lo = make_desc(sa + 2 * A_PART + B_PART);
+#pragma unroll
+                for (int kk = 0; kk < KC / 16; ++kk) {
+                    const uint64_t adv = (uint64_t)(kk * 2);            // 32 bytes along K, in 16-byte units
+                    umma_bf16(tmem_base, a_hi + adv, b_hi + adv, IDESC, (it | kk) ? 1u : 0u);
+                    umma_bf16(tmem_base, a_hi + adv, b_lo + adv, IDESC, 1u);
+                    umma_bf16(tmem_base, a_lo + adv, b_hi + adv, IDESC, 1u);
+                }
+                umma_commit(empty0 + 8 * s);
+            }
+            if (n_iters > 0) umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NT));
+    }
+}
+
+// fp32 W[G][K][Cin][Cout] -> per (g, k, 64-channel chunk, NT-column tile) block of 2 * NT * 128 bytes:
+// [hi | lo][n][64 bf16 along Cin], 16-byte pieces XOR-swizzled by (n % 8) -- the exact smem image.
+__global__ void weight_image_kernel(const float* __restrict__ W, long long total, int K, int Cin, int Cout, int NT,
+                                    unsigned char* __restrict__ img) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int co = (int)(i % Cout);
+        long long rest = i / Cout;
+        int ci = (int)(rest % Cin);
+        long long gk = rest / Cin;                       // g * K + k
+        float w = W[i];
+        __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        int c = ci / KC, kk = ci % KC, tn = co / NT, n = co % NT;
+        size_t blk = ((size_t)gk * (Cin / KC) + c) * (Cout / NT) + tn;
+        size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+        unsigned char* b = img + blk * (size_t)(2 * NT * 128);
+        *reinterpret_cast<__nv_bfloat16*>(b + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(b + (size_t)NT * 128 + off) = lo;
+    }
+}
+
+template <int NT, int STAGES>
+int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
+    constexpr int smem = STAGES * (2 * A_PART + 2 * NT * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid(tiles, a.Cout / NT);
+    spconv_tc_kernel<NT, STAGES><<<grid, NTHREADS, smem, s>>>(a);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg3d_spconv_tc_ntile(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0)); }
+
+int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream) {
+    int NT = cg3d_spconv_tc_ntile(Cout);
+    if (NT == 0 || Cin % KC != 0) return -1;
+    long long total = (long long)G * K * Cin * Cout;
+    if (total == 0) return 0;
+    long long b = (total + 255) / 256;
+    weight_image_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 256, 0, (cudaStream_t)stream>>>(W, total, K, Cin, Cout, NT, img);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
+                   int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
+                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream) {
+    if (n_out == 0) return 0;
+    int NT = cg3d_spconv_tc_ntile(Cout);
+    if (NT == 0 || Cin % KC != 0 || K > MAX_TAPS || (!nbr && K != 1)) return -1;
+    if (ldi % 4 != 0 || ldo % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15) || ((size_t)wimg & 15)) return -3;
+    TcArgs a{in, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act,
+             ldi, ldo, in_act};
+    int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
+    if (tiles == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (NT == 256) return launch_tc<256, 2>(a, tiles, s);
+    if (NT == 128) return launch_tc<128, 3>(a, tiles, s);
+    return launch_tc<64, 4>(a, tiles, s);
+}
+
+}  // extern "C"

@@ -39,11 +39,12 @@ class Profile:
     receives (name, meta, start_event, end_event); None disables it."""
     active = None
     stage = ""
+    conv_only = False
 
 
 def _call(name, *args, meta=None):
     LaunchCounter.n += 1
-    if Profile.active is None:
+    if Profile.active is None or (Profile.conv_only and not name.startswith("cg3d_spconv")):
         _lib.call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,11 +225,15 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     if n_out == 0:
         return out
     name = impl or _CONV_IMPL["name"]
-    use_tc = name == "tc" and tc_supported(Cin, Cout)
+    use_tc = (name == "tc" and tc_supported(Cin, Cout, K) and Fin.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
+              and Fin.stride(0) % 4 == 0 and out.stride(0) % 4 == 0)
     fn = "cg3d_spconv_tc" if use_tc else "cg3d_spconv_simt"
+    Wfp32 = W
+    if use_tc:
+        W = weight_image(W)
     meta = None
     if Profile.active is not None:
-        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4,
+        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=Wfp32.numel() * 4,
                     residual=residual is not None)
     _call(fn, Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K, scale, shift, residual,
           ACT[act], tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
@@ -236,8 +241,27 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     return out
 
 
-def tc_supported(Cin: int, Cout: int) -> bool:
-    return hasattr(_lib.load(), "cg3d_spconv_tc") and Cin % 32 == 0 and Cout % 32 == 0 and Cout <= 512
+def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
+    return Cin % 64 == 0 and Cout % 64 == 0 and K <= 729
+
+
+_WIMG = {}
+
+
+def weight_image(W: torch.Tensor) -> torch.Tensor:
+    """bf16 hi/lo split + UMMA-swizzled image of a weight tensor (built once, cached until W changes)."""
+    key = (W.data_ptr(), tuple(W.shape), W._version, str(W.device))
+    img = _WIMG.get(key)
+    if img is None:
+        Cin, Cout = W.shape[-2], W.shape[-1]
+        K = W.shape[-3] if W.dim() >= 3 else 1
+        G = W.shape[0] if W.dim() == 4 else 1
+        img = torch.empty((W.numel() * 4,), dtype=torch.uint8, device=W.device)
+        _call("cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
+        if len(_WIMG) > 4096:
+            _WIMG.clear()
+        _WIMG[key] = img
+    return img
 
 
 def conv(x: SparseTensor, W: torch.Tensor, k: int, stride: int = 1, **ep) -> SparseTensor:

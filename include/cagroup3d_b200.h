@@ -96,6 +96,19 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
                      const float* residual, int act, const int* tile_row0, const int* tile_rows,
                      const int* tile_group, int n_tiles, void* stream);
 
+/* Tensor-core path of the same contraction (tcgen05, accumulator in TMEM, 128 rows x NT columns per
+ * CTA, weights streamed by bulk async copies).  fp32 in / fp32 out; inside, operands are split into
+ * bf16 hi + lo and three products are accumulated in fp32 (error <= ~2^-16 relative per product).
+ * Needs Cin % 64 == 0, Cout % 64 == 0, K <= 729, 16-byte aligned in/out rows.  `wimg` is the
+ * pre-split, pre-swizzled weight image made ONCE per weight tensor by cg3d_spconv_tc_prepare
+ * (same byte count as the fp32 weights); cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).
+ * Grouped mode as above with tiles of <= 128 rows. */
+int cg3d_spconv_tc_ntile(int Cout);
+int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
+int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
+                   int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
+                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream);
+
 /* out = act(x * scale + shift + add) on an [n, C] matrix with row strides ldx / ldo; scale, shift, add
  * ([n, C] dense) may be NULL.  Pre-activation BatchNorm+ReLU of DAPPM (biresnet.py:109-174). */
 int cg3d_affine_act(const float* x, int ldx, const float* scale, const float* shift, const float* add, float* out,

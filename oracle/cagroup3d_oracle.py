@@ -244,7 +244,7 @@ class Oracle:
         local = (idx.unsqueeze(0) + 0.5) / g * size - size / 2
         if cfg["code_size"] > 6:
             local = rotate_z(local, flat[:, 6])
-        pts = (local + flat[:, 0:3].unsqueeze(1)).view(batch_size, -1, 3)
+        pts = (local + flat[:, 0:3].unsqueeze(1)).reshape(batch_size, -1, 3)
         bidx = torch.arange(batch_size, dtype=f32).view(-1, 1, 1).expand(-1, pts.shape[1], 1)
         gp = torch.cat([bidx, pts], -1).reshape(-1, 4)
         # SimplePoolingLayer (cagroup_roi_head.py:46-93)
