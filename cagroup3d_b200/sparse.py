@@ -7,6 +7,7 @@ used for device memory and streams only; every computation is a call into libcag
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
@@ -17,7 +18,7 @@ from . import _lib
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
 
 # which conv kernel the engine uses: "simt" (exact fp32) or "tc" (tcgen05 3xTF32); see engine.py
-_CONV_IMPL = {"name": "simt"}
+_CONV_IMPL = {"name": os.environ.get("CG3D_CONV", "tc")}
 
 
 def set_conv_impl(name: str) -> None:
@@ -245,22 +246,18 @@ def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
     return Cin % 64 == 0 and Cout % 64 == 0 and K <= 729
 
 
-_WIMG = {}
-
-
 def weight_image(W: torch.Tensor) -> torch.Tensor:
-    """bf16 hi/lo split + UMMA-swizzled image of a weight tensor (built once, cached until W changes)."""
-    key = (W.data_ptr(), tuple(W.shape), W._version, str(W.device))
-    img = _WIMG.get(key)
-    if img is None:
-        Cin, Cout = W.shape[-2], W.shape[-1]
-        K = W.shape[-3] if W.dim() >= 3 else 1
-        G = W.shape[0] if W.dim() == 4 else 1
-        img = torch.empty((W.numel() * 4,), dtype=torch.uint8, device=W.device)
-        _call("cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
-        if len(_WIMG) > 4096:
-            _WIMG.clear()
-        _WIMG[key] = img
+    """bf16 hi/lo split + UMMA-swizzled image of a weight tensor.  Built once and kept ON the tensor
+    object (so it dies with it); rebuilt when the tensor is modified in place or moved."""
+    cached = getattr(W, "_cg3d_wimg", None)
+    if cached is not None and cached[0] == (W.data_ptr(), W._version):
+        return cached[1]
+    Cin, Cout = W.shape[-2], W.shape[-1]
+    K = W.shape[-3] if W.dim() >= 3 else 1
+    G = W.shape[0] if W.dim() == 4 else 1
+    img = torch.empty((W.numel() * 4,), dtype=torch.uint8, device=W.device)
+    _call("cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
+    W._cg3d_wimg = ((W.data_ptr(), W._version), img)
     return img
 
 
