@@ -5,14 +5,15 @@
 // One CTA owns 128 output rows x NT output channels (NT = 64 / 128 / 256); the accumulator lives in
 // TMEM (128 lanes x NT fp32 columns).  The K loop walks (active tap, 64-channel chunk) stages through a
 // ring of shared-memory buffers:
-//   warps 0-3  gather the 128 feature rows of the stage (rows nbr < 0 are zero-filled): coalesced 32-byte
-//              pieces per lane, 8 lanes per row, split fp32 -> bf16 hi + bf16 lo in registers and written
-//              in the 128B-swizzled K-major UMMA layout; after the K loop they run the epilogue
-//              (tcgen05.ld -> folded BN / bias / residual / ReLU|ELU -> global);
-//   warp 4     streams the stage's weight tile: the weights are pre-split and pre-swizzled once into the
+//   warps 0-7  gather the 128 feature rows of the stage (rows nbr < 0 are zero-filled): coalesced 32-byte
+//              pieces per lane, 8 lanes per row, loads kept 3 stages ahead in a register ring, split
+//              fp32 -> bf16 hi + bf16 lo in registers and written in the 128B-swizzled K-major UMMA
+//              layout; after the K loop they run the epilogue (tcgen05.ld -> folded BN / bias /
+//              residual / ReLU|ELU -> global);
+//   warp 8     streams the stage's weight tile: the weights are pre-split and pre-swizzled once into the
 //              exact shared-memory image, so a stage is ONE linear bulk async copy (cp.async.bulk, TMA
 //              engine, mbarrier complete_tx);
-//   warp 5     one elected lane issues the tcgen05.mma's: per 16-wide k-step three bf16 products
+//   warp 9     one elected lane issues the tcgen05.mma's: per 16-wide k-step three bf16 products
 //              A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulated in fp32 ("bf16x3": the dropped terms are
 //              <= 2^-16 relative, fp32-class accuracy at 1/3 of the bf16 tensor rate), then tcgen05.commit
 //              releases the stage.
@@ -23,6 +24,7 @@
 // Cout % 64 == 0; the Cin = 3 stem and the narrow prediction
 // heads stay on the exact-fp32 SIMT kernel (spconv_simt.cu).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/cagroup3d_b200.h"
@@ -31,8 +33,8 @@ namespace {
 
 constexpr int TM = 128;            // output rows per CTA (UMMA M)
 constexpr int KC = 64;             // channels per stage (128 bytes of bf16 = one swizzle row)
-constexpr int NPROD = 128;         // gather / epilogue threads (warps 0-3)
-constexpr int NTHREADS = 192;
+constexpr int NPROD = 256;         // gather / epilogue threads (warps 0-7)
+constexpr int NTHREADS = NPROD + 64;
 constexpr int A_PART = TM * 128;   // bytes of one A part (hi or lo) per stage
 constexpr int MAX_TAPS = 729;
 
@@ -131,6 +133,7 @@ struct TcArgs {
     const int* tile_rows;
     const int* tile_group;
     int n_out, Cin, Cout, K, act, ldi, ldo, in_act;
+    int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads
 };
 
 template <int NT, int STAGES>
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == NPROD / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(NT));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -207,62 +210,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     const int n_iters = n_active * nchunks;
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp < 4) {
+    if (warp < NPROD / 32) {
         // ================= gather producers =================
-        const int piece = t & 7;                       // which 8-float piece of the 64-channel chunk
-        const int rbase = t >> 3;                      // rows rbase + 16 j
-        const uint32_t sw_off = (uint32_t)((rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
-        int it = 0;
-        for (int ai = 0; ai < n_active; ++ai) {
-            const int k = taps[ai];
-            int rows[8];
+        // thread -> (8-float piece of the 64-channel chunk, rows rbase + 32 j).  Loads run DEPTH stages
+        // ahead of the convert/store step (register ring), row indices one stage ahead of the loads.
+        const int piece = t & 7;
+        const int rbase = t >> 3;                      // 0..31
+        const uint32_t sw_off = (uint32_t)((rbase >> 3) * 1024 + (rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
+        constexpr int DEPTH = 3, RPT = TM / 32;        // rows per thread
+        float4 v0[DEPTH][RPT], v1[DEPTH][RPT];
+        int ridx[RPT];
+
+        auto load_idx = [&](int q) {
+            const int k = taps[q / nchunks];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int r = rbase + 16 * j;
-                rows[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) : row0 + r) : -1;
+            for (int j = 0; j < RPT; ++j) {
+                int r = rbase + 32 * j;
+                ridx[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) : row0 + r) : -1;
             }
-            for (int c = 0; c < nchunks; ++c, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                float4 v0[8], v1[8];
+        };
+        auto issue = [&](int q, float4 (&x0)[RPT], float4 (&x1)[RPT]) {
+            const int c = q % nchunks;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (rows[j] >= 0) {
-                        const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)rows[j] * a.ldi + c * KC + piece * 8);
-                        v0[j] = __ldg(src);
-                        v1[j] = __ldg(src + 1);
-                    } else {
-                        v0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v1[j] = v0[j];
-                    }
+            for (int j = 0; j < RPT; ++j) {
+                if (ridx[j] >= 0 && !(a.debug & 2)) {
+                    const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)ridx[j] * a.ldi + c * KC + piece * 8);
+                    x0[j] = __ldg(src);
+                    x1[j] = __ldg(src + 1);
+                } else {
+                    x0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    x1[j] = x0[j];
                 }
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                unsigned char* As = base_ptr + (size_t)s * STAGE_BYTES;
+            }
+            if (q + 1 < n_iters && (q + 1) % nchunks == 0) load_idx(q + 1);     // next tap's rows, one stage early
+        };
+        auto flush = [&](int it, float4 (&x0)[RPT], float4 (&x1)[RPT]) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            unsigned char* As = base_ptr + (size_t)s * STAGE_BYTES;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 hi, lo;
-                    split8(v0[j], v1[j], a.in_act == CG3D_ACT_RELU, hi, lo);
-                    uint32_t off = (uint32_t)(((rbase >> 3) + 2 * j) * 1024) + sw_off;
-                    *reinterpret_cast<uint4*>(As + off) = hi;
-                    *reinterpret_cast<uint4*>(As + A_PART + off) = lo;
+            for (int j = 0; j < RPT; ++j) {
+                uint4 hi, lo;
+                split8(x0[j], x1[j], a.in_act == CG3D_ACT_RELU, hi, lo);
+                uint32_t off = (uint32_t)(j * 4 * 1024) + sw_off;
+                *reinterpret_cast<uint4*>(As + off) = hi;
+                *reinterpret_cast<uint4*>(As + A_PART + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(full0 + 8 * s);
+        };
+
+        if (n_iters > 0) load_idx(0);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < n_iters) issue(d, v0[d], v1[d]);
+        for (int it0 = 0; it0 < n_iters; it0 += DEPTH) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                const int it = it0 + d;
+                if (it < n_iters) {
+                    flush(it, v0[d], v1[d]);
+                    if (it + DEPTH < n_iters) issue(it + DEPTH, v0[d], v1[d]);
                 }
-                fence_async_smem();
-                mbar_arrive(full0 + 8 * s);
             }
         }
-        // ================= epilogue =================
+        // ================= epilogue: warp -> TMEM lane quarter (warp % 4), column half (warp / 4) =========
         if (n_iters > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        const int r = warp * 32 + lane;
+        const int lq = warp & 3, half = warp >> 2;
+        const int r = lq * 32 + lane;
         const bool live = r < nrows;
         const size_t orow = (size_t)(row0 + r) * a.ldo, rrow = (size_t)(row0 + r) * a.Cout;
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
+        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 16) {
             uint32_t v[16];
             if (n_iters > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
@@ -270,22 +296,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
             if (live) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        int col = n0 + c0 + q * 4 + i;
-                        float x = __uint_as_float(v[q * 4 + i]);
-                        if (a.scale) x *= __ldg(a.scale + (size_t)g * a.Cout + col);
-                        if (a.shift) x += __ldg(a.shift + (size_t)g * a.Cout + col);
-                        if (a.residual) x += __ldg(a.residual + rrow + col);
-                        o[i] = cg3d_act(x, a.act);
+                    const int col = n0 + c0 + q * 4;
+                    float o[4] = {__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                  __uint_as_float(v[q * 4 + 3])};
+                    if (a.scale) {
+                        float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
+                        o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w;
                     }
-                    *reinterpret_cast<float4*>(a.out + orow + n0 + c0 + q * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (a.shift) {
+                        float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
+                        o[0] += sh.x; o[1] += sh.y; o[2] += sh.z; o[3] += sh.w;
+                    }
+                    if (a.residual) {
+                        float4 rs = __ldg(reinterpret_cast<const float4*>(a.residual + rrow + col));
+                        o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = cg3d_act(o[i], a.act);
+                    *reinterpret_cast<float4*>(a.out + orow + col) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == NPROD / 32) {
         // ================= weight-tile loader (bulk async copy) =================
         if (lane == 0) {
             int it = 0;
@@ -296,9 +329,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const size_t blk = (((size_t)g * a.K + k) * nchunks + c) * ntn + blockIdx.y;
-                    mbar_expect_tx(full0 + 8 * s, 2 * B_PART);
+                    const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)(2 * B_PART);
+                    mbar_expect_tx(full0 + 8 * s, nbytes);
                     bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + 2 * A_PART), a.wimg + blk * (size_t)(2 * B_PART),
-                                  2 * B_PART, full0 + 8 * s);
+                                  nbytes, full0 + 8 * s);
                 }
             }
         }
@@ -328,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == NPROD / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NT));
     }
@@ -396,7 +430,10 @@ int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const u
     if (NT == 0 || Cin % KC != 0 || K > MAX_TAPS || (!nbr && K != 1)) return -1;
     if (ldi % 4 != 0 || ldo % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15) || ((size_t)wimg & 15)) return -3;
     TcArgs a{in, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act,
-             ldi, ldo, in_act};
+             ldi, ldo, in_act, 0};
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    a.debug = dbg;
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;

@@ -233,7 +233,7 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     if use_tc:
         W = weight_image(W)
     meta = None
-    if Profile.active is not None:
+    if Profile.active is not None and not Profile.conv_only:
         meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=Wfp32.numel() * 4,
                     residual=residual is not None)
     _call(fn, Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K, scale, shift, residual,
