@@ -142,7 +142,11 @@ class Oracle:
         return self.conv_bn(up, b + "out.3", b + "out.4", 1, 1, "relu")
 
     # ---- dense head -------------------------------------------------------------------
-    def head(self, out, sem_thr, batch_size):
+    def head(self, out, sem_thr, batch_size, force=None):
+        """force: optional {"sem": (N,ncls), "offsets": (N,3nv)} tensors used IN PLACE of the computed ones at
+        the two discontinuities (threshold select, floor into class voxels) -- teacher forcing for tests that
+        compare against another fp32 implementation whose last-bit differences would flip a voxel."""
+        force = force or {}
         cfg, h = self.cfg, "dense_head."
         vs = cfg["voxel_size"]
         ncls = cfg["n_classes"]
@@ -162,14 +166,14 @@ class Oracle:
         nv = 3 if cfg["with_yaw"] else 1
         # voted coordinates are formed in fp32 (they get floored into voxel indices)
         base = (C[:, 1:].to(f32) * vs).view(-1, 1, 3)
-        voted = base + offs.F.to(f32).view(-1, nv, 3)
+        voted = base + force.get("offsets", offs.F).to(f32).view(-1, nv, 3)
         voted = torch.maximum(torch.minimum(voted, max_b.view(1, 1, 3)), min_b.view(1, 1, 3))
         offF = offF.view(offF.shape[0], nv, -1)
         sizes = class_voxel_sizes(ncls)
         Cf = C.to(f32)
         per_class, maps = [], []
         for cls in range(ncls):
-            s = torch.sigmoid(sem.F[:, cls])
+            s = torch.sigmoid(force.get("sem", sem.F)[:, cls])
             sel = torch.cat([torch.nonzero(s > sem_thr).squeeze(1), torch.from_numpy(pad_id)])
             vc = Cf[sel].view(-1, 1, 4).repeat(1, nv, 1)
             vc[:, :, 1:4] = voted[sel]
@@ -288,7 +292,7 @@ class Oracle:
         return final, inter
 
     # ---- detector ---------------------------------------------------------------------
-    def forward(self, points: torch.Tensor, batch_size: int, cur_epoch: int = 10, stages="all"):
+    def forward(self, points: torch.Tensor, batch_size: int, cur_epoch: int = 10, stages="all", force=None):
         """points: (N,7) fp32 [b,x,y,z,r,g,b] with colours in 0..255 (cagroup3d.py:27-50)."""
         cfg = self.cfg
         thr = max(cfg["semantic_thr"] - int(cur_epoch) * cfg["semantic_iter"], cfg["semantic_min"])
@@ -304,7 +308,7 @@ class Oracle:
         res.update(bb_coords=out.C, bb_feats=out.F, maps={s: m.coords for s, m in x.mgr.by_stride.items()})
         if stages == "backbone":
             return res
-        pred_list, hi = self.head(out, thr, batch_size)
+        pred_list, hi = self.head(out, thr, batch_size, force)
         res.update(head=hi, stage1=pred_list)
         if stages == "head":
             return res
