@@ -1,0 +1,94 @@
+"""build_dataloader (reference pcdet/datasets/__init__.py:51-80) for the indoor datasets CAGroup3D uses.
+
+No ScanNet / SUN RGB-D data is reachable offline, so both dataset names resolve to a synthetic generator with
+the same item layout ('points' (N, 6) xyz + rgb 0..255, 'gt_boxes' (M, 8), 'frame_id') and the reference's
+`collate_batch` (pcdet/datasets/dataset.py:172-177: batch index prepended to the points).  Reading the
+mmdet3d-format .bin/.pkl files is listed as "next" in SURVEY.md 8f.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+from torch.utils.data.distributed import DistributedSampler as _DistributedSampler
+
+from cagroup3d_b200 import synthetic
+
+
+class DistributedSampler(_DistributedSampler):
+    """shuffle=False -> arange padded by wrap-around, strided by rank (reference :28-48)."""
+
+    def __init__(self, dataset, num_replicas=None, rank=None, shuffle=True):
+        super().__init__(dataset, num_replicas=num_replicas, rank=rank, shuffle=shuffle)
+
+
+class SyntheticIndoorDataset(Dataset):
+    def __init__(self, dataset_cfg, class_names, training=False, logger=None, sunrgbd=False):
+        self.dataset_cfg, self.class_names, self.training, self.logger = dataset_cfg, list(class_names), training, logger
+        syn = dataset_cfg.get("SYNTHETIC", None) or {}
+        self.n_scenes = int(syn.get("NUM_SCENES", 16))
+        self.target_voxels = int(syn.get("VOXELS", 50000))
+        self.seed_group = int(syn.get("SEED_GROUP", 2))
+        self.sunrgbd = sunrgbd
+        self.n_points = 100000 if sunrgbd else None            # sunrgbd_dataset.yaml: indoor_point_sample 100000
+        self.point_cloud_range = np.array(dataset_cfg.get("POINT_CLOUD_RANGE", [-40, -40, -10, 40, 40, 10]), np.float32)
+        self.voxel_size = None
+        self.grid_size = None
+        self.depth_downsample_factor = None
+
+    def __len__(self):
+        return self.n_scenes
+
+    def __getitem__(self, i):
+        pts, boxes = synthetic.make_scene(1000 * self.seed_group + i, self.target_voxels, n_classes=len(self.class_names),
+                                          sunrgbd=self.sunrgbd, n_points=self.n_points)
+        return {"points": pts, "gt_boxes": boxes, "frame_id": i}
+
+    @staticmethod
+    def collate_batch(batch_list, _unused=False):
+        pts = [np.pad(d["points"], ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, d in enumerate(batch_list)]
+        m = max(len(d["gt_boxes"]) for d in batch_list)
+        gt = np.zeros((len(batch_list), m, 8), np.float32)
+        for i, d in enumerate(batch_list):
+            gt[i, :len(d["gt_boxes"])] = d["gt_boxes"]
+        return {"points": np.concatenate(pts, 0), "gt_boxes": gt, "frame_id": np.array([d["frame_id"] for d in batch_list]),
+                "batch_size": len(batch_list)}
+
+    @staticmethod
+    def generate_prediction_dicts(batch_dict, pred_dicts, class_names, output_path=None):
+        """scannet_dataset.py:88-139 / sunrgbd_dataset.py: one annotation dict per sample (numpy, host)."""
+        annos = []
+        names = np.array(class_names)
+        for i, d in enumerate(pred_dicts):
+            s, b, l = (d[k].detach().cpu().numpy() for k in ("pred_scores", "pred_boxes", "pred_labels"))
+            n = len(s)
+            a = {"name": names[l] if n else np.zeros(0), "labels_3d": l if n else np.zeros(0), "bbox": np.zeros((n, 4)),
+                 "dimensions": b[:, 3:6] if n else np.zeros((0, 3)), "location": b[:, 0:3] if n else np.zeros((0, 3)),
+                 "rotation_y": b[:, 6] if n else np.zeros(0), "scores_3d": s, "boxes_3d": b if n else np.zeros((0, 7)),
+                 "frame_id": batch_dict["frame_id"][i]}
+            annos.append(a)
+        return annos
+
+    def evaluation(self, det_annos, class_names, **kwargs):
+        """mAP needs real annotations; report detection counts instead."""
+        n = sum(len(a["name"]) for a in det_annos)
+        return f"synthetic data: {n} detections over {len(det_annos)} scenes (no ground-truth mAP offline)", \
+            {"detections": n, "scenes": len(det_annos)}
+
+
+__all__ = {"ScannetDataset": lambda **k: SyntheticIndoorDataset(sunrgbd=False, **k),
+           "SunrgbdDataset": lambda **k: SyntheticIndoorDataset(sunrgbd=True, **k)}
+
+
+def build_dataloader(dataset_cfg, class_names, batch_size, dist, root_path=None, workers=4, logger=None, training=True,
+                     merge_all_iters_to_one_epoch=False, total_epochs=0):
+    dataset = __all__[dataset_cfg["DATASET"]](dataset_cfg=dataset_cfg, class_names=class_names, training=training,
+                                              logger=logger)
+    sampler = None
+    if dist:
+        import torch.distributed as tdist
+        sampler = DistributedSampler(dataset, tdist.get_world_size(), tdist.get_rank(), shuffle=training)
+    loader = DataLoader(dataset, batch_size=batch_size, pin_memory=True, num_workers=workers,
+                        shuffle=(sampler is None) and training, collate_fn=dataset.collate_batch, drop_last=False,
+                        sampler=sampler, timeout=0)
+    return dataset, loader, sampler
