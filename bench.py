@@ -180,9 +180,15 @@ def main():
     def step_resident():
         return model({"points": dev_pts.clone(), "batch_size": B, "cur_epoch": 10})
 
+    from cagroup3d_b200 import dist as D
+
     def step_e2e():
+        """the user-facing call: pinned host points -> device -> model(batch_dict) -> (N > 1: gather of all ranks'
+        detections, the one collective of the path) -> host."""
         pts = host_pts.cuda(non_blocking=True)
         pred, _ = model({"points": pts, "batch_size": B, "cur_epoch": 10})
+        if world > 1:
+            pred = D.gather_detections(pred, world * B)
         outs = [(d["pred_boxes"].cpu(), d["pred_scores"].cpu(), d["pred_labels"].cpu()) for d in pred]
         return outs
 
@@ -192,7 +198,7 @@ def main():
     pred, _ = step_resident()
     torch.cuda.synchronize()
     rec, S.Profile.active = S.Profile.active, None
-    convs = [(name, meta) for name, _, meta, _, _ in rec if meta is not None]
+    convs = [(name, meta) for name, _, meta, _, _ in rec if meta is not None and name.startswith("cg3d_spconv")]
     conv_info = []
     for name, meta in convs:
         P = S.count_rules(meta["nbr"]) if meta["nbr"] is not None else meta["n_out"]
@@ -240,18 +246,35 @@ def main():
     S.Profile.conv_only = False
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
+    # the bf16 split pass of a conv's input (cg3d_split_bf16) is charged to the conv launch that follows it
     per_call = [0.0] * len(conv_info)
-    convrec = [r for r in rec if r[0].startswith("cg3d_spconv")]
-    assert len(convrec) == len(conv_info) * args.steps, (len(convrec), len(conv_info))
-    for i, r in enumerate(convrec):
-        per_call[i % len(conv_info)] += r[3].elapsed_time(r[4]) / args.steps
+    split_ms, pending, i = 0.0, 0.0, 0
+    for r in rec:
+        t = r[3].elapsed_time(r[4])
+        if r[0].startswith("cg3d_split"):
+            pending += t
+            split_ms += t / args.steps
+        else:
+            per_call[i % len(conv_info)] += (t + pending) / args.steps
+            pending = 0.0
+            i += 1
+    assert i == len(conv_info) * args.steps, (i, len(conv_info))
     for ci, t in zip(conv_info, per_call):
         ci["ms"] = t
         ci["GBps"] = ci["bytes"] / t / 1e6 if t > 0 else None
         ci["TFLOPs"] = ci["flops"] / t / 1e9 if t > 0 else None
+    try:
+        peaks_hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        peaks_hbm = 6650.0
     bb = conv_info[:n_backbone_convs]
     bb_bytes, bb_ms, bb_flops = sum(c["bytes"] for c in bb), sum(c["ms"] for c in bb), sum(c["flops"] for c in bb)
     all_ms = sum(c["ms"] for c in conv_info)
+    # the 64-channel stride-1/2 layers are the HBM-bound part of the backbone (SURVEY 8d "sanity"); reported apart
+    hb = [c for c in bb if c["Cin"] <= 64 and c["Cout"] <= 128]
+    hbm_layers = {"launches": len(hb), "ms": sum(c["ms"] for c in hb),
+                  "achieved": sum(c["bytes"] for c in hb) / max(sum(c["ms"] for c in hb), 1e-9) / 1e6, "unit": "GB/s"}
+    hbm_layers["frac"] = hbm_layers["achieved"] / peaks_hbm
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -265,7 +288,8 @@ def main():
                 "launch_bytes_avg": bb_bytes / len(bb), "launch_ms_avg": bb_ms / len(bb),
                 "backbone_ms": bb_ms, "backbone_tflops": bb_flops / bb_ms / 1e9,
                 "tensor_peak_tflops": peaks.get("bf16_tflops_sustained"),
-                "spconv_share_of_step": all_ms / ms_step}
+                "spconv_share_of_step": all_ms / ms_step, "split_pass_ms_per_step": split_ms,
+                "hbm_bound_layers": hbm_layers}
 
     # e2e: pinned host inputs -> device -> forward -> host outputs
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)

@@ -49,9 +49,9 @@ def conv_bn(x: S.SparseTensor, conv: MinkowskiConvolution, bn, fc: FoldCache, ac
                         in_act=in_act, out=out)
         return x.with_F(F)
     omap = x.cmap if s == 1 else S.strided_map(x.cmap, x.mgr, s)
-    nbr = S.neighbor_table(x.cmap, omap, k, x.mgr)
+    nbr, order = S.neighbor_table(x.cmap, omap, k, x.mgr, ordered=True)
     F = S.gemm_rows(x.F, nbr, W, omap.n, k ** 3, scale=scale, shift=shift, residual=residual, act=act,
-                    in_act=in_act, out=out)
+                    in_act=in_act, out=out, out_rows=order)
     return S.SparseTensor(F, omap, x.mgr)
 
 

@@ -203,6 +203,66 @@ __global__ void transpose_k3s3_table_kernel(const int4* __restrict__ fine, int n
     }
 }
 
+// 11 bits -> every third bit position (Morton interleave helper)
+__device__ __forceinline__ unsigned long long spread3(unsigned v) {
+    unsigned long long x = v & 0x7FFu;
+    x = (x | (x << 32)) & 0x001F00000000FFFFull;
+    x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+// key = batch << 33 | Morton(x/stride, y/stride, z/stride mod 2048): rows sorted by it are spatially coherent per sample
+__global__ void morton_keys_kernel(const int4* __restrict__ coords, int n, int stride, unsigned long long* __restrict__ keys,
+                                   int* __restrict__ vals) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = __ldg(coords + i);
+        unsigned qx = (unsigned)(cg3d_floordiv(c.y, stride) + 1024), qy = (unsigned)(cg3d_floordiv(c.z, stride) + 1024),
+                 qz = (unsigned)(cg3d_floordiv(c.w, stride) + 1024);
+        keys[i] = ((unsigned long long)(unsigned)c.x << 33) | spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+        vals[i] = i;
+    }
+}
+
+__global__ void gather_coords_kernel(const int4* __restrict__ coords, const int* __restrict__ order, int n,
+                                     int4* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = __ldg(coords + __ldg(order + i));
+}
+
+// key[o] = which taps (K <= 27) / which of the 3x3x3 coarse blocks of taps (K > 27) have a neighbour for row o.
+// Rows sorted by this key share their active taps, so a conv tile of consecutive sorted rows skips the rest.
+__global__ void table_mask_keys_kernel(const int* __restrict__ nbr, int K, int ksize, int n,
+                                       const int4* __restrict__ coords, int group_div,
+                                       unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+        unsigned m = 0;
+        if (K <= 27) {
+            for (int k = 0; k < K; ++k) m |= (unsigned)(__ldg(nbr + (size_t)k * n + o) >= 0) << k;
+        } else {
+            for (int k = 0; k < K; ++k) {
+                if (__ldg(nbr + (size_t)k * n + o) < 0) continue;
+                int bx = (k % ksize) * 3 / ksize, by = ((k / ksize) % ksize) * 3 / ksize, bz = (k / (ksize * ksize)) * 3 / ksize;
+                m |= 1u << (bx + 3 * by + 9 * bz);
+            }
+        }
+        unsigned long long g = coords ? (unsigned long long)(__ldg(coords + o).x / group_div) : 0ull;
+        keys[o] = (g << 27) | m;
+        vals[o] = o;
+    }
+}
+
+// out[k][j] = nbr[k][order[j]]
+__global__ void permute_table_kernel(const int* __restrict__ nbr, int K, int n, const int* __restrict__ order,
+                                     int* __restrict__ out) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int o = __ldg(order + j);
+        for (int k = 0; k < K; ++k) out[(size_t)k * n + j] = __ldg(nbr + (size_t)k * n + o);
+    }
+}
+
 __global__ void lookup_kernel(const int4* __restrict__ q, int n, const unsigned long long* __restrict__ keys,
                               const int* __restrict__ vals, unsigned mask, int* __restrict__ rows) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -331,6 +391,38 @@ int cg3d_transpose_table(const int* fine_coords, int n_fine, const unsigned long
                                                                           (unsigned)capacity - 1, nbr);
     else
         return -1;
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_morton_keys(const int* coords, int n, int stride, unsigned long long* keys, int* vals, void* stream) {
+    if (n == 0) return 0;
+    if (stride < 1) return -1;
+    morton_keys_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const int4*)coords, n, stride, keys, vals);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_gather_coords(const int* coords, const int* order, int n, int* out, void* stream) {
+    if (n == 0) return 0;
+    gather_coords_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>((const int4*)coords, order, n, (int4*)out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_table_mask_keys(const int* nbr, int K, int ksize, int n, const int* coords, int group_div,
+                         unsigned long long* keys, int* vals, void* stream) {
+    if (n == 0) return 0;
+    if (K != ksize * ksize * ksize || (coords && group_div < 1)) return -1;
+    table_mask_keys_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(nbr, K, ksize, n, (const int4*)coords,
+                                                                              group_div, keys, vals);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_permute_table(const int* nbr, int K, int n, const int* order, int* out, void* stream) {
+    if (n == 0) return 0;
+    permute_table_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(nbr, K, n, order, out);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

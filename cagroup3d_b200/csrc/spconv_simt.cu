@@ -30,6 +30,7 @@ struct ConvArgs {
     const int* tile_group;
     int n_out, Cin, Cout, K, act;
     int ldi, ldo, in_act;  // row strides (floats) of in / out; in_act: activation applied to gathered rows
+    const int* out_rows;   // position -> output row (tile order) or nullptr
 };
 
 __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
     for (int k = 0; k < a.K; ++k) {
         int r = -1;
         if (t < TM) {
-            if (t < nrows) r = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + t) : row0 + t;
+            if (t < nrows)
+                r = a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + t) : (a.out_rows ? __ldg(a.out_rows + row0 + t) : row0 + t);
             rows_s[t] = r;
         }
         if (!__syncthreads_or(r >= 0)) continue;
@@ -123,7 +125,8 @@ __global__ void __launch_bounds__(NT) spconv_simt_kernel(ConvArgs a) {
     for (int i = 0; i < 4; ++i) {
         int rr = ty * 4 + i;
         if (rr >= nrows) continue;
-        size_t orow = (size_t)(row0 + rr) * a.ldo, rrow = (size_t)(row0 + rr) * a.Cout;
+        const int prow = a.out_rows ? __ldg(a.out_rows + row0 + rr) : row0 + rr;
+        size_t orow = (size_t)prow * a.ldo, rrow = (size_t)prow * a.Cout;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int c = n0 + tx * 4 + j;
@@ -159,11 +162,12 @@ extern "C" {
 
 int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const float* W, float* out, int ldo, int n_out,
                      int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
-                     const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream) {
+                     const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, const int* out_rows,
+                     void* stream) {
     if (n_out == 0) return 0;
     if (!nbr && K != 1) return -1;
     ConvArgs a{in, nbr, W, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act,
-               ldi, ldo, in_act};
+               ldi, ldo, in_act, out_rows};
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     dim3 grid(tiles, cg3d_div_up(Cout, TN));

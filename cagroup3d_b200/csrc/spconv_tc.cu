@@ -24,6 +24,7 @@
 // Cout % 64 == 0; the Cin = 3 stem and the narrow prediction
 // heads stay on the exact-fp32 SIMT kernel (spconv_simt.cu).
 #include <cuda_bf16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -69,6 +70,12 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -121,6 +128,10 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, int rel
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// development aid (CG3D_TC_DEBUG & 8): per-role cycle counters summed over CTAs, printed by the host after the launch
+__device__ unsigned long long g_tc_prof[16];
+#define TC_PROF(i, v) do { if (a.debug & 8) atomicAdd(&g_tc_prof[i], (unsigned long long)(v)); } while (0)
+
 struct TcArgs {
     const float* in;
     const int* nbr;
@@ -132,6 +143,8 @@ struct TcArgs {
     const int* tile_row0;
     const int* tile_rows;
     const int* tile_group;
+    const int* out_rows;   // position -> output row (tile order) or nullptr
+    const unsigned short* in_split;   // pre-split activations [rows][hi Cin | lo Cin] bf16, or nullptr
     int n_out, Cin, Cout, K, act, ldi, ldo, in_act;
     int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads
 };
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     __shared__ int n_active_s;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const long long t_start = clock64();
     int row0, nrows, g = 0;
     if (a.tile_row0) {
         row0 = a.tile_row0[blockIdx.x];
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, NPROD + 1);
+            mbar_init(full0 + 8 * s, NPROD / 32 + 1);      // one arrival per gather warp + the weight copy's expect_tx
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
@@ -182,11 +196,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (a.nbr) {
-        for (int k = warp; k < a.K; k += NTHREADS / 32) {
-            bool any = false;
-            for (int r = lane; r < nrows; r += 32) any |= __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) >= 0;
-            any = __any_sync(0xffffffffu, any);
-            if (lane == 0) active[k] = any ? 1 : 0;
+        constexpr int NW = NTHREADS / 32, UN = 4;
+        for (int k0 = warp * UN; k0 < a.K; k0 += NW * UN) {
+            int v[UN][TM / 32];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+#pragma unroll
+                for (int j = 0; j < TM / 32; ++j) {
+                    const int r = lane + 32 * j;
+                    v[u][j] = (k0 + u < a.K && r < nrows) ? __ldg(a.nbr + (size_t)(k0 + u) * a.n_out + row0 + r) : -1;
+                }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < TM / 32; ++j) any |= v[u][j] >= 0;
+                any = __any_sync(0xffffffffu, any);
+                if (lane == 0 && k0 + u < a.K) active[k0 + u] = any ? 1 : 0;
+            }
         }
     } else {
         if (t == 0) active[0] = 1;
@@ -209,14 +236,89 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     const int n_active = n_active_s;
     const int n_iters = n_active * nchunks;
     const uint32_t tmem_base = tmem_slot;
+    const long long t_main = clock64();
+    if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
         // ================= gather producers =================
-        // thread -> (8-float piece of the 64-channel chunk, rows rbase + 32 j).  Loads run DEPTH stages
-        // ahead of the convert/store step (register ring), row indices one stage ahead of the loads.
+        // thread -> (16-byte piece of the 64-channel chunk, rows rbase + 32 j)
         const int piece = t & 7;
         const int rbase = t >> 3;                      // 0..31
         const uint32_t sw_off = (uint32_t)((rbase >> 3) * 1024 + (rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
+      if (a.in_split) {
+        // ---- pre-split input: global -> shared with cp.async, no registers, no conversion.  A row of the split
+        // matrix is [hi Cin | lo Cin] bf16; a 64-channel chunk of either part is one 128-byte swizzle row.  Rows
+        // without a neighbour are zero-filled by a 0-byte source.  Copies run LOOKAHEAD stages ahead; a stage is
+        // published (proxy fence + mbarrier arrive) once this thread's copies of it have landed.
+        constexpr int RPT = TM / 32;
+        constexpr int LOOKAHEAD = STAGES - 1;
+        constexpr int PF = 4;          // taps whose row indices are in flight ahead of their use (hides the nbr latency)
+        int rq[PF][RPT];
+        const size_t row_elems = 2 * (size_t)a.Cin;
+        auto load_rows = [&](int ai, int (&dst)[RPT]) {
+            const int k = taps[ai];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                int r = rbase + 32 * j;
+                dst[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r)
+                                            : (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r)) : -1;
+            }
+        };
+        int q = 0;
+        // publish-before-acquire: stage q - LOOKAHEAD is handed to the MMA warp as soon as this thread's copies of it
+        // have landed, BEFORE blocking on the slot of stage q -- otherwise every MMA stage would wait for the previous
+        // one's completion signal to travel through this loop.
+        auto publish = [&]() {
+            if (q >= LOOKAHEAD && q - LOOKAHEAD < n_iters) {
+                cp_async_wait<LOOKAHEAD - 1>();                  // groups <= q - LOOKAHEAD complete (q - 1 ... may be pending)
+                fence_async_smem();
+                __syncwarp();                                    // ONE arrival per warp: 256 serialized mbarrier arrivals
+                if (lane == 0) mbar_arrive(full0 + 8 * ((q - LOOKAHEAD) % STAGES));      // per stage cost more than the MMAs
+            }
+        };
+        auto stage = [&](int c, const int (&ridx)[RPT]) {
+            const long long p0 = clock64();
+            publish();
+            const long long p1 = clock64();
+            const int s = q % STAGES;
+            const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            if (t == 0) { TC_PROF(9, p1 - p0); TC_PROF(8, clock64() - p1); }
+            const uint32_t dst = base + (uint32_t)(s * STAGE_BYTES) + sw_off;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const bool ok = ridx[j] >= 0 && !(a.debug & 2);
+                const unsigned short* src = a.in_split + (ok ? (size_t)ridx[j] * row_elems : 0) + c * KC + piece * 8;
+                cp_async16(dst + (uint32_t)(j * 4 * 1024), src, ok ? 16u : 0u);
+                cp_async16(dst + (uint32_t)(A_PART + j * 4 * 1024), src + a.Cin, ok ? 16u : 0u);
+            }
+            cp_async_commit();                                   // group q
+            ++q;
+        };
+#pragma unroll
+        for (int d = 0; d < PF; ++d)
+            if (d < n_active) load_rows(d, rq[d]);
+#pragma unroll 1
+        for (int ai0 = 0; ai0 < n_active; ai0 += PF) {
+#pragma unroll
+            for (int d = 0; d < PF; ++d) {
+                const int ai = ai0 + d;
+                if (ai < n_active) {
+#pragma unroll 1
+                    for (int c = 0; c < nchunks; ++c) stage(c, rq[d]);
+                    if (ai + PF < n_active) load_rows(ai + PF, rq[d]);
+                }
+            }
+        }
+#pragma unroll 1
+        for (int e = 0; e < LOOKAHEAD; ++e) {                    // drain: publish the last LOOKAHEAD stages
+            publish();
+            cp_async_commit();                                   // empty group keeps the wait_group arithmetic uniform
+            ++q;
+        }
+      } else {
+        // ---- fp32 input: loads run DEPTH stages ahead of the convert/store step (register ring), row indices one
+        // stage ahead of the loads.
         constexpr int DEPTH = 3, RPT = TM / 32;        // rows per thread
         float4 v0[DEPTH][RPT], v1[DEPTH][RPT];
         int ridx[RPT];
@@ -226,7 +328,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 int r = rbase + 32 * j;
-                ridx[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r) : row0 + r) : -1;
+                ridx[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r)
+                                             : (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r)) : -1;
             }
         };
         auto issue = [&](int q, float4 (&x0)[RPT], float4 (&x1)[RPT]) {
@@ -258,7 +361,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                 *reinterpret_cast<uint4*>(As + A_PART + off) = lo;
             }
             fence_async_smem();
-            mbar_arrive(full0 + 8 * s);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);
         };
 
         if (n_iters > 0) load_idx(0);
@@ -275,15 +379,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                 }
             }
         }
+      }
         // ================= epilogue: warp -> TMEM lane quarter (warp % 4), column half (warp / 4) =========
+        const long long e0 = clock64();
         if (n_iters > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
+        const long long e1 = clock64();
+        if (t == 0) { TC_PROF(5, e1 - t_main); TC_PROF(11, e1 - e0); }
         const int lq = warp & 3, half = warp >> 2;
         const int r = lq * 32 + lane;
         const bool live = r < nrows;
-        const size_t orow = (size_t)(row0 + r) * a.ldo, rrow = (size_t)(row0 + r) * a.Cout;
+        const int prow = (live && a.out_rows) ? __ldg(a.out_rows + row0 + r) : row0 + r;
+        const size_t orow = (size_t)prow * a.ldo, rrow = (size_t)prow * a.Cout;
 #pragma unroll 1
         for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 16) {
             uint32_t v[16];
@@ -318,6 +427,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
             }
         }
         tc_fence_before();
+        if (t == 0) TC_PROF(6, clock64() - e1);
     } else if (warp == NPROD / 32) {
         // ================= weight-tile loader (bulk async copy) =================
         if (lane == 0) {
@@ -340,10 +450,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     } else {
         // ================= MMA issuer =================
         if (lane == 0) {
+            long long w_acc = 0, i_acc = 0;
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                const long long m0 = clock64();
                 mbar_wait(full0 + 8 * s, ph);
+                const long long m1 = clock64();
+                if (it == 0) TC_PROF(4, m1 - m0); else w_acc += m1 - m0;
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
                 const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART);
@@ -356,7 +470,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                     umma_bf16(tmem_base, a_lo + adv, b_hi + adv, IDESC, 1u);
                 }
                 umma_commit(empty0 + 8 * s);
+                i_acc += clock64() - m1;
             }
+            TC_PROF(2, w_acc); TC_PROF(3, i_acc);
             if (n_iters > 0) umma_commit(accum_bar);
         }
         __syncwarp();
@@ -366,6 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NT));
     }
+    if (t == 0) TC_PROF(7, clock64() - t_start);
 }
 
 // fp32 W[G][K][Cin][Cout] -> per (g, k, 64-channel chunk, NT-column tile) block of 2 * NT * 128 bytes:
@@ -387,6 +504,22 @@ __global__ void weight_image_kernel(const float* __restrict__ W, long long total
         unsigned char* b = img + blk * (size_t)(2 * NT * 128);
         *reinterpret_cast<__nv_bfloat16*>(b + off) = hi;
         *reinterpret_cast<__nv_bfloat16*>(b + (size_t)NT * 128 + off) = lo;
+    }
+}
+
+// fp32 [n][C] (row stride ld) -> bf16 [n][hi C | lo C], optional ReLU first (the `self.relu(x)` in front of a stage)
+__global__ void split_rows_kernel(const float* __restrict__ in, int ld, long long n8, int C, int relu,
+                                  unsigned short* __restrict__ out) {
+    const int c8 = C / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c8;
+        const int p = (int)(i % c8);
+        const float4* src = reinterpret_cast<const float4*>(in + r * ld + p * 8);
+        uint4 hi, lo;
+        split8(__ldg(src), __ldg(src + 1), relu, hi, lo);
+        unsigned short* dst = out + r * 2 * C + p * 8;
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + C) = lo;
     }
 }
 
@@ -422,24 +555,46 @@ int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsi
     return 0;
 }
 
+int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream) {
+    if (C % 8 != 0 || ld % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15)) return -3;
+    long long n8 = (long long)n * (C / 8);
+    if (n8 == 0) return 0;
+    long long b = (n8 + 255) / 256;
+    split_rows_kernel<<<(int)(b > 148 * 16 ? 148 * 16 : b), 256, 0, (cudaStream_t)stream>>>(in, ld, n8, C, relu, out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
 int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
-                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream) {
+                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
+                   const int* out_rows, const unsigned short* in_split, void* stream) {
     if (n_out == 0) return 0;
     int NT = cg3d_spconv_tc_ntile(Cout);
     if (NT == 0 || Cin % KC != 0 || K > MAX_TAPS || (!nbr && K != 1)) return -1;
-    if (ldi % 4 != 0 || ldo % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15) || ((size_t)wimg & 15)) return -3;
-    TcArgs a{in, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, n_out, Cin, Cout, K, act,
-             ldi, ldo, in_act, 0};
+    if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15)) return -3;
+    if (!in_split && (ldi % 4 != 0 || ((size_t)in & 15))) return -3;
+    if (in_split && ((size_t)in_split & 15)) return -3;
+    TcArgs a{in, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, in_split, n_out, Cin,
+             Cout, K, act, ldi, ldo, in_act, 0};
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (NT == 256) return launch_tc<256, 2>(a, tiles, s);
-    if (NT == 128) return launch_tc<128, 3>(a, tiles, s);
-    return launch_tc<64, 4>(a, tiles, s);
+    int rc = NT == 256 ? launch_tc<256, 2>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3>(a, tiles, s) : launch_tc<64, 4>(a, tiles, s));
+    if (rc == 0 && (dbg & 8)) {
+        unsigned long long h[16], z[16] = {0};
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+        cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+        double c = h[0] ? (double)h[0] : 1.0;
+        fprintf(stderr, "[tc prof] NT=%d ctas=%llu iters/cta=%.1f | per CTA clks: total %.0f prologue %.0f main->accum %.0f epilogue %.0f | "
+                        "mma: first-wait %.0f wait %.0f issue %.0f | producer0: publish-wait %.0f empty-wait %.0f accum-wait %.0f\n",
+                NT, h[0], h[10] / c, h[7] / c, h[1] / c, h[5] / c, h[6] / c, h[4] / c, h[2] / c, h[3] / c, h[9] / c, h[8] / c, h[11] / c);
+    }
+    return rc;
 }
 
 }  // extern "C"

@@ -57,13 +57,7 @@ def _u64(n, device):
     return torch.empty((max(n, 1),), dtype=torch.int64, device=device)
 
 
-def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n: int, end_bit: int = 64) -> None:
-    """in-place stable radix sort of the first n (key, value) pairs."""
-    if n <= 1:
-        return
-    dev = keys.device
-    S._call("cg3d_sort_pairs", keys, vals, n, 0, end_bit, _u64(n, dev), _i32(n, device=dev),
-            _i32(_lib.sort_workspace_ints(n), device=dev))
+sort_pairs = S.sort_pairs
 
 
 def seg_bits(nseg: int) -> int:
@@ -243,7 +237,7 @@ class CAGroup3DHead(nn.Module):
         coordsA, coordsE, ref = _i32(nf, 4, device=dev), _i32(nf, 4, device=dev), _i32(nf, 2, device=dev)
         S._call("cg3d_class_points", out.C, voted, sel_rows, meta[0], meta[1], pad_rows, P["vsA"], P["vsE"], ncls, B, nv,
                 self.expand, nf, float(self.voxel_size), coordsA, coordsE, ref)
-        mgr = S.Manager()
+        mgr = S.Manager(batch_bits=max(1, (ncls * B - 1).bit_length()))
         mapA, _, invA = S.unique_first(coordsA, 1, mgr, want_inverse=True)                  # sync 2
         mapE, _, invE = S.unique_first(coordsE, self.expand, mgr, want_inverse=True)        # sync 3
         FA = S.segment_mean(offF, offF.shape[1], out.F, out.F.shape[1], ref, invA, nf, mapA.n, C)
@@ -256,15 +250,17 @@ class CAGroup3DHead(nn.Module):
         tile = 128 if S.get_conv_impl() == "tc" else 64
         tilesA, tilesE = S.make_tiles(offA, dev, tile), S.make_tiles(offE, dev, tile)
         cat = _f32(mapA.n, 2 * C, device=dev)                                               # [up | out] (:276-277)
-        nbrA = S.neighbor_table(mapA, mapA, self.cls_kernel, None)
+        # tile order keeps rows class-major (the class is the high part of the batch index), so the per-class
+        # position ranges equal the per-class row ranges
+        nbrA, ordA = S.neighbor_table(mapA, mapA, self.cls_kernel, mgr, ordered=True, group_div=B)
         S.gemm_rows(FA, nbrA, P["W_out"], mapA.n, self.cls_kernel ** 3, scale=P["bn_out"][0], shift=P["bn_out"][1],
-                    act="elu", tiles=tilesA, out=cat[:, C:])
-        nbrE = S.neighbor_table(mapE, mapE, 5, None)
+                    act="elu", tiles=tilesA, out=cat[:, C:], out_rows=ordA)
+        nbrE, ordE = S.neighbor_table(mapE, mapE, 5, mgr, ordered=True, group_div=B)
         EF = S.gemm_rows(FE, nbrE, P["W_exp"], mapE.n, 125, scale=P["bn_exp"][0], shift=P["bn_exp"][1], act="elu",
-                         tiles=tilesE)
-        nbrU = S.transpose_table(mapE, mapA, self.expand, None)
+                         tiles=tilesE, out_rows=ordE)
+        nbrU, ordU = S.transpose_table(mapE, mapA, self.expand, mgr, ordered=True, group_div=B)
         S.gemm_rows(EF, nbrU, P["W_up"], mapA.n, self.expand ** 3, scale=P["bn_up"][0], shift=P["bn_up"][1],
-                    act="elu", tiles=tilesA, out=cat[:, :C])
+                    act="elu", tiles=tilesA, out=cat[:, :C], out_rows=ordU)
         O = S.gemm_rows(cat, None, P["W_fuse"], mapA.n, 1, scale=P["bn_fuse"][0], shift=P["bn_fuse"][1], act="elu",
                         tiles=tilesA)
         pred = S.gemm_rows(O, None, P["W_pred"], mapA.n, 1, shift=P["b_pred"])

@@ -101,10 +101,11 @@ class CAGroup3DRoIHead(nn.Module):
         S._call("cg3d_roi_grid_coords", rois, nr, rmax, g, int(self.code_size > 6), float(layer.voxel_size),
                 layer.grid_size // 2, int(self.coord_key), gc)
         umap, _, inv = S.unique_first(gc, sp.cmap.stride, None, want_inverse=True)          # sync
-        nbr = S.neighbor_table(sp.cmap, umap, layer.grid_kernel_size, None)
+        umap.uid = sp.mgr.new_uid()
+        nbr, order = S.neighbor_table(sp.cmap, umap, layer.grid_kernel_size, sp.mgr, ordered=True)
         scale, shift = self.fold.bn(layer.grid_bn)
         Fu = S.gemm_rows(sp.F, nbr, layer.grid_conv.kernel, umap.n, layer.grid_kernel_size ** 3, scale=scale,
-                         shift=shift, act="elu")
+                         shift=shift, act="elu", out_rows=order)
         ptab = _i32(g ** 3, nr, device=dev)
         S._call("cg3d_roi_pool_table", inv, nr, g, ptab)
         pscale, pshift = self.fold.bn(layer.pooling_bn)

@@ -45,7 +45,7 @@ class Profile:
 
 def _call(name, *args, meta=None):
     LaunchCounter.n += 1
-    if Profile.active is None or (Profile.conv_only and not name.startswith("cg3d_spconv")):
+    if Profile.active is None or (Profile.conv_only and not name.startswith(("cg3d_spconv", "cg3d_split"))):
         _lib.call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -71,6 +71,8 @@ class CoordMap:
     keys: torch.Tensor            # [capacity] int64 (u64 bit pattern)
     vals: torch.Tensor            # [capacity] int32
     uid: int = field(default=0)
+    order: Optional[torch.Tensor] = None          # tile order: position -> row (Morton-sorted), see tile_order()
+    ordered_coords: Optional[torch.Tensor] = None # coords[order]
 
     @property
     def n(self) -> int:
@@ -84,10 +86,11 @@ class CoordMap:
 class Manager:
     """Caches strided maps by tensor stride (ME semantics A6) and rule maps by (in, out, kind)."""
 
-    def __init__(self):
+    def __init__(self, batch_bits: int = 8):
         self.by_stride: Dict[int, CoordMap] = {}
         self.tables: Dict[Tuple, torch.Tensor] = {}
         self.rule_counts: Dict[Tuple, int] = {}
+        self.batch_bits = batch_bits          # bits of the largest batch index (bounds the tile-order sort)
         self._uid = 0
 
     def new_uid(self) -> int:
@@ -159,28 +162,86 @@ def strided_map(x_map: CoordMap, mgr: Manager, s: int) -> CoordMap:
     return mgr.by_stride[ts]
 
 
-def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager]) -> torch.Tensor:
-    key = ("conv", in_map.uid, out_map.uid, k)
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n: int, end_bit: int = 64, begin_bit: int = 0) -> None:
+    """in-place stable radix sort of the first n (key, value) pairs on key bits [begin_bit, end_bit)."""
+    if n <= 1:
+        return
+    dev = keys.device
+    _call("cg3d_sort_pairs", keys, vals, n, begin_bit, end_bit, torch.empty((n,), dtype=torch.int64, device=dev),
+          _i32(n, device=dev), _i32(_lib.sort_workspace_ints(n), device=dev))
+
+
+# which output rows share a conv tile: "none" = consecutive rows, "morton" = spatially compact patches,
+# "mask" = rows with the same set of active taps (rule maps with K <= MASK_MAX_K taps; the conv skips empty taps)
+_TILE_ORDER = {"mode": os.environ.get("CG3D_TILE_ORDER", "mask")}
+MASK_MAX_K = 27
+
+
+def mask_order(nbr: torch.Tensor, ksize: int, n: int, coords=None, group_div: int = 0, group_bits: int = 0):
+    """(positional table, order) with rows grouped by (weight group, tap pattern)."""
+    K, dev = nbr.shape[0], nbr.device
+    keys = torch.empty((n,), dtype=torch.int64, device=dev)
+    order = _i32(n, device=dev)
+    _call("cg3d_table_mask_keys", nbr, K, ksize, n, coords if group_div else None, group_div, keys, order)
+    sort_pairs(keys, order, n, end_bit=(min(K, 27) if not group_div else 27 + group_bits), begin_bit=0)
+    out = torch.empty_like(nbr)
+    _call("cg3d_permute_table", nbr, K, n, order, out)
+    return out, order
+
+
+def tile_order(cmap: CoordMap, batch_bits: int = 8):
+    """(order, coords[order]): Morton tile order of a map (cached on it); (None, coords) when disabled.
+
+    The map's own row order (ME's first-occurrence order) is untouched: `order` only decides which output
+    rows share a conv tile.  Cells of 4^3 voxels are the sort granularity (key bits below 6 are ignored)."""
+    if cmap.n < 256:
+        return None, cmap.coords
+    if cmap.order is None:
+        dev, n = cmap.coords.device, cmap.n
+        keys = torch.empty((n,), dtype=torch.int64, device=dev)
+        vals = _i32(n, device=dev)
+        _call("cg3d_morton_keys", cmap.coords, n, cmap.stride, keys, vals)
+        sort_pairs(keys, vals, n, end_bit=33 + batch_bits, begin_bit=6)
+        oc = _i32(n, 4, device=dev)
+        _call("cg3d_gather_coords", cmap.coords, vals, n, oc)
+        cmap.order, cmap.ordered_coords = vals, oc
+    return cmap.order, cmap.ordered_coords
+
+
+def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
+                   group_div: int = 0):
+    """ME kernel map as a tap-major table.  ordered=False -> nbr[k][row]; ordered=True -> (nbr[k][position], order)
+    with position -> row given by the output map's tile order (order is None when positions == rows)."""
+    key = ("conv", in_map.uid, out_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
         return mgr.tables[key]
+    use = ordered and _TILE_ORDER["mode"] == "morton"
+    order, oc = tile_order(out_map, mgr.batch_bits if mgr else 8) if use else (None, out_map.coords)
     nbr = _i32(k ** 3, max(out_map.n, 1), device=in_map.coords.device)
-    _call("cg3d_neighbor_table", out_map.coords, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k,
-          in_map.stride, nbr)
+    _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
+    if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and out_map.n >= 256:
+        nbr, order = mask_order(nbr, k, out_map.n, out_map.coords, group_div, mgr.batch_bits if mgr else 8)
+    res = (nbr, order) if ordered else nbr
     if mgr is not None:
-        mgr.tables[key] = nbr
-    return nbr
+        mgr.tables[key] = res
+    return res
 
 
-def transpose_table(in_map: CoordMap, fine_map: CoordMap, k: int, mgr: Optional[Manager]) -> torch.Tensor:
-    key = ("convT", in_map.uid, fine_map.uid, k)
+def transpose_table(in_map: CoordMap, fine_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
+                    group_div: int = 0):
+    key = ("convT", in_map.uid, fine_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
         return mgr.tables[key]
+    use = ordered and _TILE_ORDER["mode"] == "morton"
+    order, oc = tile_order(fine_map, mgr.batch_bits if mgr else 8) if use else (None, fine_map.coords)
     nbr = _i32(k ** 3, max(fine_map.n, 1), device=in_map.coords.device)
-    _call("cg3d_transpose_table", fine_map.coords, fine_map.n, in_map.keys, in_map.vals, in_map.capacity, k,
-          in_map.stride, nbr)
+    _call("cg3d_transpose_table", oc, fine_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
+    if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and fine_map.n >= 256:
+        nbr, order = mask_order(nbr, k, fine_map.n, fine_map.coords, group_div, mgr.batch_bits if mgr else 8)
+    res = (nbr, order) if ordered else nbr
     if mgr is not None:
-        mgr.tables[key] = nbr
-    return nbr
+        mgr.tables[key] = res
+    return res
 
 
 def count_rules(nbr: torch.Tensor) -> int:
@@ -212,10 +273,12 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
 
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
               scale=None, shift=None, residual=None, act=None, tiles: Optional[Tiles] = None,
-              impl: Optional[str] = None, in_act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              impl: Optional[str] = None, in_act=None, out: Optional[torch.Tensor] = None,
+              out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act((sum_k in_act(Fin[nbr[k]]) @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout].
 
-    Fin / out may be column slices of wider row-major matrices (unit column stride)."""
+    Fin / out may be column slices of wider row-major matrices (unit column stride).  out_rows: the table is
+    positional (tile order); position j is output row out_rows[j]."""
     Cin, Cout = W.shape[-2], W.shape[-1]
     assert Fin.stride(1) == 1 and W.is_contiguous() and Fin.shape[1] == Cin
     if out is None:
@@ -228,18 +291,46 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     name = impl or _CONV_IMPL["name"]
     use_tc = (name == "tc" and tc_supported(Cin, Cout, K) and Fin.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
               and Fin.stride(0) % 4 == 0 and out.stride(0) % 4 == 0)
-    fn = "cg3d_spconv_tc" if use_tc else "cg3d_spconv_simt"
-    Wfp32 = W
-    if use_tc:
-        W = weight_image(W)
     meta = None
     if Profile.active is not None and not Profile.conv_only:
-        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=Wfp32.numel() * 4,
+        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4,
                     residual=residual is not None)
-    _call(fn, Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K, scale, shift, residual,
-          ACT[act], tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
-          tiles.n if tiles else 0, meta=meta)
+    targs = (tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
+             tiles.n if tiles else 0, out_rows)
+    if use_tc:
+        Fs = split_rows(Fin, in_act) if _TC_SPLIT["on"] else None
+        _call("cg3d_spconv_tc", Fin, Fin.stride(0), ACT[in_act], nbr, weight_image(W), out, out.stride(0), n_out, Cin,
+              Cout, K, scale, shift, residual, ACT[act], *targs, Fs, meta=meta)
+    else:
+        _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,
+              scale, shift, residual, ACT[act], *targs, meta=meta)
     return out
+
+
+_TC_SPLIT = {"on": os.environ.get("CG3D_TC_SPLIT", "1") != "0"}
+
+
+def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
+    """[n, 2C] bf16 (hi | lo) copy of an activation matrix for the tensor-core conv, with the consumer's input
+    activation applied.  Cached on the tensor object; rebuilt if the tensor is modified in place."""
+    relu = 1 if in_act == "relu" else 0
+    assert in_act in (None, "none", "relu")
+    cache = getattr(F, "_cg3d_split", None)
+    if cache is None:
+        cache = {}
+        try:
+            F._cg3d_split = cache
+        except AttributeError:
+            pass
+    key = (F.data_ptr(), F._version, F.stride(0), relu)
+    if key not in cache:
+        n, C = F.shape
+        out = torch.empty((max(n, 1), 2 * C), dtype=torch.int16, device=F.device)
+        _call("cg3d_split_bf16", F, F.stride(0), n, C, relu, out)
+        if len(cache) > 1:
+            cache.clear()
+        cache[key] = out
+    return cache[key]
 
 
 def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
@@ -266,14 +357,14 @@ def conv(x: SparseTensor, W: torch.Tensor, k: int, stride: int = 1, **ep) -> Spa
     if k == 1 and stride == 1:
         return x.with_F(gemm_rows(x.F, None, W, x.cmap.n, 1, **ep))
     omap = x.cmap if stride == 1 else strided_map(x.cmap, x.mgr, stride)
-    nbr = neighbor_table(x.cmap, omap, k, x.mgr)
-    return SparseTensor(gemm_rows(x.F, nbr, W, omap.n, k ** 3, **ep), omap, x.mgr)
+    nbr, order = neighbor_table(x.cmap, omap, k, x.mgr, ordered=True)
+    return SparseTensor(gemm_rows(x.F, nbr, W, omap.n, k ** 3, out_rows=order, **ep), omap, x.mgr)
 
 
 def conv_transpose_k2s2(x: SparseTensor, W: torch.Tensor, **ep) -> SparseTensor:
     fmap = x.mgr.by_stride[x.cmap.stride // 2]
-    nbr = transpose_table(x.cmap, fmap, 2, x.mgr)
-    return SparseTensor(gemm_rows(x.F, nbr, W, fmap.n, 8, **ep), fmap, x.mgr)
+    nbr, order = transpose_table(x.cmap, fmap, 2, x.mgr, ordered=True)
+    return SparseTensor(gemm_rows(x.F, nbr, W, fmap.n, 8, out_rows=order, **ep), fmap, x.mgr)
 
 
 def affine_act(x: torch.Tensor, scale=None, shift=None, add=None, act=None, out=None) -> torch.Tensor:

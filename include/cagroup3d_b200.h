@@ -75,6 +75,26 @@ int cg3d_neighbor_table(const int* out_coords, int n_out, const unsigned long lo
 int cg3d_transpose_table(const int* fine_coords, int n_fine, const unsigned long long* keys, const int* vals,
                          int capacity, int ksize, int ts_coarse, int* nbr, void* stream);
 
+/* Tile ordering of a coordinate map.  keys[i] = b << 33 | Morton code of (x, y, z) / stride (11 bits per axis,
+ * wrapped), vals[i] = i.  Sorting the pairs on key bits [6, 33 + batch bits) with cg3d_sort_pairs gives a row
+ * permutation `order` in which every run of 128 rows is a compact patch of one sample, so a conv tile touches few
+ * distinct taps and neighbouring input rows.  ME leaves the row order of a map unspecified; here the ORDER OF THE
+ * MAP IS NOT CHANGED -- the permutation only decides which output rows share a CTA (rule maps are built for
+ * cg3d_gather_coords(coords, order) and the conv writes row order[j]). */
+int cg3d_morton_keys(const int* coords, int n, int stride, unsigned long long* keys, int* vals, void* stream);
+int cg3d_gather_coords(const int* coords, const int* order, int n, int* out, void* stream);
+
+/* Tile ordering by tap pattern.  keys[o] = bit mask of the taps of rule map `nbr` (i32[K][n], K = ksize^3) that
+ * have a neighbour for output row o (K <= 27), or of the 27 coarse blocks of taps (K > 27); vals[o] = o.  Sorting
+ * the pairs (cg3d_sort_pairs on bits [0, 27)) groups rows with the same pattern; cg3d_permute_table then gives the
+ * positional table out[k][j] = nbr[k][order[j]] whose 128-row tiles touch few taps -- the convolution skips the
+ * (tile, tap) pairs that are empty.  The map's row order is not changed (see out_rows of cg3d_spconv_*).
+ * coords != NULL: bits 27.. of the key = batch index of the row / group_div, so that sorted rows stay grouped
+ * (grouped convolutions: one weight group per class, batch index = class * B + b). */
+int cg3d_table_mask_keys(const int* nbr, int K, int ksize, int n, const int* coords, int group_div,
+                         unsigned long long* keys, int* vals, void* stream);
+int cg3d_permute_table(const int* nbr, int K, int n, const int* order, int* out, void* stream);
+
 /* *count = number of entries >= 0 (rule pairs P of SURVEY.md section 8d). */
 int cg3d_count_rules(const int* nbr, long long total, unsigned long long* count, void* stream);
 
@@ -90,11 +110,13 @@ int cg3d_count_rules(const int* nbr, long long total, unsigned long long* count,
  * Grouped mode (tile_row0 != NULL): tile t covers rows [tile_row0[t], +tile_rows[t]) (<= 64 for simt,
  * <= 128 for tc) with weight/scale/shift group tile_group[t] -- used to run all per-class convolutions
  * of cagroup_head.py:227-282 in one launch.
+ * out_rows (may be NULL): the table is POSITIONAL -- nbr[k][j] belongs to output row out_rows[j] (tile order from
+ * cg3d_morton_keys); the result / residual of position j live at row out_rows[j].  NULL: position == row.
  * cg3d_spconv_simt: exact fp32 FFMA path (any Cin/Cout). */
 int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const float* W, float* out, int ldo,
                      int n_out, int Cin, int Cout, int K, const float* scale, const float* shift,
                      const float* residual, int act, const int* tile_row0, const int* tile_rows,
-                     const int* tile_group, int n_tiles, void* stream);
+                     const int* tile_group, int n_tiles, const int* out_rows, void* stream);
 
 /* Tensor-core path of the same contraction (tcgen05, accumulator in TMEM, 128 rows x NT columns per
  * CTA, weights streamed by bulk async copies).  fp32 in / fp32 out; inside, operands are split into
@@ -102,12 +124,19 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
  * Needs Cin % 64 == 0, Cout % 64 == 0, K <= 729, 16-byte aligned in/out rows.  `wimg` is the
  * pre-split, pre-swizzled weight image made ONCE per weight tensor by cg3d_spconv_tc_prepare
  * (same byte count as the fp32 weights); cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).
- * Grouped mode as above with tiles of <= 128 rows. */
+ * Grouped mode as above with tiles of <= 128 rows.  in_split: see cg3d_split_bf16. */
 int cg3d_spconv_tc_ntile(int Cout);
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
 int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
-                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, void* stream);
+                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
+                   const int* out_rows, const unsigned short* in_split, void* stream);
+
+/* Split copy of an activation matrix for cg3d_spconv_tc: out[r] = [bf16 hi(x) (C) | bf16 lo(x) (C)], x = in[r] or
+ * relu(in[r]) (relu = 1: the activation the consumer applies to its input).  Same byte count as the fp32 rows.
+ * With in_split != NULL the conv gathers these rows straight into shared memory with cp.async (no register
+ * staging, no per-tap conversion) and ignores in / ldi / in_act. */
+int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
 
 /* out = act(x * scale + shift + add) on an [n, C] matrix with row strides ldx / ldo; scale, shift, add
  * ([n, C] dense) may be NULL.  Pre-activation BatchNorm+ReLU of DAPPM (biresnet.py:109-174). */
@@ -251,6 +280,21 @@ int cg3d_roi_pool_table(const int* inverse, int n_rois, int grid, int* nbr, void
 
 /* CAGroupResidualCoder.decode_torch + rotate + add centre (:477-510, cagroup_utils.py:147-197). */
 int cg3d_roi_decode(const float* rois, const float* reg, int n, int code_size, int sincos, float* out, void* stream);
+
+/* ---- training-loss ops (pcdet/ops/knn, pcdet/ops/rotated_iou/cuda_op) ------------------------------ */
+
+/* knn_wrapper(b, n, m, nsample, xyz, new_xyz, idx, dist2) (knn.cpp:28-46, knn_cuda.cu:58-94): for each of
+ * the m queries of every batch element the k <= 100 nearest of its n points, ascending squared distance.
+ * xyz [b,n,3], query [b,m,3] fp32; idx [b,m,k] i32, dist2 [b,m,k] f32.  Candidates are scanned in index
+ * order with strict `<`, so ties resolve as in the reference (first index wins at k = 1). */
+int cg3d_knn(const float* xyz, int b, int n, const float* query, int m, int k, int* idx, float* dist2, void* stream);
+
+/* sort_vertices_forward(vertices [b,n,m,2] f32, mask [b,n,m] bool, num_valid [b,n] i32) -> idx [b,n,9] i32
+ * (sort_vert.cpp:6-33, sort_vert_kernel.cu:42-134): counter-clockwise order of the valid polygon vertices,
+ * first index repeated, padded with an invalid intersection index.  The caller allocates idx (the reference
+ * allocates it itself); 9 <= m <= 32 (the reference passes m = 24). */
+int cg3d_sort_vertices(const float* vertices, const unsigned char* mask, const int* num_valid, int b, int n, int m,
+                       int* idx, void* stream);
 
 #ifdef __cplusplus
 }

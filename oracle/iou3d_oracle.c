@@ -142,7 +142,8 @@ void cg_oracle_knn(const float *xyz, int n, const float *q, int m, int k, int *i
         for (int t = 0; t < k; t++) { bi[t] = 0; bd[t] = 1e10f; }
         for (int i = 0; i < n; i++) {
             float dx = q[3 * j] - xyz[3 * i], dy = q[3 * j + 1] - xyz[3 * i + 1], dz = q[3 * j + 2] - xyz[3 * i + 2];
-            float d = dx * dx + dy * dy + dz * dz;
+            /* the reference binary contracts this as FMUL dy*dy, FFMA dx, FFMA dz (cuobjdump of knn_cuda.cu) */
+            float d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             if (d < bd[k - 1]) {
                 int t = k - 1;
                 while (t > 0 && bd[t - 1] > d) { bd[t] = bd[t - 1]; bi[t] = bi[t - 1]; t--; }

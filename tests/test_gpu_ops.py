@@ -160,7 +160,7 @@ def test_interp_avgpool_segment_mean(lib):
 
 
 def test_sort_pairs_stable(lib):
-    from cagroup3d_b200.head import sort_pairs
+    from cagroup3d_b200.sparse import sort_pairs
     g = torch.Generator().manual_seed(0)
     for n in (1, 2, 255, 2049, 70001):
         keys = torch.randint(0, 1 << 40, (n,), generator=g, dtype=torch.int64)

@@ -1,0 +1,177 @@
+"""GPU: the C-ABI IoU / NMS / KNN kernels against the REFERENCE's own CUDA ops, compiled unmodified from
+/root/reference into oracle/_ref by oracle/build_ref.py (the .so files travel to the GPU box; the sources do not).
+Also the CUDA path against the committed golden vectors of the reference's Python (tests/golden)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ref_iou():
+    m = build_ref.load("iou3d_nms_cuda")
+    if m is None:
+        pytest.skip("oracle/_ref/iou3d_nms_cuda.so not built")
+    return m
+
+
+def boxes(n, seed, yaw=True, spread=4.0):
+    g = torch.Generator().manual_seed(seed)
+    b = torch.cat([(torch.rand((n, 3), generator=g) - 0.5) * spread, torch.rand((n, 3), generator=g) * 1.5 + 0.2,
+                   (torch.rand((n, 1), generator=g) - 0.5) * 6.2 if yaw else torch.zeros((n, 1))], 1)
+    return b.contiguous()
+
+
+def test_pairwise_overlap_and_iou_vs_reference_cuda(lib, ref_iou):
+    from cagroup3d_b200 import sparse as S
+    a, b = boxes(257, 1).to(DEV), boxes(190, 2).to(DEV)
+    for mode, fn in ((0, ref_iou.boxes_overlap_bev_gpu), (1, ref_iou.boxes_iou_bev_gpu)):
+        want = torch.zeros((257, 190), device=DEV)
+        fn(a, b, want)
+        got = torch.empty_like(want)
+        S._call("cg3d_boxes_pairwise_bev", a, 257, b, 190, mode, got)
+        torch.cuda.synchronize()
+        assert (got - want).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("rotated", [0, 1])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 1000, 3000])
+def test_nms_vs_reference_cuda(lib, ref_iou, rotated, n):
+    """keep list of nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-186) == the set flags of cg3d_nms_segments."""
+    from cagroup3d_b200 import sparse as S
+    b = boxes(n, 10 + n, yaw=bool(rotated), spread=3.0 + n / 500).to(DEV)        # already "sorted by score"
+    keep_ref = torch.zeros((n,), dtype=torch.long)
+    fn = ref_iou.nms_gpu if rotated else ref_iou.nms_normal_gpu
+    k = fn(b, keep_ref, 0.5)
+    want = torch.zeros((n,), dtype=torch.int32)
+    want[keep_ref[:k]] = 1
+    keep = torch.empty((n,), dtype=torch.int32, device=DEV)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    cnt = torch.empty((1,), dtype=torch.int32, device=DEV)
+    S._call("cg3d_nms_segments", b, seg, 1, n, 0.5, rotated, keep, cnt)
+    assert torch.equal(keep.cpu(), want) and int(cnt.item()) == k
+
+
+def test_knn_vs_reference_cuda(lib):
+    path = os.path.join(build_ref.OUT, "libref_knn.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_knn.so not built")
+    if not hasattr(lib, "cg3d_knn"):
+        pytest.skip("cg3d_knn not in this build")
+    from cagroup3d_b200 import sparse as S
+    ref = ctypes.CDLL(path)
+    g = torch.Generator().manual_seed(0)
+    for n, m, k in ((5000, 3000, 1), (2000, 777, 8), (300, 50, 16)):
+        xyz = (torch.rand((1, n, 3), generator=g) * 4).to(DEV).contiguous()
+        q = (torch.rand((1, m, 3), generator=g) * 4).to(DEV).contiguous()
+        idx_r = torch.zeros((1, m, k), dtype=torch.int32, device=DEV)
+        d_r = torch.zeros((1, m, k), device=DEV)
+        rc = ref.ref_knn(1, n, m, k, ctypes.c_void_p(xyz.data_ptr()), ctypes.c_void_p(q.data_ptr()),
+                         ctypes.c_void_p(idx_r.data_ptr()), ctypes.c_void_p(d_r.data_ptr()),
+                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        idx, d = torch.zeros_like(idx_r), torch.zeros_like(d_r)
+        S._call("cg3d_knn", xyz, 1, n, q, m, k, idx, d)
+        torch.cuda.synchronize()
+        assert torch.equal(idx, idx_r) and torch.equal(d, d_r)
+
+
+def test_sort_vertices_vs_reference_cuda(lib):
+    m = build_ref.load("sort_vertices")
+    if m is None:
+        pytest.skip("oracle/_ref/sort_vertices.so not built")
+    if not hasattr(lib, "cg3d_sort_vertices"):
+        pytest.skip("cg3d_sort_vertices not in this build")
+    from cagroup3d_b200 import sparse as S
+    h = np.load(os.path.join(GOLD, "helpers.npz"))
+    v = torch.from_numpy(h["sv_vertices"]).to(DEV).contiguous()
+    mask = torch.from_numpy(h["sv_mask"]).to(DEV).contiguous()
+    nv = mask.int().sum(2).int().contiguous()
+    want = m.sort_vertices_forward(v, mask, nv)
+    got = torch.empty_like(want)
+    S._call("cg3d_sort_vertices", v, mask, nv, v.shape[0], v.shape[1], v.shape[2], got)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["scannet_small", "sunrgbd_small"])
+def test_cuda_forward_vs_reference_python_golden(lib, name):
+    """the CUDA model against the outputs of the reference's own Python (tests/golden/make_golden.py)."""
+    from cagroup3d_b200 import model_init, synthetic
+    from cagroup3d_b200.detector import voxelize
+    from tests.util import assert_same_coord_set
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    ncls, yaw, B = int(gold["n_classes"]), bool(gold["with_yaw"]), int(gold["batch"])
+    batch = synthetic.make_batch(B, target_voxels=int(gold["voxels"]), config=int(gold["config"]), n_classes=ncls, sunrgbd=yaw)
+    model = model_init.seeded_model(ncls, yaw, seed=int(gold["seed"]))
+    with torch.no_grad():
+        model.dense_head.semantic_conv.bias.copy_(torch.from_numpy(gold["semantic_bias"]))
+        model.dense_head.cls_conv.bias.copy_(torch.from_numpy(gold["cls_bias"]))
+    model = model.to(DEV)
+    p = torch.from_numpy(batch["points"]).to(DEV)
+    p[:, -3:] /= 255.
+    x = voxelize(p, 0.02)
+    out = model.backbone_3d.run(x)
+    pa, pb = assert_same_coord_set(out.C.cpu().numpy(), gold["bb_coords"])
+    assert np.abs(out.F.cpu().numpy()[pa] - gold["bb_feats"][pb]).max() <= 1e-3
+    model.dense_head.semantic_threshold = 0.05
+    cm = model.dense_head.class_maps(out, B)
+    assert np.abs(cm["sem"].cpu().numpy()[pa] - gold["sem"][pb]).max() <= 1e-3
+    assert np.abs(cm["offsets"].cpu().numpy()[pa] - gold["offsets"][pb]).max() <= 1e-3
+    # whole forward: detections of the reference matched one-to-one (a last-bit flip at a threshold / floor can move a
+    # few boxes, so 97 % of the reference's detections must be reproduced within 1e-3)
+    pred, _ = model({"points": torch.from_numpy(batch["points"]).to(DEV), "batch_size": B, "cur_epoch": 10})
+    for b in range(B):
+        want = gold[f"final_b{b}"]
+        wb = want[:, :-2] if want.shape[1] == 9 else np.concatenate([want[:, :6], np.zeros((len(want), 1), np.float32)], 1)
+        g = torch.cat([pred[b]["pred_boxes"], pred[b]["pred_scores"][:, None]], 1).cpu().double()
+        w = torch.from_numpy(np.concatenate([wb, want[:, -2:-1]], 1)).double()
+        assert abs(len(g) - len(w)) <= max(2, len(w) // 30)
+        d = torch.cdist(g, w, p=float("inf"))
+        lab = pred[b]["pred_labels"].cpu()[:, None].double() == torch.from_numpy(want[:, -1])[None].double()
+        d = torch.where(lab, d, torch.full_like(d, 1e9))
+        assert (d.min(0).values <= 1e-3).double().mean().item() >= 0.97
+
+
+def test_knn_vs_c_oracle_and_api(lib):
+    """pcdet/ops/knn/knn.py API mirror: (B, k, npoint) int32, ascending distance, first index wins ties."""
+    from cagroup3d_b200 import ops
+    from oracle import iou3d_oracle
+    g = torch.Generator().manual_seed(3)
+    xyz = torch.rand((2, 4000, 3), generator=g) * 3
+    xyz[0, 100] = xyz[0, 7]                                   # exact duplicate: index 7 must win at k=1
+    q = torch.cat([xyz[:, 5:9], torch.rand((2, 600, 3), generator=g) * 3], 1).contiguous()
+    for k in (1, 5):
+        if k > 1:
+            xyz[0, 100] += 1e-3            # exact ties inside a top-k > 1 are ordered by the (unstable) heap sort
+        got = ops.knn(k, xyz.to(DEV), q.to(DEV)).cpu()
+        assert got.shape == (2, k, 604) and got.dtype == torch.int32
+        for b in range(2):
+            want, _ = iou3d_oracle.knn(k, xyz[b], q[b])
+            assert torch.equal(got[b].T.contiguous(), want)
+    xyz[0, 100] = xyz[0, 7]
+    assert ops.knn(1, xyz.to(DEV), xyz[:, 5:9].contiguous().to(DEV))[0, 0, 2].item() == 7
+
+
+def test_ops_api_nms_and_iou3d(lib, ref_iou):
+    from cagroup3d_b200 import ops
+    b = boxes(500, 77).to(DEV)
+    sc = torch.rand((500,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    for fn, ref in ((ops.nms_gpu, ref_iou.nms_gpu), (ops.nms_normal_gpu, ref_iou.nms_normal_gpu)):
+        keep, _ = fn(b, sc, 0.3)
+        order = sc.sort(0, descending=True)[1]
+        kr = torch.zeros((500,), dtype=torch.long)
+        n = ref(b[order].contiguous(), kr, 0.3)
+        assert torch.equal(keep.cpu(), order.cpu()[kr[:n]])
+    want = torch.zeros((500, 500), device=DEV)
+    ref_iou.boxes_overlap_bev_gpu(b, b, want)
+    assert (ops.boxes_overlap_bev(b, b) - want).abs().max().item() <= 2e-5
+    assert ops.boxes_iou3d_gpu(b, b).diagonal().sub(1).abs().max().item() < 1e-4

@@ -52,3 +52,53 @@ def test_spconv_tc_grouped_and_slices(lib):
     assert cat[:, :64].abs().max().item() == 0
     want = S.gemm_rows(x.F, nbr, W.to(DEV), n, 27, tiles=S.make_tiles(offs, DEV, 64), impl="simt")
     assert (cat[:, 64:] - want).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_tile_ordered_rule_map_gives_identical_rows(lib, impl):
+    """Morton tile order: `order` is a permutation, the positional table is the row table permuted, and the conv
+    result is the same matrix (same rows in the same places) as with the natural order."""
+    from cagroup3d_b200 import sparse as S
+    ox = oracle_tensor(23, 64, n=6000, batch=3)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    n = x.cmap.n
+    order, oc = S.tile_order(x.cmap, 4)
+    assert order is not None and torch.equal(torch.sort(order.long())[0].cpu(), torch.arange(n))
+    assert torch.equal(oc, x.cmap.coords[order.long()])
+    b = oc[:, 0].cpu()
+    assert (b[1:] >= b[:-1]).all()                                   # samples stay contiguous
+    nbr_nat = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr)
+    S._TILE_ORDER["mode"], old = "morton", S._TILE_ORDER["mode"]
+    try:
+        nbr_ord, order2 = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr, ordered=True)
+    finally:
+        S._TILE_ORDER["mode"] = old
+    assert order2 is order and torch.equal(nbr_ord, nbr_nat[:, order.long()])
+    g = torch.Generator().manual_seed(9)
+    W = (torch.randn((27, 64, 64), generator=g) / 20).to(DEV)
+    res = torch.randn((n, 64), generator=g).to(DEV)
+    a = S.gemm_rows(x.F, nbr_nat, W, n, 27, residual=res, act="relu", impl=impl)
+    o = S.gemm_rows(x.F, nbr_ord, W, n, 27, residual=res, act="relu", impl=impl, out_rows=order)
+    assert torch.equal(a, o)                                          # same accumulation order per row -> bit identical
+
+
+@pytest.mark.parametrize("cin,cout,k", [(64, 64, 3), (128, 256, 3), (512, 128, 1), (64, 128, 5)])
+def test_presplit_cp_async_path_equals_register_path(lib, cin, cout, k):
+    """the two producers of the tensor-core kernel (fp32 rows split in registers vs pre-split bf16 rows copied with
+    cp.async) feed the MMA identical operands -> identical results, incl. ReLU on the input and zero-filled rows."""
+    from cagroup3d_b200 import sparse as S
+    ox = oracle_tensor(31, cin, n=5000, batch=2)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    n = x.cmap.n
+    g = torch.Generator().manual_seed(2)
+    W = (torch.randn((k ** 3, cin, cout), generator=g) / 20).to(DEV)
+    nbr = S.neighbor_table(x.cmap, x.cmap, k, x.mgr) if k > 1 else None
+    outs = []
+    for on in (False, True):
+        S._TC_SPLIT["on"], old = on, S._TC_SPLIT["on"]
+        try:
+            outs.append(S.gemm_rows(x.F, nbr, W if k > 1 else W[0].contiguous(), n, k ** 3, act="elu", in_act="relu", impl="tc"))
+        finally:
+            S._TC_SPLIT["on"] = old
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])

@@ -35,17 +35,17 @@ def main():
     n = cmap.n
     F = torch.randn((n, a.cin), device="cuda")
     W = torch.randn((a.k ** 3, a.cin, a.cout), device="cuda") / (a.cin * 8) ** 0.5
-    nbr = S.neighbor_table(cmap, cmap, a.k, x.mgr)
+    nbr, order = S.neighbor_table(cmap, cmap, a.k, x.mgr, ordered=True)
     P = S.count_rules(nbr)
     res = torch.randn((n, a.cout), device="cuda")
     scale = torch.rand((a.cout,), device="cuda") + 0.5
     for _ in range(3):
-        out = S.gemm_rows(F, nbr, W, n, a.k ** 3, scale=scale, shift=scale, residual=res, act="relu", impl=a.impl)
+        out = S.gemm_rows(F, nbr, W, n, a.k ** 3, scale=scale, shift=scale, residual=res, act="relu", impl=a.impl, out_rows=order)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.iters):
-        out = S.gemm_rows(F, nbr, W, n, a.k ** 3, scale=scale, shift=scale, residual=res, act="relu", impl=a.impl)
+        out = S.gemm_rows(F, nbr, W, n, a.k ** 3, scale=scale, shift=scale, residual=res, act="relu", impl=a.impl, out_rows=order)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
