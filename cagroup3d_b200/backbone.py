@@ -40,18 +40,18 @@ class FoldCache:
 
 
 def conv_bn(x: S.SparseTensor, conv: MinkowskiConvolution, bn, fc: FoldCache, act=None, in_act=None,
-            residual=None, out=None) -> S.SparseTensor:
+            residual=None, out=None, split_out=None) -> S.SparseTensor:
     scale, shift = fc.bn(bn) if bn is not None else (None, None)
     k, s = conv.kernel_size, conv.stride
     W = conv.kernel
     if k == 1 and s == 1:
         F = S.gemm_rows(x.F, None, W, x.cmap.n, 1, scale=scale, shift=shift, residual=residual, act=act,
-                        in_act=in_act, out=out)
+                        in_act=in_act, out=out, split_out=split_out)
         return x.with_F(F)
     omap = x.cmap if s == 1 else S.strided_map(x.cmap, x.mgr, s)
     nbr, order = S.neighbor_table(x.cmap, omap, k, x.mgr, ordered=True)
     F = S.gemm_rows(x.F, nbr, W, omap.n, k ** 3, scale=scale, shift=shift, residual=residual, act=act,
-                    in_act=in_act, out=out, out_rows=order)
+                    in_act=in_act, out=out, out_rows=order, split_out=split_out)
     return S.SparseTensor(F, omap, x.mgr)
 
 
@@ -71,14 +71,18 @@ class BasicBlock(nn.Module):
 
     def run(self, x: S.SparseTensor, fc: FoldCache, in_act=None) -> S.SparseTensor:
         if in_act is not None and self.downsample is None:
-            x = x.with_F(S.affine_act(x.F, act=in_act))       # the residual is relu(x) as well
+            assert in_act == "relu"
+            x = x.with_F(S.relu_rows(x.F))                    # the residual is relu(x) as well
             in_act = None
-        out = conv_bn(x, self.conv1, self.norm1, fc, act="relu", in_act=in_act)
+        # split_out: what the consumer of each result will gather (the next conv; after a no_relu block the next stage
+        # applies relu to its input, biresnet.py:366-394)
+        out = conv_bn(x, self.conv1, self.norm1, fc, act="relu", in_act=in_act, split_out="none")
         if self.downsample is not None:
             res = conv_bn(x, self.downsample[0], self.downsample[1], fc, in_act=in_act).F
         else:
             res = x.F
-        return conv_bn(out, self.conv2, self.norm2, fc, residual=res, act=None if self.no_relu else "relu")
+        return conv_bn(out, self.conv2, self.norm2, fc, residual=res, act=None if self.no_relu else "relu",
+                       split_out="relu" if self.no_relu else "none")
 
 
 class Bottleneck(nn.Module):
@@ -100,15 +104,17 @@ class Bottleneck(nn.Module):
 
     def run(self, x, fc, in_act=None):
         if in_act is not None and self.downsample is None:
-            x = x.with_F(S.affine_act(x.F, act=in_act))
+            assert in_act == "relu"
+            x = x.with_F(S.relu_rows(x.F))
             in_act = None
-        out = conv_bn(x, self.conv1, self.norm1, fc, act="relu", in_act=in_act)
-        out = conv_bn(out, self.conv2, self.norm2, fc, act="relu")
+        out = conv_bn(x, self.conv1, self.norm1, fc, act="relu", in_act=in_act, split_out="none")
+        out = conv_bn(out, self.conv2, self.norm2, fc, act="relu", split_out="none")
         if self.downsample is not None:
             res = conv_bn(x, self.downsample[0], self.downsample[1], fc, in_act=in_act).F
         else:
             res = x.F
-        return conv_bn(out, self.conv3, self.norm3, fc, residual=res, act=None if self.no_relu else "relu")
+        return conv_bn(out, self.conv3, self.norm3, fc, residual=res, act=None if self.no_relu else "relu",
+                       split_out="relu" if self.no_relu else "none")
 
 
 def _pre_act(inplanes, outplanes, k, pool=None):

@@ -34,9 +34,13 @@ __global__ void bounds_kernel(const int4* __restrict__ c, int n, int* __restrict
 
 // first[b] = smallest row index whose batch index is b (decomposition_permutations[b][0], cagroup_head.py:207)
 __global__ void first_rows_kernel(const int4* __restrict__ c, int n, int B, int* __restrict__ first) {
+    // a row can only be the first of its sample if it beats the current minimum: one relaxed read filters out all
+    // but the first few rows of every sample, and lanes of a warp that share a sample issue a single atomic
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int b = c[i].x;
-        if (b >= 0 && b < B) atomicMin(first + b, i);
+        bool cand = b >= 0 && b < B && i < *((volatile int*)(first + b));
+        unsigned peers = __match_any_sync(__activemask(), cand ? b : -1);
+        if (cand && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMin(first + b, i);   // lowest lane = lowest row
     }
 }
 

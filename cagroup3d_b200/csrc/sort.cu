@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
                                                                 const int* __restrict__ vals, int n, int shift, int nb,
                                                                 const int* __restrict__ offsets,
                                                                 unsigned long long* __restrict__ keys_out,
-                                                                int* __restrict__ vals_out) {
+                                                                int* __restrict__ vals_out, int next_shift,
+                                                                int* __restrict__ counts_next) {
     __shared__ int base[256];
     __shared__ int wcnt[RS_WARPS][256];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -57,12 +58,58 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
             for (int j = 0; j < w; ++j) off += wcnt[j][d];
             keys_out[off] = key;
             vals_out[off] = vals[i];
+            // histogram of the NEXT digit, binned by the CTA that will own position `off` in the next pass
+            if (next_shift >= 0) atomicAdd(counts_next + (size_t)((key >> next_shift) & 0xFF) * nb + off / RS_ITEMS, 1);
         }
         __syncthreads();
         int add = 0;
 #pragma unroll
         for (int j = 0; j < RS_WARPS; ++j) add += wcnt[j][t];
         base[t] += add;
+        __syncthreads();
+    }
+}
+
+// exclusive scan of `n` ints by ONE CTA (coalesced 4-wide tiles with a running carry); the digit-offset tables of the
+// radix sort are a few 10^4 entries, for which three launches of a multi-CTA scan cost more than the scan itself
+__global__ void __launch_bounds__(1024) rs_scan_single(const int* __restrict__ in, int n, int* __restrict__ out) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 4096) {
+        const int i = base + t * 4;
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? in[i + j] : 0;
+        int local = v[0] + v[1] + v[2] + v[3];
+        int x = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int s2 = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, s2, d);
+                if (lane >= d) s2 += y;
+            }
+            wsum[lane] = s2;
+        }
+        __syncthreads();
+        int excl = carry_s + (w ? wsum[w - 1] : 0) + x - local;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < n) out[i + j] = excl;
+            excl += v[j];
+        }
+        __syncthreads();
+        if (t == 1023) carry_s += wsum[31];
         __syncthreads();
     }
 }
@@ -92,7 +139,7 @@ extern "C" {
 
 int cg3d_sort_workspace_ints(int n) {
     int nb = cg3d_div_up(n > 0 ? n : 1, RS_ITEMS);
-    return 2 * 256 * nb + cg3d_scan_workspace_ints(256 * nb) + 8;
+    return 3 * 256 * nb + cg3d_scan_workspace_ints(256 * nb) + 8;
 }
 
 int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, int end_bit,
@@ -101,17 +148,27 @@ int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, i
     if (begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     int nb = cg3d_div_up(n, RS_ITEMS);
-    int* counts = workspace;
-    int* offsets = workspace + 256 * (size_t)nb;
-    int* sums = workspace + 2 * 256 * (size_t)nb;
-    int* total = sums + cg3d_scan_workspace_ints(256 * nb);
+    const size_t tab = 256 * (size_t)nb;
+    int* counts[2] = {workspace, workspace + tab};
+    int* offsets = workspace + 2 * tab;
+    int* sums = workspace + 3 * tab;
+    int* total = sums + cg3d_scan_workspace_ints((int)tab);
     unsigned long long *kin = keys, *kout = keys_tmp;
     int *vin = vals, *vout = vals_tmp;
+    // per pass: ONE scan launch + ONE scatter launch; the scatter also builds the next digit's per-CTA histogram
+    rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(kin, n, begin_bit, nb, counts[0]);
+    int cur = 0;
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
-        rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(kin, n, shift, nb, counts);
-        int rc = cg3d_exclusive_scan_i32(counts, 256 * nb, offsets, sums, total, stream);
-        if (rc) return rc;
-        rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, n, shift, nb, offsets, kout, vout);
+        const int next = shift + 8 < end_bit ? shift + 8 : -1;
+        if (tab <= (1u << 20)) {
+            rs_scan_single<<<1, 1024, 0, s>>>(counts[cur], (int)tab, offsets);
+        } else {
+            int rc = cg3d_exclusive_scan_i32(counts[cur], (int)tab, offsets, sums, total, stream);
+            if (rc) return rc;
+        }
+        if (next >= 0) cudaMemsetAsync(counts[cur ^ 1], 0, sizeof(int) * tab, s);
+        rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, n, shift, nb, offsets, kout, vout, next, counts[cur ^ 1]);
+        cur ^= 1;
         unsigned long long* tk = kin; kin = kout; kout = tk;
         int* tv = vin; vin = vout; vout = tv;
     }

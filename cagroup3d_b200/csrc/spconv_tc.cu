@@ -1,28 +1,36 @@
 // Sparse convolution as an output-stationary implicit GEMM on the 5th-gen tensor cores (tcgen05).
 //
-//   out[o, :] = epilogue( sum_k in_act(in[nbr[k][o], :]) @ W[g][k] )
+//   out[o, :] = epilogue( sum_k x[nbr[k][o], :] @ W[g][k] )            x = the (optionally ReLU'd) input rows
 //
-// One CTA owns 128 output rows x NT output channels (NT = 64 / 128 / 256); the accumulator lives in
-// TMEM (128 lanes x NT fp32 columns).  The K loop walks (active tap, 64-channel chunk) stages through a
-// ring of shared-memory buffers:
-//   warps 0-7  gather the 128 feature rows of the stage (rows nbr < 0 are zero-filled): coalesced 32-byte
-//              pieces per lane, 8 lanes per row, loads kept 3 stages ahead in a register ring, split
-//              fp32 -> bf16 hi + bf16 lo in registers and written in the 128B-swizzled K-major UMMA
-//              layout; after the K loop they run the epilogue (tcgen05.ld -> folded BN / bias /
-//              residual / ReLU|ELU -> global);
-//   warp 8     streams the stage's weight tile: the weights are pre-split and pre-swizzled once into the
-//              exact shared-memory image, so a stage is ONE linear bulk async copy (cp.async.bulk, TMA
-//              engine, mbarrier complete_tx);
-//   warp 9     one elected lane issues the tcgen05.mma's: per 16-wide k-step three bf16 products
-//              A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulated in fp32 ("bf16x3": the dropped terms are
-//              <= 2^-16 relative, fp32-class accuracy at 1/3 of the bf16 tensor rate), then tcgen05.commit
-//              releases the stage.
-// Taps for which no row of the tile has a neighbour are skipped (found by a prologue scan of the rule
-// map).  No atomics; the accumulation order is fixed (taps ascending), so results are deterministic.
+// Precision: fp32 in, fp32 out, "bf16x3" inside -- every operand is split into bf16 hi + bf16 lo and three products
+// A_hi*B_hi + A_hi*B_lo + A_lo*B_hi are accumulated in fp32 (the dropped lo*lo term is <= 2^-16 relative), which keeps
+// logits / boxes inside the 1e-3 bar through ~45 stacked layers at 1/3 of the bf16 tensor rate.
 //
-// Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 64 == 0 and
-// Cout % 64 == 0; the Cin = 3 stem and the narrow prediction
-// heads stay on the exact-fp32 SIMT kernel (spconv_simt.cu).
+// Operands are split ONCE, outside the K loop:
+//   activations  cg3d_split_bf16: fp32 [n][C] -> bf16 [n][C/32][hi 32 | lo 32]: the 128 bytes a pipeline stage needs
+//                from a row are contiguous in HBM and are exactly one 128B-swizzle row of the UMMA tile;
+//   weights      cg3d_spconv_tc_prepare: fp32 [G][K][Cin][Cout] -> per (g, tap, 32-channel chunk, NT-column tile) the
+//                exact shared-memory image [n][hi 32 | lo 32] (swizzled), so a stage is ONE linear bulk copy.
+//
+// One CTA owns 128 output rows x NT output channels (NT = 64 / 128 / 256); the accumulator lives in TMEM (128 lanes x NT
+// fp32 columns).  The K loop walks (active tap, 32-channel chunk) stages through a shared-memory ring:
+//   warps 0-7  gather: per stage every thread issues 4 cp.async of 16 bytes (global -> swizzled shared memory, no
+//              register staging, no conversion); rows without a neighbour are zero-filled by a 0-byte source; row
+//              indices are prefetched 4 taps ahead.  A stage is published (proxy fence + ONE mbarrier arrival per
+//              warp) as soon as the thread's copies have landed and BEFORE the thread blocks on the next free slot.
+//              After the K loop the same warps run the epilogue (tcgen05.ld -> folded BN / bias / residual /
+//              ReLU|ELU -> global);
+//   warp 8     one lane streams the stage's weight tile with cp.async.bulk (TMA engine, mbarrier complete_tx);
+//   warp 9     one lane issues the 6 tcgen05.mma of a stage (2 k-steps x 3 products) and tcgen05.commit's the slot.
+// Two CTAs are resident per SM (<= 96 KB of pipeline each, 2 x NT <= 512 TMEM columns), so the prologue, pipeline
+// fill and epilogue of one tile overlap the MMAs of another.
+// Taps for which no row of the tile has a neighbour are skipped (prologue scan of the rule map); with rows ordered by
+// tap pattern (cg3d_table_mask_keys) that removes most of the padding.  No atomics; the accumulation order is fixed
+// (taps ascending), so results are deterministic.
+//
+// Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 32 == 0 and Cout % 64 == 0
+// (SURVEY.md A4-A8, A12, A13, A19, A20); the Cin = 3 stem and the narrow prediction heads stay on the exact-fp32 SIMT
+// kernel (spconv_simt.cu).
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,10 +41,11 @@
 namespace {
 
 constexpr int TM = 128;            // output rows per CTA (UMMA M)
-constexpr int KC = 64;             // channels per stage (128 bytes of bf16 = one swizzle row)
-constexpr int NPROD = 256;         // gather / epilogue threads (warps 0-7)
+constexpr int KC = 32;             // channels per stage: 32 hi + 32 lo bf16 = one 128-byte swizzle row
+constexpr int NPROD = 256;         // epilogue threads (warps 0-7)
+constexpr int NGATHER = 256;       // gather threads (8 threads share a row; warps 0-7)
 constexpr int NTHREADS = NPROD + 64;
-constexpr int A_PART = TM * 128;   // bytes of one A part (hi or lo) per stage
+constexpr int A_BYTES = TM * 128;  // bytes of the A tile of a stage
 constexpr int MAX_TAPS = 729;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +81,10 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival (counted in its expected total) once all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -133,7 +146,7 @@ __device__ unsigned long long g_tc_prof[16];
 #define TC_PROF(i, v) do { if (a.debug & 8) atomicAdd(&g_tc_prof[i], (unsigned long long)(v)); } while (0)
 
 struct TcArgs {
-    const float* in;
+    const unsigned short* in_split;   // [rows][Cin/32][hi 32 | lo 32] bf16
     const int* nbr;
     const unsigned char* wimg;
     float* out;
@@ -144,20 +157,23 @@ struct TcArgs {
     const int* tile_rows;
     const int* tile_group;
     const int* out_rows;   // position -> output row (tile order) or nullptr
-    const unsigned short* in_split;   // pre-split activations [rows][hi Cin | lo Cin] bf16, or nullptr
-    int n_out, Cin, Cout, K, act, ldi, ldo, in_act;
-    int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads
+    unsigned short* out_split;        // optional second output: the result (ReLU'd if out_split_relu) in the split layout
+    int out_split_relu;
+    int n_out, Cin, Cout, K, act, ldo;
+    int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads, 4 = no gather
+                 // copies at all, 8 = cycle counters, 16 = no MMAs
 };
 
 template <int NT, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
-    constexpr int B_PART = NT * 128;                      // bytes of one B part (hi or lo) per stage
-    constexpr int STAGE_BYTES = 2 * A_PART + 2 * B_PART;
+__global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
+    constexpr int B_BYTES = NT * 128;                     // bytes of the B tile of a stage
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    constexpr int RPT = TM / (NGATHER / 8);               // rows per gather thread (8 threads share a row)
+    constexpr int PF = 4;                                 // taps of row indices in flight ahead of their use
 
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    unsigned char* base_ptr = smem_raw + (base - smem_u32(smem_raw));
 
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
     __shared__ uint32_t tmem_slot;
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, NPROD / 32 + 1);      // one arrival per gather warp + the weight copy's expect_tx
+            mbar_init(full0 + 8 * s, NGATHER + 1);        // one async arrival per gather thread + the weight copy's expect_tx
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
@@ -196,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (a.nbr) {
-        constexpr int NW = NTHREADS / 32, UN = 4;
+        constexpr int NW = NTHREADS / 32, UN = 4;         // 4 taps per warp per round, all loads issued before the votes
         for (int k0 = warp * UN; k0 < a.K; k0 += NW * UN) {
             int v[UN][TM / 32];
 #pragma unroll
@@ -240,60 +256,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
+      if (warp < NGATHER / 32) {
         // ================= gather producers =================
-        // thread -> (16-byte piece of the 64-channel chunk, rows rbase + 32 j)
+        // thread -> (16-byte piece of the 128-byte stage row, rows rbase + (NGATHER / 8) j).  Every thread attaches an asynchronous
+        // arrival to its own copies (cp.async.mbarrier.arrive.noinc): the stage's full barrier completes when the last
+        // copy has landed, no thread comes back to publish it, and the slots of the ring circulate independently.
         const int piece = t & 7;
-        const int rbase = t >> 3;                      // 0..31
+        const int rbase = t >> 3;
         const uint32_t sw_off = (uint32_t)((rbase >> 3) * 1024 + (rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
-      if (a.in_split) {
-        // ---- pre-split input: global -> shared with cp.async, no registers, no conversion.  A row of the split
-        // matrix is [hi Cin | lo Cin] bf16; a 64-channel chunk of either part is one 128-byte swizzle row.  Rows
-        // without a neighbour are zero-filled by a 0-byte source.  Copies run LOOKAHEAD stages ahead; a stage is
-        // published (proxy fence + mbarrier arrive) once this thread's copies of it have landed.
-        constexpr int RPT = TM / 32;
-        constexpr int LOOKAHEAD = STAGES - 1;
-        constexpr int PF = 4;          // taps whose row indices are in flight ahead of their use (hides the nbr latency)
-        int rq[PF][RPT];
         const size_t row_elems = 2 * (size_t)a.Cin;
+        int rq[PF][RPT];
         auto load_rows = [&](int ai, int (&dst)[RPT]) {
             const int k = taps[ai];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-                int r = rbase + 32 * j;
+                int r = rbase + (NGATHER / 8) * j;
                 dst[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r)
                                             : (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r)) : -1;
             }
         };
         int q = 0;
-        // publish-before-acquire: stage q - LOOKAHEAD is handed to the MMA warp as soon as this thread's copies of it
-        // have landed, BEFORE blocking on the slot of stage q -- otherwise every MMA stage would wait for the previous
-        // one's completion signal to travel through this loop.
-        auto publish = [&]() {
-            if (q >= LOOKAHEAD && q - LOOKAHEAD < n_iters) {
-                cp_async_wait<LOOKAHEAD - 1>();                  // groups <= q - LOOKAHEAD complete (q - 1 ... may be pending)
-                fence_async_smem();
-                __syncwarp();                                    // ONE arrival per warp: 256 serialized mbarrier arrivals
-                if (lane == 0) mbar_arrive(full0 + 8 * ((q - LOOKAHEAD) % STAGES));      // per stage cost more than the MMAs
-            }
-        };
-        auto stage = [&](int c, const int (&ridx)[RPT]) {
-            const long long p0 = clock64();
-            publish();
-            const long long p1 = clock64();
-            const int s = q % STAGES;
-            const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            if (t == 0) { TC_PROF(9, p1 - p0); TC_PROF(8, clock64() - p1); }
-            const uint32_t dst = base + (uint32_t)(s * STAGE_BYTES) + sw_off;
+        uint32_t zeroed = 0;                           // bit s * RPT + j: row j of slot s currently holds zeros
+        auto tap = [&](const int (&ridx)[RPT]) {
+            const unsigned short* rp[RPT];
+            uint32_t okm = 0;
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 const bool ok = ridx[j] >= 0 && !(a.debug & 2);
-                const unsigned short* src = a.in_split + (ok ? (size_t)ridx[j] * row_elems : 0) + c * KC + piece * 8;
-                cp_async16(dst + (uint32_t)(j * 4 * 1024), src, ok ? 16u : 0u);
-                cp_async16(dst + (uint32_t)(A_PART + j * 4 * 1024), src + a.Cin, ok ? 16u : 0u);
+                okm |= (uint32_t)ok << j;
+                rp[j] = a.in_split + (ok ? (size_t)ridx[j] * row_elems : 0) + piece * 8;
             }
-            cp_async_commit();                                   // group q
-            ++q;
+#pragma unroll 1
+            for (int c = 0; c < nchunks; ++c) {
+                const long long p1 = clock64();
+                const int s = q % STAGES;
+                const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                if (t == 0) TC_PROF(8, clock64() - p1);
+                const uint32_t dst = base + (uint32_t)(s * STAGE_BYTES) + sw_off;
+                const uint32_t zs = (zeroed >> (s * RPT)) & ((1u << RPT) - 1u);
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const bool ok = (okm >> j) & 1u;
+                    // a row that needs zeros and already holds zeros in this slot is left alone
+                    if ((ok || !((zs >> j) & 1u)) && !(a.debug & 4))
+                        cp_async16(dst + (uint32_t)(j * (NGATHER / 64) * 1024), rp[j] + c * (2 * KC), ok ? 16u : 0u);
+                }
+                zeroed = (zeroed & ~(((1u << RPT) - 1u) << (s * RPT))) | ((~okm & ((1u << RPT) - 1u)) << (s * RPT));
+                cp_async_arrive_noinc(full0 + 8 * s);
+                ++q;
+            }
         };
 #pragma unroll
         for (int d = 0; d < PF; ++d)
@@ -304,78 +316,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
             for (int d = 0; d < PF; ++d) {
                 const int ai = ai0 + d;
                 if (ai < n_active) {
-#pragma unroll 1
-                    for (int c = 0; c < nchunks; ++c) stage(c, rq[d]);
+                    tap(rq[d]);
                     if (ai + PF < n_active) load_rows(ai + PF, rq[d]);
-                }
-            }
-        }
-#pragma unroll 1
-        for (int e = 0; e < LOOKAHEAD; ++e) {                    // drain: publish the last LOOKAHEAD stages
-            publish();
-            cp_async_commit();                                   // empty group keeps the wait_group arithmetic uniform
-            ++q;
-        }
-      } else {
-        // ---- fp32 input: loads run DEPTH stages ahead of the convert/store step (register ring), row indices one
-        // stage ahead of the loads.
-        constexpr int DEPTH = 3, RPT = TM / 32;        // rows per thread
-        float4 v0[DEPTH][RPT], v1[DEPTH][RPT];
-        int ridx[RPT];
-
-        auto load_idx = [&](int q) {
-            const int k = taps[q / nchunks];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                int r = rbase + 32 * j;
-                ridx[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r)
-                                             : (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r)) : -1;
-            }
-        };
-        auto issue = [&](int q, float4 (&x0)[RPT], float4 (&x1)[RPT]) {
-            const int c = q % nchunks;
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                if (ridx[j] >= 0 && !(a.debug & 2)) {
-                    const float4* src = reinterpret_cast<const float4*>(a.in + (size_t)ridx[j] * a.ldi + c * KC + piece * 8);
-                    x0[j] = __ldg(src);
-                    x1[j] = __ldg(src + 1);
-                } else {
-                    x0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    x1[j] = x0[j];
-                }
-            }
-            if (q + 1 < n_iters && (q + 1) % nchunks == 0) load_idx(q + 1);     // next tap's rows, one stage early
-        };
-        auto flush = [&](int it, float4 (&x0)[RPT], float4 (&x1)[RPT]) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            unsigned char* As = base_ptr + (size_t)s * STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                uint4 hi, lo;
-                split8(x0[j], x1[j], a.in_act == CG3D_ACT_RELU, hi, lo);
-                uint32_t off = (uint32_t)(j * 4 * 1024) + sw_off;
-                *reinterpret_cast<uint4*>(As + off) = hi;
-                *reinterpret_cast<uint4*>(As + A_PART + off) = lo;
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
-        };
-
-        if (n_iters > 0) load_idx(0);
-#pragma unroll
-        for (int d = 0; d < DEPTH; ++d)
-            if (d < n_iters) issue(d, v0[d], v1[d]);
-        for (int it0 = 0; it0 < n_iters; it0 += DEPTH) {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) {
-                const int it = it0 + d;
-                if (it < n_iters) {
-                    flush(it, v0[d], v1[d]);
-                    if (it + DEPTH < n_iters) issue(it + DEPTH, v0[d], v1[d]);
                 }
             }
         }
@@ -388,43 +330,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
         }
         const long long e1 = clock64();
         if (t == 0) { TC_PROF(5, e1 - t_main); TC_PROF(11, e1 - e0); }
+        // The TMEM load gives lane = row; writing global memory in that shape would put 32 different rows into every
+        // store instruction (16-byte pieces).  Each warp therefore transposes 32-column panels of its 32 rows through a
+        // private shared-memory patch (the pipeline ring is idle now) and writes / reads the residual in 128-byte row
+        // segments: 8 lanes per row, 4 rows per instruction.
         const int lq = warp & 3, half = warp >> 2;
         const int r = lq * 32 + lane;
-        const bool live = r < nrows;
-        const int prow = (live && a.out_rows) ? __ldg(a.out_rows + row0 + r) : row0 + r;
-        const size_t orow = (size_t)prow * a.ldo, rrow = (size_t)prow * a.Cout;
+        const int prow = (r < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r) : -1;
+        float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + warp * (32 * 36);
+        const int sub = lane >> 3, pc = lane & 7;                  // read-back: row it * 4 + sub, floats pc * 4 .. + 3
 #pragma unroll 1
-        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 16) {
-            uint32_t v[16];
+        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
+            uint32_t v[16], w[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c0 + 16), w);
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0u;
+                for (int i = 0; i < 16; ++i) v[i] = w[i] = 0u;
             }
-            if (live) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = n0 + c0 + q * 4;
-                    float o[4] = {__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
-                                  __uint_as_float(v[q * 4 + 3])};
-                    if (a.scale) {
-                        float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
-                        o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w;
-                    }
-                    if (a.shift) {
-                        float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
-                        o[0] += sh.x; o[1] += sh.y; o[2] += sh.z; o[3] += sh.w;
-                    }
+            for (int i = 0; i < 4; ++i) {
+                *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                *reinterpret_cast<uint4*>(stg + lane * 36 + 16 + 4 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            }
+            __syncwarp();
+            const int col = n0 + c0 + pc * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
+            if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + sub;
+                const int pr = __shfl_sync(0xffffffffu, prow, rr);
+                const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + pc * 4);
+                if (pr >= 0) {
+                    float o[4] = {x.x * sc.x + sh.x, x.y * sc.y + sh.y, x.z * sc.z + sh.z, x.w * sc.w + sh.w};
                     if (a.residual) {
-                        float4 rs = __ldg(reinterpret_cast<const float4*>(a.residual + rrow + col));
+                        const float4 rs = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)pr * a.Cout + col));
                         o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) o[i] = cg3d_act(o[i], a.act);
-                    *reinterpret_cast<float4*>(a.out + orow + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(a.out + (size_t)pr * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    if (a.out_split) {                 // the next conv's operand, so that it needs no separate split pass
+                        uint32_t h[2], l[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float x0 = o[2 * i], x1 = o[2 * i + 1];
+                            if (a.out_split_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+                            __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+                            h[i] = *reinterpret_cast<uint32_t*>(&hh);
+                            l[i] = *reinterpret_cast<uint32_t*>(&ll);
+                        }
+                        unsigned short* d = a.out_split + (size_t)pr * 2 * a.Cout + (col >> 5) * 64 + (col & 31);
+                        *reinterpret_cast<uint2*>(d) = make_uint2(h[0], h[1]);
+                        *reinterpret_cast<uint2*>(d + 32) = make_uint2(l[0], l[1]);
+                    }
                 }
             }
+            __syncwarp();
         }
         tc_fence_before();
         if (t == 0) TC_PROF(6, clock64() - e1);
@@ -439,10 +405,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const size_t blk = (((size_t)g * a.K + k) * nchunks + c) * ntn + blockIdx.y;
-                    const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)(2 * B_PART);
+                    const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)B_BYTES;
                     mbar_expect_tx(full0 + 8 * s, nbytes);
-                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + 2 * A_PART), a.wimg + blk * (size_t)(2 * B_PART),
-                                  nbytes, full0 + 8 * s);
+                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + A_BYTES), a.wimg + blk * (size_t)B_BYTES, nbytes,
+                                  full0 + 8 * s);
                 }
             }
         }
@@ -458,16 +424,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
                 mbar_wait(full0 + 8 * s, ph);
                 const long long m1 = clock64();
                 if (it == 0) TC_PROF(4, m1 - m0); else w_acc += m1 - m0;
+                fence_async_smem();                   // cp.async wrote the A tile through the generic proxy
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
-                const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART);
-                const uint64_t b_hi = make_desc(sa + 2 * A_PART), b_lo = make_desc(sa + 2 * A_PART + B_PART);
+                // a 128-byte row holds [hi k0..31 | lo k0..31]: hi k-step kk at +32 kk bytes, lo at +64 + 32 kk bytes
+                const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < KC / 16; ++kk) {
-                    const uint64_t adv = (uint64_t)(kk * 2);            // 32 bytes along K, in 16-byte units
-                    umma_bf16(tmem_base, a_hi + adv, b_hi + adv, IDESC, (it | kk) ? 1u : 0u);
-                    umma_bf16(tmem_base, a_hi + adv, b_lo + adv, IDESC, 1u);
-                    umma_bf16(tmem_base, a_lo + adv, b_hi + adv, IDESC, 1u);
+                    if (a.debug & 16) break;
+                    const uint64_t hi = (uint64_t)(kk * 2), lo = (uint64_t)(4 + kk * 2);     // in 16-byte units
+                    umma_bf16(tmem_base, da + hi, db + hi, IDESC, (it | kk) ? 1u : 0u);
+                    umma_bf16(tmem_base, da + hi, db + lo, IDESC, 1u);
+                    umma_bf16(tmem_base, da + lo, db + hi, IDESC, 1u);
                 }
                 umma_commit(empty0 + 8 * s);
                 i_acc += clock64() - m1;
@@ -485,8 +453,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) spconv_tc_kernel(TcArgs a) {
     if (t == 0) TC_PROF(7, clock64() - t_start);
 }
 
-// fp32 W[G][K][Cin][Cout] -> per (g, k, 64-channel chunk, NT-column tile) block of 2 * NT * 128 bytes:
-// [hi | lo][n][64 bf16 along Cin], 16-byte pieces XOR-swizzled by (n % 8) -- the exact smem image.
+// fp32 W[G][K][Cin][Cout] -> per (g, k, 32-channel chunk, NT-column tile) block of NT * 128 bytes:
+// row n = [hi 32 bf16 along Cin | lo 32 bf16], 16-byte pieces XOR-swizzled by (n % 8) -- the exact smem image.
 __global__ void weight_image_kernel(const float* __restrict__ W, long long total, int K, int Cin, int Cout, int NT,
                                     unsigned char* __restrict__ img) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -500,36 +468,39 @@ __global__ void weight_image_kernel(const float* __restrict__ W, long long total
         __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
         int c = ci / KC, kk = ci % KC, tn = co / NT, n = co % NT;
         size_t blk = ((size_t)gk * (Cin / KC) + c) * (Cout / NT) + tn;
-        size_t off = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128 + (size_t)(((kk >> 3) ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-        unsigned char* b = img + blk * (size_t)(2 * NT * 128);
-        *reinterpret_cast<__nv_bfloat16*>(b + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(b + (size_t)NT * 128 + off) = lo;
+        size_t rowb = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128;
+        int p_hi = kk >> 3, p_lo = 4 + (kk >> 3);         // 16-byte piece inside the 128-byte row
+        unsigned char* b = img + blk * (size_t)(NT * 128);
+        *reinterpret_cast<__nv_bfloat16*>(b + rowb + (size_t)((p_hi ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(b + rowb + (size_t)((p_lo ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2) = lo;
     }
 }
 
-// fp32 [n][C] (row stride ld) -> bf16 [n][hi C | lo C], optional ReLU first (the `self.relu(x)` in front of a stage)
+// fp32 [n][C] (row stride ld) -> bf16 [n][C/32][hi 32 | lo 32], optional ReLU first (the `self.relu(x)` in front of a
+// BiResNet stage)
 __global__ void split_rows_kernel(const float* __restrict__ in, int ld, long long n8, int C, int relu,
                                   unsigned short* __restrict__ out) {
     const int c8 = C / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / c8;
-        const int p = (int)(i % c8);
+        const int p = (int)(i % c8);                     // 8-channel piece
         const float4* src = reinterpret_cast<const float4*>(in + r * ld + p * 8);
         uint4 hi, lo;
         split8(__ldg(src), __ldg(src + 1), relu, hi, lo);
-        unsigned short* dst = out + r * 2 * C + p * 8;
+        unsigned short* dst = out + r * 2 * C + (p >> 2) * 64 + (p & 3) * 8;
         *reinterpret_cast<uint4*>(dst) = hi;
-        *reinterpret_cast<uint4*>(dst + C) = lo;
+        *reinterpret_cast<uint4*>(dst + 32) = lo;
     }
 }
 
 template <int NT, int STAGES>
 int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
-    constexpr int smem = STAGES * (2 * A_PART + 2 * NT * 128) + 1024;
+    constexpr int smem = STAGES * (A_BYTES + NT * 128) + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT);
@@ -556,7 +527,7 @@ int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsi
 }
 
 int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream) {
-    if (C % 8 != 0 || ld % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15)) return -3;
+    if (C % KC != 0 || ld % 4 != 0 || ((size_t)in & 15) || ((size_t)out & 15)) return -3;
     long long n8 = (long long)n * (C / 8);
     if (n8 == 0) return 0;
     long long b = (n8 + 255) / 256;
@@ -565,24 +536,24 @@ int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned sh
     return 0;
 }
 
-int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
-                   int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
-                   int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
-                   const int* out_rows, const unsigned short* in_split, void* stream) {
+int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
+                   int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
+                   const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, const int* out_rows,
+                   unsigned short* out_split, int out_split_relu, void* stream) {
     if (n_out == 0) return 0;
     int NT = cg3d_spconv_tc_ntile(Cout);
     if (NT == 0 || Cin % KC != 0 || K > MAX_TAPS || (!nbr && K != 1)) return -1;
-    if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15)) return -3;
-    if (!in_split && (ldi % 4 != 0 || ((size_t)in & 15))) return -3;
-    if (in_split && ((size_t)in_split & 15)) return -3;
-    TcArgs a{in, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, in_split, n_out, Cin,
-             Cout, K, act, ldi, ldo, in_act, 0};
+    if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15) || ((size_t)in_split & 15)) return -3;
+    if (out_split && (((size_t)out_split & 15) || Cout % 32 != 0)) return -3;
+    TcArgs a{in_split, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, out_split,
+             out_split_relu, n_out, Cin, Cout, K, act, ldo, 0};
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    // <= 96 KB of pipeline per CTA so that two CTAs share an SM
     int rc = NT == 256 ? launch_tc<256, 2>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3>(a, tiles, s) : launch_tc<64, 4>(a, tiles, s));
     if (rc == 0 && (dbg & 8)) {
         unsigned long long h[16], z[16] = {0};
@@ -591,8 +562,9 @@ int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const u
         cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
         double c = h[0] ? (double)h[0] : 1.0;
         fprintf(stderr, "[tc prof] NT=%d ctas=%llu iters/cta=%.1f | per CTA clks: total %.0f prologue %.0f main->accum %.0f epilogue %.0f | "
-                        "mma: first-wait %.0f wait %.0f issue %.0f | producer0: publish-wait %.0f empty-wait %.0f accum-wait %.0f\n",
-                NT, h[0], h[10] / c, h[7] / c, h[1] / c, h[5] / c, h[6] / c, h[4] / c, h[2] / c, h[3] / c, h[9] / c, h[8] / c, h[11] / c);
+                        "mma: first-wait %.0f wait %.0f issue %.0f | producer0: publish %.0f empty-wait %.0f accum-wait %.0f\n",
+                NT, h[0], h[10] / c, h[7] / c, h[1] / c, h[5] / c, h[6] / c, h[4] / c, h[2] / c, h[3] / c, h[9] / c, h[8] / c,
+                h[11] / c);
     }
     return rc;
 }

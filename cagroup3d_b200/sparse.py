@@ -183,7 +183,8 @@ def mask_order(nbr: torch.Tensor, ksize: int, n: int, coords=None, group_div: in
     keys = torch.empty((n,), dtype=torch.int64, device=dev)
     order = _i32(n, device=dev)
     _call("cg3d_table_mask_keys", nbr, K, ksize, n, coords if group_div else None, group_div, keys, order)
-    sort_pairs(keys, order, n, end_bit=(min(K, 27) if not group_div else 27 + group_bits), begin_bit=0)
+    # 24 key bits (3 radix passes) group almost as well as all 27 taps
+    sort_pairs(keys, order, n, end_bit=(min(K, 27) if not group_div else 27 + group_bits), begin_bit=max(0, min(K, 27) - 24))
     out = torch.empty_like(nbr)
     _call("cg3d_permute_table", nbr, K, n, order, out)
     return out, order
@@ -274,11 +275,12 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
               scale=None, shift=None, residual=None, act=None, tiles: Optional[Tiles] = None,
               impl: Optional[str] = None, in_act=None, out: Optional[torch.Tensor] = None,
-              out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out_rows: Optional[torch.Tensor] = None, split_out: Optional[str] = None) -> torch.Tensor:
     """out = act((sum_k in_act(Fin[nbr[k]]) @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout].
 
     Fin / out may be column slices of wider row-major matrices (unit column stride).  out_rows: the table is
-    positional (tile order); position j is output row out_rows[j]."""
+    positional (tile order); position j is output row out_rows[j].  split_out ("none" | "relu"): the tensor-core
+    kernel also emits the split-bf16 copy of the result a following conv with that input activation will ask for."""
     Cin, Cout = W.shape[-2], W.shape[-1]
     assert Fin.stride(1) == 1 and W.is_contiguous() and Fin.shape[1] == Cin
     if out is None:
@@ -289,8 +291,9 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     if n_out == 0:
         return out
     name = impl or _CONV_IMPL["name"]
-    use_tc = (name == "tc" and tc_supported(Cin, Cout, K) and Fin.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0
-              and Fin.stride(0) % 4 == 0 and out.stride(0) % 4 == 0)
+    use_tc = (name == "tc" and tc_supported(Cin, Cout, K) and in_act in (None, "none", "relu")
+              and Fin.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and Fin.stride(0) % 4 == 0
+              and out.stride(0) % 4 == 0)
     meta = None
     if Profile.active is not None and not Profile.conv_only:
         meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4,
@@ -298,21 +301,21 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
     targs = (tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
              tiles.n if tiles else 0, out_rows)
     if use_tc:
-        Fs = split_rows(Fin, in_act) if _TC_SPLIT["on"] else None
-        _call("cg3d_spconv_tc", Fin, Fin.stride(0), ACT[in_act], nbr, weight_image(W), out, out.stride(0), n_out, Cin,
-              Cout, K, scale, shift, residual, ACT[act], *targs, Fs, meta=meta)
+        So = None
+        if split_out is not None and Cout % 32 == 0 and out.stride(0) == Cout:
+            So = torch.empty((n_out, 2 * Cout), dtype=torch.int16, device=out.device)
+            out._cg3d_split = {(out.data_ptr(), out._version, out.stride(0), 1 if split_out == "relu" else 0): So}
+        _call("cg3d_spconv_tc", split_rows(Fin, in_act), nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
+              scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
     else:
         _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,
               scale, shift, residual, ACT[act], *targs, meta=meta)
     return out
 
 
-_TC_SPLIT = {"on": os.environ.get("CG3D_TC_SPLIT", "1") != "0"}
-
-
 def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
-    """[n, 2C] bf16 (hi | lo) copy of an activation matrix for the tensor-core conv, with the consumer's input
-    activation applied.  Cached on the tensor object; rebuilt if the tensor is modified in place."""
+    """[n, 2C] bf16 copy (per 32-channel chunk: hi | lo) of an activation matrix for the tensor-core conv, with the
+    consumer's input activation applied.  Cached on the tensor object; rebuilt if the tensor is modified in place."""
     relu = 1 if in_act == "relu" else 0
     assert in_act in (None, "none", "relu")
     cache = getattr(F, "_cg3d_split", None)
@@ -334,7 +337,7 @@ def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
 
 
 def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
-    return Cin % 64 == 0 and Cout % 64 == 0 and K <= 729
+    return Cin % 32 == 0 and Cout % 64 == 0 and K <= 729
 
 
 def weight_image(W: torch.Tensor) -> torch.Tensor:
@@ -375,6 +378,15 @@ def affine_act(x: torch.Tensor, scale=None, shift=None, add=None, act=None, out=
     if add is not None:
         assert add.is_contiguous()
     _call("cg3d_affine_act", x, x.stride(0), scale, shift, add, out, out.stride(0), x.shape[0], x.shape[1], ACT[act])
+    return out
+
+
+def relu_rows(F: torch.Tensor) -> torch.Tensor:
+    """relu(F) as a new matrix; a cached split copy of F made for a relu-consuming conv is the plain split of the result."""
+    out = affine_act(F, act="relu")
+    for (ptr, ver, ld, relu), Sp in (getattr(F, "_cg3d_split", None) or {}).items():
+        if relu == 1 and ptr == F.data_ptr() and ver == F._version and ld == F.stride(0):
+            out._cg3d_split = {(out.data_ptr(), out._version, out.stride(0), 0): Sp}
     return out
 
 

@@ -118,25 +118,26 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
                      const float* residual, int act, const int* tile_row0, const int* tile_rows,
                      const int* tile_group, int n_tiles, const int* out_rows, void* stream);
 
-/* Tensor-core path of the same contraction (tcgen05, accumulator in TMEM, 128 rows x NT columns per
- * CTA, weights streamed by bulk async copies).  fp32 in / fp32 out; inside, operands are split into
- * bf16 hi + lo and three products are accumulated in fp32 (error <= ~2^-16 relative per product).
- * Needs Cin % 64 == 0, Cout % 64 == 0, K <= 729, 16-byte aligned in/out rows.  `wimg` is the
- * pre-split, pre-swizzled weight image made ONCE per weight tensor by cg3d_spconv_tc_prepare
- * (same byte count as the fp32 weights); cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).
- * Grouped mode as above with tiles of <= 128 rows.  in_split: see cg3d_split_bf16. */
+/* Tensor-core path of the same contraction (tcgen05, accumulator in TMEM, 128 rows x NT columns per CTA, two CTAs
+ * per SM).  fp32 in / fp32 out; inside, both operands are split into bf16 hi + lo and three products are
+ * accumulated in fp32 (error <= ~2^-16 relative per product).  Needs Cin % 32 == 0, Cout % 64 == 0, K <= 729.
+ * Both operands are split ONCE, outside the kernel:
+ *   cg3d_split_bf16         activations: out[r] = per 32-channel chunk [bf16 hi (32) | bf16 lo (32)] of in[r] (or of
+ *                           relu(in[r]) when relu = 1: the activation the consumer applies to its input); same byte
+ *                           count as the fp32 rows.  The conv gathers these rows straight into shared memory with
+ *                           cp.async (no register staging, no per-tap conversion);
+ *   cg3d_spconv_tc_prepare  weights: the pre-swizzled shared-memory image of W, made once per weight tensor (same
+ *                           byte count as the fp32 weights), streamed by bulk async copies.
+ * cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).  Grouped mode / out_rows as above with tiles of <= 128 rows.
+ * out_split (may be NULL): the epilogue also writes the result (ReLU'd when out_split_relu = 1) in the split layout
+ * [n_out][2 * Cout], i.e. the operand of the next convolution, which then needs no cg3d_split_bf16 pass. */
 int cg3d_spconv_tc_ntile(int Cout);
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
-int cg3d_spconv_tc(const float* in, int ldi, int in_act, const int* nbr, const unsigned char* wimg, float* out, int ldo,
+int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
+int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
                    int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
-                   const int* out_rows, const unsigned short* in_split, void* stream);
-
-/* Split copy of an activation matrix for cg3d_spconv_tc: out[r] = [bf16 hi(x) (C) | bf16 lo(x) (C)], x = in[r] or
- * relu(in[r]) (relu = 1: the activation the consumer applies to its input).  Same byte count as the fp32 rows.
- * With in_split != NULL the conv gathers these rows straight into shared memory with cp.async (no register
- * staging, no per-tap conversion) and ignores in / ldi / in_act. */
-int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
+                   const int* out_rows, unsigned short* out_split, int out_split_relu, void* stream);
 
 /* out = act(x * scale + shift + add) on an [n, C] matrix with row strides ldx / ldo; scale, shift, add
  * ([n, C] dense) may be NULL.  Pre-activation BatchNorm+ReLU of DAPPM (biresnet.py:109-174). */

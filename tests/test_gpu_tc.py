@@ -82,23 +82,14 @@ def test_tile_ordered_rule_map_gives_identical_rows(lib, impl):
     assert torch.equal(a, o)                                          # same accumulation order per row -> bit identical
 
 
-@pytest.mark.parametrize("cin,cout,k", [(64, 64, 3), (128, 256, 3), (512, 128, 1), (64, 128, 5)])
-def test_presplit_cp_async_path_equals_register_path(lib, cin, cout, k):
-    """the two producers of the tensor-core kernel (fp32 rows split in registers vs pre-split bf16 rows copied with
-    cp.async) feed the MMA identical operands -> identical results, incl. ReLU on the input and zero-filled rows."""
+def test_split_rows_layout(lib):
+    """cg3d_split_bf16: per 32-channel chunk [hi 32 | lo 32]; hi + lo reproduces x to 2^-16 relative; ReLU variant."""
     from cagroup3d_b200 import sparse as S
-    ox = oracle_tensor(31, cin, n=5000, batch=2)
-    x = to_gpu_sparse(ox.C, ox.F, 1)
-    n = x.cmap.n
-    g = torch.Generator().manual_seed(2)
-    W = (torch.randn((k ** 3, cin, cout), generator=g) / 20).to(DEV)
-    nbr = S.neighbor_table(x.cmap, x.cmap, k, x.mgr) if k > 1 else None
-    outs = []
-    for on in (False, True):
-        S._TC_SPLIT["on"], old = on, S._TC_SPLIT["on"]
-        try:
-            outs.append(S.gemm_rows(x.F, nbr, W if k > 1 else W[0].contiguous(), n, k ** 3, act="elu", in_act="relu", impl="tc"))
-        finally:
-            S._TC_SPLIT["on"] = old
-    torch.cuda.synchronize()
-    assert torch.equal(outs[0], outs[1])
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((777, 96), generator=g).to(DEV)
+    for act in (None, "relu"):
+        s = S.split_rows(x, act).view(torch.bfloat16).view(777, 3, 2, 32).float()
+        want = torch.relu(x) if act else x
+        hi, lo = s[:, :, 0].reshape(777, 96), s[:, :, 1].reshape(777, 96)
+        assert torch.equal(hi, want.to(torch.bfloat16).float())
+        assert ((hi + lo) - want).abs().max().item() <= 2 ** -16 * want.abs().max().item()
