@@ -14,12 +14,17 @@
 //
 // One CTA owns 128 output rows x NT output channels (NT = 64 / 128 / 256); the accumulator lives in TMEM (128 lanes x NT
 // fp32 columns).  The K loop walks (active tap, 32-channel chunk) stages through a shared-memory ring:
-//   warps 0-7  gather: per stage every thread issues 4 cp.async of 16 bytes (global -> swizzled shared memory, no
-//              register staging, no conversion); rows without a neighbour are zero-filled by a 0-byte source; row
-//              indices are prefetched 4 taps ahead.  A stage is published (proxy fence + ONE mbarrier arrival per
-//              warp) as soon as the thread's copies have landed and BEFORE the thread blocks on the next free slot.
+//   warps 0-7  gather: every ring slot has its own team of 8 / STAGES warps which fills the slot each time it comes
+//              round, 64 (32) rows per warp -- 16 (8) cp.async of 16 bytes per lane (global -> swizzled shared
+//              memory, no register staging, no conversion; 8 lanes share a row, so one warp instruction moves four
+//              128-byte row segments); rows without a neighbour are zero-filled by a 0-byte source.  Every lane
+//              attaches an asynchronous mbarrier arrival to its copies, so a warp never blocks on data, the STAGES
+//              teams issue their stages concurrently and the per-stage bookkeeping (slot wait, index fetch, address
+//              set-up) is paid once per 16 copies instead of once per 4.  For K <= 27 the tile's rule-map columns are
+//              stashed in shared memory by the prologue scan, so the K loop reads no indices from global memory.
 //              After the K loop the same warps run the epilogue (tcgen05.ld -> folded BN / bias / residual /
-//              ReLU|ELU -> global);
+//              ReLU|ELU -> global; the residual rows of a 32-column panel are fetched in one batch before the
+//              accumulator is awaited);
 //   warp 8     one lane streams the stage's weight tile with cp.async.bulk (TMA engine, mbarrier complete_tx);
 //   warp 9     one lane issues the 6 tcgen05.mma of a stage (2 k-steps x 3 products) and tcgen05.commit's the slot.
 // Two CTAs are resident per SM (<= 96 KB of pipeline each, 2 x NT <= 512 TMEM columns), so the prologue, pipeline
@@ -43,7 +48,9 @@ namespace {
 constexpr int TM = 128;            // output rows per CTA (UMMA M)
 constexpr int KC = 32;             // channels per stage: 32 hi + 32 lo bf16 = one 128-byte swizzle row
 constexpr int NPROD = 256;         // epilogue threads (warps 0-7)
-constexpr int NGATHER = 256;       // gather threads (8 threads share a row; warps 0-7)
+constexpr int NGATHER = 256;       // gather threads (warps 0-7; a stage is filled by ONE of these warps)
+constexpr int NGW = NGATHER / 32;
+constexpr int STASH_K = 27;        // rule maps with <= 27 taps keep the tile's columns in shared memory
 constexpr int NTHREADS = NPROD + 64;
 constexpr int A_BYTES = TM * 128;  // bytes of the A tile of a stage
 constexpr int MAX_TAPS = 729;
@@ -161,24 +168,28 @@ struct TcArgs {
     int out_split_relu;
     int n_out, Cin, Cout, K, act, ldo;
     int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads, 4 = no gather
-                 // copies at all, 8 = cycle counters, 16 = no MMAs
+                 // copies at all, 8 = cycle counters, 16 = no MMAs, 64 = no rule-map loads in the K loop, 128 = no stash
 };
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, bool STASH>
 __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     constexpr int B_BYTES = NT * 128;                     // bytes of the B tile of a stage
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    constexpr int RPT = TM / (NGATHER / 8);               // rows per gather thread (8 threads share a row)
-    constexpr int PF = 4;                                 // taps of row indices in flight ahead of their use
+    constexpr int KCAP = STASH ? 32 : MAX_TAPS + 3;
+    constexpr int WPS = NGW / STAGES;                     // gather warps per ring slot
+    constexpr int RW = TM / WPS;                          // rows of a stage one warp fills
+    static_assert(RW % 32 == 0 && WPS * RW == TM, "a warp fills whole 32-row groups");
 
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // STASH: rule-map columns of this tile, [K][TM] int32, behind the pipeline ring
+    int* nbr_s = reinterpret_cast<int*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES);
 
     __shared__ __align__(8) unsigned long long bars[2 * STAGES + 1];
     __shared__ uint32_t tmem_slot;
-    __shared__ unsigned short taps[MAX_TAPS + 1];
-    __shared__ unsigned char active[MAX_TAPS + 3];
+    __shared__ unsigned short taps[KCAP];
+    __shared__ unsigned char active[KCAP];
     __shared__ int n_active_s;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, NGATHER + 1);        // one async arrival per gather thread + the weight copy's expect_tx
+            mbar_init(full0 + 8 * s, 32 * WPS + 1);       // one async arrival per lane of the slot's team + the weight copy's expect_tx
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
@@ -226,7 +237,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
             for (int u = 0; u < UN; ++u) {
                 bool any = false;
 #pragma unroll
-                for (int j = 0; j < TM / 32; ++j) any |= v[u][j] >= 0;
+                for (int j = 0; j < TM / 32; ++j) {
+                    any |= v[u][j] >= 0;
+                    if (STASH && k0 + u < a.K) nbr_s[(k0 + u) * TM + lane + 32 * j] = v[u][j];
+                }
                 any = __any_sync(0xffffffffu, any);
                 if (lane == 0 && k0 + u < a.K) active[k0 + u] = any ? 1 : 0;
             }
@@ -256,73 +270,86 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
-      if (warp < NGATHER / 32) {
+      if (warp < WPS * STAGES) {
         // ================= gather producers =================
-        // thread -> (16-byte piece of the 128-byte stage row, rows rbase + (NGATHER / 8) j).  Every thread attaches an asynchronous
-        // arrival to its own copies (cp.async.mbarrier.arrive.noinc): the stage's full barrier completes when the last
-        // copy has landed, no thread comes back to publish it, and the slots of the ring circulate independently.
-        const int piece = t & 7;
-        const int rbase = t >> 3;
-        const uint32_t sw_off = (uint32_t)((rbase >> 3) * 1024 + (rbase & 7) * 128 + ((piece ^ (rbase & 7)) << 4));
-        const size_t row_elems = 2 * (size_t)a.Cin;
-        int rq[PF][RPT];
-        auto load_rows = [&](int ai, int (&dst)[RPT]) {
-            const int k = taps[ai];
+        // Ring slot s is filled by its own team of WPS warps (warp = s + STAGES * part), every time it comes round:
+        // stage q = (active tap q / nchunks, channel chunk q % nchunks) lives in slot q % STAGES.  A warp therefore
+        // sees every phase of its slot's barriers (a parity wait cannot tell phases two apart) and the STAGES teams
+        // issue their stages concurrently.  A warp fills RW = 128 / WPS rows: lane -> (16-byte piece lane & 7 of the
+        // 128-byte stage row, row rbase + 4 i + (lane >> 3) in copy i).  The lane that owns the rule-map entry of row
+        // rbase + r is lane r & 31 (register r >> 5); the copy's lane gets it by shuffle.
+        const int slot = warp % STAGES, rbase = (warp / STAGES) * RW;
+        const int piece = lane & 7, rsub = lane >> 3;
+        const uint32_t lane_off0 = (uint32_t)(rsub * 128 + ((piece ^ rsub) << 4));              // rows 8 m + rsub
+        const uint32_t lane_off1 = (uint32_t)((4 + rsub) * 128 + ((piece ^ (4 + rsub)) << 4));  // rows 8 m + 4 + rsub
+        const size_t row_bytes = 4 * (size_t)a.Cin;
+        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_split) + piece * 16;
+        const uint32_t dst0 = base + (uint32_t)(slot * STAGE_BYTES + (rbase >> 3) * 1024);
+        const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
+        auto fetch = [&](int q, int (&dst)[RW / 32]) {
+            const int k = taps[q / nchunks];
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                int r = rbase + (NGATHER / 8) * j;
-                dst[j] = r < nrows ? (a.nbr ? __ldg(a.nbr + (size_t)k * a.n_out + row0 + r)
-                                            : (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r)) : -1;
+            for (int j = 0; j < RW / 32; ++j) {
+                const int r = rbase + lane + 32 * j;
+                int v = -1;
+                if (r < nrows) {
+                    if (STASH) v = nbr_s[k * TM + r];
+                    else if (a.nbr) v = (a.debug & 64) ? row0 + r : __ldg(a.nbr + (size_t)k * a.n_out + row0 + r);
+                    else v = a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
+                }
+                dst[j] = (a.debug & 2) ? -1 : v;
             }
         };
-        int q = 0;
-        uint32_t zeroed = 0;                           // bit s * RPT + j: row j of slot s currently holds zeros
-        auto tap = [&](const int (&ridx)[RPT]) {
-            const unsigned short* rp[RPT];
-            uint32_t okm = 0;
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const bool ok = ridx[j] >= 0 && !(a.debug & 2);
-                okm |= (uint32_t)ok << j;
-                rp[j] = a.in_split + (ok ? (size_t)ridx[j] * row_elems : 0) + piece * 8;
-            }
+        int cur[RW / 32], nxt[RW / 32];
+        if (slot < n_iters) fetch(slot, cur);
+        uint32_t ph = 1u;                              // parity to wait for on the slot's empty barrier
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
-                const long long p1 = clock64();
-                const int s = q % STAGES;
-                const uint32_t ph = (uint32_t)(q / STAGES) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                if (t == 0) TC_PROF(8, clock64() - p1);
-                const uint32_t dst = base + (uint32_t)(s * STAGE_BYTES) + sw_off;
-                const uint32_t zs = (zeroed >> (s * RPT)) & ((1u << RPT) - 1u);
+        for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
+            if (q + STAGES < n_iters) fetch(q + STAGES, nxt);
+            const long long p1 = clock64();
+            mbar_wait(empty_s, ph);
+            if (t == 0) TC_PROF(8, clock64() - p1);
+            const unsigned char* src = src0 + (size_t)(q % nchunks) * 128;
+            if (!(a.debug & 4)) {
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) {
-                    const bool ok = (okm >> j) & 1u;
-                    // a row that needs zeros and already holds zeros in this slot is left alone
-                    if ((ok || !((zs >> j) & 1u)) && !(a.debug & 4))
-                        cp_async16(dst + (uint32_t)(j * (NGATHER / 64) * 1024), rp[j] + c * (2 * KC), ok ? 16u : 0u);
-                }
-                zeroed = (zeroed & ~(((1u << RPT) - 1u) << (s * RPT))) | ((~okm & ((1u << RPT) - 1u)) << (s * RPT));
-                cp_async_arrive_noinc(full0 + 8 * s);
-                ++q;
-            }
-        };
-#pragma unroll
-        for (int d = 0; d < PF; ++d)
-            if (d < n_active) load_rows(d, rq[d]);
-#pragma unroll 1
-        for (int ai0 = 0; ai0 < n_active; ai0 += PF) {
-#pragma unroll
-            for (int d = 0; d < PF; ++d) {
-                const int ai = ai0 + d;
-                if (ai < n_active) {
-                    tap(rq[d]);
-                    if (ai + PF < n_active) load_rows(ai + PF, rq[d]);
+                for (int i = 0; i < RW / 4; ++i) {
+                    const int idx = __shfl_sync(0xffffffffu, cur[i >> 3], 4 * (i & 7) + rsub);
+                    const bool ok = idx >= 0;
+                    cp_async16(dst0 + (uint32_t)((i >> 1) * 1024) + ((i & 1) ? lane_off1 : lane_off0),
+                               src + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
                 }
             }
+            cp_async_arrive_noinc(full_s);
+#pragma unroll
+            for (int j = 0; j < RW / 32; ++j) cur[j] = nxt[j];
         }
       }
         // ================= epilogue: warp -> TMEM lane quarter (warp % 4), column half (warp / 4) =========
+        // The TMEM load gives lane = row; writing global memory in that shape would put 32 different rows into every
+        // store instruction (16-byte pieces).  Each warp therefore transposes 32-column panels of its 32 rows through a
+        // private shared-memory patch (the pipeline ring is idle now) and writes / reads the residual in 128-byte row
+        // segments: 8 lanes per row, 4 rows per instruction.  Everything that does not depend on the accumulator
+        // (output row numbers, BN scale / shift, the residual rows of the first panel) is fetched BEFORE the wait.
+        const int lq = warp & 3, half = warp >> 2;
+        const int r = lq * 32 + lane;
+        const int prow = (r < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r) : -1;
+        float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + warp * (32 * 36);
+        const int sub = lane >> 3, pc = lane & 7;                  // read-back: row it * 4 + sub, floats pc * 4 .. + 3
+        int prs[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, prow, it * 4 + sub);
+        float4 rs[8];
+        auto load_residual = [&](int c0) {
+            const int col = n0 + c0 + pc * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                rs[it] = (a.residual && prs[it] >= 0)
+                             ? __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)prs[it] * a.Cout + col))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        constexpr int C_BEGIN_STEP = 32;
+        const int c_begin = half * (NT / 2), c_end = (half + 1) * (NT / 2);
+        load_residual(c_begin);
         const long long e0 = clock64();
         if (n_iters > 0) {
             mbar_wait(accum_bar, 0);
@@ -330,17 +357,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         }
         const long long e1 = clock64();
         if (t == 0) { TC_PROF(5, e1 - t_main); TC_PROF(11, e1 - e0); }
-        // The TMEM load gives lane = row; writing global memory in that shape would put 32 different rows into every
-        // store instruction (16-byte pieces).  Each warp therefore transposes 32-column panels of its 32 rows through a
-        // private shared-memory patch (the pipeline ring is idle now) and writes / reads the residual in 128-byte row
-        // segments: 8 lanes per row, 4 rows per instruction.
-        const int lq = warp & 3, half = warp >> 2;
-        const int r = lq * 32 + lane;
-        const int prow = (r < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r) : -1;
-        float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + warp * (32 * 36);
-        const int sub = lane >> 3, pc = lane & 7;                  // read-back: row it * 4 + sub, floats pc * 4 .. + 3
 #pragma unroll 1
-        for (int c0 = half * (NT / 2); c0 < (half + 1) * (NT / 2); c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += C_BEGIN_STEP) {
             uint32_t v[16], w[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
@@ -359,17 +377,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
             if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
+            float4 x[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub) * 36 + pc * 4);
+            __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + sub;
-                const int pr = __shfl_sync(0xffffffffu, prow, rr);
-                const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + pc * 4);
+                const int pr = prs[it];
                 if (pr >= 0) {
-                    float o[4] = {x.x * sc.x + sh.x, x.y * sc.y + sh.y, x.z * sc.z + sh.z, x.w * sc.w + sh.w};
-                    if (a.residual) {
-                        const float4 rs = __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)pr * a.Cout + col));
-                        o[0] += rs.x; o[1] += rs.y; o[2] += rs.z; o[3] += rs.w;
-                    }
+                    float o[4] = {x[it].x * sc.x + sh.x + rs[it].x, x[it].y * sc.y + sh.y + rs[it].y,
+                                  x[it].z * sc.z + sh.z + rs[it].z, x[it].w * sc.w + sh.w + rs[it].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) o[i] = cg3d_act(o[i], a.act);
                     *reinterpret_cast<float4*>(a.out + (size_t)pr * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -390,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                     }
                 }
             }
-            __syncwarp();
+            if (c0 + C_BEGIN_STEP < c_end) load_residual(c0 + C_BEGIN_STEP);
         }
         tc_fence_before();
         if (t == 0) TC_PROF(6, clock64() - e1);
@@ -493,18 +510,18 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int ld, long lon
     }
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, bool STASH>
 int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
-    constexpr int smem = STAGES * (A_BYTES + NT * 128) + 1024;
+    constexpr int smem = STAGES * (A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT);
-    spconv_tc_kernel<NT, STAGES><<<grid, NTHREADS, smem, s>>>(a);
+    spconv_tc_kernel<NT, STAGES, STASH><<<grid, NTHREADS, smem, s>>>(a);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -553,8 +570,19 @@ int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigne
     int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    // <= 96 KB of pipeline per CTA so that two CTAs share an SM
-    int rc = NT == 256 ? launch_tc<256, 2>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3>(a, tiles, s) : launch_tc<64, 4>(a, tiles, s));
+    // Few row tiles (the stride-16/32 layers): narrower column tiles multiply the CTA count until 148 SMs x 2 are
+    // covered; the replicated gather comes out of L2.  The weight image does not depend on NT.
+    static int adapt = -1;
+    if (adapt < 0) { const char* e = getenv("CG3D_TC_ADAPT_NT"); adapt = e ? atoi(e) : 1; }
+    if (adapt)
+        while (NT > 64 && (long long)tiles * (Cout / NT) < 2 * 148) NT >>= 1;
+    // <= 96 KB of pipeline (+ 13.5 KB of stashed rule-map columns) per CTA so that two CTAs share an SM
+    const bool stash = nbr && K <= STASH_K && !(dbg & 128);
+    int rc;
+    if (stash)
+        rc = NT == 256 ? launch_tc<256, 2, true>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tiles, s) : launch_tc<64, 4, true>(a, tiles, s));
+    else
+        rc = NT == 256 ? launch_tc<256, 2, false>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tiles, s) : launch_tc<64, 4, false>(a, tiles, s));
     if (rc == 0 && (dbg & 8)) {
         unsigned long long h[16], z[16] = {0};
         cudaStreamSynchronize(s);

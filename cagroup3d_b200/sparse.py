@@ -173,7 +173,7 @@ def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n: int, end_bit: int = 64
 
 # which output rows share a conv tile: "none" = consecutive rows, "morton" = spatially compact patches,
 # "mask" = rows with the same set of active taps (rule maps with K <= MASK_MAX_K taps; the conv skips empty taps)
-_TILE_ORDER = {"mode": os.environ.get("CG3D_TILE_ORDER", "mask")}
+_TILE_ORDER = {"mode": os.environ.get("CG3D_TILE_ORDER", "mask"), "big": os.environ.get("CG3D_TILE_ORDER_BIG", "none")}
 MASK_MAX_K = 27
 
 
@@ -210,13 +210,20 @@ def tile_order(cmap: CoordMap, batch_bits: int = 8):
 
 
 def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
-                   group_div: int = 0):
+                   group_div: int = 0, spatial: Optional[bool] = None):
     """ME kernel map as a tap-major table.  ordered=False -> nbr[k][row]; ordered=True -> (nbr[k][position], order)
-    with position -> row given by the output map's tile order (order is None when positions == rows)."""
+    with position -> row given by the output map's tile order (order is None when positions == rows).
+
+    Tile order: k^3 <= 27 taps -> rows grouped by tap pattern ("mask"); wider kernels (the 9^3 / 5^3 class convs)
+    keep the map's row order: their maps are ~13 % occupied volumes, where even a Morton-compact 128-row tile reaches
+    ~87 % of the 729 taps (measured: 634 active taps per tile either way, profiles/r1_stage_times_tc.log), so the
+    sort does not pay (CG3D_TILE_ORDER_BIG=morton enables it).  spatial=False forces the map's own row order."""
     key = ("conv", in_map.uid, out_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
         return mgr.tables[key]
-    use = ordered and _TILE_ORDER["mode"] == "morton"
+    if spatial is None:
+        spatial = _TILE_ORDER["mode"] == "mask" and k ** 3 > MASK_MAX_K and _TILE_ORDER["big"] == "morton"
+    use = ordered and (_TILE_ORDER["mode"] == "morton" or spatial)
     order, oc = tile_order(out_map, mgr.batch_bits if mgr else 8) if use else (None, out_map.coords)
     nbr = _i32(k ** 3, max(out_map.n, 1), device=in_map.coords.device)
     _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)

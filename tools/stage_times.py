@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--voxels", type=int, default=50000)
     ap.add_argument("--conv", default="simt")
     ap.add_argument("--p_box", type=float, default=0.002)
+    ap.add_argument("--top", type=int, default=60)
     a = ap.parse_args()
     S.set_conv_impl(a.conv)
     t0 = time.time()
@@ -87,17 +88,17 @@ def main():
         k = (stage, name)
         agg[k][0] += 1
         agg[k][1] += ea.elapsed_time(eb)
-    for (stage, name), (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+    for (stage, name), (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         print(f"  {stage:18s} {name:28s} x{cnt:4d} {t:9.3f} ms")
-    print("  conv layers (backbone):")
+    print("  conv layers:")
     for name, stage, meta, ea, eb in rec:
-        if meta and stage == "backbone":
+        if meta:
             P = S.count_rules(meta["nbr"]) if meta["nbr"] is not None else meta["n_out"]
             byts = 4 * (meta["n_in"] * meta["Cin"] + meta["n_out"] * meta["Cout"]) + meta["w_bytes"] + \
                 (8 * P if meta["nbr"] is not None else 0) + (4 * meta["n_out"] * meta["Cout"] if meta["residual"] else 0)
             t = ea.elapsed_time(eb)
             fl = 2.0 * P * meta["Cin"] * meta["Cout"]
-            print(f"    {name[5:]:12s} K={meta['K']:3d} {meta['Cin']:4d}->{meta['Cout']:4d} n_out={meta['n_out']:7d} P={P:8d} "
+            print(f"    {stage:16s} {name[5:]:12s} K={meta['K']:3d} {meta['Cin']:4d}->{meta['Cout']:4d} n_out={meta['n_out']:7d} P={P:8d} "
                   f"{t:8.3f} ms  {byts / t / 1e6:8.1f} GB/s  {fl / t / 1e9:8.2f} TFLOP/s")
 
 
