@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         int cur[RW / 32], nxt[RW / 32];
         if (slot < n_iters) fetch(slot, cur);
         uint32_t ph = 1u;                              // parity to wait for on the slot's empty barrier
+        uint32_t zeroed = 0u;                          // bit i: this lane's piece of row rbase + 4 i + rsub holds zeros
 #pragma unroll 1
         for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
             if (q + STAGES < n_iters) fetch(q + STAGES, nxt);
@@ -315,8 +316,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                 for (int i = 0; i < RW / 4; ++i) {
                     const int idx = __shfl_sync(0xffffffffu, cur[i >> 3], 4 * (i & 7) + rsub);
                     const bool ok = idx >= 0;
-                    cp_async16(dst0 + (uint32_t)((i >> 1) * 1024) + ((i & 1) ? lane_off1 : lane_off0),
-                               src + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
+                    // a piece that needs zeros and still holds the zeros of an earlier round of this slot is left alone
+                    if (ok || !((zeroed >> i) & 1u))
+                        cp_async16(dst0 + (uint32_t)((i >> 1) * 1024) + ((i & 1) ? lane_off1 : lane_off0),
+                                   src + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
+                    zeroed = ok ? (zeroed & ~(1u << i)) : (zeroed | (1u << i));
                 }
             }
             cp_async_arrive_noinc(full_s);

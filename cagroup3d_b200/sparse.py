@@ -312,8 +312,13 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
         if split_out is not None and Cout % 32 == 0 and out.stride(0) == Cout:
             So = torch.empty((n_out, 2 * Cout), dtype=torch.int16, device=out.device)
             out._cg3d_split = {(out.data_ptr(), out._version, out.stride(0), 1 if split_out == "relu" else 0): So}
-        _call("cg3d_spconv_tc", split_rows(Fin, in_act), nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
-              scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
+        if nbr is not None and K >= PAIRS_MIN_K and _PAIRS["on"] and Cin == 64:
+            # wide kernel over a thinly occupied map: GEMM over compacted rule pairs (spconv_pairs.cu)
+            _call("cg3d_spconv_pairs", split_rows(Fin, in_act), nbr, weight_image(W, pairs=True), out, out.stride(0), n_out,
+                  Cin, Cout, K, scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
+        else:
+            _call("cg3d_spconv_tc", split_rows(Fin, in_act), nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
+                  scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
     else:
         _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,
               scale, shift, residual, ACT[act], *targs, meta=meta)
@@ -343,22 +348,31 @@ def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
     return cache[key]
 
 
+# CG3D_PAIRS=1 sends rule maps with at least this many taps to the pair-compacted kernel (spconv_pairs.cu).  It is
+# parity-tested but OFF by default: on B200 its per-stage role overhead (~1500 clk per (tile, tap) at ~17 pairs) is
+# above the row-stationary kernel's (~1170 clk), see profiles/r1_pairs_kernel.md.
+PAIRS_MIN_K = 64
+_PAIRS = {"on": os.environ.get("CG3D_PAIRS", "0") == "1"}
+
+
 def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
     return Cin % 32 == 0 and Cout % 64 == 0 and K <= 729
 
 
-def weight_image(W: torch.Tensor) -> torch.Tensor:
+def weight_image(W: torch.Tensor, pairs: bool = False) -> torch.Tensor:
     """bf16 hi/lo split + UMMA-swizzled image of a weight tensor.  Built once and kept ON the tensor
-    object (so it dies with it); rebuilt when the tensor is modified in place or moved."""
-    cached = getattr(W, "_cg3d_wimg", None)
+    object (so it dies with it); rebuilt when the tensor is modified in place or moved.
+    pairs=True: the stacked [W_hi ; W_lo] image of the pair-compacted kernel."""
+    attr = "_cg3d_wimg_pairs" if pairs else "_cg3d_wimg"
+    cached = getattr(W, attr, None)
     if cached is not None and cached[0] == (W.data_ptr(), W._version):
         return cached[1]
     Cin, Cout = W.shape[-2], W.shape[-1]
     K = W.shape[-3] if W.dim() >= 3 else 1
     G = W.shape[0] if W.dim() == 4 else 1
     img = torch.empty((W.numel() * 4,), dtype=torch.uint8, device=W.device)
-    _call("cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
-    W._cg3d_wimg = ((W.data_ptr(), W._version), img)
+    _call("cg3d_spconv_pairs_prepare" if pairs else "cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
+    setattr(W, attr, ((W.data_ptr(), W._version), img))
     return img
 
 
