@@ -7,6 +7,8 @@ in front of each stage fused into the gather (`in_act`).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -168,6 +170,17 @@ class DAPPM(nn.Module):
         return self._bn_relu_conv(x, self.shortcut, fc, residual=comp)
 
 
+_TWO_STREAMS = {"on": os.environ.get("CG3D_STREAMS", "1") != "0"}
+_SIDE = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class BiResNet(nn.Module):
     """biresnet.py:227-406.  forward(batch_dict) -> {'sp_tensor': stride-2, 64-channel SparseTensor}."""
 
@@ -246,25 +259,45 @@ class BiResNet(nn.Module):
         return super()._load_from_state_dict(*a, **k)
 
     def run(self, x: S.SparseTensor) -> S.SparseTensor:
+        """biresnet.py:358-406.  The high-resolution branch (layer3_/4_/5_, 128 channels at stride 4) and the
+        low-resolution branch (layer3/4/5 + DAPPM, few rows, many small launches) are independent between their
+        fusion points, so they are issued on two CUDA streams: the low-resolution kernels (tens of CTAs) run in the
+        tail waves of the wide ones instead of after them.  Every tensor that crosses a stream is produced before the
+        fork or consumed after the join, and stays referenced until the join (caching-allocator safety)."""
         fc, R = self.fold, "relu"
+        main = torch.cuda.current_stream()
+        side = _side_stream(x.F.device) if _TWO_STREAMS["on"] else None
+
+        def fork_join(side_fn, main_fn):
+            if side is None:
+                return side_fn(), main_fn()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                a = side_fn()
+            b = main_fn()
+            main.wait_stream(side)
+            return a, b
+
         x = conv_bn(x, self.conv1[0], self.conv1[1], fc, act=R)
         x = conv_bn(x, self.conv1[3], self.conv1[4], fc, act=R)
         x = self._run_layer(self.layer1, x, fc)                                  # stride 2
         l1 = self._run_layer(self.layer2, x, fc, in_act=R)                       # stride 4
-        l2 = self._run_layer(self.layer3, l1, fc, in_act=R)                      # stride 8
-        x_ = self._run_layer(self.layer3_, l1, fc, in_act=R)                     # stride 4
+        S.split_rows(l1.F, R)                                                    # operand of both branches: made before the fork
+        x_, l2 = fork_join(lambda: self._run_layer(self.layer3_, l1, fc, in_act=R),        # stride 4
+                           lambda: self._run_layer(self.layer3, l1, fc, in_act=R))         # stride 8
         x = conv_bn(x_, self.down3[0], self.down3[1], fc, in_act=R, residual=l2.F)          # x + down3(relu(x_))
         c3 = conv_bn(l2, self.compression3[0], self.compression3[1], fc, in_act=R)
         x_ = x_.with_F(S.interp(c3, x_.C, base=x_.F))
-        l3 = self._run_layer(self.layer4, x, fc, in_act=R)                       # stride 16
-        x_ = self._run_layer(self.layer4_, x_, fc, in_act=R)
+        x4_, l3 = fork_join(lambda: self._run_layer(self.layer4_, x_, fc, in_act=R),
+                            lambda: self._run_layer(self.layer4, x, fc, in_act=R))         # stride 16
+        x_ = x4_
         d = conv_bn(x_, self.down4[0], self.down4[1], fc, in_act=R, act=R)
         x = conv_bn(d, self.down4[3], self.down4[4], fc, residual=l3.F)
         c4 = conv_bn(l3, self.compression4[0], self.compression4[1], fc, in_act=R)
         x_ = x_.with_F(S.interp(c4, x_.C, base=x_.F))
-        x_ = self._run_layer(self.layer5_, x_, fc, in_act=R)
-        x5 = self._run_layer(self.layer5, x, fc, in_act=R)                       # stride 32
-        x_ = x_.with_F(S.interp(self.spp.run(x5, fc), x_.C, base=x_.F))
+        x5_, ctx = fork_join(lambda: self._run_layer(self.layer5_, x_, fc, in_act=R),
+                             lambda: self.spp.run(self._run_layer(self.layer5, x, fc, in_act=R), fc))   # stride 32
+        x_ = x5_.with_F(S.interp(ctx, x5_.C, base=x5_.F))
         scale, shift = fc.bn(self.out[1])
         up = S.conv_transpose_k2s2(x_, self.out[0].kernel, scale=scale, shift=shift, act=R)   # stride 2
         return conv_bn(up, self.out[3], self.out[4], fc, act=R)

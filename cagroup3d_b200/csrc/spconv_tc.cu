@@ -171,11 +171,21 @@ struct TcArgs {
                  // copies at all, 8 = cycle counters, 16 = no MMAs, 64 = no rule-map loads in the K loop, 128 = no stash
 };
 
-template <int NT, int STAGES, bool STASH>
+// STK (Cout == 64 layers, NT = 64): a stage holds 64 channels -- A as a hi tile and a lo tile (128 rows x 128 bytes each),
+// B as ONE 128-row tile [W_hi (64 columns) ; W_lo (64 columns)] x 64 channels -- so that a 16-channel k-step takes two
+// MMAs instead of three: A_hi x [W_hi | W_lo] (N = 128: columns 0-63 collect hi*hi, columns 64-127 hi*lo) and
+// A_lo x W_hi (N = 64).  tcgen05.mma costs >= ~46 clk per instruction for any N <= 64 (profiles/r1_mma_probe.txt), so the
+// instruction count is what the 64-channel layers pay for.  The epilogue adds the two column halves.
+template <int NT, int STAGES, bool STASH, bool STK>
 __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
-    constexpr int B_BYTES = NT * 128;                     // bytes of the B tile of a stage
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(!STK || NT == 64, "the stacked-weights variant is the 64-column kernel");
+    constexpr int KCH = STK ? 64 : KC;                    // channels per stage
+    constexpr int A_TILE = STK ? 2 * A_BYTES : A_BYTES;   // STK: hi tile + lo tile
+    constexpr int B_BYTES = STK ? 128 * 128 : NT * 128;   // bytes of the B tile of a stage
+    constexpr int STAGE_BYTES = A_TILE + B_BYTES;
+    constexpr int TCOLS = STK ? 128 : NT;                 // TMEM columns of the accumulator
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     constexpr int KCAP = STASH ? 32 : MAX_TAPS + 3;
     constexpr int WPS = NGW / STAGES;                     // gather warps per ring slot
     constexpr int RW = TM / WPS;                          // rows of a stage one warp fills
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         nrows = min(TM, a.n_out - row0);
     }
     const int n0 = blockIdx.y * NT;
-    const int nchunks = a.Cin / KC;
+    const int nchunks = a.Cin / KCH;
     const int ntn = a.Cout / NT;
 
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
@@ -219,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NPROD / 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(NT));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (a.nbr) {
@@ -283,7 +293,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         const uint32_t lane_off0 = (uint32_t)(rsub * 128 + ((piece ^ rsub) << 4));              // rows 8 m + rsub
         const uint32_t lane_off1 = (uint32_t)((4 + rsub) * 128 + ((piece ^ (4 + rsub)) << 4));  // rows 8 m + 4 + rsub
         const size_t row_bytes = 4 * (size_t)a.Cin;
-        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(a.in_split) + piece * 16;
+        // STK: piece p of the hi (lo) tile = channels 8 p .. 8 p + 7 of the 64-channel chunk, which the split layout keeps
+        // as [32-ch half p / 4][hi | lo][16-byte piece p % 4]
+        const unsigned char* xin = reinterpret_cast<const unsigned char*>(a.in_split);
+        const unsigned char* src0 = xin + (STK ? (piece >> 2) * 128 + (piece & 3) * 16 : piece * 16);
         const uint32_t dst0 = base + (uint32_t)(slot * STAGE_BYTES + (rbase >> 3) * 1024);
         const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
         auto fetch = [&](int q, int (&dst)[RW / 32]) {
@@ -303,24 +316,22 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         int cur[RW / 32], nxt[RW / 32];
         if (slot < n_iters) fetch(slot, cur);
         uint32_t ph = 1u;                              // parity to wait for on the slot's empty barrier
-        uint32_t zeroed = 0u;                          // bit i: this lane's piece of row rbase + 4 i + rsub holds zeros
 #pragma unroll 1
         for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
             if (q + STAGES < n_iters) fetch(q + STAGES, nxt);
             const long long p1 = clock64();
             mbar_wait(empty_s, ph);
             if (t == 0) TC_PROF(8, clock64() - p1);
-            const unsigned char* src = src0 + (size_t)(q % nchunks) * 128;
+            const unsigned char* src = src0 + (size_t)(q % nchunks) * (STK ? 256 : 128);
             if (!(a.debug & 4)) {
 #pragma unroll
-                for (int i = 0; i < RW / 4; ++i) {
-                    const int idx = __shfl_sync(0xffffffffu, cur[i >> 3], 4 * (i & 7) + rsub);
+                for (int i = 0; i < (STK ? RW / 2 : RW / 4); ++i) {
+                    const int m = STK ? (i >> 1) : i;             // 4-row group; STK: copy i fills tile i & 1 (hi, lo)
+                    const int tile = STK ? (i & 1) : 0;
+                    const int idx = __shfl_sync(0xffffffffu, cur[m >> 3], 4 * (m & 7) + rsub);
                     const bool ok = idx >= 0;
-                    // a piece that needs zeros and still holds the zeros of an earlier round of this slot is left alone
-                    if (ok || !((zeroed >> i) & 1u))
-                        cp_async16(dst0 + (uint32_t)((i >> 1) * 1024) + ((i & 1) ? lane_off1 : lane_off0),
-                                   src + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
-                    zeroed = ok ? (zeroed & ~(1u << i)) : (zeroed | (1u << i));
+                    cp_async16(dst0 + (uint32_t)(tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0),
+                               src + tile * 64 + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
                 }
             }
             cp_async_arrive_noinc(full_s);
@@ -367,6 +378,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c0 + 16), w);
+                if constexpr (STK) {                   // + the hi*lo products collected in columns 64 .. 127
+                    uint32_t v2[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(NT + c0), v2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(NT + c0 + 16), v2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(v2[i]));
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = w[i] = 0u;
@@ -428,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                     const size_t blk = (((size_t)g * a.K + k) * nchunks + c) * ntn + blockIdx.y;
                     const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)B_BYTES;
                     mbar_expect_tx(full0 + 8 * s, nbytes);
-                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + A_BYTES), a.wimg + blk * (size_t)B_BYTES, nbytes,
+                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + A_TILE), a.wimg + blk * (size_t)B_BYTES, nbytes,
                                   full0 + 8 * s);
                 }
             }
@@ -449,14 +469,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
                 // a 128-byte row holds [hi k0..31 | lo k0..31]: hi k-step kk at +32 kk bytes, lo at +64 + 32 kk bytes
-                const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
+                const uint64_t da = make_desc(sa), db = make_desc(sa + A_TILE);
+                if constexpr (STK) {
+                    const uint64_t dal = make_desc(sa + A_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < KC / 16; ++kk) {
-                    if (a.debug & 16) break;
-                    const uint64_t hi = (uint64_t)(kk * 2), lo = (uint64_t)(4 + kk * 2);     // in 16-byte units
-                    umma_bf16(tmem_base, da + hi, db + hi, IDESC, (it | kk) ? 1u : 0u);
-                    umma_bf16(tmem_base, da + hi, db + lo, IDESC, 1u);
-                    umma_bf16(tmem_base, da + lo, db + hi, IDESC, 1u);
+                    for (int kk = 0; kk < KCH / 16; ++kk) {
+                        if (a.debug & 16) break;
+                        const uint64_t off = (uint64_t)(kk * 2);                             // in 16-byte units
+                        umma_bf16(tmem_base, da + off, db + off, IDESC2, (it | kk) ? 1u : 0u);   // A_hi x [W_hi | W_lo]
+                        umma_bf16(tmem_base, dal + off, db + off, IDESC, 1u);                    // A_lo x W_hi
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < KC / 16; ++kk) {
+                        if (a.debug & 16) break;
+                        const uint64_t hi = (uint64_t)(kk * 2), lo = (uint64_t)(4 + kk * 2);     // in 16-byte units
+                        umma_bf16(tmem_base, da + hi, db + hi, IDESC, (it | kk) ? 1u : 0u);
+                        umma_bf16(tmem_base, da + hi, db + lo, IDESC, 1u);
+                        umma_bf16(tmem_base, da + lo, db + hi, IDESC, 1u);
+                    }
                 }
                 umma_commit(empty0 + 8 * s);
                 i_acc += clock64() - m1;
@@ -469,15 +500,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     __syncthreads();
     if (warp == NPROD / 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NT));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
     }
     if (t == 0) TC_PROF(7, clock64() - t_start);
 }
 
 // fp32 W[G][K][Cin][Cout] -> per (g, k, 32-channel chunk, NT-column tile) block of NT * 128 bytes:
 // row n = [hi 32 bf16 along Cin | lo 32 bf16], 16-byte pieces XOR-swizzled by (n % 8) -- the exact smem image.
+// stacked = 1 (Cout == 64 layers): per (g, k, 64-channel chunk) ONE block of 128 rows x 128 bytes: row n = bf16 hi of
+// W[.][n] over the chunk's 64 channels, row 64 + n = bf16 lo, same swizzle.
 __global__ void weight_image_kernel(const float* __restrict__ W, long long total, int K, int Cin, int Cout, int NT,
-                                    unsigned char* __restrict__ img) {
+                                    int stacked, unsigned char* __restrict__ img) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         int co = (int)(i % Cout);
@@ -487,6 +520,14 @@ __global__ void weight_image_kernel(const float* __restrict__ W, long long total
         float w = W[i];
         __nv_bfloat16 hi = __float2bfloat16_rn(w);
         __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        if (stacked) {
+            const int c = ci / 64, p = (ci % 64) >> 3, slice = co / 64, m = co % 64;
+            unsigned char* b = img + (((size_t)gk * (Cin / 64) + c) * (Cout / 64) + slice) * (size_t)(128 * 128);
+            const int rh = m, rl = 64 + m;
+            *reinterpret_cast<__nv_bfloat16*>(b + (rh >> 3) * 1024 + (rh & 7) * 128 + ((p ^ (rh & 7)) << 4) + (ci & 7) * 2) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(b + (rl >> 3) * 1024 + (rl & 7) * 128 + ((p ^ (rl & 7)) << 4) + (ci & 7) * 2) = lo;
+            continue;
+        }
         int c = ci / KC, kk = ci % KC, tn = co / NT, n = co % NT;
         size_t blk = ((size_t)gk * (Cin / KC) + c) * (Cout / NT) + tn;
         size_t rowb = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128;
@@ -514,18 +555,18 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int ld, long lon
     }
 }
 
-template <int NT, int STAGES, bool STASH>
+template <int NT, int STAGES, bool STASH, bool STK = false>
 int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
-    constexpr int smem = STAGES * (A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
+    constexpr int smem = STAGES * (STK ? 3 * A_BYTES : A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT);
-    spconv_tc_kernel<NT, STAGES, STASH><<<grid, NTHREADS, smem, s>>>(a);
+    spconv_tc_kernel<NT, STAGES, STASH, STK><<<grid, NTHREADS, smem, s>>>(a);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -536,13 +577,22 @@ extern "C" {
 
 int cg3d_spconv_tc_ntile(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0)); }
 
+/* 1: the layer runs on the stacked-weights variant (two MMAs per k-step) and its weight image has that layout */
+int cg3d_spconv_tc_stacked(int Cin, int Cout) {
+    // opt-in (CG3D_TC_STACKED=1): measured equal to the three-MMA variant on B200 (profiles/r1_conv_experiments.md)
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("CG3D_TC_STACKED"); on = (e && e[0] == '1') ? 1 : 0; }
+    return (on && Cout == 64 && Cin % 64 == 0) ? 1 : 0;
+}
+
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream) {
     int NT = cg3d_spconv_tc_ntile(Cout);
     if (NT == 0 || Cin % KC != 0) return -1;
     long long total = (long long)G * K * Cin * Cout;
     if (total == 0) return 0;
     long long b = (total + 255) / 256;
-    weight_image_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 256, 0, (cudaStream_t)stream>>>(W, total, K, Cin, Cout, NT, img);
+    weight_image_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 256, 0, (cudaStream_t)stream>>>(W, total, K, Cin, Cout, NT,
+                                                                                               cg3d_spconv_tc_stacked(Cin, Cout), img);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -583,7 +633,9 @@ int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigne
     // <= 96 KB of pipeline (+ 13.5 KB of stashed rule-map columns) per CTA so that two CTAs share an SM
     const bool stash = nbr && K <= STASH_K && !(dbg & 128);
     int rc;
-    if (stash)
+    if (cg3d_spconv_tc_stacked(Cin, Cout))
+        rc = stash ? launch_tc<64, 2, true, true>(a, tiles, s) : launch_tc<64, 2, false, true>(a, tiles, s);
+    else if (stash)
         rc = NT == 256 ? launch_tc<256, 2, true>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tiles, s) : launch_tc<64, 4, true>(a, tiles, s));
     else
         rc = NT == 256 ? launch_tc<256, 2, false>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tiles, s) : launch_tc<64, 4, false>(a, tiles, s));

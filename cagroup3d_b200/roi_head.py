@@ -102,7 +102,7 @@ class CAGroup3DRoIHead(nn.Module):
                 layer.grid_size // 2, int(self.coord_key), gc)
         umap, _, inv = S.unique_first(gc, sp.cmap.stride, None, want_inverse=True)          # sync
         umap.uid = sp.mgr.new_uid()
-        nbr, order = S.neighbor_table(sp.cmap, umap, layer.grid_kernel_size, sp.mgr, ordered=True, spatial=False)
+        nbr, order = S.neighbor_table(sp.cmap, umap, layer.grid_kernel_size, sp.mgr, ordered=True, spatial=False, coarse_mask=True)
         scale, shift = self.fold.bn(layer.grid_bn)
         Fu = S.gemm_rows(sp.F, nbr, layer.grid_conv.kernel, umap.n, layer.grid_kernel_size ** 3, scale=scale,
                          shift=shift, act="elu", out_rows=order)

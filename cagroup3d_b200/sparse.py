@@ -210,14 +210,17 @@ def tile_order(cmap: CoordMap, batch_bits: int = 8):
 
 
 def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
-                   group_div: int = 0, spatial: Optional[bool] = None):
+                   group_div: int = 0, spatial: Optional[bool] = None, coarse_mask: bool = False):
     """ME kernel map as a tap-major table.  ordered=False -> nbr[k][row]; ordered=True -> (nbr[k][position], order)
     with position -> row given by the output map's tile order (order is None when positions == rows).
 
     Tile order: k^3 <= 27 taps -> rows grouped by tap pattern ("mask"); wider kernels (the 9^3 / 5^3 class convs)
     keep the map's row order: their maps are ~13 % occupied volumes, where even a Morton-compact 128-row tile reaches
     ~87 % of the 729 taps (measured: 634 active taps per tile either way, profiles/r1_stage_times_tc.log), so the
-    sort does not pay (CG3D_TILE_ORDER_BIG=morton enables it).  spatial=False forces the map's own row order."""
+    sort does not pay (CG3D_TILE_ORDER_BIG=morton enables it).  spatial=False forces the map's own row order.
+    coarse_mask=True (wide kernel over a map where a row has only a handful of neighbours, i.e. the RoI grid conv with
+    3.7 of 125): rows are grouped by WHICH of the 3x3x3 coarse blocks of taps they reach, so a tile touches a few
+    blocks' taps instead of 89 of 125, and rows without any neighbour form tiles without work."""
     key = ("conv", in_map.uid, out_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
         return mgr.tables[key]
@@ -226,8 +229,11 @@ def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Ma
     use = ordered and (_TILE_ORDER["mode"] == "morton" or spatial)
     order, oc = tile_order(out_map, mgr.batch_bits if mgr else 8) if use else (None, out_map.coords)
     nbr = _i32(k ** 3, max(out_map.n, 1), device=in_map.coords.device)
-    _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
-    if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and out_map.n >= 256:
+    if in_map is out_map and oc is out_map.coords and (k & 1) and k > 1 and out_map.n > 0:
+        _call("cg3d_neighbor_table_symmetric", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
+    else:
+        _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
+    if ordered and _TILE_ORDER["mode"] == "mask" and (k ** 3 <= MASK_MAX_K or coarse_mask) and out_map.n >= 256:
         nbr, order = mask_order(nbr, k, out_map.n, out_map.coords, group_div, mgr.batch_bits if mgr else 8)
     res = (nbr, order) if ordered else nbr
     if mgr is not None:

@@ -67,6 +67,11 @@ int cg3d_hash_lookup(const int* query, int n, const unsigned long long* keys, co
  * centred for odd ksize and 0..k-1 for even ksize; step = the input's tensor stride. */
 int cg3d_neighbor_table(const int* out_coords, int n_out, const unsigned long long* keys, const int* vals,
                         int capacity, int ksize, int step, int* nbr, void* stream);
+/* The same table when the output rows ARE the input map's rows (same-stride convolution, odd ksize): the rule map is
+ * symmetric (nbr[t][o] = i <=> nbr[K-1-t][i] = o), so only the taps below the centre are probed and every hit also
+ * writes its mirror entry.  Result identical to cg3d_neighbor_table. */
+int cg3d_neighbor_table_symmetric(const int* coords, int n, const unsigned long long* keys, const int* vals, int capacity,
+                                  int ksize, int step, int* nbr, void* stream);
 
 /* transposed-convolution kernel maps onto existing fine coordinates:
  *   ksize 2: MinkowskiConvolutionTranspose(k=2,s=2) (biresnet.py:309; A8), ts_coarse = input stride
@@ -132,6 +137,7 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
  * out_split (may be NULL): the epilogue also writes the result (ReLU'd when out_split_relu = 1) in the split layout
  * [n_out][2 * Cout], i.e. the operand of the next convolution, which then needs no cg3d_split_bf16 pass. */
 int cg3d_spconv_tc_ntile(int Cout);
+int cg3d_spconv_tc_stacked(int Cin, int Cout);   /* 1: Cout == 64 layer, weights stacked [hi ; lo] along N (2 MMAs per k-step) */
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
 int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
 int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo,

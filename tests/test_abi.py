@@ -28,7 +28,7 @@ def test_every_stream_entry_point_ends_with_stream():
     from cagroup3d_b200 import _lib
     _lib.parse_header()
     assert _lib._host_only == {"cg3d_hash_capacity", "cg3d_scan_workspace_ints", "cg3d_sort_workspace_ints",
-                               "cg3d_spconv_tc_ntile"}
+                               "cg3d_spconv_tc_ntile", "cg3d_spconv_tc_stacked", "cg3d_spconv_pairs_supported"}
 
 
 def test_host_only_helpers(lib):
@@ -38,6 +38,7 @@ def test_host_only_helpers(lib):
         assert _lib.scan_workspace_ints(n) >= 1
         assert _lib.sort_workspace_ints(n) >= 1
     assert [_lib.host("cg3d_spconv_tc_ntile", c) for c in (64, 128, 192, 256, 512, 18)] == [64, 128, 64, 256, 256, 0]
+    assert [_lib.host("cg3d_spconv_pairs_supported", *a) for a in ((64, 64, 729), (64, 128, 125), (128, 64, 27), (64, 64, 1))] == [1, 1, 0, 0]
 
 
 def test_header_cites_reference_lines():

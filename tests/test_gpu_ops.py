@@ -73,6 +73,21 @@ def test_rule_maps_exact(lib, k, stride):
     assert S.count_rules(nbr) == len(rules_from_table(nbr))
 
 
+@pytest.mark.parametrize("k", [3, 5, 9])
+def test_symmetric_rule_map_equals_probed_rule_map(lib, k):
+    """cg3d_neighbor_table_symmetric (half the probes + mirrored writes) == cg3d_neighbor_table, bit for bit."""
+    from cagroup3d_b200 import sparse as S
+    ox = oracle_tensor(40 + k, 8, n=5000, batch=3)
+    x = to_gpu_sparse(ox.C, ox.F, 2)
+    n = x.cmap.n
+    a = torch.empty((k ** 3, n), dtype=torch.int32, device=DEV)
+    b = torch.full((k ** 3, n), 12345, dtype=torch.int32, device=DEV)
+    S._call("cg3d_neighbor_table", x.cmap.coords, n, x.cmap.keys, x.cmap.vals, x.cmap.capacity, k, 2, a)
+    S._call("cg3d_neighbor_table_symmetric", x.cmap.coords, n, x.cmap.keys, x.cmap.vals, x.cmap.capacity, k, 2, b)
+    assert torch.equal(a, b)
+    assert torch.equal(S.neighbor_table(x.cmap, x.cmap, k, x.mgr), a)          # the host routes same-map odd kernels to it
+
+
 @pytest.mark.parametrize("cin,cout,k,stride", [(3, 64, 3, 1), (64, 64, 3, 2), (64, 128, 1, 2), (32, 48, 5, 1), (20, 7, 3, 1)])
 def test_spconv_simt_vs_oracle(lib, cin, cout, k, stride):
     from cagroup3d_b200 import sparse as S
