@@ -93,6 +93,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -330,8 +333,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                     const int tile = STK ? (i & 1) : 0;
                     const int idx = __shfl_sync(0xffffffffu, cur[m >> 3], 4 * (m & 7) + rsub);
                     const bool ok = idx >= 0;
-                    cp_async16(dst0 + (uint32_t)(tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0),
-                               src + tile * 64 + (ok ? (size_t)idx * row_bytes : 0), ok ? 16u : 0u);
+                    const uint32_t dst = dst0 + (uint32_t)(tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
+                    // rows without a neighbour get zeros from a plain 16-byte shared store, not from a 0-byte cp.async:
+                    // an LDGSTS that mixes copying and zero-filling lanes costs extra shared-memory wavefronts (ncu:
+                    // half of the LSU wavefronts of the K = 729 layer were such conflicts, profiles/r1_ncu_spconv_tc.md)
+                    if (ok) cp_async16(dst, src + tile * 64 + (size_t)idx * row_bytes, 16u);
+                    else st_shared_zero16(dst);
                 }
             }
             cp_async_arrive_noinc(full_s);
