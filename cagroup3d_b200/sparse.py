@@ -175,6 +175,10 @@ def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, n: int, end_bit: int = 64
 # "mask" = rows with the same set of active taps (rule maps with K <= MASK_MAX_K taps; the conv skips empty taps)
 _TILE_ORDER = {"mode": os.environ.get("CG3D_TILE_ORDER", "mask"), "big": os.environ.get("CG3D_TILE_ORDER_BIG", "none")}
 MASK_MAX_K = 27
+# maps with fewer rows keep their row order (measured 256 / 20000 / 60000: 30.25 / 30.15 / 29.76 ms per step): the three
+# radix passes (~55 us of launches) cost more than the few taps
+# the grouping saves on a map of a few dozen tiles
+MASK_MIN_ROWS = int(os.environ.get("CG3D_MASK_MIN_ROWS", "60000"))
 
 
 def mask_order(nbr: torch.Tensor, ksize: int, n: int, coords=None, group_div: int = 0, group_bits: int = 0):
@@ -233,7 +237,7 @@ def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Ma
         _call("cg3d_neighbor_table_symmetric", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
     else:
         _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
-    if ordered and _TILE_ORDER["mode"] == "mask" and (k ** 3 <= MASK_MAX_K or coarse_mask) and out_map.n >= 256:
+    if ordered and _TILE_ORDER["mode"] == "mask" and (k ** 3 <= MASK_MAX_K or coarse_mask) and out_map.n >= MASK_MIN_ROWS:
         nbr, order = mask_order(nbr, k, out_map.n, out_map.coords, group_div, mgr.batch_bits if mgr else 8)
     res = (nbr, order) if ordered else nbr
     if mgr is not None:
@@ -250,7 +254,7 @@ def transpose_table(in_map: CoordMap, fine_map: CoordMap, k: int, mgr: Optional[
     order, oc = tile_order(fine_map, mgr.batch_bits if mgr else 8) if use else (None, fine_map.coords)
     nbr = _i32(k ** 3, max(fine_map.n, 1), device=in_map.coords.device)
     _call("cg3d_transpose_table", oc, fine_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
-    if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and fine_map.n >= 256:
+    if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and fine_map.n >= MASK_MIN_ROWS:
         nbr, order = mask_order(nbr, k, fine_map.n, fine_map.coords, group_div, mgr.batch_bits if mgr else 8)
     res = (nbr, order) if ordered else nbr
     if mgr is not None:

@@ -51,6 +51,23 @@ def test_backbone_features(setup):
     assert d <= TOL, d
 
 
+def test_backbone_two_streams_equals_one_stream(setup, monkeypatch):
+    """the two-stream issue order of the backbone branches changes no bit of the result (and repeats exactly)."""
+    from cagroup3d_b200 import backbone as BB
+    from cagroup3d_b200.detector import voxelize
+    s = setup
+    p = s["pts"].clone()
+    p[:, -3:] /= 255.
+    outs = []
+    for on in (True, False, True):
+        monkeypatch.setitem(BB._TWO_STREAMS, "on", on)
+        out = s["model"].backbone_3d.run(voxelize(p.to(DEV), 0.02))
+        torch.cuda.synchronize()
+        outs.append((out.C.clone(), out.F.clone()))
+    for c, f in outs[1:]:
+        assert torch.equal(c, outs[0][0]) and torch.equal(f, outs[0][1])
+
+
 def _oracle_out(s):
     r = s["res"]
     return to_gpu_sparse(r["bb_coords"], r["bb_feats"], 2)
