@@ -36,9 +36,11 @@
 // Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 32 == 0 and Cout % 64 == 0
 // (SURVEY.md A4-A8, A12, A13, A19, A20); the Cin = 3 stem and the narrow prediction heads stay on the exact-fp32 SIMT
 // kernel (spconv_simt.cu).
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "../../include/cagroup3d_b200.h"
@@ -95,6 +97,15 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 }
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
+}
+// TMA row gather: four rows (r0..r3; out-of-range, e.g. -1, gives a zero row) of the 2-D bf16 tensor behind `tmap`, 64
+// elements (128 bytes) from column `col`, written as four consecutive 128-byte rows of a 128B-swizzled tile at `dst`
+// (512-byte aligned inside a 1024-byte atom); 512 bytes are credited to the mbarrier (tools/probe/gather4_probe.cu).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -179,9 +190,13 @@ struct TcArgs {
 // MMAs instead of three: A_hi x [W_hi | W_lo] (N = 128: columns 0-63 collect hi*hi, columns 64-127 hi*lo) and
 // A_lo x W_hi (N = 64).  tcgen05.mma costs >= ~46 clk per instruction for any N <= 64 (profiles/r1_mma_probe.txt), so the
 // instruction count is what the 64-channel layers pay for.  The epilogue adds the two column halves.
-template <int NT, int STAGES, bool STASH, bool STK>
-__global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
+// TMAG: the A tile of a stage is fetched by the TMA engine (tile::gather4, one instruction per lane = 4 rows, one warp per
+// ring slot) instead of 1024 cp.async per stage: the gather warps were issue-bound (a handful of extra ALU instructions
+// per copy cost 10-15 % of the layer), the TMA path needs ~10 instructions per stage and no per-thread arrivals.
+template <int NT, int STAGES, bool STASH, bool STK, bool TMAG>
+__global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     static_assert(!STK || NT == 64, "the stacked-weights variant is the 64-column kernel");
+    static_assert(!(STK && TMAG), "the stacked variant keeps the cp.async gather");
     constexpr int KCH = STK ? 64 : KC;                    // channels per stage
     constexpr int A_TILE = STK ? 2 * A_BYTES : A_BYTES;   // STK: hi tile + lo tile
     constexpr int B_BYTES = STK ? 128 * 128 : NT * 128;   // bytes of the B tile of a stage
@@ -225,7 +240,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 32 * WPS + 1);       // one async arrival per lane of the slot's team + the weight copy's expect_tx
+            // TMAG: the gather warp's expect_tx arrival + the weight copy's; else one async arrival per lane of the slot's
+            // team + the weight copy's expect_tx
+            mbar_init(full0 + 8 * s, TMAG ? 2 : 32 * WPS + 1);
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
@@ -283,7 +300,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
-      if (warp < WPS * STAGES) {
+      if (TMAG && warp < STAGES) {
+        // ================= gather producer of ring slot `warp` (TMA) =================
+        // stage q = (active tap q / nchunks, channel chunk q % nchunks) lives in slot q % STAGES; lane l fetches rows
+        // 4 l .. 4 l + 3 of the tile with ONE tile::gather4 (rows without a neighbour: index -1 -> zero rows).
+        const int slot = warp;
+        const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
+        const uint32_t dst = base + (uint32_t)(slot * STAGE_BYTES + lane * 512);
+        auto fetch4 = [&](int q, int (&d)[4]) {
+            const int k = taps[q / nchunks];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = 4 * lane + j;
+                int v = -1;
+                if (r < nrows) {
+                    if (STASH) v = nbr_s[k * TM + r];
+                    else if (a.nbr) v = __ldg(a.nbr + (size_t)k * a.n_out + row0 + r);
+                    else v = a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
+                }
+                d[j] = (a.debug & 2) ? -1 : v;
+            }
+        };
+        int cur[4], nxt[4];
+        if (slot < n_iters) fetch4(slot, cur);
+        uint32_t ph = 1u;
+#pragma unroll 1
+        for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
+            if (q + STAGES < n_iters) fetch4(q + STAGES, nxt);
+            const long long p1 = clock64();
+            mbar_wait(empty_s, ph);
+            if (t == 0) TC_PROF(8, clock64() - p1);
+            if (lane == 0) mbar_expect_tx(full_s, (uint32_t)A_BYTES);
+            __syncwarp();
+            tma_gather4(dst, &tmap, (q % nchunks) * (2 * KC), cur[0], cur[1], cur[2], cur[3], full_s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+        }
+      } else if (!TMAG && warp < WPS * STAGES) {
         // ================= gather producers =================
         // Ring slot s is filled by its own team of WPS warps (warp = s + STAGES * part), every time it comes round:
         // stage q = (active tap q / nchunks, channel chunk q % nchunks) lives in slot q % STAGES.  A warp therefore
@@ -562,18 +615,18 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int ld, long lon
     }
 }
 
-template <int NT, int STAGES, bool STASH, bool STK = false>
-int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
+template <int NT, int STAGES, bool STASH, bool STK = false, bool TMAG = false>
+int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t s) {
     constexpr int smem = STAGES * (STK ? 3 * A_BYTES : A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT);
-    spconv_tc_kernel<NT, STAGES, STASH, STK><<<grid, NTHREADS, smem, s>>>(a);
+    spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG><<<grid, NTHREADS, smem, s>>>(a, tmap);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -614,8 +667,8 @@ int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned sh
     return 0;
 }
 
-int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
-                   int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
+int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, const unsigned char* wimg, float* out, int ldo,
+                   int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
                    const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, const int* out_rows,
                    unsigned short* out_split, int out_split_relu, void* stream) {
     if (n_out == 0) return 0;
@@ -639,13 +692,40 @@ int cg3d_spconv_tc(const unsigned short* in_split, const int* nbr, const unsigne
         while (NT > 64 && (long long)tiles * (Cout / NT) < 2 * 148) NT >>= 1;
     // <= 96 KB of pipeline (+ 13.5 KB of stashed rule-map columns) per CTA so that two CTAs share an SM
     const bool stash = nbr && K <= STASH_K && !(dbg & 128);
+    // the split activation matrix as a 2-D bf16 tensor [n_in][2 Cin] for the TMA row gather: box = 64 elements x 1 row,
+    // 128B swizzle (the UMMA K-major tile layout); rows outside [0, n_in) read as zeros
+    static int use_tma = -1;
+    // "cpasync" (default) | "tma": on B200 the TMA row gather is parity-green but slower (a gather4 instruction costs the
+    // TMA unit ~25 clk whether its rows exist or not: K = 729 layer 11.2 ms vs 7.2 ms, backbone 10.3 vs 8.8 ms;
+    // profiles/r1_conv_experiments.md)
+    if (use_tma < 0) { const char* e = getenv("CG3D_TC_GATHER"); use_tma = (e && e[0] == 't') ? 1 : 0; }
+    const bool stacked = cg3d_spconv_tc_stacked(Cin, Cout) != 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (use_tma && !stacked) {
+        cuuint64_t gdim[2] = {(cuuint64_t)(2 * Cin), (cuuint64_t)(n_in > 0 ? n_in : 1)};
+        cuuint64_t gstride[1] = {(cuuint64_t)Cin * 4};
+        cuuint32_t box[2] = {2 * KC, 1};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)in_split, gdim, gstride, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return -4;
+    }
     int rc;
-    if (cg3d_spconv_tc_stacked(Cin, Cout))
-        rc = stash ? launch_tc<64, 2, true, true>(a, tiles, s) : launch_tc<64, 2, false, true>(a, tiles, s);
-    else if (stash)
-        rc = NT == 256 ? launch_tc<256, 2, true>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tiles, s) : launch_tc<64, 4, true>(a, tiles, s));
+    if (stacked)
+        rc = stash ? launch_tc<64, 2, true, true>(a, tmap, tiles, s) : launch_tc<64, 2, false, true>(a, tmap, tiles, s);
+    else if (use_tma) {
+        if (stash)
+            rc = NT == 256 ? launch_tc<256, 2, true, false, true>(a, tmap, tiles, s)
+                           : (NT == 128 ? launch_tc<128, 3, true, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, true, false, true>(a, tmap, tiles, s));
+        else
+            rc = NT == 256 ? launch_tc<256, 2, false, false, true>(a, tmap, tiles, s)
+                           : (NT == 128 ? launch_tc<128, 3, false, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, false, false, true>(a, tmap, tiles, s));
+    } else if (stash)
+        rc = NT == 256 ? launch_tc<256, 2, true>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tmap, tiles, s) : launch_tc<64, 4, true>(a, tmap, tiles, s));
     else
-        rc = NT == 256 ? launch_tc<256, 2, false>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tiles, s) : launch_tc<64, 4, false>(a, tiles, s));
+        rc = NT == 256 ? launch_tc<256, 2, false>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tmap, tiles, s) : launch_tc<64, 4, false>(a, tmap, tiles, s));
     if (rc == 0 && (dbg & 8)) {
         unsigned long long h[16], z[16] = {0};
         cudaStreamSynchronize(s);

@@ -327,7 +327,7 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
             _call("cg3d_spconv_pairs", split_rows(Fin, in_act), nbr, weight_image(W, pairs=True), out, out.stride(0), n_out,
                   Cin, Cout, K, scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
         else:
-            _call("cg3d_spconv_tc", split_rows(Fin, in_act), nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
+            _call("cg3d_spconv_tc", split_rows(Fin, in_act), Fin.shape[0], nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
                   scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
     else:
         _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,

@@ -158,3 +158,24 @@ def test_spconv_pairs_at_query_coordinates(lib, monkeypatch):
     assert (got - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
     empty = (nbr < 0).all(0)
     assert empty.any() and got[empty].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("k,coarse", [(3, False), (5, True)])
+def test_mask_ordered_rule_map_gives_identical_rows(lib, monkeypatch, k, coarse):
+    """tap-pattern tile order (27-tap maps) and coarse tap-block order (RoI grid conv): `order` is a permutation, the
+    positional table is the row table permuted, and the conv writes the same matrix as with the natural order."""
+    from cagroup3d_b200 import sparse as S
+    monkeypatch.setattr(S, "MASK_MIN_ROWS", 256)
+    ox = oracle_tensor(51, 64, n=6000, batch=2)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    n = x.cmap.n
+    nbr_nat = S.neighbor_table(x.cmap, x.cmap, k, x.mgr)
+    nbr_ord, order = S.neighbor_table(x.cmap, x.cmap, k, x.mgr, ordered=True, spatial=False, coarse_mask=coarse)
+    assert order is not None and torch.equal(torch.sort(order.long())[0].cpu(), torch.arange(n))
+    assert torch.equal(nbr_ord, nbr_nat[:, order.long()])
+    g = torch.Generator().manual_seed(9)
+    W = (torch.randn((k ** 3, 64, 64), generator=g) / 20).to(DEV)
+    res = torch.randn((n, 64), generator=g).to(DEV)
+    a = S.gemm_rows(x.F, nbr_nat, W, n, k ** 3, residual=res, act="relu", impl="tc")
+    o = S.gemm_rows(x.F, nbr_ord, W, n, k ** 3, residual=res, act="relu", impl="tc", out_rows=order)
+    assert torch.equal(a, o)
