@@ -95,6 +95,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async16_full(uint32_t dst, unsigned long long src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
 }
@@ -348,11 +351,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         const int piece = lane & 7, rsub = lane >> 3;
         const uint32_t lane_off0 = (uint32_t)(rsub * 128 + ((piece ^ rsub) << 4));              // rows 8 m + rsub
         const uint32_t lane_off1 = (uint32_t)((4 + rsub) * 128 + ((piece ^ (4 + rsub)) << 4));  // rows 8 m + 4 + rsub
-        const size_t row_bytes = 4 * (size_t)a.Cin;
+        const uint32_t row_bytes = 4u * (uint32_t)a.Cin;
         // STK: piece p of the hi (lo) tile = channels 8 p .. 8 p + 7 of the 64-channel chunk, which the split layout keeps
         // as [32-ch half p / 4][hi | lo][16-byte piece p % 4]
-        const unsigned char* xin = reinterpret_cast<const unsigned char*>(a.in_split);
-        const unsigned char* src0 = xin + (STK ? (piece >> 2) * 128 + (piece & 3) * 16 : piece * 16);
+        // the source address of a copy is ONE 32 x 32 + 64-bit multiply-add (IMAD.WIDE.U32): base + row * row_bytes; the gather
+        // warps are issue-bound, every instruction per copy counts (profiles/r1_conv_experiments.md)
+        const unsigned long long src0 = (unsigned long long)a.in_split + (unsigned)(STK ? (piece >> 2) * 128 + (piece & 3) * 16 : piece * 16);
         const uint32_t dst0 = base + (uint32_t)(slot * STAGE_BYTES + (rbase >> 3) * 1024);
         const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
         auto fetch = [&](int q, int (&dst)[RW / 32]) {
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
             const long long p1 = clock64();
             mbar_wait(empty_s, ph);
             if (t == 0) TC_PROF(8, clock64() - p1);
-            const unsigned char* src = src0 + (size_t)(q % nchunks) * (STK ? 256 : 128);
+            const unsigned long long src = src0 + (unsigned)((q % nchunks) * (STK ? 256 : 128));
             if (!(a.debug & 4)) {
 #pragma unroll
                 for (int i = 0; i < (STK ? RW / 2 : RW / 4); ++i) {
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                     // rows without a neighbour get zeros from a plain 16-byte shared store, not from a 0-byte cp.async:
                     // an LDGSTS that mixes copying and zero-filling lanes costs extra shared-memory wavefronts (ncu:
                     // half of the LSU wavefronts of the K = 729 layer were such conflicts, profiles/r1_ncu_spconv_tc.md)
-                    if (ok) cp_async16(dst, src + tile * 64 + (size_t)idx * row_bytes, 16u);
+                    if (ok) cp_async16_full(dst, (src + (unsigned)(tile * 64)) + (unsigned long long)(unsigned)idx * row_bytes);
                     else st_shared_zero16(dst);
                 }
             }
