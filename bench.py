@@ -289,8 +289,16 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = bb_bytes / bb_ms / 1e6
+    # DRAM traffic per launch of the same 56 launches: from the committed ncu --set full capture (it cannot be measured
+    # live: a number taken under a profiler is never a bench value, and the bench never runs under one)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_spconv_traffic.json")))
+        traffic, traffic_src = tj["traffic_bytes_per_launch_avg"], f"profiles/r1_spconv_traffic.json ({tj['launches']} launches, {tj['metric']})"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "kernel": f"cg3d_spconv_{conv} (56 backbone launches per step, algorithmic bytes = SURVEY 8d formula)",
                 "launch_bytes_avg": bb_bytes / len(bb), "launch_ms_avg": bb_ms / len(bb),
                 "backbone_ms": bb_ms, "backbone_tflops": bb_flops / bb_ms / 1e9,
