@@ -86,7 +86,8 @@ __global__ void avgpool_kernel(const int4* __restrict__ oc, const int4* __restri
 // sums[inverse[p], :] += feat(p); feat(p) = src[row(p)*ld + col_off(p) ...] with optional indirection
 __global__ void segment_accumulate_kernel(const float* __restrict__ srcA, int ldA, const float* __restrict__ srcB,
                                           int ldB, const int2* __restrict__ ref, const int* __restrict__ inverse,
-                                          int n, int C, float* __restrict__ sums, float* __restrict__ counts) {
+                                          int n, int C, unsigned long long* __restrict__ sums,
+                                          float* __restrict__ counts) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int p = warp; p < n; p += nwarps) {
@@ -98,16 +99,20 @@ __global__ void segment_accumulate_kernel(const float* __restrict__ srcA, int ld
             src = srcA + (size_t)p * ldA;
         }
         int u = __ldg(inverse + p);
-        for (int ch = lane; ch < C; ch += 32) atomicAdd(sums + (size_t)u * C + ch, __ldg(src + ch));
+        // fixed point (2^-30 units, 64-bit integer atomics): the sum does not depend on the order in which the points of a
+        // voxel arrive, so the forward is bit-repeatable; float atomics made the class maps differ in the last bits
+        // from run to run.  |feature| < 2^21 and the 2^-31 rounding of tiny values are far inside the 1e-3 parity bar.
+        for (int ch = lane; ch < C; ch += 32)
+            atomicAdd(sums + (size_t)u * C + ch, (unsigned long long)__float2ll_rn(__ldg(src + ch) * 1073741824.f));
         if (lane == 0) atomicAdd(counts + u, 1.f);
     }
 }
 
-__global__ void segment_divide_kernel(float* __restrict__ sums, const float* __restrict__ counts, long long total,
-                                      int C) {
+__global__ void segment_divide_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ counts,
+                                      long long total, int C, float* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x)
-        sums[i] = sums[i] / counts[i / C];
+        out[i] = (float)((double)(long long)sums[i] * (1.0 / 1073741824.0) / (double)counts[i / C]);
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, int ld, int col0, const int* __restrict__ rows, int n,
@@ -153,16 +158,17 @@ int cg3d_avgpool_window(const int* out_coords, int n_out, const int* in_coords, 
 }
 
 int cg3d_segment_mean(const float* srcA, int ldA, const float* srcB, int ldB, const int* ref, const int* inverse,
-                      int n, int n_unique, int C, float* out, float* counts, void* stream) {
+                      int n, int n_unique, int C, float* out, float* counts, long long* workspace, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_unique == 0) return 0;
-    cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_unique * C, s);
+    unsigned long long* sums = reinterpret_cast<unsigned long long*>(workspace);
+    cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * (size_t)n_unique * C, s);
     cudaMemsetAsync(counts, 0, sizeof(float) * (size_t)n_unique, s);
-    if (n == 0) return 0;
+    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_unique * C, s); return 0; }
     segment_accumulate_kernel<<<flat_grid((long long)n * 32, 256), 256, 0, s>>>(srcA, ldA, srcB, ldB, (const int2*)ref,
-                                                                                 inverse, n, C, out, counts);
-    segment_divide_kernel<<<flat_grid((long long)n_unique * C, 256), 256, 0, s>>>(out, counts,
-                                                                                   (long long)n_unique * C, C);
+                                                                                 inverse, n, C, sums, counts);
+    segment_divide_kernel<<<flat_grid((long long)n_unique * C, 256), 256, 0, s>>>(sums, counts,
+                                                                                   (long long)n_unique * C, C, out);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

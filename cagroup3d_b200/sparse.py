@@ -442,7 +442,8 @@ def segment_mean(srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C) -> torch.Te
     dev = inverse.device
     out = _f32(n_unique, C, device=dev)
     cnt = _f32(max(n_unique, 1), device=dev)
-    _call("cg3d_segment_mean", srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C, out, cnt)
+    ws = torch.empty((max(n_unique, 1) * C,), dtype=torch.int64, device=dev)
+    _call("cg3d_segment_mean", srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C, out, cnt, ws)
     return out
 
 

@@ -180,9 +180,11 @@ int cg3d_avgpool_window(const int* out_coords, int n_out, const int* in_coords, 
 
 /* UNWEIGHTED_AVERAGE quantisation (cagroup_head.py:257-271; A3): out[u] = mean over points p with
  * inverse[p] == u of feat(p); ref == NULL: feat(p) = srcA[p*ldA ..]; else ref[p] = (row, kind):
- * kind >= 0 -> srcA[row*ldA + kind*C ..], kind < 0 -> srcB[row*ldB ..].  counts: n_unique floats. */
+ * kind >= 0 -> srcA[row*ldA + kind*C ..], kind < 0 -> srcB[row*ldB ..].  counts: n_unique floats; workspace: n_unique * C
+ * 64-bit integers (the sums are accumulated in 2^-30 fixed point so that the result does not depend on the order of
+ * the atomics: bit-repeatable forward). */
 int cg3d_segment_mean(const float* srcA, int ldA, const float* srcB, int ldB, const int* ref, const int* inverse,
-                      int n, int n_unique, int C, float* out, float* counts, void* stream);
+                      int n, int n_unique, int C, float* out, float* counts, long long* workspace, void* stream);
 
 /* out[r, :] = src[rows[r]*ld + col0 .. +C] / divisor  (rows == NULL: identity). */
 int cg3d_gather_rows(const float* src, int ld, int col0, const int* rows, int n, int C, float divisor, float* out,

@@ -1,0 +1,193 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's FULL sizes (batch 8 x ~50k voxels, the bench
+configuration; plus the 200k-voxel end of the density sweep), where the CPU oracle is too slow to be the checker:
+uniqueness / round trips of the coordinate maps, symmetry and geometric consistency of the rule maps, sortedness +
+stability of the radix sort, linearity of the sparse conv and agreement of the tensor-core kernel with the exact fp32
+kernel, idempotence of NMS, and bit-exact repeatability of the whole forward.  torch ops are used only as checkers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def scene8(lib):
+    from cagroup3d_b200 import synthetic
+    from cagroup3d_b200.detector import voxelize
+    data = synthetic.make_batch(8, target_voxels=50000, config=2)
+    pts = torch.from_numpy(data["points"]).to(DEV)
+    p = pts.clone()
+    p[:, -3:] /= 255.
+    return dict(pts=pts, x=voxelize(p, 0.02), scaled=p)
+
+
+def _keys(c):
+    c = c.long()
+    return (c[:, 0] << 48) | ((c[:, 1] + 32768) << 32) | ((c[:, 2] + 32768) << 16) | (c[:, 3] + 32768)
+
+
+def test_voxelisation_unique_complete_and_first_occurrence(scene8):
+    from cagroup3d_b200 import sparse as S
+    x, p = scene8["x"], scene8["scaled"]
+    n = x.cmap.n
+    assert 8 * 48000 <= n <= 8 * 53000
+    k = _keys(x.C)
+    assert torch.unique(k).numel() == n                                   # rows are unique
+    # every point's voxel, independently (tensor / tensor is an IEEE division like the kernel's and the CPU reference's;
+    # tensor / python-scalar is a multiplication by the reciprocal on CUDA and differs on voxel boundaries)
+    vs = torch.full((1,), 0.02, dtype=torch.float32, device=DEV)
+    q = torch.cat([p[:, :1], torch.floor(p[:, 1:4] / vs)], 1).int()
+    kq = _keys(q)
+    assert torch.equal(torch.unique(kq), torch.sort(k)[0])                # same SET of voxels as torch.unique
+    rows = torch.empty((q.shape[0],), dtype=torch.int32, device=DEV)      # round trip: point -> voxel row -> coords
+    S._call("cg3d_hash_lookup", q.contiguous(), q.shape[0], x.cmap.keys, x.cmap.vals, x.cmap.capacity, rows)
+    assert int(rows.min()) >= 0 and torch.equal(x.C[rows.long()], q)
+    first = torch.full((n,), q.shape[0], dtype=torch.int64, device=DEV)   # first-occurrence order (ME CPU semantics)
+    first.scatter_reduce_(0, rows.long(), torch.arange(q.shape[0], device=DEV), reduce="amin")
+    assert bool((first[1:] > first[:-1]).all())
+    assert torch.equal(x.F, p[first, 4:])                                 # the first point's colour
+
+
+@pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1)])
+def test_rule_map_geometry_and_symmetry_full_size(scene8, k, stride):
+    from cagroup3d_b200 import sparse as S
+    x = scene8["x"]
+    omap = x.cmap if stride == 1 else S.strided_map(x.cmap, x.mgr, stride)
+    nbr = S.neighbor_table(x.cmap, omap, k, x.mgr)
+    K, n_out = nbr.shape
+    c = k // 2
+    total = 0
+    for t in range(K):
+        off = torch.tensor([0, t % k - c, (t // k) % k - c, t // (k * k) - c], device=DEV, dtype=torch.int32)
+        v = nbr[t].long()
+        m = v >= 0
+        total += int(m.sum())
+        assert torch.equal(x.C[v[m]], omap.coords[m] + off)               # a rule points at the voxel it claims
+    assert S.count_rules(nbr) == total
+    if stride == 1:
+        assert torch.equal(nbr[K // 2], torch.arange(n_out, device=DEV, dtype=torch.int32))
+        for t in (0, 5, K // 2 - 1):                                      # nbr[t][o] = i  <=>  nbr[K-1-t][i] = o
+            v = nbr[t].long()
+            m = v >= 0
+            o = torch.nonzero(m).squeeze(1)
+            assert torch.equal(nbr[K - 1 - t][v[m]].long(), o)
+    # completeness against an independent count: |{(o, t): coord_o + off_t in map}| via sorted-key search
+    kin = torch.sort(_keys(x.C))[0]
+    t = K - 1
+    off = torch.tensor([0, t % k - c, (t // k) % k - c, t // (k * k) - c], device=DEV, dtype=torch.int32)
+    probe = _keys(omap.coords + off)
+    pos = torch.searchsorted(kin, probe).clamp(max=kin.numel() - 1)
+    assert int((kin[pos] == probe).sum()) == int((nbr[t] >= 0).sum())
+
+
+def test_radix_sort_sorted_stable_permutation_full_size(lib):
+    from cagroup3d_b200 import sparse as S
+    g = torch.Generator(device=DEV).manual_seed(3)
+    n = 3_000_000
+    keys = torch.randint(0, 1 << 20, (n,), device=DEV, generator=g, dtype=torch.int64) << 7   # bits 7..26, many ties
+    vals = torch.arange(n, device=DEV, dtype=torch.int32)
+    k0 = keys.clone()
+    S.sort_pairs(keys, vals, n, end_bit=27, begin_bit=7)
+    assert bool((keys[1:] >= keys[:-1]).all())                            # sorted
+    assert torch.equal(k0[vals.long()], keys)                             # pairs stay together
+    assert torch.equal(torch.sort(vals.long())[0], torch.arange(n, device=DEV))     # permutation
+    tie = keys[1:] == keys[:-1]
+    assert bool((vals[1:][tie] > vals[:-1][tie]).all())                   # stable
+
+
+def test_conv_tc_vs_exact_fp32_and_linearity_full_size(scene8):
+    """the tcgen05 kernel (bf16x3) against the exact fp32 SIMT kernel on the 400k-row stride-1 map and on the strided
+    map, with tap-pattern tile order; and conv(a x + b y) == a conv(x) + b conv(y)."""
+    from cagroup3d_b200 import sparse as S
+    x = scene8["x"]
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n = x.cmap.n
+    F = torch.randn((n, 64), device=DEV, generator=g)
+    G = torch.randn((n, 64), device=DEV, generator=g)
+    W = torch.randn((27, 64, 128), device=DEV, generator=g) / 40
+    for stride in (1, 2):
+        omap = x.cmap if stride == 1 else S.strided_map(x.cmap, x.mgr, stride)
+        nbr_nat = S.neighbor_table(x.cmap, omap, 3, x.mgr)
+        nbr, order = S.neighbor_table(x.cmap, omap, 3, x.mgr, ordered=True)
+        assert order is not None                                          # >= 60000 rows: tap-pattern order is on
+        tc = S.gemm_rows(F, nbr, W, omap.n, 27, impl="tc", out_rows=order)
+        ex = S.gemm_rows(F, nbr_nat, W, omap.n, 27, impl="simt")
+        mag = ex.abs().max().item()
+        assert (tc - ex).abs().max().item() <= 1e-4 * mag
+        lin = S.gemm_rows(2.5 * F - 0.75 * G, nbr, W, omap.n, 27, impl="tc", out_rows=order)
+        tg = S.gemm_rows(G, nbr, W, omap.n, 27, impl="tc", out_rows=order)
+        assert (lin - (2.5 * tc - 0.75 * tg)).abs().max().item() <= 2e-4 * mag
+        assert torch.equal(tc, S.gemm_rows(F, nbr, W, omap.n, 27, impl="tc", out_rows=order))   # repeatable
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_nms_properties_full_size(lib, rotated):
+    """kept boxes of a segment do not overlap above the threshold, every dropped box overlaps a better kept one, and
+    NMS of the kept set keeps everything (idempotence); 20000 boxes in 144 (sample, class) segments."""
+    from cagroup3d_b200 import ops, sparse as S
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n, nseg = 20000, 144
+    boxes = torch.cat([torch.rand((n, 3), device=DEV, generator=g) * 6, torch.rand((n, 3), device=DEV, generator=g) + 0.2,
+                       (torch.rand((n, 1), device=DEV, generator=g) - 0.5) * 3 * float(rotated)], 1).contiguous()
+    seg = torch.sort(torch.randint(0, nseg, (n,), device=DEV, generator=g))[0].int()
+    scores = torch.rand((n,), device=DEV, generator=g)
+    order = torch.argsort(seg.long() * 2 - scores.double())                    # by segment, score descending
+    boxes, seg, scores = boxes[order].contiguous(), seg[order].contiguous(), scores[order]
+    counts = torch.bincount(seg.long(), minlength=nseg).int()
+    seg_off = torch.cat([torch.zeros(1, dtype=torch.int32, device=DEV), torch.cumsum(counts, 0).int()]).contiguous()
+    keep = torch.empty((n,), dtype=torch.int32, device=DEV)
+    S._call("cg3d_nms_segments", boxes, seg_off, nseg, n, 0.5, int(rotated), keep, None)
+    iou = lambda a, b: ops._pairwise(a, b, 1 if rotated else 2)       # the op NMS itself uses (rotated / axis-aligned BEV IoU)
+    for s in (0, 17, nseg - 1):
+        a, b = int(seg_off[s]), int(seg_off[s + 1])
+        kb, kk = boxes[a:b], keep[a:b].bool()
+        m = iou(kb, kb)
+        mk = m[kk][:, kk]
+        assert float((mk - torch.diag(torch.diag(mk))).max()) <= 0.5 + 1e-6
+        dropped = torch.nonzero(~kk).squeeze(1)
+        kept = torch.nonzero(kk).squeeze(1)
+        if dropped.numel():
+            better = kept[None, :] < dropped[:, None]                     # kept boxes that come earlier (higher score)
+            assert bool(((m[dropped][:, kept] > 0.5) & better).any(1).all())
+    kept_boxes = boxes[keep.bool()].contiguous()
+    kc = torch.bincount(seg[keep.bool()].long(), minlength=nseg).int()
+    koff = torch.cat([torch.zeros(1, dtype=torch.int32, device=DEV), torch.cumsum(kc, 0).int()]).contiguous()
+    keep2 = torch.empty((kept_boxes.shape[0],), dtype=torch.int32, device=DEV)
+    S._call("cg3d_nms_segments", kept_boxes, koff, nseg, kept_boxes.shape[0], 0.5, int(rotated), keep2, None)
+    assert bool(keep2.bool().all())
+
+
+@pytest.mark.parametrize("voxels,batch", [(50000, 8), (200000, 2), (10000, 4)])
+def test_forward_repeatable_and_well_formed(lib, voxels, batch):
+    """the whole detector at the bench size and at both ends of the density sweep: two runs give bit-identical
+    detections; boxes are finite with positive sizes, labels in range, scores in (score_thr, 1], sorted per class by NMS
+    construction; the per-sample lists have the pcdet keys."""
+    from cagroup3d_b200 import model_init, synthetic
+    from cagroup3d_b200.detector import voxelize
+    data = synthetic.make_batch(batch, target_voxels=voxels, config=5)
+    pts = torch.from_numpy(data["points"]).to(DEV)
+    model = model_init.seeded_model(18, False, seed=0).to(DEV)
+    p = pts.clone()
+    p[:, -3:] /= 255.
+    out = model.backbone_3d.run(voxelize(p, 0.02))
+    model_init.calibrate_semantic_bias(model, out.F, 1.0 / 18)
+    model.dense_head.semantic_threshold = 0.05
+    cm = model.dense_head.class_maps(out, batch)
+    model_init.calibrate_cls_bias(model, cm["pred"], 0.002)
+    runs = []
+    for _ in range(2):
+        pred, _ = model({"points": pts.clone(), "batch_size": batch, "cur_epoch": 10})
+        torch.cuda.synchronize()
+        runs.append(pred)
+    assert len(runs[0]) == batch
+    n_det = 0
+    for a, b in zip(*runs):
+        assert set(a) >= {"pred_boxes", "pred_scores", "pred_labels"}
+        for key in ("pred_boxes", "pred_scores", "pred_labels"):
+            assert torch.equal(a[key], b[key])
+        bx, sc, lb = a["pred_boxes"], a["pred_scores"], a["pred_labels"]
+        n_det += len(bx)
+        assert bx.shape[1] == 7 and bool(torch.isfinite(bx).all()) and bool((bx[:, 3:6] > 0).all())
+        assert bool(((sc > 0) & (sc <= 1)).all()) and bool(((lb >= 0) & (lb <= 18)).all())
+    assert n_det > 0
