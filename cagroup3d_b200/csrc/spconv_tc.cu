@@ -711,9 +711,21 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
         cuuint64_t gstride[1] = {(cuuint64_t)Cin * 4};
         cuuint32_t box[2] = {2 * KC, 1};
         cuuint32_t estr[2] = {1, 1};
-        CUresult cr = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)in_split, gdim, gstride, box, estr,
-                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        // the driver entry point is looked up through the runtime, so the library has no link-time dependency on
+        // libcuda.so.1 (it must load, and export its symbols, on a box without a driver)
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeTiled encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -4;
+            encode = (EncodeTiled)fn;
+        }
+        CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)in_split, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return -4;
     }
     int rc;
