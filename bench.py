@@ -200,10 +200,26 @@ def main():
     rec, S.Profile.active = S.Profile.active, None
     convs = [(name, meta) for name, _, meta, _, _ in rec if meta is not None and name.startswith("cg3d_spconv")]
     conv_info = []
+    def active_tile_taps(meta):
+        """(128-row tile, tap) pairs the tensor-core kernel actually runs: a tap is skipped when no row of the tile has
+        a neighbour for it.  Counted from the rule map the launch got (positional = tile order), untimed."""
+        n_out, nbr = meta["n_out"], meta["nbr"]
+        tiles = (n_out + 127) // 128
+        if nbr is None:
+            return tiles
+        pad = tiles * 128 - n_out
+        m = nbr[:, :n_out] >= 0
+        if pad:
+            m = torch.cat([m, torch.zeros((m.shape[0], pad), dtype=torch.bool, device=m.device)], 1)
+        return int(m.view(m.shape[0], tiles, 128).any(-1).sum().item())
+
     for name, meta in convs:
         P = S.count_rules(meta["nbr"]) if meta["nbr"] is not None else meta["n_out"]
+        tt = active_tile_taps(meta) if (name == "cg3d_spconv_tc" and len(conv_info) < 56) else None
         conv_info.append(dict(kernel=name, K=meta["K"], Cin=meta["Cin"], Cout=meta["Cout"], n_in=meta["n_in"],
-                              n_out=meta["n_out"], P=P, bytes=conv_bytes(meta, P), flops=2.0 * P * meta["Cin"] * meta["Cout"]))
+                              n_out=meta["n_out"], P=P, bytes=conv_bytes(meta, P), flops=2.0 * P * meta["Cin"] * meta["Cout"],
+                              tile_taps=tt,
+                              mma_flops=(3 * 2.0 * tt * 128 * meta["Cin"] * meta["Cout"]) if tt is not None else None))
     n_backbone_convs = 56
     del rec, convs
     n_det = sum(len(d["pred_boxes"]) for d in pred)
@@ -307,6 +323,20 @@ def main():
                 "timed_in": "separate pass of the same steps, single stream, CUDA events around each launch "
                             f"({ms_serial / args.steps:.2f} ms/step)",
                 "hbm_bound_layers": hbm_layers}
+    # the same launches read against the TENSOR roof: bf16 MMA work the kernel executes (3 products of the bf16x3 split x
+    # 128-row tiles x the taps a tile does not skip) / measured sustained cuBLAS bf16 rate
+    tcl = [c for c in bb if c.get("mma_flops")]
+    if tcl and peaks.get("bf16_tflops_sustained"):
+        t_ms = sum(c["ms"] for c in tcl)
+        ach = sum(c["mma_flops"] for c in tcl) / t_ms / 1e9
+        big = [c for c in tcl if c["Cin"] >= 128 and c["K"] > 1]
+        roofline["tensor"] = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                              "frac": ach / peaks["bf16_tflops_sustained"], "launches": len(tcl),
+                              "what": "executed bf16 MMA FLOPs (bf16x3: 3 products; zero rows of a gathered tile included, skipped taps "
+                                      "excluded) of the backbone tensor-core launches / sum of their durations",
+                              "k27_layers_cin_ge_128": {"launches": len(big),
+                                                        "achieved": sum(c["mma_flops"] for c in big) / max(sum(c["ms"] for c in big), 1e-9) / 1e9}}
+        roofline["tensor"]["k27_layers_cin_ge_128"]["frac"] = roofline["tensor"]["k27_layers_cin_ge_128"]["achieved"] / peaks["bf16_tflops_sustained"]
 
     # e2e: pinned host inputs -> device -> forward -> host outputs
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)

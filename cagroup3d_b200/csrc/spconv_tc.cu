@@ -231,7 +231,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         nrows = a.tile_rows[blockIdx.x];
         g = a.tile_group[blockIdx.x];
     } else {
-        row0 = blockIdx.x * TM;
+        // tap-pattern ordered rows (out_rows): the sort key grows with the taps a row reaches, so the tiles with the most
+        // stages are the LAST ones; CTAs are dispatched in blockIdx order, so walk the tiles backwards -- the long tiles
+        // start first and the short ones fill the tail wave
+        const int bx = (a.out_rows && !(a.debug & 512)) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+        row0 = bx * TM;
         nrows = min(TM, a.n_out - row0);
     }
     const int n0 = blockIdx.y * NT;

@@ -158,20 +158,23 @@ def test_nms_properties_full_size(lib, rotated):
     assert bool(keep2.bool().all())
 
 
-@pytest.mark.parametrize("voxels,batch", [(50000, 8), (200000, 2), (10000, 4)])
-def test_forward_repeatable_and_well_formed(lib, voxels, batch):
+@pytest.mark.parametrize("voxels,batch,ncls,yaw", [(50000, 8, 18, False), (200000, 2, 18, False), (10000, 4, 18, False),
+                                                   (50000, 16, 10, True)],
+                         ids=["scannet-b8-50k", "sweep-200k", "sweep-10k", "sunrgbd-b16"])
+def test_forward_repeatable_and_well_formed(lib, voxels, batch, ncls, yaw):
     """the whole detector at the bench size and at both ends of the density sweep: two runs give bit-identical
     detections; boxes are finite with positive sizes, labels in range, scores in (score_thr, 1], sorted per class by NMS
     construction; the per-sample lists have the pcdet keys."""
     from cagroup3d_b200 import model_init, synthetic
     from cagroup3d_b200.detector import voxelize
-    data = synthetic.make_batch(batch, target_voxels=voxels, config=5)
+    data = synthetic.make_batch(batch, target_voxels=voxels, config=5, n_classes=ncls, sunrgbd=yaw,
+                                n_points=100000 if yaw else None)      # BASELINE configs[1], [4] ends, [2]
     pts = torch.from_numpy(data["points"]).to(DEV)
-    model = model_init.seeded_model(18, False, seed=0).to(DEV)
+    model = model_init.seeded_model(ncls, yaw, seed=0).to(DEV)
     p = pts.clone()
     p[:, -3:] /= 255.
     out = model.backbone_3d.run(voxelize(p, 0.02))
-    model_init.calibrate_semantic_bias(model, out.F, 1.0 / 18)
+    model_init.calibrate_semantic_bias(model, out.F, 1.0 / ncls)
     model.dense_head.semantic_threshold = 0.05
     cm = model.dense_head.class_maps(out, batch)
     model_init.calibrate_cls_bias(model, cm["pred"], 0.002)
@@ -189,5 +192,5 @@ def test_forward_repeatable_and_well_formed(lib, voxels, batch):
         bx, sc, lb = a["pred_boxes"], a["pred_scores"], a["pred_labels"]
         n_det += len(bx)
         assert bx.shape[1] == 7 and bool(torch.isfinite(bx).all()) and bool((bx[:, 3:6] > 0).all())
-        assert bool(((sc > 0) & (sc <= 1)).all()) and bool(((lb >= 0) & (lb <= 18)).all())
+        assert bool(((sc > 0) & (sc <= 1)).all()) and bool(((lb >= 0) & (lb <= ncls)).all())
     assert n_det > 0
