@@ -260,15 +260,15 @@ def main():
     ms_total, launches, _ = timed(step_resident, args.steps, args.warmup)
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    # roofline pass: the same K steps with CUDA events around every sparse-conv launch, the backbone's two branches
-    # issued on ONE stream so that a launch is timed alone (in the value pass they overlap on two streams)
+    # roofline pass: the same K steps with CUDA events around every sparse-conv launch, everything issued
+    # on ONE stream so that a launch is timed alone (in the value pass the backbone branches and the rule-map builds overlap)
     from cagroup3d_b200 import backbone as BB
-    two = BB._TWO_STREAMS["on"]
-    BB._TWO_STREAMS["on"] = False
+    two, coord = BB._TWO_STREAMS["on"], BB._COORD_STREAM["on"]
+    BB._TWO_STREAMS["on"] = BB._COORD_STREAM["on"] = False
     S.Profile.conv_only = True
     ms_serial, _, rec = timed(step_resident, args.steps, 1, profile_convs=True)
     S.Profile.conv_only = False
-    BB._TWO_STREAMS["on"] = two
+    BB._TWO_STREAMS["on"], BB._COORD_STREAM["on"] = two, coord
     # the bf16 split pass of a conv's input (cg3d_split_bf16) is charged to the conv launch that follows it
     per_call = [0.0] * len(conv_info)
     split_ms, pending, i = 0.0, 0.0, 0
@@ -358,7 +358,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "voxels_per_scene": n_vox // B,
                        "stride2_voxels_per_scene": n_vox2 // B, "points_per_batch": int(host_pts.shape[0]),
-                       "conv_impl": conv, "backbone_streams": 2 if two else 1, "p_sel": P_SEL, "p_box": P_BOX, "detections_per_batch": n_det,
+                       "conv_impl": conv, "backbone_streams": 2 if two else 1, "coordinate_stream": bool(coord), "p_sel": P_SEL, "p_box": P_BOX, "detections_per_batch": n_det,
                        "weights": "seed-0 random init (no checkpoint offline), eval-mode BatchNorm",
                        "l2": "working set > L2: 506 MB of weights + activations re-streamed every step, no flush needed"},
             "e2e": {"value": e2e_value, "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,

@@ -171,11 +171,12 @@ class DAPPM(nn.Module):
 
 
 _TWO_STREAMS = {"on": os.environ.get("CG3D_STREAMS", "1") != "0"}
+_COORD_STREAM = {"on": os.environ.get("CG3D_COORD_STREAM", "1") != "0"}
 _SIDE = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def _side_stream(device, role: str = "side") -> "torch.cuda.Stream":
+    key = (role, device.type, device.index if device.index is not None else torch.cuda.current_device())
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=device)
     return _SIDE[key]
@@ -267,6 +268,20 @@ class BiResNet(nn.Module):
         fc, R = self.fold, "relu"
         main = torch.cuda.current_stream()
         side = _side_stream(x.F.device) if _TWO_STREAMS["on"] else None
+        # coordinate stream: the strided maps, rule maps and tile orders of the backbone depend on the voxel coordinates
+        # only; built on their own stream they run next to the convolutions instead of in front of them, and the host
+        # syncs that read a map's size wait for the (short) coordinate work, not for the queued convolutions
+        if _COORD_STREAM["on"]:
+            x.mgr.stream = _side_stream(x.F.device, "coord")
+            x.mgr.stream.wait_stream(main)
+        try:
+            return self._run(x, fc, R, main, side)
+        finally:
+            if x.mgr.stream is not None:
+                main.wait_stream(x.mgr.stream)
+                x.mgr.stream = None
+
+    def _run(self, x, fc, R, main, side):
 
         def fork_join(side_fn, main_fn):
             if side is None:

@@ -240,6 +240,15 @@ class CAGroup3DHead(nn.Module):
         mgr = S.Manager(batch_bits=max(1, (ncls * B - 1).bit_length()))
         mapA, _, invA = S.unique_first(coordsA, 1, mgr, want_inverse=True)                  # sync 2
         mapE, _, invE = S.unique_first(coordsE, self.expand, mgr, want_inverse=True)        # sync 3
+        # the 9^3 rule map of the class voxels (1.2 ms of hash probes) depends on coordinates only: it is built on the
+        # coordinate stream while this stream averages the features and runs the 5^3 / transposed branch
+        from .backbone import _COORD_STREAM, _side_stream
+        if _COORD_STREAM["on"]:
+            main = torch.cuda.current_stream()
+            mgr.stream = _side_stream(dev, "coord")
+            mgr.stream.wait_stream(main)
+            S.neighbor_table(mapA, mapA, self.cls_kernel, mgr, ordered=True, group_div=B, wait=False)
+            mgr.stream = None
         FA = S.segment_mean(offF, offF.shape[1], out.F, out.F.shape[1], ref, invA, nf, mapA.n, C)
         FE = S.segment_mean(offF, offF.shape[1], out.F, out.F.shape[1], ref, invE, nf, mapE.n, C)
         # class row ranges: the first fused point of a class is a first occurrence, so its unique row
@@ -252,15 +261,15 @@ class CAGroup3DHead(nn.Module):
         cat = _f32(mapA.n, 2 * C, device=dev)                                               # [up | out] (:276-277)
         # tile order keeps rows class-major (the class is the high part of the batch index), so the per-class
         # position ranges equal the per-class row ranges
-        nbrA, ordA = S.neighbor_table(mapA, mapA, self.cls_kernel, mgr, ordered=True, group_div=B)
-        S.gemm_rows(FA, nbrA, P["W_out"], mapA.n, self.cls_kernel ** 3, scale=P["bn_out"][0], shift=P["bn_out"][1],
-                    act="elu", tiles=tilesA, out=cat[:, C:], out_rows=ordA)
         nbrE, ordE = S.neighbor_table(mapE, mapE, 5, mgr, ordered=True, group_div=B)
         EF = S.gemm_rows(FE, nbrE, P["W_exp"], mapE.n, 125, scale=P["bn_exp"][0], shift=P["bn_exp"][1], act="elu",
                          tiles=tilesE, out_rows=ordE)
         nbrU, ordU = S.transpose_table(mapE, mapA, self.expand, mgr, ordered=True, group_div=B)
         S.gemm_rows(EF, nbrU, P["W_up"], mapA.n, self.expand ** 3, scale=P["bn_up"][0], shift=P["bn_up"][1],
                     act="elu", tiles=tilesA, out=cat[:, :C], out_rows=ordU)
+        nbrA, ordA = S.neighbor_table(mapA, mapA, self.cls_kernel, mgr, ordered=True, group_div=B)
+        S.gemm_rows(FA, nbrA, P["W_out"], mapA.n, self.cls_kernel ** 3, scale=P["bn_out"][0], shift=P["bn_out"][1],
+                    act="elu", tiles=tilesA, out=cat[:, C:], out_rows=ordA)
         O = S.gemm_rows(cat, None, P["W_fuse"], mapA.n, 1, scale=P["bn_fuse"][0], shift=P["bn_fuse"][1], act="elu",
                         tiles=tilesA)
         pred = S.gemm_rows(O, None, P["W_pred"], mapA.n, 1, shift=P["b_pred"])

@@ -89,6 +89,12 @@ class Manager:
     def __init__(self, batch_bits: int = 8):
         self.by_stride: Dict[int, CoordMap] = {}
         self.tables: Dict[Tuple, torch.Tensor] = {}
+        # Coordinate stream (optional): strided maps, rule maps and tile orders depend on coordinates only, so while it
+        # is set they are built on this stream -- next to the feature kernels of the calling stream instead of in
+        # front of them -- and the host syncs that read a map's size wait for this stream only.  Every cached object
+        # carries a CUDA event; whoever fetches it makes ITS stream wait for that event.
+        self.stream: Optional["torch.cuda.Stream"] = None
+        self.events: Dict[Tuple, "torch.cuda.Event"] = {}
         self.rule_counts: Dict[Tuple, int] = {}
         self.batch_bits = batch_bits          # bits of the largest batch index (bounds the tile-order sort)
         self._uid = 0
@@ -152,13 +158,43 @@ def quantize(points4: torch.Tensor, ld: int, n: int, vs, mul: int = 1) -> torch.
     return out[:n], err
 
 
+class _coord_scope:
+    """with _coord_scope(mgr, key): body runs on the manager's coordinate stream (if any); on exit an event is recorded
+    under `key`.  _fetched(mgr, key) makes the current stream wait for it."""
+
+    def __init__(self, mgr, key):
+        self.mgr, self.key = mgr, key
+        self.ctx = torch.cuda.stream(mgr.stream) if (mgr is not None and mgr.stream is not None) else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.mgr.stream)
+            self.mgr.events[self.key] = ev
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _fetched(mgr, key):
+    ev = mgr.events.get(key) if mgr is not None else None
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+
+
 def strided_map(x_map: CoordMap, mgr: Manager, s: int) -> CoordMap:
     ts = x_map.stride * s
     if ts not in mgr.by_stride:
-        c = _i32(max(x_map.n, 1), 4, device=x_map.coords.device)
-        _call("cg3d_stride_coords", x_map.coords, x_map.n, ts, c)
-        cm, _, _ = unique_first(c[:x_map.n], ts, mgr)
-        mgr.by_stride[ts] = cm
+        with _coord_scope(mgr, ("map", ts)):
+            c = _i32(max(x_map.n, 1), 4, device=x_map.coords.device)
+            _call("cg3d_stride_coords", x_map.coords, x_map.n, ts, c)
+            cm, _, _ = unique_first(c[:x_map.n], ts, mgr)
+            mgr.by_stride[ts] = cm
+    _fetched(mgr, ("map", ts))
     return mgr.by_stride[ts]
 
 
@@ -214,7 +250,7 @@ def tile_order(cmap: CoordMap, batch_bits: int = 8):
 
 
 def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
-                   group_div: int = 0, spatial: Optional[bool] = None, coarse_mask: bool = False):
+                   group_div: int = 0, spatial: Optional[bool] = None, coarse_mask: bool = False, wait: bool = True):
     """ME kernel map as a tap-major table.  ordered=False -> nbr[k][row]; ordered=True -> (nbr[k][position], order)
     with position -> row given by the output map's tile order (order is None when positions == rows).
 
@@ -227,7 +263,19 @@ def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Ma
     blocks' taps instead of 89 of 125, and rows without any neighbour form tiles without work."""
     key = ("conv", in_map.uid, out_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
+        if wait:
+            _fetched(mgr, key)
         return mgr.tables[key]
+    with _coord_scope(mgr, key):
+        res = _build_neighbor_table(in_map, out_map, k, mgr, ordered, group_div, spatial, coarse_mask)
+    if mgr is not None:
+        mgr.tables[key] = res
+    if wait:                    # wait=False: prefetch on the coordinate stream; the later (cached) fetch waits
+        _fetched(mgr, key)
+    return res
+
+
+def _build_neighbor_table(in_map, out_map, k, mgr, ordered, group_div, spatial, coarse_mask):
     if spatial is None:
         spatial = _TILE_ORDER["mode"] == "mask" and k ** 3 > MASK_MAX_K and _TILE_ORDER["big"] == "morton"
     use = ordered and (_TILE_ORDER["mode"] == "morton" or spatial)
@@ -239,27 +287,31 @@ def neighbor_table(in_map: CoordMap, out_map: CoordMap, k: int, mgr: Optional[Ma
         _call("cg3d_neighbor_table", oc, out_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
     if ordered and _TILE_ORDER["mode"] == "mask" and (k ** 3 <= MASK_MAX_K or coarse_mask) and out_map.n >= MASK_MIN_ROWS:
         nbr, order = mask_order(nbr, k, out_map.n, out_map.coords, group_div, mgr.batch_bits if mgr else 8)
-    res = (nbr, order) if ordered else nbr
-    if mgr is not None:
-        mgr.tables[key] = res
-    return res
+    return (nbr, order) if ordered else nbr
 
 
 def transpose_table(in_map: CoordMap, fine_map: CoordMap, k: int, mgr: Optional[Manager], ordered: bool = False,
                     group_div: int = 0):
     key = ("convT", in_map.uid, fine_map.uid, k, ordered)
     if mgr is not None and key in mgr.tables:
+        _fetched(mgr, key)
         return mgr.tables[key]
+    with _coord_scope(mgr, key):
+        res = _build_transpose_table(in_map, fine_map, k, mgr, ordered, group_div)
+    if mgr is not None:
+        mgr.tables[key] = res
+    _fetched(mgr, key)
+    return res
+
+
+def _build_transpose_table(in_map, fine_map, k, mgr, ordered, group_div):
     use = ordered and _TILE_ORDER["mode"] == "morton"
     order, oc = tile_order(fine_map, mgr.batch_bits if mgr else 8) if use else (None, fine_map.coords)
     nbr = _i32(k ** 3, max(fine_map.n, 1), device=in_map.coords.device)
     _call("cg3d_transpose_table", oc, fine_map.n, in_map.keys, in_map.vals, in_map.capacity, k, in_map.stride, nbr)
     if ordered and _TILE_ORDER["mode"] == "mask" and k ** 3 <= MASK_MAX_K and fine_map.n >= MASK_MIN_ROWS:
         nbr, order = mask_order(nbr, k, fine_map.n, fine_map.coords, group_div, mgr.batch_bits if mgr else 8)
-    res = (nbr, order) if ordered else nbr
-    if mgr is not None:
-        mgr.tables[key] = res
-    return res
+    return (nbr, order) if ordered else nbr
 
 
 def count_rules(nbr: torch.Tensor) -> int:

@@ -64,8 +64,9 @@ def test_backbone_two_streams_equals_one_stream(setup, monkeypatch):
     p = s["pts"].clone()
     p[:, -3:] /= 255.
     outs = []
-    for on in (True, False, True):
+    for on, coord in ((True, True), (False, False), (True, False), (False, True), (True, True)):
         monkeypatch.setitem(BB._TWO_STREAMS, "on", on)
+        monkeypatch.setitem(BB._COORD_STREAM, "on", coord)          # rule maps / strided maps on their own stream
         out = s["model"].backbone_3d.run(voxelize(p.to(DEV), 0.02))
         torch.cuda.synchronize()
         outs.append((out.C.clone(), out.F.clone()))
