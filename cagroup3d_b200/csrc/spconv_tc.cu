@@ -17,7 +17,7 @@
 //   warps 0-7  gather: every ring slot has its own team of 8 / STAGES warps which fills the slot each time it comes
 //              round, 64 (32) rows per warp -- 16 (8) cp.async of 16 bytes per lane (global -> swizzled shared
 //              memory, no register staging, no conversion; 8 lanes share a row, so one warp instruction moves four
-//              128-byte row segments); rows without a neighbour are zero-filled by a 0-byte source.  Every lane
+//              128-byte row segments); rows without a neighbour get zeros from a plain 16-byte shared store.  Every lane
 //              attaches an asynchronous mbarrier arrival to its copies, so a warp never blocks on data, the STAGES
 //              teams issue their stages concurrently and the per-stage bookkeeping (slot wait, index fetch, address
 //              set-up) is paid once per 16 copies instead of once per 4.  For K <= 27 the tile's rule-map columns are
@@ -32,6 +32,9 @@
 // Taps for which no row of the tile has a neighbour are skipped (prologue scan of the rule map); with rows ordered by
 // tap pattern (cg3d_table_mask_keys) that removes most of the padding.  No atomics; the accumulation order is fixed
 // (taps ascending), so results are deterministic.
+// Opt-in variants kept for the record (parity-tested, measured slower on B200, profiles/r1_conv_experiments.md):
+// STK (CG3D_TC_STACKED=1, two MMAs per k-step for Cout = 64) and TMAG (CG3D_TC_GATHER=tma, the gather as TMA
+// tile::gather4 instructions).
 //
 // Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 32 == 0 and Cout % 64 == 0
 // (SURVEY.md A4-A8, A12, A13, A19, A20); the Cin = 3 stem and the narrow prediction heads stay on the exact-fp32 SIMT

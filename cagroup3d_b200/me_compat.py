@@ -3,7 +3,7 @@
 A reference checkpoint stores `...kernel` (K, Cin, Cout) / (Cin, Cout), `...bias` (1, Cout) and
 `...bn.{weight,bias,running_mean,running_var,num_batches_tracked}`.
 These modules only hold parameters under those names so `load_state_dict` works on reference
-checkpoints; the arithmetic is done by the fused execution plan in `engine.py`, which reads them.
+checkpoints; the arithmetic is done by the fused execution plans in `backbone.py` / `head.py` / `roi_head.py`, which read them.
 """
 from __future__ import annotations
 

@@ -17,7 +17,7 @@ from . import _lib
 
 ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
 
-# which conv kernel the engine uses: "simt" (exact fp32) or "tc" (tcgen05 3xTF32); see engine.py
+# which conv kernel gemm_rows uses: "simt" (exact fp32 FFMA) or "tc" (tcgen05, bf16 hi/lo split x 3 products, fp32 accumulate)
 _CONV_IMPL = {"name": os.environ.get("CG3D_CONV", "tc")}
 
 
