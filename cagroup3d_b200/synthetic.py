@@ -23,8 +23,9 @@ def _box_surface(rng, n, center, size):
 
 
 def make_scene(seed: int, target_voxels: int = 50000, voxel_size: float = 0.02, n_classes: int = 18,
-               sunrgbd: bool = False, n_points: int | None = None):
-    """-> (points (N,6) f32 [x,y,z,r,g,b] colours 0..255, gt_boxes (12,8) [x,y,z,dx,dy,dz,yaw,cls])."""
+               sunrgbd: bool = False, n_points: int | None = None, boxes_only: bool = False):
+    """-> (points (N,6) f32 [x,y,z,r,g,b] colours 0..255, gt_boxes (12,8) [x,y,z,dx,dy,dz,yaw,cls]); boxes_only: just the
+    boxes (they are drawn first from the scene's seed, so they equal the boxes of the full scene)."""
     rng = np.random.default_rng(seed)
     L, W, H = rng.uniform(4, 8), rng.uniform(3, 6), 2.6
     boxes = []
@@ -35,6 +36,8 @@ def make_scene(seed: int, target_voxels: int = 50000, voxel_size: float = 0.02, 
         yaw = rng.uniform(-np.pi, np.pi) if sunrgbd else 0.0
         boxes.append(np.concatenate([c, sz, [yaw, i % n_classes]]))
     boxes = np.array(boxes, dtype=np.float32)
+    if boxes_only:
+        return boxes
 
     def sample(n):
         parts = []

@@ -69,11 +69,30 @@ class SyntheticIndoorDataset(Dataset):
             annos.append(a)
         return annos
 
+    def gt_annos(self):
+        """ground truth of every scene in the reference's annotation layout (scannet_dataset.py:144-145:
+        info['annos'] = {'gt_num', 'gt_boxes_upright_depth', 'class'})."""
+        annos = []
+        for i in range(self.n_scenes):
+            boxes = synthetic.make_scene(1000 * self.seed_group + i, 0, n_classes=len(self.class_names),
+                                         sunrgbd=self.sunrgbd, boxes_only=True)
+            annos.append({"gt_num": len(boxes), "gt_boxes_upright_depth": boxes[:, :7] if self.sunrgbd else boxes[:, :6],
+                          "class": boxes[:, 7].astype(np.int64)})
+        return annos
+
     def evaluation(self, det_annos, class_names, **kwargs):
-        """mAP needs real annotations; report detection counts instead."""
-        n = sum(len(a["name"]) for a in det_annos)
-        return f"synthetic data: {n} detections over {len(det_annos)} scenes (no ground-truth mAP offline)", \
-            {"detections": n, "scenes": len(det_annos)}
+        """scannet_dataset.py:141-150 / sunrgbd_dataset.py: indoor mAP / mAR at IoU 0.25 and 0.5 against the scenes'
+        ground-truth boxes (here: the boxes the synthetic generator placed); returns (ret_dict, ret_dict) like the
+        reference.  det_annos must be in dataset order (frame_id = scene index)."""
+        from .indoor_eval import axis_aligned_bev_overlap, indoor_eval
+        gts = self.gt_annos()
+        by_frame = {int(a["frame_id"]): a for a in det_annos}
+        dets = [by_frame.get(i, {"labels_3d": np.zeros(0, np.int64), "boxes_3d": np.zeros((0, 7), np.float32),
+                                 "scores_3d": np.zeros(0, np.float32)}) for i in range(self.n_scenes)]
+        label2cat = {i: c for i, c in enumerate(class_names)}
+        ret = indoor_eval(gts, dets, [0.25, 0.5], label2cat, logger=kwargs.get("logger"),
+                          bev_overlap_fn=None if self.sunrgbd else axis_aligned_bev_overlap)
+        return ret, ret
 
 
 __all__ = {"ScannetDataset": lambda **k: SyntheticIndoorDataset(sunrgbd=False, **k),
