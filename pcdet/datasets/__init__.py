@@ -23,7 +23,7 @@ class DistributedSampler(_DistributedSampler):
 
 
 class SyntheticIndoorDataset(Dataset):
-    def __init__(self, dataset_cfg, class_names, training=False, logger=None, sunrgbd=False):
+    def __init__(self, dataset_cfg, class_names, training=False, logger=None, sunrgbd=False, root_path=None):
         self.dataset_cfg, self.class_names, self.training, self.logger = dataset_cfg, list(class_names), training, logger
         syn = dataset_cfg.get("SYNTHETIC", None) or {}
         self.n_scenes = int(syn.get("NUM_SCENES", 16))
@@ -95,14 +95,41 @@ class SyntheticIndoorDataset(Dataset):
         return ret, ret
 
 
-__all__ = {"ScannetDataset": lambda **k: SyntheticIndoorDataset(sunrgbd=False, **k),
-           "SunrgbdDataset": lambda **k: SyntheticIndoorDataset(sunrgbd=True, **k)}
+def _indoor_dataset(sunrgbd: bool, **k):
+    """the reference's ScannetDataset / SunrgbdDataset when their info files are on disk (DATA_PATH / INFO_PATH, or
+    root_path), else the synthetic generator with the same item layout."""
+    from pathlib import Path
+    from .indoor_files import IndoorFileDataset
+    cfg = k["dataset_cfg"]
+    root = Path(k.get("root_path") or cfg.get("DATA_PATH", "."))
+    infos = (cfg.get("INFO_PATH") or {}).get("test", [])
+    if infos and not k.get("training", False) and any((root / p).exists() for p in infos):
+        ds = IndoorFileDataset(sunrgbd=sunrgbd, **k)
+        # collate / prediction dicts / evaluation are shared with the synthetic dataset
+        ds.collate_batch = SyntheticIndoorDataset.collate_batch
+        ds.generate_prediction_dicts = SyntheticIndoorDataset.generate_prediction_dicts
+        ds.n_scenes = len(ds)
+        ds.evaluation = lambda det_annos, class_names, **kw: _file_evaluation(ds, det_annos, class_names, **kw)
+        return ds
+    return SyntheticIndoorDataset(sunrgbd=sunrgbd, **k)
+
+
+def _file_evaluation(ds, det_annos, class_names, **kwargs):
+    """scannet_dataset.py:141-150: detections and ground truth in dataset order."""
+    from .indoor_eval import axis_aligned_bev_overlap, indoor_eval
+    ret = indoor_eval(ds.gt_annos(), det_annos, [0.25, 0.5], {i: c for i, c in enumerate(class_names)},
+                      logger=kwargs.get("logger"), bev_overlap_fn=None if ds.sunrgbd else axis_aligned_bev_overlap)
+    return ret, ret
+
+
+__all__ = {"ScannetDataset": lambda **k: _indoor_dataset(False, **k),
+           "SunrgbdDataset": lambda **k: _indoor_dataset(True, **k)}
 
 
 def build_dataloader(dataset_cfg, class_names, batch_size, dist, root_path=None, workers=4, logger=None, training=True,
                      merge_all_iters_to_one_epoch=False, total_epochs=0):
     dataset = __all__[dataset_cfg["DATASET"]](dataset_cfg=dataset_cfg, class_names=class_names, training=training,
-                                              logger=logger)
+                                              logger=logger, root_path=root_path)
     sampler = None
     if dist:
         import torch.distributed as tdist
