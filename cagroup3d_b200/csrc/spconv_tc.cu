@@ -113,6 +113,14 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tma
         ::"r"(dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
         : "memory");
 }
+// TMA tiled load: a box of the 2-D tensor behind `tmap` (here 64 bf16 columns x 128 rows, 128B swizzle = the UMMA K-major
+// A tile) starting at (col, row); rows past the end of the tensor arrive as zeros; the whole box is credited to the mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int col, int row, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tmap), "r"(col), "r"(row), "r"(bar)
+        : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -187,6 +195,7 @@ struct TcArgs {
     unsigned short* out_split;        // optional second output: the result (ReLU'd if out_split_relu) in the split layout
     int out_split_relu;
     int n_out, Cin, Cout, K, act, ldo;
+    int dense;   // 1: plain GEMM rows (K = 1, no rule map, no row permutation): the A tile is ONE tiled TMA load per stage
     int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads, 4 = no gather
                  // copies at all, 8 = cycle counters, 16 = no MMAs, 64 = no rule-map loads in the K loop, 128 = no stash
 };
@@ -331,11 +340,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                 d[j] = (a.debug & 2) ? -1 : v;
             }
         };
-        int cur[4], nxt[4];
-        if (slot < n_iters) fetch4(slot, cur);
         uint32_t ph = 1u;
+        if (a.dense) {
+            // 1x1 convolution / linear layer: output row r reads input row r, so a stage's A tile is a contiguous
+            // 128-row x 64-column box of the split activation matrix -- one TMA instruction instead of 1024 cp.async
 #pragma unroll 1
-        for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
+            for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
+                mbar_wait(empty_s, ph);
+                if (lane == 0) {
+                    mbar_expect_tx(full_s, (uint32_t)A_BYTES);
+                    tma_load_2d(base + (uint32_t)(slot * STAGE_BYTES), &tmap, (q % nchunks) * (2 * KC), row0, full_s);
+                }
+                __syncwarp();
+            }
+        }
+        int cur[4], nxt[4];
+        if (!a.dense && slot < n_iters) fetch4(slot, cur);
+#pragma unroll 1
+        for (int q = slot; !a.dense && q < n_iters; q += STAGES, ph ^= 1u) {
             if (q + STAGES < n_iters) fetch4(q + STAGES, nxt);
             const long long p1 = clock64();
             mbar_wait(empty_s, ph);
@@ -688,7 +710,7 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15) || ((size_t)in_split & 15)) return -3;
     if (out_split && (((size_t)out_split & 15) || Cout % 32 != 0)) return -3;
     TcArgs a{in_split, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, out_split,
-             out_split_relu, n_out, Cin, Cout, K, act, ldo, 0};
+             out_split_relu, n_out, Cin, Cout, K, act, ldo, 0, 0};
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
@@ -711,12 +733,18 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     // profiles/r1_conv_experiments.md)
     if (use_tma < 0) { const char* e = getenv("CG3D_TC_GATHER"); use_tma = (e && e[0] == 't') ? 1 : 0; }
     const bool stacked = cg3d_spconv_tc_stacked(Cin, Cout) != 0;
+    // plain GEMM rows (1x1 convs, linear layers): tiled TMA loads of the A operand.  Opt-in (CG3D_TC_DENSE=1): parity-green,
+    // but the 1x1 layers are not gather-bound (they already run at 2-4.3 TB/s of algorithmic bytes): 1.64 vs 1.59 ms summed
+    static int use_dense = -1;
+    if (use_dense < 0) { const char* e = getenv("CG3D_TC_DENSE"); use_dense = (e && e[0] == '1') ? 1 : 0; }
+    const bool dense = use_dense && !stacked && !nbr && !out_rows && K == 1;
+    a.dense = dense ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (use_tma && !stacked) {
+    if ((use_tma || dense) && !stacked) {
         cuuint64_t gdim[2] = {(cuuint64_t)(2 * Cin), (cuuint64_t)(n_in > 0 ? n_in : 1)};
         cuuint64_t gstride[1] = {(cuuint64_t)Cin * 4};
-        cuuint32_t box[2] = {2 * KC, 1};
+        cuuint32_t box[2] = {2 * KC, dense ? (cuuint32_t)TM : 1u};
         cuuint32_t estr[2] = {1, 1};
         // the driver entry point is looked up through the runtime, so the library has no link-time dependency on
         // libcuda.so.1 (it must load, and export its symbols, on a box without a driver)
@@ -738,7 +766,7 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     int rc;
     if (stacked)
         rc = stash ? launch_tc<64, 2, true, true>(a, tmap, tiles, s) : launch_tc<64, 2, false, true>(a, tmap, tiles, s);
-    else if (use_tma) {
+    else if (use_tma || dense) {
         if (stash)
             rc = NT == 256 ? launch_tc<256, 2, true, false, true>(a, tmap, tiles, s)
                            : (NT == 128 ? launch_tc<128, 3, true, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, true, false, true>(a, tmap, tiles, s));
