@@ -195,6 +195,8 @@ struct TcArgs {
     unsigned short* out_split;        // optional second output: the result (ReLU'd if out_split_relu) in the split layout
     int out_split_relu;
     int n_out, Cin, Cout, K, act, ldo;
+    int ksplit;  // split-K: gridDim.z CTAs share a tile, CTA z runs the z-th slice of the active taps and writes its raw
+    long long zstride;   // accumulator to out + z * zstride (a partial slab); cg3d_spconv_tc adds the slabs in order afterwards
     int dense;   // 1: plain GEMM rows (K = 1, no rule map, no row permutation): the A tile is ONE tiled TMA load per stage
     int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads, 4 = no gather
                  // copies at all, 8 = cycle counters, 16 = no MMAs, 64 = no rule-map loads in the K loop, 128 = no stash
@@ -313,7 +315,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
     }
     __syncthreads();
     const int n_active = n_active_s;
-    const int n_iters = n_active * nchunks;
+    // split-K: CTA z runs the active taps whose ABSOLUTE index lies in [z K / ks, (z + 1) K / ks) -- a fixed partition of the
+    // taps, so the grouping of a row's fp32 sum does not depend on which rows share its tile (results stay bit-identical
+    // under any tile order).  taps[] is ascending: two lower bounds.
+    auto lower_bound_tap = [&](int v) {
+        int lo = 0, hi = n_active;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)taps[mid] < v) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    const int a0 = a.ksplit > 1 ? lower_bound_tap((int)(((long long)a.K * blockIdx.z) / a.ksplit)) : 0;
+    const int a1 = a.ksplit > 1 ? lower_bound_tap((int)(((long long)a.K * (blockIdx.z + 1)) / a.ksplit)) : n_active;
+    const int n_iters = (a1 - a0) * nchunks;
+    float* const outp = a.out + (size_t)blockIdx.z * a.zstride;
     const uint32_t tmem_base = tmem_slot;
     const long long t_main = clock64();
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
         const uint32_t dst = base + (uint32_t)(slot * STAGE_BYTES + lane * 512);
         auto fetch4 = [&](int q, int (&d)[4]) {
-            const int k = taps[q / nchunks];
+            const int k = taps[a0 + q / nchunks];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = 4 * lane + j;
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         const uint32_t dst0 = base + (uint32_t)(slot * STAGE_BYTES + (rbase >> 3) * 1024);
         const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
         auto fetch = [&](int q, int (&dst)[RW / 32]) {
-            const int k = taps[q / nchunks];
+            const int k = taps[a0 + q / nchunks];
 #pragma unroll
             for (int j = 0; j < RW / 32; ++j) {
                 const int r = rbase + lane + 32 * j;
@@ -506,7 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                                   x[it].z * sc.z + sh.z + rs[it].z, x[it].w * sc.w + sh.w + rs[it].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) o[i] = cg3d_act(o[i], a.act);
-                    *reinterpret_cast<float4*>(a.out + (size_t)pr * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(outp + (size_t)pr * a.ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
                     if (a.out_split) {                 // the next conv's operand, so that it needs no separate split pass
                         uint32_t h[2], l[2];
 #pragma unroll
@@ -532,7 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         // ================= weight-tile loader (bulk async copy) =================
         if (lane == 0) {
             int it = 0;
-            for (int ai = 0; ai < n_active; ++ai) {
+            for (int ai = a0; ai < a1; ++ai) {
                 const int k = taps[ai];
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     const int s = it % STAGES;
@@ -648,6 +661,72 @@ __global__ void split_rows_kernel(const float* __restrict__ in, int ld, long lon
     }
 }
 
+// split-K second pass: out = act((sum_z partial[z]) * scale + shift + residual), slabs added in z order (deterministic),
+// plus the optional split-bf16 copy; 4 columns per thread.
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ks, long long n_out, int Cout, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ residual, int act,
+                                     float* __restrict__ out, int ldo, unsigned short* __restrict__ out_split, int out_split_relu) {
+    const long long total = n_out * (Cout / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (Cout / 4);
+        const int col = (int)(i % (Cout / 4)) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < ks; ++z) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(partial + ((size_t)z * n_out + r) * Cout + col));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (scale) o[j] *= __ldg(scale + col + j);
+            if (shift) o[j] += __ldg(shift + col + j);
+            if (residual) o[j] += __ldg(residual + r * Cout + col + j);
+            o[j] = cg3d_act(o[j], act);
+        }
+        *reinterpret_cast<float4*>(out + r * ldo + col) = make_float4(o[0], o[1], o[2], o[3]);
+        if (out_split) {
+            uint32_t h[2], l[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float x0 = o[2 * j], x1 = o[2 * j + 1];
+                if (out_split_relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+                __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - __bfloat162float(hh.x), x1 - __bfloat162float(hh.y));
+                h[j] = *reinterpret_cast<uint32_t*>(&hh);
+                l[j] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            unsigned short* d = out_split + (size_t)r * 2 * Cout + (col >> 5) * 64 + (col & 31);
+            *reinterpret_cast<uint2*>(d) = make_uint2(h[0], h[1]);
+            *reinterpret_cast<uint2*>(d + 32) = make_uint2(l[0], l[1]);
+        }
+    }
+}
+
+// column-tile width and split-K factor of a launch (one place: cg3d_spconv_tc and cg3d_spconv_tc_splitk must agree)
+void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_tiles, int& NT, int& tiles, int& ks) {
+    static int adapt = -1, splitk = -1;
+    if (adapt < 0) { const char* e = getenv("CG3D_TC_ADAPT_NT"); adapt = e ? atoi(e) : 1; }
+    if (splitk < 0) { const char* e = getenv("CG3D_TC_SPLITK"); splitk = e ? atoi(e) : 1; }
+    NT = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
+    tiles = grouped ? n_tiles : cg3d_div_up(n_out, TM);
+    ks = 1;
+    if (NT == 0 || tiles == 0) return;
+    // Few row tiles (the stride-16/32 layers): narrower column tiles multiply the CTA count until 148 SMs x 2 are
+    // covered; the replicated gather comes out of L2.  The weight image does not depend on NT.
+    if (adapt)
+        while (NT > 64 && (long long)tiles * (Cout / NT) < 2 * 148) NT >>= 1;
+    // still under half of the 296 CTA slots and a long K loop (the 7^3 RoI pooling contraction: 25 row tiles x 1372
+    // stages): split the taps over gridDim.z CTAs per tile, partial slabs added in order by a second pass
+    const long long ctas = (long long)tiles * (Cout / NT);
+    const long long stages = (long long)K * (Cin / KC);
+    if (splitk && !grouped && cg3d_spconv_tc_stacked(Cin, Cout) == 0 && ctas * 2 <= 148 && stages >= 64) {
+        ks = (int)(296 / ctas);
+        if (ks > 8) ks = 8;
+        if (ks > K) ks = K;
+        if (ks < 1) ks = 1;
+    }
+}
+
 template <int NT, int STAGES, bool STASH, bool STK = false, bool TMAG = false>
 int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t s) {
     constexpr int smem = STAGES * (STK ? 3 * A_BYTES : A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
@@ -658,7 +737,7 @@ int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t 
         cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
-    dim3 grid(tiles, a.Cout / NT);
+    dim3 grid(tiles, a.Cout / NT, a.ksplit);
     spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG><<<grid, NTHREADS, smem, s>>>(a, tmap);
     CG3D_LAUNCH_CHECK();
     return 0;
@@ -669,6 +748,13 @@ int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t 
 extern "C" {
 
 int cg3d_spconv_tc_ntile(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0)); }
+
+/* split-K factor cg3d_spconv_tc will use for this launch shape (1 = none): the caller passes ks * n_out * Cout floats */
+int cg3d_spconv_tc_splitk(int n_out, int Cin, int Cout, int K, int grouped, int n_tiles) {
+    int NT, tiles, ks;
+    tc_launch_shape(n_out, Cin, Cout, K, grouped != 0, n_tiles, NT, tiles, ks);
+    return ks;
+}
 
 /* 1: the layer runs on the stacked-weights variant (two MMAs per k-step) and its weight image has that layout */
 int cg3d_spconv_tc_stacked(int Cin, int Cout) {
@@ -703,26 +789,26 @@ int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned sh
 int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
                    const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles, const int* out_rows,
-                   unsigned short* out_split, int out_split_relu, void* stream) {
+                   unsigned short* out_split, int out_split_relu, float* splitk_ws, void* stream) {
     if (n_out == 0) return 0;
-    int NT = cg3d_spconv_tc_ntile(Cout);
+    int NT, tiles, ks;
+    tc_launch_shape(n_out, Cin, Cout, K, tile_row0 != nullptr, n_tiles, NT, tiles, ks);
     if (NT == 0 || Cin % KC != 0 || K > MAX_TAPS || (!nbr && K != 1)) return -1;
+    if (ks > 1 && !splitk_ws) ks = 1;                  // no workspace given: run unsplit
     if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15) || ((size_t)in_split & 15)) return -3;
     if (out_split && (((size_t)out_split & 15) || Cout % 32 != 0)) return -3;
     TcArgs a{in_split, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, out_split,
-             out_split_relu, n_out, Cin, Cout, K, act, ldo, 0, 0};
+             out_split_relu, n_out, Cin, Cout, K, act, ldo, 1, 0, 0, 0};
+    if (ks > 1) {                                      // CTA z writes its raw accumulator into slab z of the workspace
+        if ((size_t)splitk_ws & 15) return -3;
+        a.out = splitk_ws; a.ldo = Cout; a.scale = a.shift = a.residual = nullptr; a.act = 0; a.out_split = nullptr;
+        a.ksplit = ks; a.zstride = (long long)n_out * Cout;
+    }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
-    int tiles = tile_row0 ? n_tiles : cg3d_div_up(n_out, TM);
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    // Few row tiles (the stride-16/32 layers): narrower column tiles multiply the CTA count until 148 SMs x 2 are
-    // covered; the replicated gather comes out of L2.  The weight image does not depend on NT.
-    static int adapt = -1;
-    if (adapt < 0) { const char* e = getenv("CG3D_TC_ADAPT_NT"); adapt = e ? atoi(e) : 1; }
-    if (adapt)
-        while (NT > 64 && (long long)tiles * (Cout / NT) < 2 * 148) NT >>= 1;
     // <= 96 KB of pipeline (+ 13.5 KB of stashed rule-map columns) per CTA so that two CTAs share an SM
     const bool stash = nbr && K <= STASH_K && !(dbg & 128);
     // the split activation matrix as a 2-D bf16 tensor [n_in][2 Cin] for the TMA row gather: box = 64 elements x 1 row,
@@ -777,6 +863,13 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
         rc = NT == 256 ? launch_tc<256, 2, true>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tmap, tiles, s) : launch_tc<64, 4, true>(a, tmap, tiles, s));
     else
         rc = NT == 256 ? launch_tc<256, 2, false>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tmap, tiles, s) : launch_tc<64, 4, false>(a, tmap, tiles, s));
+    if (rc == 0 && ks > 1) {
+        const long long total = (long long)n_out * (Cout / 4);
+        const long long b = (total + 255) / 256;
+        splitk_reduce_kernel<<<(int)(b > 148 * 16 ? 148 * 16 : b), 256, 0, s>>>(splitk_ws, ks, n_out, Cout, scale, shift, residual, act, out,
+                                                                                ldo, out_split, out_split_relu);
+        CG3D_LAUNCH_CHECK();
+    }
     if (rc == 0 && (dbg & 8)) {
         unsigned long long h[16], z[16] = {0};
         cudaStreamSynchronize(s);

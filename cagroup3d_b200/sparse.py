@@ -379,8 +379,10 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
             _call("cg3d_spconv_pairs", split_rows(Fin, in_act), nbr, weight_image(W, pairs=True), out, out.stride(0), n_out,
                   Cin, Cout, K, scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
         else:
+            ks = _lib.host("cg3d_spconv_tc_splitk", n_out, Cin, Cout, K, 1 if tiles else 0, tiles.n if tiles else 0)
+            ws = torch.empty((ks * n_out * Cout,), dtype=torch.float32, device=out.device) if ks > 1 else None
             _call("cg3d_spconv_tc", split_rows(Fin, in_act), Fin.shape[0], nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
-                  scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
+                  scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, ws, meta=meta)
     else:
         _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,
               scale, shift, residual, ACT[act], *targs, meta=meta)

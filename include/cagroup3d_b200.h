@@ -136,16 +136,20 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
  * cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).  Grouped mode / out_rows as above with tiles of <= 128 rows.
  * n_in: rows of in_split (the gather is a TMA tile::gather4 over the [n_in][2 Cin] bf16 tensor; rule-map entries outside
  * [0, n_in), i.e. the -1 of a missing neighbour, read as zero rows).
+ * splitk_ws (may be NULL): launches with few row tiles and a long K loop (the 7^3 RoI pooling contraction) are split over
+ * cg3d_spconv_tc_splitk(...) CTAs per tile; the partial slabs (that many x n_out x Cout floats) are added in a fixed order
+ * by a second pass, so the result stays deterministic.
  * out_split (may be NULL): the epilogue also writes the result (ReLU'd when out_split_relu = 1) in the split layout
  * [n_out][2 * Cout], i.e. the operand of the next convolution, which then needs no cg3d_split_bf16 pass. */
 int cg3d_spconv_tc_ntile(int Cout);
 int cg3d_spconv_tc_stacked(int Cin, int Cout);   /* 1: Cout == 64 layer, weights stacked [hi ; lo] along N (2 MMAs per k-step) */
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
 int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
+int cg3d_spconv_tc_splitk(int n_out, int Cin, int Cout, int K, int grouped, int n_tiles);   /* split-K factor (1 = none) */
 int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
                    int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
-                   const int* out_rows, unsigned short* out_split, int out_split_relu, void* stream);
+                   const int* out_rows, unsigned short* out_split, int out_split_relu, float* splitk_ws, void* stream);
 
 /* Same contraction for WIDE kernels over thinly occupied maps (Cin == 64, Cout % 64 == 0, 1 < K <= 729): the 9^3 / 5^3
  * per-class convolutions of cagroup_head.py:255-266 and the 5^3 RoI grid convolution of cagroup_roi_head.py:69, where a
