@@ -715,15 +715,22 @@ void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_ti
     // covered; the replicated gather comes out of L2.  The weight image does not depend on NT.
     if (adapt)
         while (NT > 64 && (long long)tiles * (Cout / NT) < 2 * 148) NT >>= 1;
-    // still under half of the 296 CTA slots and a long K loop (the 7^3 RoI pooling contraction: 25 row tiles x 1372
-    // stages): split the taps over gridDim.z CTAs per tile, partial slabs added in order by a second pass
+    // Split-K: the taps of a tile are cut into ks fixed ranges run by gridDim.z CTAs, partial slabs added in order by a
+    // second pass.  Used when the launch has fewer CTAs than the 296 slots (the 7^3 RoI pooling contraction: 50 CTAs x
+    // 1372 stages; the stride-32 layers) and the slabs are small.  (Launches of 1.1 - 1.2 waves were NOT split: their
+    // CTAs differ in length and the measured tensor-pipe occupancy of those layers is already 80 %, the wave model
+    // overestimates their tail.)  ks minimises a two-term estimate: waves(ctas * ks) / ks CTA-times of
+    // (stages x ~0.15 + 0.0016 NT us, measured per-stage cost) + slab traffic (written and read once, ~4 TB/s).
     const long long ctas = (long long)tiles * (Cout / NT);
     const long long stages = (long long)K * (Cin / KC);
-    if (splitk && !grouped && cg3d_spconv_tc_stacked(Cin, Cout) == 0 && ctas * 2 <= 148 && stages >= 64) {
-        ks = (int)(296 / ctas);
-        if (ks > 8) ks = 8;
-        if (ks > K) ks = K;
-        if (ks < 1) ks = 1;
+    if (splitk && !grouped && cg3d_spconv_tc_stacked(Cin, Cout) == 0 && stages >= 64 && ctas < 296) {
+        const double t_cta = (double)stages * (0.15 + 0.0016 * NT);
+        double best = 1e30;
+        for (int c = 1; c <= 8 && c <= K && stages / c >= 24; ++c) {
+            const double slab_us = c > 1 ? 2.0 * c * (double)n_out * Cout * 4.0 / 4e6 : 0.0;
+            const double t = (double)((ctas * c + 295) / 296) / c * t_cta + slab_us + (c > 1 ? 3.0 : 0.0);
+            if (t < best * 0.97) { best = t; ks = c; }      // a further split has to buy at least 3 %
+        }
     }
 }
 
