@@ -300,21 +300,23 @@ class BiResNet(nn.Module):
         S.split_rows(l1.F, R)                                                    # operand of both branches: made before the fork
         x_, l2 = fork_join(lambda: self._run_layer(self.layer3_, l1, fc, in_act=R),        # stride 4
                            lambda: self._run_layer(self.layer3, l1, fc, in_act=R))         # stride 8
-        x = conv_bn(x_, self.down3[0], self.down3[1], fc, in_act=R, residual=l2.F)          # x + down3(relu(x_))
+        # split_out: the epilogue also writes the bf16 hi/lo copy the NEXT conv gathers from (here relu'd: layer4 reads relu(x)),
+        # which saves a separate read-convert-write pass over the tensor
+        x = conv_bn(x_, self.down3[0], self.down3[1], fc, in_act=R, residual=l2.F, split_out="relu")   # x + down3(relu(x_))
         c3 = conv_bn(l2, self.compression3[0], self.compression3[1], fc, in_act=R)
         x_ = x_.with_F(S.interp(c3, x_.C, base=x_.F))
         x4_, l3 = fork_join(lambda: self._run_layer(self.layer4_, x_, fc, in_act=R),
                             lambda: self._run_layer(self.layer4, x, fc, in_act=R))         # stride 16
         x_ = x4_
-        d = conv_bn(x_, self.down4[0], self.down4[1], fc, in_act=R, act=R)
-        x = conv_bn(d, self.down4[3], self.down4[4], fc, residual=l3.F)
+        d = conv_bn(x_, self.down4[0], self.down4[1], fc, in_act=R, act=R, split_out="none")
+        x = conv_bn(d, self.down4[3], self.down4[4], fc, residual=l3.F, split_out="relu")
         c4 = conv_bn(l3, self.compression4[0], self.compression4[1], fc, in_act=R)
         x_ = x_.with_F(S.interp(c4, x_.C, base=x_.F))
         x5_, ctx = fork_join(lambda: self._run_layer(self.layer5_, x_, fc, in_act=R),
                              lambda: self.spp.run(self._run_layer(self.layer5, x, fc, in_act=R), fc))   # stride 32
         x_ = x5_.with_F(S.interp(ctx, x5_.C, base=x5_.F))
         scale, shift = fc.bn(self.out[1])
-        up = S.conv_transpose_k2s2(x_, self.out[0].kernel, scale=scale, shift=shift, act=R)   # stride 2
+        up = S.conv_transpose_k2s2(x_, self.out[0].kernel, scale=scale, shift=shift, act=R, split_out="none")   # stride 2
         return conv_bn(up, self.out[3], self.out[4], fc, act=R)
 
     def forward(self, input_dict):

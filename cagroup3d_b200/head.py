@@ -216,7 +216,7 @@ class CAGroup3DHead(nn.Module):
         mm = _i32(6, device=dev)
         S._call("cg3d_coord_bounds", out.C, N, mm)
         ob = self.offset_block
-        h = conv_bn(out, ob[0], ob[1], fc, act="elu")
+        h = conv_bn(out, ob[0], ob[1], fc, act="elu", split_out="none")      # + the split copy the next conv gathers from
         h = conv_bn(h, ob[3], ob[4], fc, act="elu")
         offs = conv_bn(h, ob[6], None, fc).F
         offF = conv_bn(out, self.feature_offset[0], self.feature_offset[1], fc, act="elu").F
@@ -263,7 +263,7 @@ class CAGroup3DHead(nn.Module):
         # position ranges equal the per-class row ranges
         nbrE, ordE = S.neighbor_table(mapE, mapE, 5, mgr, ordered=True, group_div=B)
         EF = S.gemm_rows(FE, nbrE, P["W_exp"], mapE.n, 125, scale=P["bn_exp"][0], shift=P["bn_exp"][1], act="elu",
-                         tiles=tilesE, out_rows=ordE)
+                         tiles=tilesE, out_rows=ordE, split_out="none")
         nbrU, ordU = S.transpose_table(mapE, mapA, self.expand, mgr, ordered=True, group_div=B)
         S.gemm_rows(EF, nbrU, P["W_up"], mapA.n, self.expand ** 3, scale=P["bn_up"][0], shift=P["bn_up"][1],
                     act="elu", tiles=tilesA, out=cat[:, :C], out_rows=ordU)

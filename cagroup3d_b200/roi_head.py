@@ -105,7 +105,7 @@ class CAGroup3DRoIHead(nn.Module):
         nbr, order = S.neighbor_table(sp.cmap, umap, layer.grid_kernel_size, sp.mgr, ordered=True, spatial=False, coarse_mask=True)
         scale, shift = self.fold.bn(layer.grid_bn)
         Fu = S.gemm_rows(sp.F, nbr, layer.grid_conv.kernel, umap.n, layer.grid_kernel_size ** 3, scale=scale,
-                         shift=shift, act="elu", out_rows=order)
+                         shift=shift, act="elu", out_rows=order, split_out="none")      # the pooling contraction's operand
         ptab = _i32(g ** 3, nr, device=dev)
         S._call("cg3d_roi_pool_table", inv, nr, g, ptab)
         pscale, pshift = self.fold.bn(layer.pooling_bn)
