@@ -70,20 +70,33 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned l
     }
 }
 
-// exclusive scan of `n` ints by ONE CTA (coalesced 4-wide tiles with a running carry); the digit-offset tables of the
-// radix sort are a few 10^4 entries, for which three launches of a multi-CTA scan cost more than the scan itself
+// exclusive scan of `n` ints by ONE CTA (16 ints per thread per round, coalesced int4 loads, a running carry); the
+// digit-offset tables of the radix sort are a few 10^4 entries, for which three launches of a multi-CTA scan cost more than
+// the scan itself.  16384 entries per round: the 50k-entry table of a 400k-key sort takes 4 rounds.
 __global__ void __launch_bounds__(1024) rs_scan_single(const int* __restrict__ in, int n, int* __restrict__ out) {
+    constexpr int PER = 16;
     __shared__ int wsum[32];
     __shared__ int carry_s;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 4096) {
-        const int i = base + t * 4;
-        int v[4];
+    const bool vec = ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) & 15) == 0;
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int i = base + t * PER;
+        int v[PER];
+        if (vec && i + PER <= n) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i + j < n) ? in[i + j] : 0;
-        int local = v[0] + v[1] + v[2] + v[3];
+            for (int j = 0; j < PER / 4; ++j) {
+                const int4 q = __ldg(reinterpret_cast<const int4*>(in + i) + j);
+                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) v[j] = (i + j < n) ? in[i + j] : 0;
+        }
+        int local = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) local += v[j];
         int x = local;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -103,10 +116,22 @@ __global__ void __launch_bounds__(1024) rs_scan_single(const int* __restrict__ i
         }
         __syncthreads();
         int excl = carry_s + (w ? wsum[w - 1] : 0) + x - local;
+        if (vec && i + PER <= n) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i + j < n) out[i + j] = excl;
-            excl += v[j];
+            for (int j = 0; j < PER / 4; ++j) {
+                int4 q;
+                q.x = excl; excl += v[4 * j];
+                q.y = excl; excl += v[4 * j + 1];
+                q.z = excl; excl += v[4 * j + 2];
+                q.w = excl; excl += v[4 * j + 3];
+                reinterpret_cast<int4*>(out + i)[j] = q;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                if (i + j < n) out[i + j] = excl;
+                excl += v[j];
+            }
         }
         __syncthreads();
         if (t == 1023) carry_s += wsum[31];
