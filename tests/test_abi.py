@@ -66,3 +66,19 @@ def test_product_never_imports_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M) or "tests.golden" in s:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_splitk_factor_selection(lib):
+    """cg3d_spconv_tc_splitk: only launches with fewer CTAs than the 296 slots and a long K loop are split; grouped
+    launches, 1x1 convs and well-filled launches never are (host-only helper, no GPU needed)."""
+    from cagroup3d_b200 import _lib
+    sk = lambda *a: _lib.host("cg3d_spconv_tc_splitk", *a)
+    assert sk(3192, 128, 128, 343, 0, 0) > 1                   # 7^3 RoI pooling contraction: 50 CTAs x 1372 stages
+    assert sk(2719, 512, 512, 27, 0, 0) > 1                    # stride-32 bottleneck conv
+    assert sk(153503, 128, 128, 27, 0, 0) == 1                 # 1200 tiles: well filled
+    assert sk(42500, 256, 256, 27, 0, 0) == 1                  # 1.1 waves: not split (see spconv_tc.cu)
+    assert sk(2719, 1024, 128, 1, 0, 0) == 1                   # K = 1: nothing to split
+    assert sk(3192, 128, 128, 343, 1, 25) == 1                 # grouped launches are never split
+    for n in (1, 100, 5000):
+        k = sk(n, 64, 128, 125, 0, 0)
+        assert 1 <= k <= 8 and (125 * 2) // k >= 24            # >= 24 stages left per CTA
