@@ -23,9 +23,12 @@ def _box_surface(rng, n, center, size):
 
 
 def make_scene(seed: int, target_voxels: int = 50000, voxel_size: float = 0.02, n_classes: int = 18,
-               sunrgbd: bool = False, n_points: int | None = None, boxes_only: bool = False):
+               sunrgbd: bool = False, n_points: int | None = None, boxes_only: bool = False, return_masks: bool = False):
     """-> (points (N,6) f32 [x,y,z,r,g,b] colours 0..255, gt_boxes (12,8) [x,y,z,dx,dy,dz,yaw,cls]); boxes_only: just the
-    boxes (they are drawn first from the scene's seed, so they equal the boxes of the full scene)."""
+    boxes (they are drawn first from the scene's seed, so they equal the boxes of the full scene).  return_masks: also the
+    per-point (semantic_mask, instance_mask) int64 arrays of the ScanNet training items (scannet_dataset.py:68-76): a
+    point sampled on box i has instance 5 + i and the box's class, floor / wall points have instances 0..4 and the
+    background class n_classes.  The masks are derived from the part counts, the random stream is unchanged."""
     rng = np.random.default_rng(seed)
     L, W, H = rng.uniform(4, 8), rng.uniform(3, 6), 2.6
     boxes = []
@@ -59,22 +62,30 @@ def make_scene(seed: int, target_voxels: int = 50000, voxel_size: float = 0.02, 
                 q[:, :2] = q[:, :2] @ np.array([[c_, s_], [-s_, c_]])
             parts.append(q + b[:3])
         p = np.concatenate(parts)
+        part_of.append(np.repeat(np.arange(17), counts))
         return p + rng.normal(0, 0.004, p.shape)
 
+    part_of = []
     pts = sample(int(target_voxels * 1.05))
     for _ in range(40):
         nv = len(np.unique(np.floor(pts / voxel_size).astype(np.int64), axis=0))
         if nv >= target_voxels:
             break
         pts = np.concatenate([pts, sample(max(256, int((target_voxels - nv) * 1.3)))])
+    part = np.concatenate(part_of)
     if sunrgbd:
         ang = np.arctan2(pts[:, 1], pts[:, 0] + L / 2 + 0.5)
-        pts = pts[np.abs(ang) < np.pi / 6]
+        sel = np.abs(ang) < np.pi / 6
+        pts, part = pts[sel], part[sel]
     if n_points is not None:
         idx = rng.choice(len(pts), n_points, replace=len(pts) < n_points)
-        pts = pts[idx]
+        pts, part = pts[idx], part[idx]
     rgb = rng.integers(0, 256, (len(pts), 3)).astype(np.float32)
-    return np.concatenate([pts.astype(np.float32), rgb], 1), boxes
+    out = np.concatenate([pts.astype(np.float32), rgb], 1)
+    if return_masks:
+        sem = np.where(part >= 5, boxes[np.clip(part - 5, 0, 11), 7].astype(np.int64), n_classes)
+        return out, boxes, sem.astype(np.int64), part.astype(np.int64)
+    return out, boxes
 
 
 def collate_batch(scenes):

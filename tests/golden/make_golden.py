@@ -35,8 +35,11 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("CG3D_REFERENCE", "/root/reference")
-sys.path.insert(0, ROOT)
-sys.path.insert(1, REF)
+# the reference's `pcdet` must win over this repo's drop-in `pcdet` package; everything else comes from the repo
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+for _m in [m for m in sys.modules if m == "pcdet" or m.startswith("pcdet.")]:
+    del sys.modules[_m]
 
 STUB_TOP = {"spconv", "cumm", "SharedArray", "tensorboardX", "skimage", "open3d", "terminaltables", "kornia",
             "mayavi", "av2", "nuscenes", "waymo_open_dataset", "tensorflow", "lyft_dataset_sdk", "pandaset", "cv2",
