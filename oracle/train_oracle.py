@@ -1,0 +1,126 @@
+"""CPU restatement of the TRAINING-side arithmetic of the first stage (ORACLE / TEST INFRASTRUCTURE -- the product never
+imports this; it is the checker the CUDA training path of the next round will be compared with).
+
+Follows, for the ScanNet configuration (WITH_YAW False; the yaw handling of the assigner is included):
+  pcdet/models/dense_heads/target_assigner/cagroup3d_assigner.py:9-37   find_points_in_boxes
+  ...:40-47    compute_centerness          ...:64-133   CAGroup3DAssigner.assign          ...:135-158  assign_semantic
+  pcdet/utils/loss_utils.py:813-846  binary_cross_entropy (CrossEntropy, use_sigmoid)      :917-961, 1012-1032  FocalLoss
+  pcdet/utils/loss_utils.py:1042-1074  smooth_l1_loss       pcdet/utils/iou3d_loss.py:31-58 + loss_utils.py:419-537  IoU loss
+  pcdet/models/dense_heads/cagroup_head.py:505-554  the loss terms of _loss_single (no-yaw branch)
+Pinned by tests/golden/train_parts.npz (tests/golden/make_train_golden.py runs the reference's own classes on seeded
+random inputs) in tests/test_train_oracle.py.  torch CPU, fp32 like the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+FLOAT_MAX = 1e8
+
+
+def face_distances(points: torch.Tensor, boxes: torch.Tensor) -> torch.Tensor:
+    """(n, 3) points x (m, 7) boxes -> (n, m, 6) distances to the -x,+x,-y,+y,-z,+z faces in each box's own frame
+    (positive inside); assigner.py:17-32 with rotation_3d_in_axis(shift, -yaw)."""
+    d = points[:, None, :3] - boxes[None, :, :3]
+    c, s = torch.cos(-boxes[:, 6])[None], torch.sin(-boxes[:, 6])[None]
+    # rotation_3d_in_axis(axis=2): [x, y] @ [[cos, -sin], [sin, cos]]  (cagroup_utils.py)
+    x = d[..., 0] * c + d[..., 1] * s
+    y = -d[..., 0] * s + d[..., 1] * c
+    h = boxes[None, :, 3:6] / 2
+    return torch.stack((x + h[..., 0], h[..., 0] - x, y + h[..., 1], h[..., 1] - y, d[..., 2] + h[..., 2], h[..., 2] - d[..., 2]), -1)
+
+
+def centerness_of(t: torch.Tensor) -> torch.Tensor:
+    """sqrt(prod over axes of min/max of the two face distances); assigner.py:40-47."""
+    p = t[..., 0::2], t[..., 1::2]
+    lo, hi = torch.minimum(*p), torch.maximum(*p)
+    return torch.sqrt((lo[..., 0] / hi[..., 0]) * (lo[..., 1] / hi[..., 1]) * (lo[..., 2] / hi[..., 2]))
+
+
+def assign(points_per_class, gt_boxes: torch.Tensor, gt_labels: torch.Tensor, topk: int):
+    """CAGroup3DAssigner.assign: per class map, a location is positive for the smallest-volume box of ITS class that
+    contains it and for which it is among the top-k locations by centerness.  -> (centerness (N,), boxes (N, 7), labels (N,))"""
+    cts, bxs, lbs = [], [], []
+    for cls_id, pts in enumerate(points_per_class):
+        n = len(pts)
+        assert n > 0
+        sel = torch.nonzero(gt_labels == cls_id).squeeze(1)
+        if len(sel) == 0:
+            cts.append(torch.zeros(n)); bxs.append(torch.zeros((n, 7))); lbs.append(torch.full((n,), -1, dtype=torch.long))
+            continue
+        b = gt_boxes[sel]
+        t = face_distances(pts, b)                                        # (n, m, 6)
+        inside = t.min(-1)[0] > 0
+        ctr = torch.where(inside, centerness_of(t), torch.full((n, len(sel)), -1.0))
+        kth = torch.topk(ctr, min(topk + 1, n), dim=0).values[-1]          # (topk+1)-th best centerness per box
+        keep = inside & (ctr > kth[None])
+        vol = torch.where(keep, (b[:, 3] * b[:, 4] * b[:, 5])[None].expand(n, -1), torch.full((n, len(sel)), FLOAT_MAX))
+        mv, mi = vol.min(1)
+        lab = torch.where(mv == FLOAT_MAX, torch.full((n,), -1, dtype=torch.long), gt_labels[sel][mi])
+        cts.append(centerness_of(t[torch.arange(n), mi]))
+        bxs.append(b[mi].clone())
+        lbs.append(lab)
+    return torch.cat(cts), torch.cat(bxs), torch.cat(lbs)
+
+
+def assign_semantic(points: torch.Tensor, gt_boxes: torch.Tensor, gt_labels: torch.Tensor):
+    """assign_semantic: label of the smallest box containing the point (-1 outside all), instance = box index + 1 (0 outside)."""
+    n, m = len(points), len(gt_boxes)
+    inside = face_distances(points, gt_boxes).min(-1)[0] > 0
+    vol = torch.where(inside, (gt_boxes[:, 3] * gt_boxes[:, 4] * gt_boxes[:, 5])[None].expand(n, m), torch.full((n, m), FLOAT_MAX))
+    mv, mi = vol.min(1)
+    labels = torch.where(mv == FLOAT_MAX, torch.full((n,), -1, dtype=torch.long), gt_labels[mi])
+    return labels, (mi + 1) * (inside.sum(1) != 0)
+
+
+def focal_loss(pred: torch.Tensor, labels: torch.Tensor, avg_factor: float, gamma: float = 2.0, alpha: float = 0.25):
+    """FocalLoss(use_sigmoid) with labels in [0, C) and -1 = background; sum / avg_factor."""
+    C = pred.shape[1]
+    tgt = F.one_hot(torch.where(labels < 0, torch.full_like(labels, C), labels), C + 1)[:, :C].to(pred.dtype)
+    p = pred.sigmoid()
+    pt = (1 - p) * tgt + p * (1 - tgt)
+    w = (alpha * tgt + (1 - alpha) * (1 - tgt)) * pt.pow(gamma)
+    return (F.binary_cross_entropy_with_logits(pred, tgt, reduction="none") * w).sum() / avg_factor
+
+
+def bce_loss(pred: torch.Tensor, target: torch.Tensor, avg_factor: float):
+    """CrossEntropy(use_sigmoid) on same-shaped pred / target: mask (target >= 0), sum / (avg_factor + eps)."""
+    valid = (target >= 0).float()
+    loss = F.binary_cross_entropy_with_logits(pred, target.float(), reduction="none") * valid
+    return loss.sum() / (avg_factor + torch.finfo(torch.float32).eps)
+
+
+def smooth_l1_sum(pred: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, beta: float = 0.04):
+    d = (pred - target).abs()
+    return (torch.where(d < beta, 0.5 * d * d / beta, d - 0.5 * beta) * weight).sum()
+
+
+def axis_aligned_iou_loss(pred: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, avg_factor: float):
+    """1 - IoU of (x, y, z, dx, dy, dz) boxes, weighted, sum / avg_factor; IoU3DLoss(with_yaw=False): returns
+    pred.sum() * weight.sum() (= 0) when no weight is positive (iou3d_loss.py:75-76)."""
+    if not torch.any(weight > 0):
+        return pred.sum() * weight.sum()
+    lo1, hi1 = pred[:, :3] - pred[:, 3:6] / 2, pred[:, :3] + pred[:, 3:6] / 2
+    lo2, hi2 = target[:, :3] - target[:, 3:6] / 2, target[:, :3] + target[:, 3:6] / 2
+    inter = (torch.minimum(hi1, hi2) - torch.maximum(lo1, lo2)).clamp(min=0).prod(-1)
+    union = (hi1 - lo1).prod(-1) + (hi2 - lo2).prod(-1) - inter
+    iou = inter / torch.maximum(union, torch.tensor(1e-6))
+    return ((1 - iou) * weight).sum() / avg_factor
+
+
+def head_loss_terms(centerness, bbox_decoded, cls_scores, centerness_targets, bbox_targets, labels,
+                    semantic_scores, semantic_labels, offset_preds, offset_targets, offset_masks):
+    """the five terms of _loss_single (cagroup_head.py:505-554), no-yaw branch, single process (reduce_mean = identity).
+    bbox_decoded: predictions already turned into boxes by _bbox_pred_to_bbox for ALL locations."""
+    w = (offset_masks.float() / torch.ones_like(offset_masks).float().sum() + 1e-6)[:, None].repeat(1, 3)
+    loss_vote = smooth_l1_sum(offset_preds, offset_targets, w)
+    loss_sem = focal_loss(semantic_scores, semantic_labels, max(float((semantic_labels >= 0).sum()), 1.0))
+    pos = torch.nonzero(labels >= 0).squeeze(1)
+    n_pos = max(float(len(pos)), 1.0)
+    loss_cls = focal_loss(cls_scores, labels, n_pos)
+    if len(pos) == 0:
+        return centerness[pos].sum(), bbox_decoded[pos].sum(), loss_cls, loss_sem, loss_vote
+    ct = centerness_targets[pos][:, None]
+    loss_ctr = bce_loss(centerness[pos], ct, n_pos)
+    loss_box = axis_aligned_iou_loss(bbox_decoded[pos][:, :6], bbox_targets[pos][:, :6], ct.squeeze(1), max(float(ct.sum()), 1e-6))
+    return loss_ctr, loss_box, loss_cls, loss_sem, loss_vote

@@ -95,5 +95,58 @@ def main():
     print({k: round(v, 5) for k, v in tb.items()}, "rois", out["n_rois"], "params with grad", int((out["grad_norms"] >= 0).sum()), "/", len(names))
 
 
+def parts():
+    """tests/golden/train_parts.npz: the reference's assigner and loss CLASSES on seeded random inputs."""
+    MG.install()
+    from pcdet.models.dense_heads.target_assigner.cagroup3d_assigner import CAGroup3DAssigner, compute_centerness, find_points_in_boxes
+    from pcdet.utils.loss_utils import CrossEntropy, FocalLoss, SmoothL1Loss
+    from pcdet.utils.iou3d_loss import IoU3DLoss
+    g = torch.Generator().manual_seed(11)
+    ncls, m = 6, 14
+    boxes = torch.cat([(torch.rand((m, 3), generator=g) - 0.5) * 4, torch.rand((m, 3), generator=g) * 1.5 + 0.3,
+                       (torch.rand((m, 1), generator=g) - 0.5) * 3], 1)
+    boxes[:5, 6] = 0
+    labels = torch.randint(0, ncls - 1, (m,), generator=g)                    # class ncls-1 has no box
+    pts = [(torch.rand((int(n), 3), generator=g) - 0.5) * 5 for n in torch.randint(40, 400, (ncls,), generator=g)]
+    for c in range(ncls - 1):                                               # make sure many locations fall inside boxes
+        b = boxes[labels == c]
+        if len(b):
+            k = len(pts[c]) // 2
+            pts[c][:k] = b[torch.randint(0, len(b), (k,), generator=g), :3] + (torch.rand((k, 3), generator=g) - 0.5) * 0.8
+    cfg = MG.EasyDict(LIMIT=27, TOPK=18, N_SCALES=4)
+    ct, bt, lb = CAGroup3DAssigner(cfg).assign(pts, boxes, labels)
+    allp = torch.cat(pts)
+    sl, il = CAGroup3DAssigner.assign_semantic(allp, boxes, labels, ncls)
+    inside = find_points_in_boxes(allp, boxes)
+    out = {"boxes": MG.t2n(boxes), "labels": MG.t2n(labels), "n_per_class": np.array([len(p) for p in pts]), "points": MG.t2n(allp),
+           "assign_centerness": MG.t2n(ct), "assign_boxes": MG.t2n(bt), "assign_labels": MG.t2n(lb), "sem_labels": MG.t2n(sl),
+           "ins_labels": MG.t2n(il), "inside": MG.t2n(inside)}
+    N = len(allp)
+    cls_scores = torch.randn((N, ncls), generator=g) * 2
+    sem_scores = torch.randn((N, ncls), generator=g) * 2
+    ctr_pred = torch.randn((N, 1), generator=g)
+    box_pred = torch.cat([bt[:, :3] + torch.randn((N, 3), generator=g) * 0.1, (bt[:, 3:6] + torch.randn((N, 3), generator=g) * 0.1).abs() + 0.05], 1)
+    off_pred, off_tgt = torch.randn((N, 3), generator=g) * 0.1, torch.randn((N, 3), generator=g) * 0.1
+    off_mask = (torch.rand((N,), generator=g) > 0.4).float()
+    pos = torch.nonzero(lb >= 0).squeeze(1)
+    n_pos = max(float(len(pos)), 1.0)
+    out.update(cls_scores=MG.t2n(cls_scores), sem_scores=MG.t2n(sem_scores), ctr_pred=MG.t2n(ctr_pred), box_pred=MG.t2n(box_pred),
+               off_pred=MG.t2n(off_pred), off_tgt=MG.t2n(off_tgt), off_mask=MG.t2n(off_mask))
+    out["loss_cls"] = float(FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)(cls_scores, lb.clone(), avg_factor=n_pos))
+    out["loss_sem"] = float(FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)(
+        sem_scores, sl.clone(), avg_factor=max(float((sl >= 0).sum()), 1.0)))
+    out["loss_ctr"] = float(CrossEntropy(use_sigmoid=True, loss_weight=1.0)(ctr_pred[pos], ct[pos].unsqueeze(1), avg_factor=n_pos))
+    out["loss_box"] = float(IoU3DLoss(with_yaw=False, loss_weight=1.0)(box_pred[pos], bt[pos][:, :6], weight=ct[pos],
+                                                                       avg_factor=max(float(ct[pos].sum()), 1e-6)))
+    w = (off_mask.float() / torch.ones_like(off_mask).float().sum() + 1e-6).unsqueeze(1).repeat(1, 3)
+    out["loss_vote"] = float(SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0)(off_pred, off_tgt, weight=w))
+    out["centerness_fn"] = MG.t2n(compute_centerness(torch.rand((32, 7), generator=g) + 0.01))
+    g2 = torch.Generator().manual_seed(11)
+    np.savez_compressed(os.path.join(HERE, "train_parts.npz"), **out)
+    print("parts:", {k: round(out[k], 5) for k in ("loss_cls", "loss_sem", "loss_ctr", "loss_box", "loss_vote")}, "positives", len(pos), "of", N)
+
+
 if __name__ == "__main__":
-    main()
+    if "--parts-only" not in sys.argv:
+        main()
+    parts()

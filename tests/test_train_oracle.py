@@ -1,0 +1,59 @@
+"""oracle/train_oracle.py (assigner + first-stage loss terms) against the reference's own classes
+(tests/golden/train_parts.npz, made by tests/golden/make_train_golden.py --parts-only)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import train_oracle as T
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_parts.npz"))
+t = lambda k: torch.from_numpy(G[k])
+
+
+def _points_per_class():
+    pts, out, o = t("points"), [], 0
+    for n in G["n_per_class"].tolist():
+        out.append(pts[o:o + n])
+        o += n
+    return out
+
+
+def test_point_in_box_and_centerness():
+    d = T.face_distances(t("points"), t("boxes"))
+    assert np.array_equal((d.min(-1)[0] > 0).numpy(), G["inside"])
+    x = torch.from_numpy(np.random.default_rng(0).random((8, 7)).astype(np.float32)) + 0.01
+    c = T.centerness_of(x[:, :6])
+    lo = torch.stack([x[:, 0:2].min(1)[0], x[:, 2:4].min(1)[0], x[:, 4:6].min(1)[0]], 1)
+    hi = torch.stack([x[:, 0:2].max(1)[0], x[:, 2:4].max(1)[0], x[:, 4:6].max(1)[0]], 1)
+    assert torch.allclose(c, torch.sqrt((lo / hi).prod(1)))
+
+
+def test_assign_matches_reference():
+    ct, bx, lb = T.assign(_points_per_class(), t("boxes"), t("labels"), topk=18)
+    assert np.array_equal(lb.numpy(), G["assign_labels"])
+    assert int((lb >= 0).sum()) > 100 and int((lb < 0).sum()) > 100                 # both outcomes are exercised
+    pos = lb >= 0
+    assert np.allclose(bx[pos].numpy(), G["assign_boxes"][pos.numpy()], atol=0)
+    assert np.allclose(ct[pos].numpy(), G["assign_centerness"][pos.numpy()], rtol=1e-5, atol=1e-6)
+
+
+def test_assign_semantic_matches_reference():
+    sl, il = T.assign_semantic(t("points"), t("boxes"), t("labels"))
+    assert np.array_equal(sl.numpy(), G["sem_labels"]) and np.array_equal(il.numpy(), G["ins_labels"])
+
+
+def test_loss_terms_match_reference():
+    lb, ct, bt = t("assign_labels"), t("assign_centerness"), t("assign_boxes")
+    ctr, box, cls, sem, vote = T.head_loss_terms(t("ctr_pred"), t("box_pred"), t("cls_scores"), ct, bt, lb, t("sem_scores"),
+                                                 t("sem_labels"), t("off_pred"), t("off_tgt"), t("off_mask"))
+    for got, key in ((ctr, "loss_ctr"), (box, "loss_box"), (cls, "loss_cls"), (sem, "loss_sem"), (vote, "loss_vote")):
+        assert abs(float(got) - float(G[key])) <= 1e-5 * max(1.0, abs(float(G[key]))), (key, float(got), float(G[key]))
+
+
+def test_loss_terms_without_positives():
+    n = 50
+    z = torch.zeros
+    ctr, box, cls, sem, vote = T.head_loss_terms(z((n, 1)), torch.rand((n, 6)), torch.randn((n, 4)), z(n), z((n, 7)),
+                                                 torch.full((n,), -1), torch.randn((n, 4)), torch.full((n,), -1), z((n, 3)), z((n, 3)), z(n))
+    assert float(ctr) == 0 and float(box) == 0 and float(cls) > 0 and float(sem) > 0
