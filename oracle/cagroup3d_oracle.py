@@ -55,13 +55,14 @@ class Oracle:
         self.p = {k: v.detach().cpu() for k, v in params.items()}
         self.cfg = cfg
         self.dt = dtype
+        self.train_bn = False          # True: batch statistics in every BatchNorm (the reference's model.train())
 
     # ---- small helpers ----------------------------------------------------------------
     def W(self, name):
         return self.p[name].to(self.dt)
 
     def bn(self, F, prefix):
-        return me.batchnorm(F, self.p, prefix + ".bn.")
+        return me.batchnorm(F, self.p, prefix + ".bn.", train=self.train_bn)
 
     def conv_bn(self, x, cname, bname, k, stride=1, act=None):
         y = me.conv(x, self.W(cname + ".kernel"), k, stride)

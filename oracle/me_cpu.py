@@ -247,8 +247,12 @@ def features_at(x: SparseTensor, q: np.ndarray) -> torch.Tensor:
     return out
 
 
-def batchnorm(F: torch.Tensor, p: dict, prefix: str, eps: float = 1e-5) -> torch.Tensor:
-    """nn.BatchNorm1d in eval mode (A11)."""
+def batchnorm(F: torch.Tensor, p: dict, prefix: str, eps: float = 1e-5, train: bool = False) -> torch.Tensor:
+    """nn.BatchNorm1d in eval mode (A11); train=True: normalise with the statistics of the rows at hand (biased variance),
+    what MinkowskiBatchNorm does in training mode (the running statistics are not updated here)."""
     t = F.dtype
+    if train:
+        mean, var = F.mean(0), F.var(0, unbiased=False)
+        return (F - mean) / torch.sqrt(var + eps) * p[prefix + "weight"].to(t) + p[prefix + "bias"].to(t)
     return (F - p[prefix + "running_mean"].to(t)) / torch.sqrt(p[prefix + "running_var"].to(t) + eps) \
         * p[prefix + "weight"].to(t) + p[prefix + "bias"].to(t)

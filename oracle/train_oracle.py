@@ -12,6 +12,7 @@ random inputs) in tests/test_train_oracle.py.  torch CPU, fp32 like the referenc
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -124,3 +125,64 @@ def head_loss_terms(centerness, bbox_decoded, cls_scores, centerness_targets, bb
     loss_ctr = bce_loss(centerness[pos], ct, n_pos)
     loss_box = axis_aligned_iou_loss(bbox_decoded[pos][:, :6], bbox_targets[pos][:, :6], ct.squeeze(1), max(float(ct.sum()), 1e-6))
     return loss_ctr, loss_box, loss_cls, loss_sem, loss_vote
+
+
+# ---- first-stage training loss of a whole batch, on top of the inference oracle ---------------------------------------------
+def vote_targets_from_masks(scene_points, voxel_points, gt_boxes, sem_mask, ins_mask, n_classes):
+    """cagroup_head.py:454-496 (ScanNet branch): every foreground instance votes for the centre of the ground-truth box
+    nearest to its own axis-aligned centre; a stride-2 voxel takes the instance of its nearest scene point (k = 1).
+    -> (offset targets (n, 3), mask (n,))."""
+    n_ins = int(ins_mask.max()) + 1
+    inst_center = torch.zeros((n_ins, 3))
+    for i in torch.unique(ins_mask):
+        idx = torch.nonzero(ins_mask == i).squeeze(1)
+        if sem_mask[idx[0]] < n_classes:
+            p = scene_points[idx, :3]
+            c = 0.5 * (p.min(0)[0] + p.max(0)[0])
+            inst_center[i] = gt_boxes[torch.argmin(torch.cdist(c.view(1, 3), gt_boxes[:, :3]).view(-1)), :3]
+        else:
+            inst_center[i] = -10000.0
+    nearest = torch.cdist(voxel_points, scene_points[:, :3]).argmin(1)             # knn, k = 1, first index on ties
+    t = inst_center[ins_mask[nearest]] - voxel_points
+    m = (t >= -100.0).all(1)
+    return torch.where(t < -100.0, torch.zeros_like(t), t), m.float()
+
+
+def first_stage_loss(orc, points, batch_size, gt_boxes_list, gt_labels_list, sem_masks, ins_masks, cur_epoch=10, topk=18,
+                     force=None):
+    """CAGroup3DHead.loss (cagroup_head.py:322-398) over a batch, with the oracle run in training mode (batch-statistics
+    BatchNorm).  orc: oracle.cagroup3d_oracle.Oracle; force: see Oracle.head (teacher-forced offsets for the class-voxel
+    floor).  The vote loss always uses the oracle's own offsets.  Returns the dict of the five terms and their sum."""
+    from oracle.cagroup3d_oracle import bbox_pred_to_bbox
+    orc.train_bn = True
+    try:
+        res = orc.forward(points, batch_size, cur_epoch=cur_epoch, stages="head", force=force)
+    finally:
+        orc.train_bn = False
+    cfg, hi = orc.cfg, res["head"]
+    vs, ncls = cfg["voxel_size"], cfg["n_classes"]
+    C = torch.from_numpy(res["bb_coords"])
+    pts7 = points.detach().cpu().float()
+    terms = []
+    for b in range(batch_size):
+        rows = torch.nonzero(C[:, 0] == b).squeeze(1)
+        vox_pts = C[rows, 1:].float() * vs
+        scene = pts7[pts7[:, 0] == b][:, 1:4]
+        gtb, gtl = gt_boxes_list[b], gt_labels_list[b]
+        sem_labels, _ = assign_semantic(vox_pts, gtb, gtl)
+        ppc, ctr, box, cls = [], [], [], []
+        for c in range(ncls):
+            m = hi["maps"][c]
+            r = np.nonzero(m["coords"][:, 0] == b)[0]
+            from oracle.cagroup3d_oracle import class_voxel_sizes
+            p = torch.from_numpy(m["coords"][r, 1:]).float() * torch.tensor(class_voxel_sizes(ncls)[c], dtype=torch.float32)
+            ppc.append(p)
+            ctr.append(m["ctr"][r]); box.append(bbox_pred_to_bbox(p, m["bbox"][r])); cls.append(m["cls"][r])
+        ct_t, box_t, lab = assign(ppc, gtb, gtl, topk)
+        off_t, off_m = vote_targets_from_masks(scene, vox_pts, gtb, sem_masks[b], ins_masks[b], ncls)
+        terms.append(head_loss_terms(torch.cat(ctr), torch.cat(box), torch.cat(cls), ct_t, box_t, lab, hi["sem"][rows], sem_labels,
+                                     hi["offsets"][rows], off_t, off_m))
+    names = ("loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote")
+    out = {n: float(torch.stack([t[i] for t in terms]).mean()) for i, n in enumerate(names)}
+    out["one_stage_loss"] = sum(out[n] for n in names)
+    return out
