@@ -1,0 +1,105 @@
+"""Backward of the sparse convolution through the C ABI, and its torch.autograd binding (first
+brick of the training path: MinkowskiConvolution / ConvolutionTranspose backward as the reference gets it from
+MinkowskiEngine when tools/train.py calls loss.backward()).
+
+    dX = conv(dY) over the TRANSPOSED rule map with W[k]^T     cg3d_table_transpose + cg3d_transpose_weights + the
+                                                               forward kernel (cg3d_spconv_tc / cg3d_spconv_simt)
+    dW[k] = sum over the rule pairs of tap k of X[i]^T (x) dY[o]     cg3d_spconv_wgrad (deterministic slab reduction)
+
+torch is the autograd tape and device memory only; there is no torch or CPU fallback for the arithmetic.
+Checked against oracle/backward_oracle.py in tests/test_gpu_wgrad.py.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from . import sparse as S
+
+
+def table_transpose(nbr: torch.Tensor, n_in: int, out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nbrT[k][i] = output row o with nbr[k][o] == i (-1 where none); nbr may be positional (out_rows)."""
+    K, n_cols = nbr.shape
+    T = torch.empty((K, max(n_in, 1)), dtype=torch.int32, device=nbr.device)
+    S._call("cg3d_table_transpose", nbr, K, n_cols, out_rows, n_in, T)
+    return T
+
+
+def transpose_weights(W: torch.Tensor) -> torch.Tensor:
+    """[..., Cin, Cout] -> [..., Cout, Cin] (contiguous copy)."""
+    assert W.is_contiguous() and W.dtype == torch.float32
+    Cin, Cout = W.shape[-2], W.shape[-1]
+    Wt = torch.empty(W.shape[:-2] + (Cout, Cin), dtype=torch.float32, device=W.device)
+    S._call("cg3d_transpose_weights", W, W.numel() // (Cin * Cout), Cin, Cout, Wt)
+    return Wt
+
+
+def wgrad(X: torch.Tensor, nbr: Optional[torch.Tensor], dY: torch.Tensor, K: int, out_rows: Optional[torch.Tensor] = None,
+          in_act=None, cols=None) -> torch.Tensor:
+    """dW [K, Cin, Cout] of Y[row(j)] = sum_k in_act(X[nbr[k][j]]) @ W[k] over the columns `cols` = (col0, col1) of the
+    table (default: all)."""
+    assert X.stride(1) == 1 and dY.stride(1) == 1 and X.dtype == dY.dtype == torch.float32
+    Cin, Cout = X.shape[1], dY.shape[1]
+    n_cols = nbr.shape[1] if nbr is not None else dY.shape[0]
+    c0, c1 = cols if cols is not None else (0, min(n_cols, dY.shape[0]))      # an empty map's table still has one column
+    dW = torch.empty((K, Cin, Cout), dtype=torch.float32, device=X.device)
+    ns = _lib.host("cg3d_spconv_wgrad_slabs", c1 - c0, Cin, Cout, K)
+    slabs = torch.empty((ns * K * Cin * Cout,), dtype=torch.float32, device=X.device) if ns > 1 else None
+    S._call("cg3d_spconv_wgrad", X, X.stride(0), S.ACT[in_act], nbr, dY, dY.stride(0), n_cols, c0, c1, Cin, Cout, K,
+            out_rows, slabs, dW)
+    return dW
+
+
+def conv_backward(X: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor], dY: torch.Tensor, K: int,
+                  out_rows: Optional[torch.Tensor] = None, need_dx: bool = True, need_dw: bool = True,
+                  nbrT: Optional[torch.Tensor] = None, impl: Optional[str] = None):
+    """(dX, dW) of Y = gemm_rows(X, nbr, W, n_out, K, out_rows=out_rows) (no epilogue, one weight group)."""
+    dY = dY.contiguous()
+    dX = dW = None
+    if need_dx and (dY.shape[0] == 0 or X.shape[0] == 0):
+        dX, need_dx = torch.zeros_like(X), False
+    if need_dx:
+        Wt = transpose_weights(W.detach().reshape(K, X.shape[1], dY.shape[1]))
+        if nbr is None:
+            dX = S.gemm_rows(dY, None, Wt[0], X.shape[0], 1, impl=impl)
+        else:
+            if nbrT is None:
+                nbrT = table_transpose(nbr, X.shape[0], out_rows)
+            dX = S.gemm_rows(dY, nbrT, Wt, X.shape[0], K, impl=impl)
+    if need_dw:
+        dW = wgrad(X.detach(), nbr, dY, K, out_rows).reshape(W.shape)
+    return dX, dW
+
+
+class SparseConvFunction(torch.autograd.Function):
+    """Y = sum_k X[nbr[k]] @ W[k] with gradients for X and W."""
+
+    @staticmethod
+    def forward(ctx, X, W, nbr, out_rows, n_out, K, impl):
+        ctx.save_for_backward(X, W)
+        ctx.nbr, ctx.out_rows, ctx.K, ctx.impl = nbr, out_rows, K, impl
+        return S.gemm_rows(X.detach(), nbr, W.detach(), n_out, K, out_rows=out_rows, impl=impl)
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dX, dW = conv_backward(X, W, ctx.nbr, dY, ctx.K, ctx.out_rows, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                               impl=ctx.impl)
+        return dX, dW, None, None, None, None, None
+
+
+def conv(x: S.SparseTensor, W: torch.Tensor, k: int, stride: int = 1, impl: Optional[str] = None) -> S.SparseTensor:
+    """differentiable MinkowskiConvolution (no fused epilogue: training-mode BatchNorm follows with batch statistics)."""
+    if k == 1 and stride == 1:
+        return x.with_F(SparseConvFunction.apply(x.F, W, None, None, x.cmap.n, 1, impl))
+    omap = x.cmap if stride == 1 else S.strided_map(x.cmap, x.mgr, stride)
+    nbr, order = S.neighbor_table(x.cmap, omap, k, x.mgr, ordered=True)
+    return S.SparseTensor(SparseConvFunction.apply(x.F, W, nbr, order, omap.n, k ** 3, impl), omap, x.mgr)
+
+
+def conv_transpose_k2s2(x: S.SparseTensor, W: torch.Tensor, impl: Optional[str] = None) -> S.SparseTensor:
+    fmap = x.mgr.by_stride[x.cmap.stride // 2]
+    nbr, order = S.transpose_table(x.cmap, fmap, 2, x.mgr, ordered=True)
+    return S.SparseTensor(SparseConvFunction.apply(x.F, W, nbr, order, fmap.n, 8, impl), fmap, x.mgr)

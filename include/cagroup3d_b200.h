@@ -325,6 +325,27 @@ int cg3d_knn(const float* xyz, int b, int n, const float* query, int m, int k, i
 int cg3d_sort_vertices(const float* vertices, const unsigned char* mask, const int* num_valid, int b, int n, int m,
                        int* idx, void* stream);
 
+/* ---- backward of the sparse convolution (training; MinkowskiEngine's ConvolutionBackward over the forward's kernel
+ * map; called from cagroup_head.py:322-555 / tools/train.py via loss.backward()) -------- */
+
+/* nbrT: i32[K][n_in], nbrT[k][i] = output row o with nbr[k][o] == i, -1 where none (a convolution's rule map holds an
+ * input row at most once per tap).  nbr: i32[K][n_cols]; out_rows (may be NULL): the table is positional, column j
+ * belongs to output row out_rows[j].  dX = cg3d_spconv_*(dY, nbrT, transposed weights). */
+int cg3d_table_transpose(const int* nbr, int K, int n_cols, const int* out_rows, int n_in, int* nbrT, void* stream);
+
+/* Wt[m][co][ci] = W[m][ci][co] for n_mats = G * K matrices (the weights dX is convolved with). */
+int cg3d_transpose_weights(const float* W, int n_mats, int Cin, int Cout, float* Wt, void* stream);
+
+/* dW[k] = sum over columns j in [col0, col1) with nbr[k][j] >= 0 of  in_act(x[nbr[k][j]])^T (x) dy[row(j)],
+ * row(j) = out_rows ? out_rows[j] : j;  dW: f32[K][Cin][Cout].  nbr == NULL with K == 1: identity rows (1x1 conv /
+ * Linear).  [col0, col1) selects the contiguous columns of one weight group of a grouped convolution (one call per
+ * group).  Deterministic: chunks of columns write partial slabs that are added in order; `slabs` holds
+ * cg3d_spconv_wgrad_slabs(col1 - col0, Cin, Cout, K) * K * Cin * Cout floats (may be NULL when that count is 1).
+ * in_act: 0 none, 1 ReLU (the forward's in_act).  fp32 FFMA. */
+int cg3d_spconv_wgrad_slabs(int n_cols, int Cin, int Cout, int K);
+int cg3d_spconv_wgrad(const float* x, int ldx, int in_act, const int* nbr, const float* dy, int ldy, int n_cols, int col0,
+                      int col1, int Cin, int Cout, int K, const int* out_rows, float* slabs, float* dW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,119 @@
+"""Backward of the sparse convolution (cg3d_table_transpose, cg3d_transpose_weights, cg3d_spconv_wgrad + the forward
+kernels over the transposed table) through the C ABI against oracle/backward_oracle.py / autograd through the forward
+oracle, on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backward_oracle as Bk
+from oracle import me_cpu as me
+from tests.test_gpu_ops import oracle_tensor
+from tests.util import to_gpu_sparse
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _oracle_grads(ox, W, k, stride, seed):
+    X = ox.F.double().requires_grad_(True)
+    Wd = W.double().requires_grad_(True)
+    y = me.conv(ox.with_F(X), Wd[0] if (k == 1 and stride == 1) else Wd, k, stride)
+    dY = torch.randn(tuple(y.F.shape), generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+    (y.F * dY).sum().backward()
+    return y, dY, X.grad, Wd.grad
+
+
+def _close(got, want, tol):
+    err, mag = (got.double().cpu() - want).abs().max().item(), max(1.0, want.abs().max().item())
+    assert err <= tol * mag, (err, mag)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,impl", [(64, 64, 3, 1, "tc"), (64, 128, 3, 2, "tc"), (128, 64, 3, 2, "tc"),
+                                                    (3, 64, 3, 1, "simt"), (64, 18, 1, 1, "simt"), (128, 256, 1, 1, "tc"),
+                                                    (70, 36, 3, 1, "simt")])
+def test_conv_backward_vs_oracle(lib, cin, cout, k, stride, impl):
+    from cagroup3d_b200 import autograd as A, sparse as S
+    ox = oracle_tensor(31, cin, n=3000)
+    W = torch.randn((k ** 3, cin, cout), generator=torch.Generator().manual_seed(3)) / np.sqrt(cin * min(k ** 3, 8))
+    y, dY, dX_ref, dW_ref = _oracle_grads(ox, W, k, stride, 17)
+    x = to_gpu_sparse(ox.C, ox.F, 1, strided={y.cmap.stride: y.cmap.coords})
+    X = x.F.clone().requires_grad_(True)
+    Wg = (W[0] if (k == 1 and stride == 1) else W).to(DEV).contiguous().requires_grad_(True)
+    out = A.conv(x.with_F(X), Wg, k, stride, impl=impl)
+    assert np.array_equal(out.C.cpu().numpy(), y.cmap.coords)
+    _close(out.F.detach(), y.F.detach(), 2e-4)
+    out.F.backward(dY.float().to(DEV))
+    torch.cuda.synchronize()
+    _close(X.grad, dX_ref, 2e-4)
+    _close(Wg.grad.reshape(dW_ref.shape), dW_ref, 2e-4)
+
+
+def test_transposed_conv_backward_vs_oracle(lib):
+    """MinkowskiConvolutionTranspose k2 s2 (biresnet.py out block): same backward over the transposed-conv table."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    ox = oracle_tensor(34, 16)
+    coarse_o = me.conv(ox, torch.randn(27, 16, 64, generator=torch.Generator().manual_seed(1)) / 20, 3, 2)
+    W = torch.randn((8, 64, 64), generator=torch.Generator().manual_seed(2)) / 8
+    X = coarse_o.F.double().requires_grad_(True)
+    Wd = W.double().requires_grad_(True)
+    ref = me.conv_transpose_k2s2(coarse_o.with_F(X), Wd)
+    dY = torch.randn(tuple(ref.F.shape), generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    (ref.F * dY).sum().backward()
+    x = to_gpu_sparse(ox.C, ox.F, 1, strided={2: coarse_o.C})
+    Xg = coarse_o.F.to(DEV).requires_grad_(True)
+    Wg = W.to(DEV).requires_grad_(True)
+    y = A.conv_transpose_k2s2(S.SparseTensor(Xg, x.mgr.by_stride[2], x.mgr), Wg)
+    assert (y.C.cpu().numpy() == ref.C).all()
+    _close(y.F.detach(), ref.F.detach(), 2e-4)
+    y.F.backward(dY.float().to(DEV))
+    torch.cuda.synchronize()
+    _close(Xg.grad, X.grad, 2e-4)
+    _close(Wg.grad, Wd.grad, 2e-4)
+
+
+def test_transposed_table_and_positional_order(lib, monkeypatch):
+    """the transposed table is exactly the oracle's, also from a positional (tap-pattern ordered) table; dW from the
+    positional table equals dW from the row-ordered one BIT FOR BIT only where the slab split is the same, so the
+    comparison is to the oracle."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    monkeypatch.setattr(S, "MASK_MIN_ROWS", 256)
+    ox = oracle_tensor(32, 64, n=5000, batch=3)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    n = x.cmap.n
+    nbr = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr)
+    nbr_pos, order = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr, ordered=True)
+    assert order is not None
+    want = Bk.table_transpose(nbr.cpu().numpy(), n)
+    assert np.array_equal(A.table_transpose(nbr, n).cpu().numpy(), want)
+    assert np.array_equal(A.table_transpose(nbr_pos, n, order).cpu().numpy(), want)
+    g = torch.Generator().manual_seed(4)
+    W, dY = torch.randn((27, 64, 64), generator=g) / 20, torch.randn((n, 64), generator=g)
+    dX_ref, dW_ref = Bk.conv_backward(ox.F.double(), W.double(), nbr.cpu().numpy(), dY.double())
+    for tab, rows in ((nbr, None), (nbr_pos, order)):
+        dX, dW = A.conv_backward(x.F, W.to(DEV), tab, dY.to(DEV), 27, out_rows=rows, impl="simt")
+        _close(dX, dX_ref, 1e-5)
+        _close(dW, dW_ref, 1e-5)
+    # twice the same call: the same bits (no atomics)
+    a = A.wgrad(x.F, nbr, dY.to(DEV), 27)
+    b = A.wgrad(x.F, nbr, dY.to(DEV), 27)
+    assert torch.equal(a, b)
+    assert np.array_equal(A.transpose_weights(W.to(DEV)).cpu().numpy(), W.transpose(1, 2).contiguous().numpy())
+
+
+def test_wgrad_column_ranges_relu_and_empty(lib):
+    """[col0, col1) restricts the sum to one weight group's rows; in_act = ReLU gathers relu(x); an empty range gives 0."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    ox = oracle_tensor(33, 64, n=2500)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    n = x.cmap.n
+    nbr = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr)
+    t = nbr.cpu().numpy()
+    dY = torch.randn((n, 64), generator=torch.Generator().manual_seed(8))
+    Z = torch.zeros((27, 64, 64), dtype=torch.float64)
+    for c0, c1 in ((0, n // 3), (n // 3, n // 3 + 77), (n // 3 + 77, n)):
+        masked = t.copy()
+        masked[:, :c0] = -1
+        masked[:, c1:] = -1
+        _, want = Bk.conv_backward(torch.relu(ox.F).double(), Z, masked, dY.double())
+        _close(A.wgrad(x.F, nbr, dY.to(DEV), 27, in_act="relu", cols=(c0, c1)), want, 1e-5)
+    assert A.wgrad(x.F, nbr, dY.to(DEV), 27, cols=(5, 5)).abs().max().item() == 0
