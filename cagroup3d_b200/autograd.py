@@ -7,7 +7,7 @@ MinkowskiEngine when tools/train.py calls loss.backward()).
     dW[k] = sum over the rule pairs of tap k of X[i]^T (x) dY[o]     cg3d_spconv_wgrad (deterministic slab reduction)
 
 torch is the autograd tape and device memory only; there is no torch or CPU fallback for the arithmetic.
-Checked against oracle/backward_oracle.py in tests/test_gpu_wgrad.py.
+Checked against oracle/backward_oracle.py in tests/test_zz_gpu_spconv_backward.py.
 """
 from __future__ import annotations
 
