@@ -58,3 +58,87 @@ def test_gather_detections_world2_gloo():
 def test_gather_single_process_is_identity():
     d = [_fake_dets(i) for i in range(3)]
     assert D.gather_detections(d, 3) is not None and len(D.gather_detections(d, 2)) == 2
+
+
+# ---- training collectives: gradient all-reduce in flat buckets, reduce_mean -------------------------------------
+def _toy_model(seed=0):
+    torch.manual_seed(seed)
+    m = torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.ReLU(), torch.nn.Linear(33, 5, bias=False),
+                            torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 3))
+    m[2].weight.requires_grad_(False)            # a frozen parameter stays out of the buckets
+    return m
+
+
+def _toy_batch(rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    return torch.randn((16, 7), generator=g), torch.randn((16, 3), generator=g)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = _toy_model()
+    red = D.GradientAllReducer(m.parameters(), bucket_mb=0.0005)      # ~131 floats per bucket -> more than one bucket
+    ok = len(red.buckets) >= 2
+    for step in range(2):
+        red.zero_grad()
+        x, y = _toy_batch(rank)
+        ((m(x) - y) ** 2).mean().backward()
+        n_coll = red.reduce()
+        ok &= n_coll == len(red.buckets)
+        # the average of the per-rank gradients, computed independently on every rank
+        want = None
+        for r in range(world):
+            mr = _toy_model()
+            xr, yr = _toy_batch(r)
+            ((mr(xr) - yr) ** 2).mean().backward()
+            gs = [p.grad for p in mr.parameters() if p.requires_grad]
+            want = gs if want is None else [a + b for a, b in zip(want, gs)]
+        got = [p.grad for p in m.parameters() if p.requires_grad]
+        ok &= all(torch.allclose(a, b / world, rtol=1e-6, atol=1e-7) for a, b in zip(got, want))
+        ok &= all(p.grad.data_ptr() == red._view(p).data_ptr() for p in red.params)
+    # a gradient replaced behind the reducer's back (optimizer.zero_grad(set_to_none=True)) is still reduced
+    for p in red.params:
+        p.grad = None
+    next(iter(red.params)).grad = torch.full_like(next(iter(red.params)), float(rank + 1))
+    red.reduce()
+    ok &= torch.allclose(next(iter(red.params)).grad, torch.full_like(next(iter(red.params)), (1 + world) / 2))
+    ok &= all(float(p.grad.abs().max()) == 0 for p in list(red.params)[1:])
+    # reduce_mean: cagroup_utils.py:6-12
+    t = torch.tensor([float(rank), 10.0 * (rank + 1)])
+    rm = D.reduce_mean(t)
+    ok &= torch.allclose(rm, torch.tensor([(world - 1) / 2, 10.0 * (world + 1) / 2])) and float(t[0]) == float(rank)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_reduce_mean_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(30) for p in ps]
+    assert res == [(0, True), (1, True)]
+
+
+def test_gradient_reducer_single_process():
+    m = _toy_model()
+    red = D.GradientAllReducer(m.parameters(), bucket_mb=64)
+    assert len(red.buckets) == 1 and red.nbytes >= 4 * sum(p.numel() for p in m.parameters() if p.requires_grad)
+    x, y = _toy_batch(0)
+    ((m(x) - y) ** 2).mean().backward()
+    ref = _toy_model()
+    ((ref(x) - y) ** 2).mean().backward()
+    assert red.reduce() == 0
+    for a, b in zip(m.parameters(), ref.parameters()):
+        if a.requires_grad:
+            assert torch.equal(a.grad, b.grad)
+    t = torch.tensor([3.0])
+    assert D.reduce_mean(t) is t
+    red.zero_grad()
+    assert all(float(p.grad.abs().max()) == 0 for p in red.params)
