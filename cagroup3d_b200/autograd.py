@@ -103,3 +103,90 @@ def conv_transpose_k2s2(x: S.SparseTensor, W: torch.Tensor, impl: Optional[str] 
     fmap = x.mgr.by_stride[x.cmap.stride // 2]
     nbr, order = S.transpose_table(x.cmap, fmap, 2, x.mgr, ordered=True)
     return S.SparseTensor(SparseConvFunction.apply(x.F, W, nbr, order, fmap.n, 8, impl), fmap, x.mgr)
+
+
+# ---- training-mode BatchNorm (+ residual + ReLU) --------------------------------------------------------------
+def bn_train_stats(F: torch.Tensor, gamma=None, beta=None, running_mean=None, running_var=None, eps: float = 1e-5,
+                   momentum: float = 0.1):
+    """(mean, rstd, scale, shift) of the rows of F; running statistics updated in place (BatchNorm1d semantics)."""
+    assert F.stride(1) == 1 and F.dtype == torch.float32
+    n, C = F.shape
+    dev = F.device
+    mean, rstd, scale, shift = (torch.empty((C,), dtype=torch.float32, device=dev) for _ in range(4))
+    ws = torch.empty((_lib.host("cg3d_bn_train_workspace", n, C),), dtype=torch.float32, device=dev)
+    S._call("cg3d_bn_train_stats", F, F.stride(0), n, C, float(eps), float(momentum), gamma, beta, ws, mean, rstd, scale,
+            shift, running_mean, running_var)
+    return mean, rstd, scale, shift
+
+
+class BatchNormTrainFunction(torch.autograd.Function):
+    """y = act(gamma * (x - mean_batch) / sqrt(var_batch + eps) + beta (+ residual)), act in (None, "relu")."""
+
+    @staticmethod
+    def forward(ctx, X, gamma, beta, residual, running_mean, running_var, eps, momentum, act):
+        assert act in (None, "none", "relu")
+        Xd = X.detach()
+        mean, rstd, scale, shift = bn_train_stats(Xd, gamma.detach(), beta.detach(), running_mean, running_var, eps, momentum)
+        Y = S.affine_act(Xd, scale, shift, residual.detach().contiguous() if residual is not None else None, act)
+        relu = act == "relu"
+        ctx.save_for_backward(Xd, gamma.detach(), mean, rstd, Y if relu else None)
+        ctx.has_res = residual is not None
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, gamma, mean, rstd, Y = ctx.saved_tensors
+        dY = dY.contiguous()
+        n, C = X.shape
+        dev = X.device
+        dX = torch.empty((n, C), dtype=torch.float32, device=dev)
+        dres = torch.empty((n, C), dtype=torch.float32, device=dev) if ctx.has_res else None
+        dgamma, dbeta = (torch.empty((C,), dtype=torch.float32, device=dev) for _ in range(2))
+        ws = torch.empty((_lib.host("cg3d_bn_train_workspace", n, C),), dtype=torch.float32, device=dev)
+        S._call("cg3d_bn_train_backward", X, X.stride(0), dY, dY.stride(0), Y, Y.stride(0) if Y is not None else 0, n, C,
+                mean, rstd, gamma, ws, dX, C, dres, C, dgamma, dbeta)
+        return dX, dgamma, dbeta, dres, None, None, None, None, None
+
+
+def batch_norm_train(F: torch.Tensor, gamma, beta, running_mean=None, running_var=None, eps: float = 1e-5,
+                     momentum: float = 0.1, act=None, residual=None) -> torch.Tensor:
+    """MinkowskiBatchNorm in training mode over the rows of a sparse tensor, with the block's residual add and ReLU
+    (biresnet.py:31-50,79-103) in the same pass."""
+    return BatchNormTrainFunction.apply(F, gamma, beta, residual, running_mean, running_var, eps, momentum, act)
+
+
+# ---- features_at_coordinates / quantise-average ---------------------------------------------------------------
+class InterpFunction(torch.autograd.Function):
+    """base + x.features_at_coordinates(rows of the query map); gradient for the source features (and base)."""
+
+    @staticmethod
+    def forward(ctx, Fsrc, base, src_map, query_map):
+        ctx.src_map, ctx.query_map, ctx.has_base = src_map, query_map, base is not None
+        nq, C = query_map.n, Fsrc.shape[1]
+        out = torch.empty((nq, C), dtype=torch.float32, device=Fsrc.device)
+        S._call("cg3d_interp_trilinear", query_map.coords, nq, src_map.keys, src_map.vals, src_map.capacity, src_map.stride,
+                Fsrc.detach().contiguous(), C, base.detach().contiguous() if base is not None else None, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        dOut = dOut.contiguous()
+        sm, qm = ctx.src_map, ctx.query_map
+        dF = torch.zeros((sm.n, dOut.shape[1]), dtype=torch.float32, device=dOut.device)
+        S._call("cg3d_interp_trilinear_backward", sm.coords, sm.n, sm.stride, qm.keys, qm.vals, qm.capacity, qm.stride, dOut,
+                dOut.shape[1], dF)
+        return dF, (dOut if ctx.has_base else None), None, None
+
+
+def interp(x: S.SparseTensor, query_map: S.CoordMap, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """differentiable S.interp for the backbone's call sites (the query rows are all rows of a coordinate map)."""
+    return InterpFunction.apply(x.F, base, x.cmap, query_map)
+
+
+def segment_mean_backward(dOut: torch.Tensor, inverse: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """dIn[p] = dOut[inverse[p]] / counts[inverse[p]] (backward of the UNWEIGHTED_AVERAGE quantisation, plain sources)."""
+    dOut = dOut.contiguous()
+    n, C = inverse.shape[0], dOut.shape[1]
+    dIn = torch.empty((n, C), dtype=torch.float32, device=dOut.device)
+    S._call("cg3d_segment_mean_backward", dOut, inverse, counts, n, C, dIn, C)
+    return dIn

@@ -346,6 +346,39 @@ int cg3d_spconv_wgrad_slabs(int n_cols, int Cin, int Cout, int K);
 int cg3d_spconv_wgrad(const float* x, int ldx, int in_act, const int* nbr, const float* dy, int ldy, int n_cols, int col0,
                       int col1, int Cin, int Cout, int K, const int* out_rows, float* slabs, float* dW, void* stream);
 
+/* ---- training-mode BatchNorm and the backward of the row-gather ops (training; MinkowskiBatchNorm = BatchNorm1d over
+ * the rows of a sparse tensor, biresnet.py:8-103; features_at_coordinates backward, biresnet.py:182-197,376-394;
+ * UNWEIGHTED_AVERAGE quantisation backward, cagroup_head.py:257-271).  No float atomics: bit-repeatable. ---------- */
+
+/* floats of `workspace` the two BatchNorm calls below need for an [n, C] matrix */
+int cg3d_bn_train_workspace(long long n, int C);
+
+/* Batch statistics of x: f32[n][C] (row stride ldx): mean[c], rstd[c] = 1 / sqrt(biased var + eps), and the folded
+ * scale[c] = gamma[c] * rstd[c], shift[c] = beta[c] - mean[c] * scale[c] that cg3d_affine_act / the conv epilogues apply
+ * (gamma / beta / scale / shift may be NULL).  running_mean / running_var (may be NULL) are updated as
+ * torch.nn.BatchNorm1d does: r = (1 - momentum) * r + momentum * (mean | unbiased var).  n == 0 is an error, as in torch. */
+int cg3d_bn_train_stats(const float* x, int ldx, long long n, int C, float eps, float momentum, const float* gamma,
+                        const float* beta, float* workspace, float* mean, float* rstd, float* scale, float* shift,
+                        float* running_mean, float* running_var, void* stream);
+
+/* Backward of y = act(gamma * (x - mean) * rstd + beta (+ residual)):  dgamma[c], dbeta[c], dx: f32[n][C] (row stride lddx).
+ * y_mask (may be NULL; row stride ldm): the forward's OUTPUT when act is ReLU -- dy counts only where y_mask > 0.
+ * dres (may be NULL; row stride lddr): the gradient of the residual (= the masked dy). */
+int cg3d_bn_train_backward(const float* x, int ldx, const float* dy, int ldy, const float* y_mask, int ldm, long long n, int C,
+                           const float* mean, const float* rstd, const float* gamma, float* workspace, float* dx, int lddx,
+                           float* dres, int lddr, float* dgamma, float* dbeta, void* stream);
+
+/* Backward of cg3d_interp_trilinear when the query rows are ALL rows of a coordinate map of stride tq (tq divides ts), in
+ * that map's row order (true for every call site of the backbone): dF[r] = sum over query voxels q at c_r + d,
+ * d in (-ts, ts)^3, of prod_axis(1 - |d| / ts) * dOut[q].  src_coords: i32[n_src][4] rows of the stride-ts source map;
+ * (qkeys, qvals, qcapacity): the query map's hash table; dOut: f32[nq][C]; dF: f32[n_src][C] (written, not added to). */
+int cg3d_interp_trilinear_backward(const int* src_coords, int n_src, int ts, const unsigned long long* qkeys, const int* qvals,
+                                   int qcapacity, int tq, const float* dOut, int C, float* dF, void* stream);
+
+/* Backward of cg3d_segment_mean with ref == NULL: dIn[p] = dOut[inverse[p]] / counts[inverse[p]] (row stride ldi). */
+int cg3d_segment_mean_backward(const float* dOut, const int* inverse, const float* counts, long long n, int C, float* dIn,
+                               int ldi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,3 +117,116 @@ def test_wgrad_column_ranges_relu_and_empty(lib):
         _, want = Bk.conv_backward(torch.relu(ox.F).double(), Z, masked, dY.double())
         _close(A.wgrad(x.F, nbr, dY.to(DEV), 27, in_act="relu", cols=(c0, c1)), want, 1e-5)
     assert A.wgrad(x.F, nbr, dY.to(DEV), 27, cols=(5, 5)).abs().max().item() == 0
+
+
+# ---- training-mode BatchNorm, interpolation / quantise-average backward (csrc/train_bwd.cu) -----------------------
+@pytest.mark.parametrize("n,C", [(5000, 64), (300, 7), (70000, 128), (1, 32), (257, 33)])
+def test_bn_train_forward_backward_vs_oracle(lib, n, C):
+    from cagroup3d_b200 import autograd as A
+    g = torch.Generator().manual_seed(n + C)
+    X = torch.randn((n, C), generator=g) * 3 + torch.randn((C,), generator=g) * 5
+    gamma, beta = torch.rand((C,), generator=g) + 0.5, torch.randn((C,), generator=g)
+    dY = torch.randn((n, C), generator=g)
+    bn = torch.nn.BatchNorm1d(C).double()
+    bn.weight.data, bn.bias.data = gamma.double(), beta.double()
+    Xd = X.double().requires_grad_(True)
+    rm, rv = torch.zeros((C,), device=DEV), torch.ones((C,), device=DEV)
+    Xg = X.to(DEV).requires_grad_(True)
+    gg, bg = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    if n == 1:                                   # torch refuses a single row in training mode; the statistics are defined
+        Y = A.batch_norm_train(Xg, gg, bg, rm, rv)          # x - mean = 0, rstd = 1 / sqrt(eps): y = beta up to fp32 rounding of
+        assert torch.allclose(Y.detach().cpu(), beta[None, :], atol=2e-2)      # x * scale - mean * scale at scale ~ 316
+        assert torch.allclose(rm.cpu(), 0.1 * X[0], rtol=1e-6) and torch.isfinite(rv).all()
+        return
+    want = bn(Xd)
+    (want * dY.double()).sum().backward()
+    Y = A.batch_norm_train(Xg, gg, bg, rm, rv)
+    _close(Y.detach(), want.detach(), 1e-5)
+    _close(rm, bn.running_mean, 1e-5)
+    _close(rv, bn.running_var, 1e-5)
+    Y.backward(dY.to(DEV))
+    torch.cuda.synchronize()
+    dF, dg, db = Bk.batchnorm_train_backward(X.double(), gamma.double(), dY.double())
+    assert torch.allclose(dF, Xd.grad, rtol=1e-9, atol=1e-12)
+    _close(Xg.grad, dF, 2e-5)
+    _close(gg.grad, dg, 2e-5)
+    _close(bg.grad, db, 2e-5)
+    # the same call twice: the same bits (chunk partials added in order, no atomics)
+    Y2 = A.batch_norm_train(Xg.detach(), gg.detach(), bg.detach())
+    assert torch.equal(Y2, Y.detach())
+
+
+def test_bn_train_residual_relu_backward(lib):
+    """y = relu(bn(x) + residual) (BasicBlock / Bottleneck tail, biresnet.py:45-49,98-102): gradients of x, gamma, beta
+    and the residual against torch autograd in fp64."""
+    from cagroup3d_b200 import autograd as A
+    n, C = 3000, 64
+    g = torch.Generator().manual_seed(5)
+    X, R = torch.randn((n, C), generator=g) * 2 + 1, torch.randn((n, C), generator=g)
+    gamma, beta, dY = torch.rand((C,), generator=g) + 0.5, torch.randn((C,), generator=g) * 0.3, torch.randn((n, C), generator=g)
+    Xd, Rd = X.double().requires_grad_(True), R.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    want = torch.relu(torch.nn.functional.batch_norm(Xd, None, None, gd, bd, training=True) + Rd)
+    (want * dY.double()).sum().backward()
+    Xg, Rg = X.to(DEV).requires_grad_(True), R.to(DEV).requires_grad_(True)
+    gg, bg = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    Y = A.batch_norm_train(Xg, gg, bg, act="relu", residual=Rg)
+    # values within 1e-5 of 0 may land on either side of the ReLU in fp32: leave them out of the gradient comparison
+    safe = (want.detach().abs() > 1e-4) | (want.detach() == 0) & ((torch.nn.functional.batch_norm(
+        X.double(), None, None, gamma.double(), beta.double(), training=True) + R.double()) < -1e-4)
+    assert safe.float().mean() > 0.999
+    _close(Y.detach(), want.detach(), 1e-5)
+    Y.backward(dY.to(DEV))
+    torch.cuda.synchronize()
+    assert ((Rg.grad.cpu().double() - Rd.grad).abs() * safe).max().item() <= 1e-6
+    if bool(safe.all()):
+        _close(Xg.grad, Xd.grad, 5e-5)
+        _close(gg.grad, gd.grad, 5e-5)
+        _close(bg.grad, bd.grad, 5e-5)
+
+
+@pytest.mark.parametrize("ts,tq,C", [(2, 1, 64), (4, 1, 128), (8, 2, 40), (8, 1, 300)])
+def test_interp_backward_vs_oracle(lib, ts, tq, C):
+    """features_at_coordinates backward as a gather over the query map == the oracle's scatter over the 8 corners."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    rng = np.random.default_rng(ts * 10 + tq)
+    q = np.unique(np.concatenate([rng.integers(0, 2, (4000, 1)), rng.integers(-40, 40, (4000, 3)) * tq], 1), axis=0)
+    src = q.copy()
+    src[:, 1:] = np.floor_divide(src[:, 1:], ts) * ts
+    src = np.unique(src, axis=0)
+    src = src[rng.random(len(src)) < 0.7]                 # some corners are absent
+    extra = src[:50].copy()
+    extra[:, 1:] += 1000 * ts                             # source voxels no query touches: zero gradient
+    src = np.concatenate([src, extra])
+    qm = me.CoordMap(q.astype(np.int64), tq)
+    sm = me.CoordMap(src.astype(np.int64), ts)
+    Fs = torch.from_numpy(rng.standard_normal((len(src), C))).double().requires_grad_(True)
+    want = me.features_at(me.SparseTensor(Fs, sm, me.Manager()), q.astype(np.int64))
+    dOut = torch.from_numpy(rng.standard_normal(tuple(want.shape)))
+    (want * dOut).sum().backward()
+    rows, w = Bk.interp_corners(sm, q.astype(np.int64))
+    assert torch.allclose(Bk.interp_backward(dOut, rows, w, len(src)), Fs.grad, rtol=1e-12, atol=1e-12)
+    mgr = S.Manager()
+    qmap = S.build_map(torch.from_numpy(q.astype(np.int32)).to(DEV), tq, mgr)
+    smap = S.build_map(torch.from_numpy(src.astype(np.int32)).to(DEV), ts, mgr)
+    Fg = Fs.detach().float().to(DEV).requires_grad_(True)
+    base = torch.randn((len(q), C), generator=torch.Generator().manual_seed(1)).to(DEV).requires_grad_(True)
+    y = A.interp(S.SparseTensor(Fg, smap, mgr), qmap, base)
+    _close(y.detach() - base.detach(), want.detach(), 1e-5)
+    y.backward(dOut.float().to(DEV))
+    torch.cuda.synchronize()
+    _close(Fg.grad, Fs.grad, 1e-5)
+    assert torch.equal(base.grad.cpu(), dOut.float())
+    assert Fg.grad[-50:].abs().max().item() == 0
+
+
+def test_segment_mean_backward_vs_oracle(lib):
+    from cagroup3d_b200 import autograd as A
+    rng = np.random.default_rng(3)
+    n, U, C = 20000, 3000, 64
+    inv = rng.integers(0, U, n)
+    inv[:U] = np.arange(U)
+    dOut = torch.from_numpy(rng.standard_normal((U, C))).float()
+    counts = torch.bincount(torch.from_numpy(inv), minlength=U).float()
+    got = A.segment_mean_backward(dOut.to(DEV), torch.from_numpy(inv.astype(np.int32)).to(DEV), counts.to(DEV))
+    _close(got, Bk.segment_mean_backward(dOut.double(), inv, n), 1e-6)
