@@ -190,3 +190,58 @@ def segment_mean_backward(dOut: torch.Tensor, inverse: torch.Tensor, counts: tor
     dIn = torch.empty((n, C), dtype=torch.float32, device=dOut.device)
     S._call("cg3d_segment_mean_backward", dOut, inverse, counts, n, C, dIn, C)
     return dIn
+
+
+# ---- activations / average pooling ------------------------------------------------------------------------------
+class ActFunction(torch.autograd.Function):
+    """MinkowskiReLU / MinkowskiELU on a feature matrix; the backward reads the forward's output."""
+
+    @staticmethod
+    def forward(ctx, X, act):
+        Y = S.affine_act(X.detach(), act=act)
+        ctx.save_for_backward(Y)
+        ctx.act = act
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        (Y,) = ctx.saved_tensors
+        dY = dY.contiguous()
+        dX = torch.empty_like(Y)
+        S._call("cg3d_act_backward", dY, dY.stride(0), Y, Y.stride(0), Y.shape[0], Y.shape[1], S.ACT[ctx.act], dX, dX.stride(0))
+        return dX, None
+
+
+def relu(F: torch.Tensor) -> torch.Tensor:
+    return ActFunction.apply(F, "relu")
+
+
+def elu(F: torch.Tensor) -> torch.Tensor:
+    return ActFunction.apply(F, "elu")
+
+
+class AvgPoolFunction(torch.autograd.Function):
+    """MinkowskiAvgPooling (DAPPM, biresnet.py:109-127) over the all-pairs window test of cg3d_avgpool_window."""
+
+    @staticmethod
+    def forward(ctx, Fin, in_map, out_map, half):
+        ctx.in_map, ctx.out_map, ctx.half = in_map, out_map, half
+        C = Fin.shape[1]
+        out = torch.empty((out_map.n, C), dtype=torch.float32, device=Fin.device)
+        S._call("cg3d_avgpool_window", out_map.coords, out_map.n, in_map.coords, in_map.n, half, Fin.detach().contiguous(), C, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        dOut = dOut.contiguous()
+        im, om = ctx.in_map, ctx.out_map
+        C = dOut.shape[1]
+        dIn = torch.empty((im.n, C), dtype=torch.float32, device=dOut.device)
+        cnt = torch.empty((max(om.n, 1),), dtype=torch.float32, device=dOut.device)
+        S._call("cg3d_avgpool_window_backward", om.coords, om.n, im.coords, im.n, ctx.half, dOut, C, cnt, dIn)
+        return dIn, None, None, None
+
+
+def avg_pool(x: S.SparseTensor, k: int, stride: int) -> S.SparseTensor:
+    omap = S.strided_map(x.cmap, x.mgr, stride)
+    return S.SparseTensor(AvgPoolFunction.apply(x.F, x.cmap, omap, (k // 2) * x.cmap.stride), omap, x.mgr)

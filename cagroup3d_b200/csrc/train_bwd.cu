@@ -9,6 +9,8 @@
 //   cg3d_bn_train_backward   dgamma, dbeta, dx (and the gradient of a residual added before the ReLU)
 //   cg3d_interp_trilinear_backward   dF[r] = sum over query voxels q around r of w(q, r) * dOut[q]  (gather form)
 //   cg3d_segment_mean_backward       dIn[p] = dOut[inverse[p]] / count[inverse[p]]
+//   cg3d_avgpool_window_backward     dIn[i] = sum over outputs o whose window holds i of dOut[o] / count[o]  (DAPPM pools)
+//   cg3d_act_backward                ReLU / ELU backward through the forward's output
 //
 // All HBM-bound streaming reductions.  Nothing uses float atomics: row chunks write partial results that are combined
 // in chunk order, and the interpolation backward is a gather over the query map's hash table (a source voxel asks for
@@ -226,6 +228,69 @@ __global__ void segment_mean_bwd_kernel(const float* __restrict__ dOut, const in
     }
 }
 
+
+// out[o, ch] = sum over candidate rows j of the same batch with |c_j - c_o| <= half on every axis of F[j, ch] / rowdiv[j]
+// (F == nullptr: 1; rowdiv == nullptr: 1).  One CTA per centre voxel, all-pairs against the (tiny) candidate set, matches
+// compacted in row order so the sum has a fixed order.  The average pooling's window relation is symmetric, so this one
+// kernel gives both the window counts (centres = outputs, F = 1) and dIn (centres = inputs, F = dOut, rowdiv = counts).
+__global__ void window_sum_kernel(const int4* __restrict__ oc, const int4* __restrict__ ic, int n_in, int half,
+                                  const float* __restrict__ F, int C, const float* __restrict__ rowdiv, float* __restrict__ out) {
+    extern __shared__ int match[];
+    __shared__ int n_match;
+    __shared__ int warp_cnt[32];
+    const int4 o = oc[blockIdx.x];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) n_match = 0;
+    __syncthreads();
+    for (int base = 0; base < n_in; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool m = false;
+        if (i < n_in) {
+            const int4 c = __ldg(ic + i);
+            m = c.x == o.x && abs(c.y - o.y) <= half && abs(c.z - o.z) <= half && abs(c.w - o.w) <= half;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, m);
+        if (lane == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int off = n_match;
+        for (int j = 0; j < w; ++j) off += warp_cnt[j];
+        if (m) match[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int j = 0; j < nw; ++j) tot += warp_cnt[j];
+            n_match += tot;
+        }
+        __syncthreads();
+    }
+    const int nm = n_match;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < nm; ++j) {
+            const int r = match[j];
+            float v = F ? __ldg(F + (size_t)r * C + ch) : 1.f;
+            if (rowdiv) v = v / __ldg(rowdiv + r);
+            acc += v;
+        }
+        out[(size_t)blockIdx.x * C + ch] = acc;
+    }
+}
+
+// dx = dy * act'(x) written through the forward's OUTPUT y: ReLU: y > 0; ELU (alpha = 1): y > 0 ? 1 : y + 1
+__global__ void act_backward_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ y, int ldyy, long long n,
+                                    int C, int act, float* __restrict__ dx, int lddx) {
+    const long long total = n * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / C;
+        const int c = (int)(e % C);
+        const float g = __ldg(dy + (size_t)r * ldy + c), v = __ldg(y + (size_t)r * ldyy + c);
+        float d = g;
+        if (act == CG3D_ACT_RELU) d = v > 0.f ? g : 0.f;
+        else if (act == CG3D_ACT_ELU) d = v > 0.f ? g : g * (v + 1.f);
+        dx[(size_t)r * lddx + c] = d;
+    }
+}
+
 inline int flat_blocks(long long work, int nt) {
     long long b = (work + nt - 1) / nt;
     const long long cap = 148LL * 16;
@@ -288,6 +353,31 @@ int cg3d_segment_mean_backward(const float* dOut, const int* inverse, const floa
                                int ldi, void* stream) {
     if (n == 0 || C == 0) return 0;
     segment_mean_bwd_kernel<<<flat_blocks(n * C, 256), 256, 0, (cudaStream_t)stream>>>(dOut, inverse, counts, n, C, dIn, ldi);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_avgpool_window_backward(const int* out_coords, int n_out, const int* in_coords, int n_in, int half, const float* dOut,
+                                 int C, float* counts, float* dIn, void* stream) {
+    if (n_in == 0 || C == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out == 0) return (int)cudaMemsetAsync(dIn, 0, sizeof(float) * (size_t)n_in * C, st);
+    const size_t smem = sizeof(int) * (size_t)(n_in > n_out ? n_in : n_out);
+    if (smem > 200 * 1024) return -2;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(window_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    window_sum_kernel<<<n_out, 256, smem, st>>>((const int4*)out_coords, (const int4*)in_coords, n_in, half, nullptr, 1, nullptr,
+                                                counts);
+    CG3D_LAUNCH_CHECK();
+    window_sum_kernel<<<n_in, 256, smem, st>>>((const int4*)in_coords, (const int4*)out_coords, n_out, half, dOut, C, counts, dIn);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_act_backward(const float* dy, int ldy, const float* y, int ldyy, long long n, int C, int act, float* dx, int lddx,
+                      void* stream) {
+    if (n == 0 || C == 0) return 0;
+    if (act != CG3D_ACT_NONE && act != CG3D_ACT_RELU && act != CG3D_ACT_ELU) return -1;
+    act_backward_kernel<<<flat_blocks(n * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, ldy, y, ldyy, n, C, act, dx, lddx);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

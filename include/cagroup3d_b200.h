@@ -379,6 +379,16 @@ int cg3d_interp_trilinear_backward(const int* src_coords, int n_src, int ts, con
 int cg3d_segment_mean_backward(const float* dOut, const int* inverse, const float* counts, long long n, int C, float* dIn,
                                int ldi, void* stream);
 
+/* Backward of cg3d_avgpool_window: dIn[i] = sum over output rows o with |c_i - c_o| <= half (same batch) of
+ * dOut[o] / count[o], count[o] = the inputs in o's window (recomputed into `counts`, n_out floats).  dIn: f32[n_in][C]. */
+int cg3d_avgpool_window_backward(const int* out_coords, int n_out, const int* in_coords, int n_in, int half, const float* dOut,
+                                 int C, float* counts, float* dIn, void* stream);
+
+/* dx = dy * act'(.) evaluated through the forward's OUTPUT y (MinkowskiReLU / MinkowskiELU backward): ReLU: y > 0;
+ * ELU (alpha 1): y > 0 ? 1 : y + 1; act 0: copy.  Row strides ldy / ldyy / lddx. */
+int cg3d_act_backward(const float* dy, int ldy, const float* y, int ldyy, long long n, int C, int act, float* dx, int lddx,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

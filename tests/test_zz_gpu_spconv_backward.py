@@ -230,3 +230,82 @@ def test_segment_mean_backward_vs_oracle(lib):
     counts = torch.bincount(torch.from_numpy(inv), minlength=U).float()
     got = A.segment_mean_backward(dOut.to(DEV), torch.from_numpy(inv.astype(np.int32)).to(DEV), counts.to(DEV))
     _close(got, Bk.segment_mean_backward(dOut.double(), inv, n), 1e-6)
+
+
+def test_activation_and_avgpool_backward(lib):
+    """cg3d_act_backward (ReLU / ELU through the output) and the DAPPM average pool's backward against autograd through
+    the oracle's pooling (all-pairs window test, A10)."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    g = torch.Generator().manual_seed(2)
+    X, dY = torch.randn((777, 40), generator=g), torch.randn((777, 40), generator=g)
+    for name, fn in (("relu", torch.relu), ("elu", torch.nn.functional.elu)):
+        Xd = X.double().requires_grad_(True)
+        (fn(Xd) * dY.double()).sum().backward()
+        Xg = X.to(DEV).requires_grad_(True)
+        Y = A.ActFunction.apply(Xg, name)
+        Y.backward(dY.to(DEV))
+        _close(Y.detach(), fn(X.double()), 1e-6)
+        _close(Xg.grad, Xd.grad, 1e-6)
+    ox = oracle_tensor(35, 24, n=3000)
+    coarse = me.conv(ox, torch.zeros(27, 24, 8), 3, 2)
+    for _ in range(3):
+        coarse = me.conv(coarse, torch.zeros(27, 8, 8), 3, 2)            # a stride-16 map of a few dozen voxels
+    for k, s in ((5, 2), (9, 4)):
+        Fd = torch.randn((len(coarse.C), 16), generator=g).double().requires_grad_(True)
+        want = me.avg_pool(coarse.with_F(Fd), k, s)
+        dO = torch.randn(tuple(want.F.shape), generator=g)
+        (want.F * dO.double()).sum().backward()
+        x = to_gpu_sparse(coarse.C, Fd.detach(), coarse.cmap.stride, strided={want.cmap.stride: want.C})
+        Fg = x.F.clone().requires_grad_(True)
+        y = A.avg_pool(x.with_F(Fg), k, s)
+        assert np.array_equal(y.C.cpu().numpy(), want.C)
+        _close(y.F.detach(), want.F.detach(), 1e-6)
+        y.F.backward(dO.to(DEV))
+        _close(Fg.grad, Fd.grad, 1e-6)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_backbone_training_forward_backward_vs_oracle(lib, impl):
+    """BiResNet under model.train() (batch-statistics BatchNorm): output features and the gradient of EVERY backbone
+    parameter (56 kernels, 56 x 2 BatchNorm affine vectors) against autograd through the fp64 oracle.  The fp32
+    oracle's own distance from fp64 on this case is 2.5e-5 (features) / <= 1e-4 (relative, per parameter)."""
+    from cagroup3d_b200 import backbone_train as BT, model_init, synthetic
+    from cagroup3d_b200.detector import voxelize
+    from oracle import cagroup3d_oracle as O
+    B = 2
+    batch = synthetic.make_batch(B, target_voxels=1500, config=11)
+    model = model_init.seeded_model(18, False, seed=2)
+    pts = torch.from_numpy(batch["points"])
+    orc = O.Oracle(model.state_dict(), O.default_cfg(18, False), dtype=torch.float64)
+    names = [k for k in orc.p if k.startswith("backbone_3d.") and k.endswith(("kernel", "bn.weight", "bn.bias"))]
+    for k in names:
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    orc.train_bn = True
+    res = orc.forward(pts, B, stages="backbone")
+    dY = torch.randn(tuple(res["bb_feats"].shape), generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    (res["bb_feats"] * dY).sum().backward()
+
+    bb = model.backbone_3d.to(DEV).train()
+    rv0 = bb.conv1[1].bn.running_var.clone()
+    p = pts.clone()
+    p[:, -3:] /= 255.
+    out = BT.run_train(bb, voxelize(p.to(DEV).contiguous(), 0.02), impl=impl)
+    assert np.array_equal(out.C.cpu().numpy(), res["bb_coords"])
+    _close(out.F.detach(), res["bb_feats"].detach(), 1e-3)
+    out.F.backward(dY.float().to(DEV))
+    torch.cuda.synchronize()
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    worst = (0.0, None)
+    for k in names:
+        want = orc.p[k].grad
+        got = params[k].grad
+        assert got is not None, k
+        err = float((got.double().cpu().reshape(want.shape) - want).norm())
+        rel = err / (float(want.norm()) + 1e-5 * G)
+        worst = max(worst, (rel, k))
+    print("worst relative gradient error", worst)
+    # bounds to be tightened after the first run on hardware: the split-bf16 products of the tensor-core convs carry
+    # ~2^-17 relative rounding (~100 x fp32), and the BatchNorm chain amplifies rounding ~25 x (median) .. ~1500 x (worst)
+    assert worst[0] <= (5e-3 if impl == "simt" else 5e-2), worst
+    assert not torch.equal(bb.conv1[1].bn.running_var, rv0) and int(bb.conv1[1].bn.num_batches_tracked) == 1
