@@ -1,0 +1,96 @@
+"""First-stage training targets and the focal loss on the C ABI (host-side mirror of
+pcdet/models/dense_heads/target_assigner/cagroup3d_assigner.py and pcdet/utils/loss_utils.py:FocalLoss).
+
+Same class / method names, argument meaning and return values as the reference, so cagroup_head.py:400-470
+(get_targets / _loss_single) can call them unchanged:
+
+    CAGroup3DAssigner(cfg).assign(points_list, gt_bboxes, gt_labels) -> (centerness_targets, gt_bbox_targets, labels)
+    CAGroup3DAssigner.assign_semantic(points, gt_bboxes, gt_labels, n_classes) -> (labels, ins_labels)
+    FocalLoss(gamma, alpha, loss_weight)(pred, target, avg_factor=...) -> scalar (differentiable)
+
+The reference builds dense (n_points x n_boxes x 7) tensors per class in an 18-iteration Python loop with a torch.topk
+per class; here one sample is two kernel launches (cg3d_assign).  No torch / CPU fallback: CUDA tensors only.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from . import sparse as S
+
+
+class CAGroup3DAssigner:
+    def __init__(self, cfg):
+        g = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
+        self.limit, self.topk, self.n_scales = g("LIMIT", 27), g("TOPK", 18), g("N_SCALES", 4)
+        self.return_ins_label = g("RETURN_INS_LABEL", True)
+
+    def assign(self, points_list: Sequence[torch.Tensor], gt_bboxes_ori: torch.Tensor, gt_labels_ori: torch.Tensor,
+               return_index: bool = False):
+        """cagroup3d_assigner.py:62-133."""
+        dev = gt_bboxes_ori.device
+        assert dev.type == "cuda", "the assigner runs on the CUDA path only"
+        for c, p in enumerate(points_list):
+            assert len(p) > 0, "empty points in class {}".format(c)
+        offs = [0]
+        for p in points_list:
+            offs.append(offs[-1] + len(p))
+        locs = torch.cat([p[:, :3].float() for p in points_list]).contiguous()
+        n, m = locs.shape[0], gt_bboxes_ori.shape[0]
+        boxes = gt_bboxes_ori[:, :7].float().contiguous()
+        labels_in = gt_labels_ori.to(torch.int32).contiguous()
+        offsets = torch.tensor(offs, dtype=torch.int32, device=dev)
+        kth = torch.empty((max(m, 1),), dtype=torch.float32, device=dev)
+        ctr = torch.empty((n,), dtype=torch.float32, device=dev)
+        box_t = torch.empty((n, 7), dtype=torch.float32, device=dev)
+        labels = torch.empty((n,), dtype=torch.int64, device=dev)
+        idx = torch.empty((n,), dtype=torch.int32, device=dev) if return_index else None
+        S._call("cg3d_assign", locs, n, offsets, len(points_list), boxes, labels_in, m, int(self.topk), kth, ctr, box_t, labels, idx)
+        return (ctr, box_t, labels, idx) if return_index else (ctr, box_t, labels)
+
+    @classmethod
+    def assign_semantic(cls, points: torch.Tensor, gt_bboxes: torch.Tensor, gt_labels: torch.Tensor, n_classes: int = 0):
+        """cagroup3d_assigner.py:135-158."""
+        assert points.is_cuda
+        pts = points[:, :3].float().contiguous()
+        n, m = pts.shape[0], gt_bboxes.shape[0]
+        labels = torch.empty((n,), dtype=torch.int64, device=pts.device)
+        ins = torch.empty((n,), dtype=torch.int64, device=pts.device)
+        S._call("cg3d_assign_semantic", pts, n, gt_bboxes[:, :7].float().contiguous(), gt_labels.to(torch.int32).contiguous(), m,
+                labels, ins)
+        return labels, ins
+
+
+class _FocalLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, labels, gamma, alpha, avg_factor):
+        p = pred.detach().contiguous()
+        n, C = p.shape
+        loss = torch.empty((1,), dtype=torch.float32, device=p.device)
+        grad = torch.empty_like(p)
+        ws = torch.empty((_lib.host("cg3d_focal_loss_workspace", n, C),), dtype=torch.float32, device=p.device)
+        S._call("cg3d_focal_loss", p, labels.contiguous(), n, C, float(gamma), float(alpha), float(avg_factor), ws, loss, grad)
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dL):
+        (grad,) = ctx.saved_tensors
+        return grad * dL, None, None, None, None
+
+
+class FocalLoss(torch.nn.Module):
+    """loss_utils.py:1012-1032 with use_sigmoid=True, reduction 'mean' and an avg_factor (the only way the head calls it):
+    target holds class indices, any value outside [0, C) is background."""
+
+    def __init__(self, use_sigmoid=True, gamma=2.0, alpha=0.25, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        assert use_sigmoid and reduction == "mean"
+        self.gamma, self.alpha, self.loss_weight = gamma, alpha, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
+        assert weight is None and reduction_override is None and pred.is_cuda and pred.dtype == torch.float32
+        af = float(avg_factor) if avg_factor is not None else float(pred.shape[0] * pred.shape[1])
+        return self.loss_weight * _FocalLossFunction.apply(pred, target.long(), self.gamma, self.alpha, af)

@@ -389,6 +389,29 @@ int cg3d_avgpool_window_backward(const int* out_coords, int n_out, const int* in
 int cg3d_act_backward(const float* dy, int ldy, const float* y, int ldyy, long long n, int C, int act, float* dx, int lddx,
                       void* stream);
 
+/* ---- first-stage training targets and the focal loss (cagroup_head.py:400-555 _loss_single / get_targets) ----------- */
+
+/* CAGroup3DAssigner.assign (cagroup3d_assigner.py:62-133) for ONE sample.  locs: f32[n][3], the locations of all class
+ * maps concatenated in class order; cls_offsets: i32[n_cls + 1], class c owns rows [cls_offsets[c], cls_offsets[c+1]);
+ * gt_boxes: f32[m][7] (x, y, z, dx, dy, dz, yaw); gt_labels: i32[m].  A location is positive for the smallest-volume box of
+ * its class that contains it and for which its centerness is above the box's (topk+1)-th best (first box index on ties).
+ * Outputs: kth f32[m] (scratch: the per-box thresholds), centerness f32[n], box_targets f32[n][7], labels i64[n] (-1 =
+ * negative), box_index i32[n] (may be NULL; index into gt_boxes of the chosen box, -1 when the class has no box). */
+int cg3d_assign(const float* locs, int n, const int* cls_offsets, int n_cls, const float* gt_boxes, const int* gt_labels, int m,
+                int topk, float* kth, float* centerness, float* box_targets, long long* labels, int* box_index, void* stream);
+
+/* CAGroup3DAssigner.assign_semantic (cagroup3d_assigner.py:135-158): label of the smallest box containing the point (-1
+ * outside all boxes) and instance label (box index + 1, 0 outside). */
+int cg3d_assign_semantic(const float* points, int n, const float* gt_boxes, const int* gt_labels, int m, long long* labels,
+                         long long* ins_labels, void* stream);
+
+/* FocalLoss(use_sigmoid=True) (loss_utils.py:917-961,1012-1032): loss[0] = sum over [n][C] of the sigmoid focal loss /
+ * avg_factor with labels i64[n] in [0, C) or negative / >= C for background; grad (may be NULL): f32[n][C] = d loss / d pred.
+ * workspace: cg3d_focal_loss_workspace(n, C) floats (chunk partial sums, added in order). */
+int cg3d_focal_loss_workspace(long long n, int C);
+int cg3d_focal_loss(const float* pred, const long long* labels, long long n, int C, float gamma, float alpha, float avg_factor,
+                    float* workspace, float* loss, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,69 @@ def test_backbone_training_forward_backward_vs_oracle(lib, impl):
     # ~2^-17 relative rounding (~100 x fp32), and the BatchNorm chain amplifies rounding ~25 x (median) .. ~1500 x (worst)
     assert worst[0] <= (5e-3 if impl == "simt" else 5e-2), worst
     assert not torch.equal(bb.conv1[1].bn.running_var, rv0) and int(bb.conv1[1].bn.num_batches_tracked) == 1
+
+
+# ---- first-stage training targets and focal loss (csrc/train_assign.cu) ------------------------------------------
+def _assign_case(yaw: bool):
+    g = torch.Generator().manual_seed(21 if yaw else 20)
+    ncls, m = 6, 14
+    boxes = torch.cat([(torch.rand((m, 3), generator=g) - 0.5) * 4, torch.rand((m, 3), generator=g) * 1.5 + 0.3,
+                       ((torch.rand((m, 1), generator=g) - 0.5) * 3) if yaw else torch.zeros((m, 1))], 1)
+    labels = torch.randint(0, ncls - 1, (m,), generator=g)                       # the last class has no box
+    boxes[3] = boxes[2]                                                           # equal volumes: the first index wins
+    labels[3] = labels[2]
+    pts = [(torch.rand((int(n), 3), generator=g) - 0.5) * 5 for n in torch.randint(40, 1500, (ncls,), generator=g)]
+    for c in range(ncls - 1):
+        b = boxes[labels == c]
+        if len(b):
+            k = len(pts[c]) // 2
+            pts[c][:k] = b[torch.randint(0, len(b), (k,), generator=g), :3] + (torch.rand((k, 3), generator=g) - 0.5) * 0.8
+    pts[0][:30] = pts[0][30:60]                                                  # duplicated locations: tied centerness
+    return pts, boxes, labels, ncls
+
+
+@pytest.mark.parametrize("yaw", [False, True])
+def test_assigner_vs_oracle(lib, yaw):
+    """cg3d_assign / cg3d_assign_semantic against oracle/train_oracle.py (pinned to the reference's CAGroup3DAssigner by
+    tests/golden/train_parts.npz).  yaw = 0: labels, boxes and the positives' centerness exact up to the oracle's own
+    product order (1e-6); yaw != 0: a location within one ulp of a box face or of the top-k threshold may differ."""
+    from cagroup3d_b200.train_targets import CAGroup3DAssigner
+    from oracle import train_oracle as T
+    pts, boxes, labels, ncls = _assign_case(yaw)
+    for topk in (18, 3):
+        ct, bt, lb = T.assign(pts, boxes, labels, topk)
+        a = CAGroup3DAssigner({"TOPK": topk})
+        gc, gb, gl, gi = a.assign([p.to(DEV) for p in pts], boxes.to(DEV), labels.to(DEV), return_index=True)
+        gl_c, lb_n = gl.cpu(), lb
+        mism = (gl_c != lb_n).float().mean().item()
+        assert mism <= (0.0 if not yaw else 2e-3), mism
+        same = gl_c == lb_n
+        pos = same & (lb_n >= 0)
+        assert pos.sum() > 20
+        assert torch.equal(gb.cpu()[pos], bt[pos])
+        assert (gc.cpu()[pos] - ct[pos]).abs().max().item() <= 1e-5
+        nobox = torch.cat([torch.full((len(p),), float(bool((labels == c).any()))) for c, p in enumerate(pts)]) == 0
+        assert (gl_c[nobox] == -1).all() and gb.cpu()[nobox].abs().max().item() == 0 and (gi.cpu()[nobox] == -1).all()
+    allp = torch.cat(pts)
+    sl, il = T.assign_semantic(allp, boxes, labels)
+    gs, gi2 = CAGroup3DAssigner.assign_semantic(allp.to(DEV), boxes.to(DEV), labels.to(DEV), ncls)
+    bad = ((gs.cpu() != sl) | (gi2.cpu() != il)).float().mean().item()
+    assert bad <= (0.0 if not yaw else 2e-3), bad
+
+
+def test_focal_loss_and_gradient_vs_oracle(lib):
+    from cagroup3d_b200.train_targets import FocalLoss
+    from oracle import train_oracle as T
+    g = torch.Generator().manual_seed(6)
+    for n, C in ((5000, 18), (37, 10), (1, 3)):
+        pred = (torch.randn((n, C), generator=g) * 3)
+        labels = torch.randint(-1, C, (n,), generator=g)
+        avg = max(float((labels >= 0).sum()), 1.0)
+        pd = pred.double().requires_grad_(True)
+        want = T.focal_loss(pd, labels, avg)
+        want.backward()
+        pg = pred.to(DEV).requires_grad_(True)
+        got = FocalLoss()(pg, labels.to(DEV), avg_factor=avg)
+        (got * 2.0).backward()
+        assert abs(got.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+        _close(pg.grad, 2.0 * pd.grad, 1e-5)
