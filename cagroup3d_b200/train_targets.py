@@ -94,3 +94,75 @@ class FocalLoss(torch.nn.Module):
         assert weight is None and reduction_override is None and pred.is_cuda and pred.dtype == torch.float32
         af = float(avg_factor) if avg_factor is not None else float(pred.shape[0] * pred.shape[1])
         return self.loss_weight * _FocalLossFunction.apply(pred, target.long(), self.gamma, self.alpha, af)
+
+
+class _RowLossFunction(torch.autograd.Function):
+    """loss (1 float) and d loss / d pred from one C-ABI call; `fn(pred, loss, grad, ws)` issues it."""
+
+    @staticmethod
+    def forward(ctx, pred, fn, rows):
+        p = pred.detach().contiguous()
+        loss = torch.empty((1,), dtype=torch.float32, device=p.device)
+        grad = torch.zeros_like(p)
+        ws = torch.empty((_lib.host("cg3d_loss_workspace", int(rows)),), dtype=torch.float32, device=p.device)
+        fn(p, loss, grad, ws)
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dL):
+        (grad,) = ctx.saved_tensors
+        return grad * dL, None, None
+
+
+class CrossEntropy(torch.nn.Module):
+    """loss_utils.py:849-893 with use_sigmoid=True as the head uses it for the centerness (pred, target: (P, 1))."""
+
+    def __init__(self, use_sigmoid=True, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        assert use_sigmoid and reduction == "mean"
+        self.loss_weight = loss_weight
+
+    def forward(self, cls_score, label, weight=None, avg_factor=None, **kw):
+        assert weight is None and cls_score.is_cuda and cls_score.shape == label.shape
+        n = cls_score.numel()
+        af = float(avg_factor) if avg_factor is not None else float(max(n, 1))
+        t = label.detach().float().contiguous()
+        fn = lambda p, loss, grad, ws: S._call("cg3d_bce_loss", p, t, n, af, ws, loss, grad)
+        return self.loss_weight * _RowLossFunction.apply(cls_score, fn, n)
+
+
+class IoU3DLoss(torch.nn.Module):
+    """iou3d_loss.py:61-98 with with_yaw=False (ScanNet): axis-aligned (x, y, z, dx, dy, dz) boxes."""
+
+    def __init__(self, with_yaw=False, reduction="mean", loss_weight=1.0):
+        super().__init__()
+        if with_yaw:
+            raise NotImplementedError("the rotated IoU loss (SUN RGB-D) is not on the CUDA training path yet")
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, **kw):
+        assert pred.is_cuda and weight is not None and avg_factor is not None
+        if not bool(torch.any(weight > 0)):
+            return pred.sum() * weight.sum()                      # iou3d_loss.py:75-76
+        n = pred.shape[0]
+        t, w = target.detach().float().contiguous(), weight.detach().float().contiguous()
+        fn = lambda p, loss, grad, ws: S._call("cg3d_iou_loss_aa", p, p.stride(0), t, t.stride(0), w, n, float(avg_factor), ws,
+                                               loss, grad, grad.stride(0))
+        return self.loss_weight * _RowLossFunction.apply(pred[:, :6], fn, n)
+
+
+class SmoothL1Loss(torch.nn.Module):
+    """loss_utils.py:1077-1110 with reduction='sum' and an element weight (the vote loss, cagroup_head.py:507-513)."""
+
+    def __init__(self, beta=1.0, reduction="sum", loss_weight=1.0):
+        super().__init__()
+        assert reduction == "sum"
+        self.beta, self.loss_weight = beta, loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, **kw):
+        assert pred.is_cuda and weight is not None and weight.shape == pred.shape and avg_factor is None
+        n, C = pred.shape
+        t, w = target.detach().float().contiguous(), weight.detach().float().contiguous()
+        fn = lambda p, loss, grad, ws: S._call("cg3d_smooth_l1_loss", p, t, w, n, C, float(self.beta), ws, loss, grad)
+        return self.loss_weight * _RowLossFunction.apply(pred, fn, n * C)

@@ -412,6 +412,22 @@ int cg3d_focal_loss_workspace(long long n, int C);
 int cg3d_focal_loss(const float* pred, const long long* labels, long long n, int C, float gamma, float alpha, float avg_factor,
                     float* workspace, float* loss, float* grad, void* stream);
 
+/* The other first-stage loss terms (cagroup_head.py:505-554), each with its gradient in the same pass; `workspace`:
+ * cg3d_loss_workspace(rows) floats; loss: 1 float; grad may be NULL.
+ *   bce:       CrossEntropy(use_sigmoid) (loss_utils.py:813-846) over n logits / targets in [0, 1] (target < 0: ignored),
+ *              sum / (avg_factor + fp32 eps);
+ *   iou_aa:    IoU3DLoss(with_yaw=False) (iou3d_loss.py:31-76): sum of weight * (1 - IoU) / avg_factor of axis-aligned
+ *              (x, y, z, dx, dy, dz) boxes, rows strided by ldp / ldt; grad: first 6 columns of f32[n][ldg].  The caller
+ *              skips the call when no weight is positive (the reference returns 0 then);
+ *   smooth_l1: SmoothL1Loss(beta, reduction='sum') (loss_utils.py:1042-1074) over [n][C] with an [n][C] weight. */
+int cg3d_loss_workspace(long long n);
+int cg3d_bce_loss(const float* pred, const float* target, int n, float avg_factor, float* workspace, float* loss, float* grad,
+                  void* stream);
+int cg3d_iou_loss_aa(const float* pred, int ldp, const float* target, int ldt, const float* weight, int n, float avg_factor,
+                     float* workspace, float* loss, float* grad, int ldg, void* stream);
+int cg3d_smooth_l1_loss(const float* pred, const float* target, const float* weight, long long n, int C, float beta,
+                        float* workspace, float* loss, float* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,3 +375,48 @@ def test_focal_loss_and_gradient_vs_oracle(lib):
         (got * 2.0).backward()
         assert abs(got.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
         _close(pg.grad, 2.0 * pd.grad, 1e-5)
+
+
+def test_centerness_iou_vote_losses_vs_oracle(lib):
+    """cg3d_bce_loss / cg3d_iou_loss_aa / cg3d_smooth_l1_loss behind the reference's loss-class interfaces: values and
+    gradients against the pinned oracle + autograd in fp64."""
+    from cagroup3d_b200.train_targets import CrossEntropy, IoU3DLoss, SmoothL1Loss
+    from oracle import train_oracle as T
+    g = torch.Generator().manual_seed(9)
+    P = 1500
+    tgt = torch.cat([torch.randn((P, 3), generator=g), torch.rand((P, 3), generator=g) + 0.3], 1)
+    pred = tgt + torch.randn((P, 6), generator=g) * 0.3
+    pred[:, 3:] = pred[:, 3:].abs() + 0.05
+    pred[:40, :3] += 5.0                                         # disjoint boxes: IoU 0, zero gradient through the overlap
+    w = torch.rand((P,), generator=g)
+    avg = float(w.sum())
+    pd = pred.double().requires_grad_(True)
+    want = T.axis_aligned_iou_loss(pd, tgt.double(), w.double(), avg)
+    want.backward()
+    pg = pred.to(DEV).requires_grad_(True)
+    got = IoU3DLoss(with_yaw=False)(pg, tgt.to(DEV), weight=w.to(DEV), avg_factor=avg)
+    got.backward()
+    assert abs(got.item() - want.item()) <= 1e-5
+    _close(pg.grad, pd.grad, 2e-5)
+    zero = IoU3DLoss()(pg, tgt.to(DEV), weight=torch.zeros((P,), device=DEV), avg_factor=1e-6)
+    assert zero.item() == 0
+
+    x, t = torch.randn((P, 1), generator=g) * 2, torch.rand((P, 1), generator=g)
+    xd = x.double().requires_grad_(True)
+    wb = T.bce_loss(xd, t.double(), 37.0)
+    wb.backward()
+    xg = x.to(DEV).requires_grad_(True)
+    gb = CrossEntropy(use_sigmoid=True)(xg, t.to(DEV), avg_factor=37.0)
+    gb.backward()
+    assert abs(gb.item() - wb.item()) <= 1e-5 * max(1.0, abs(wb.item()))
+    _close(xg.grad, xd.grad, 1e-6)
+
+    p, tt, ww = torch.randn((P, 3), generator=g) * 0.1, torch.randn((P, 3), generator=g) * 0.1, torch.rand((P, 3), generator=g)
+    pd2 = p.double().requires_grad_(True)
+    ws_ = T.smooth_l1_sum(pd2, tt.double(), ww.double())
+    ws_.backward()
+    pg2 = p.to(DEV).requires_grad_(True)
+    gs = SmoothL1Loss(beta=0.04, reduction="sum")(pg2, tt.to(DEV), weight=ww.to(DEV))
+    gs.backward()
+    assert abs(gs.item() - ws_.item()) <= 1e-5 * max(1.0, abs(ws_.item()))
+    _close(pg2.grad, pd2.grad, 1e-6)
