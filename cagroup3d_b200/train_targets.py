@@ -21,6 +21,12 @@ from . import _lib
 from . import sparse as S
 
 
+def _require_cuda(t: torch.Tensor) -> None:
+    """there is no CPU implementation behind these classes"""
+    if not t.is_cuda:
+        raise RuntimeError("cagroup3d_b200.train_targets runs on CUDA tensors only (no CPU / PyTorch fallback)")
+
+
 class CAGroup3DAssigner:
     def __init__(self, cfg):
         g = cfg.get if hasattr(cfg, "get") else (lambda k, d=None: getattr(cfg, k, d))
@@ -31,7 +37,7 @@ class CAGroup3DAssigner:
                return_index: bool = False):
         """cagroup3d_assigner.py:62-133."""
         dev = gt_bboxes_ori.device
-        assert dev.type == "cuda", "the assigner runs on the CUDA path only"
+        _require_cuda(gt_bboxes_ori)
         for c, p in enumerate(points_list):
             assert len(p) > 0, "empty points in class {}".format(c)
         offs = [0]
@@ -53,7 +59,7 @@ class CAGroup3DAssigner:
     @classmethod
     def assign_semantic(cls, points: torch.Tensor, gt_bboxes: torch.Tensor, gt_labels: torch.Tensor, n_classes: int = 0):
         """cagroup3d_assigner.py:135-158."""
-        assert points.is_cuda
+        _require_cuda(points)
         pts = points[:, :3].float().contiguous()
         n, m = pts.shape[0], gt_bboxes.shape[0]
         labels = torch.empty((n,), dtype=torch.int64, device=pts.device)
@@ -91,7 +97,8 @@ class FocalLoss(torch.nn.Module):
         self.gamma, self.alpha, self.loss_weight = gamma, alpha, loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None):
-        assert weight is None and reduction_override is None and pred.is_cuda and pred.dtype == torch.float32
+        _require_cuda(pred)
+        assert weight is None and reduction_override is None and pred.dtype == torch.float32
         af = float(avg_factor) if avg_factor is not None else float(pred.shape[0] * pred.shape[1])
         return self.loss_weight * _FocalLossFunction.apply(pred, target.long(), self.gamma, self.alpha, af)
 
@@ -124,7 +131,8 @@ class CrossEntropy(torch.nn.Module):
         self.loss_weight = loss_weight
 
     def forward(self, cls_score, label, weight=None, avg_factor=None, **kw):
-        assert weight is None and cls_score.is_cuda and cls_score.shape == label.shape
+        _require_cuda(cls_score)
+        assert weight is None and cls_score.shape == label.shape
         n = cls_score.numel()
         af = float(avg_factor) if avg_factor is not None else float(max(n, 1))
         t = label.detach().float().contiguous()
@@ -142,7 +150,8 @@ class IoU3DLoss(torch.nn.Module):
         self.loss_weight = loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, **kw):
-        assert pred.is_cuda and weight is not None and avg_factor is not None
+        _require_cuda(pred)
+        assert weight is not None and avg_factor is not None
         if not bool(torch.any(weight > 0)):
             return pred.sum() * weight.sum()                      # iou3d_loss.py:75-76
         n = pred.shape[0]
@@ -161,7 +170,8 @@ class SmoothL1Loss(torch.nn.Module):
         self.beta, self.loss_weight = beta, loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, **kw):
-        assert pred.is_cuda and weight is not None and weight.shape == pred.shape and avg_factor is None
+        _require_cuda(pred)
+        assert weight is not None and weight.shape == pred.shape and avg_factor is None
         n, C = pred.shape
         t, w = target.detach().float().contiguous(), weight.detach().float().contiguous()
         fn = lambda p, loss, grad, ws: S._call("cg3d_smooth_l1_loss", p, t, w, n, C, float(self.beta), ws, loss, grad)

@@ -1,0 +1,326 @@
+"""CPU emulation of the C-ABI entry points the TRAINING path calls (TEST INFRASTRUCTURE, like oracle/: the product never
+imports this).
+
+Purpose: the host side of the training path (cagroup3d_b200/autograd.py, backbone_train.py, train_targets.py) is Python
+that can only run against the CUDA library.  To check that host logic on a machine without a GPU -- argument order of every
+call, shapes, the autograd wiring (which gradient goes where, how many `None`s), the order of the layers -- `install()`
+replaces `_lib.call` by a dispatcher that binds the positional arguments to the PARAMETER NAMES parsed from
+include/cagroup3d_b200.h and runs a plain torch restatement of each entry point's documented contract on CPU tensors.  A
+call with the wrong number / order of arguments fails here exactly as it would corrupt memory on the GPU.
+
+Coordinate maps are built with the oracle (oracle/me_cpu.py): `cpu_map()` makes a `sparse.CoordMap` whose "hash table" is
+simply (sorted keys, rows), which the emulated lookups understand; `sparse.strided_map / neighbor_table /
+transpose_table` are replaced by oracle-backed versions.  What this does NOT check is the CUDA code itself -- that is
+what the `-m gpu` parity tests are for.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+import torch
+
+from oracle import backward_oracle as Bk
+from oracle import me_cpu as me
+
+_ACT = {0: lambda v: v, 1: torch.relu, 2: torch.nn.functional.elu}
+
+
+def _param_names():
+    from cagroup3d_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"\bint\s+(cg3d_\w+)\s*\(([^)]*)\)\s*;", src):
+        names = [a.strip().split()[-1].lstrip("*") for a in m.group(2).split(",") if a.strip()]
+        out[m.group(1)] = [n for n in names if n != "stream"]
+    return out
+
+
+# ---- coordinate maps ---------------------------------------------------------------------------------------------------
+_ME = {}            # id(keys tensor) -> me.CoordMap
+
+
+def cpu_map(coords: np.ndarray, stride: int, mgr):
+    from cagroup3d_b200 import sparse as S
+    cm = me.CoordMap(np.asarray(coords, np.int64), stride)
+    keys = torch.from_numpy(me.pack(cm.coords)) if len(cm) else torch.zeros((0,), dtype=torch.int64)
+    m = S.CoordMap(torch.from_numpy(cm.coords.astype(np.int32)), stride, keys, torch.arange(len(cm), dtype=torch.int32), mgr.new_uid())
+    _ME[id(keys)] = cm
+    m._me = cm
+    return m
+
+
+def _me_of_keys(keys) -> me.CoordMap:
+    return _ME[id(keys)]
+
+
+def _strided_map(x_map, mgr, s):
+    ts = x_map.stride * s
+    if ts not in mgr.by_stride:
+        c = x_map._me.coords.copy()
+        c[:, 1:] = np.floor_divide(c[:, 1:], ts) * ts
+        mgr.by_stride[ts] = cpu_map(me.unique_first(c)[0], ts, mgr)
+    return mgr.by_stride[ts]
+
+
+def _neighbor_table(in_map, out_map, k, mgr, ordered=False, **kw):
+    rules = me.kernel_map(in_map._me, out_map._me.coords, k, in_map.stride)
+    nbr = torch.from_numpy(Bk.rules_to_table(rules, max(out_map.n, 1)).astype(np.int32))
+    if not ordered:
+        return nbr
+    # a positional table in a non-trivial order, so the out_rows plumbing is exercised
+    perm = torch.from_numpy(np.random.default_rng(out_map.n + k).permutation(out_map.n).astype(np.int32))
+    return nbr[:, perm.long()].contiguous(), perm
+
+
+def _transpose_table(in_map, fine_map, k, mgr, ordered=False, **kw):
+    assert k == 2
+    f = fine_map._me.coords
+    ts_c, ts_f = in_map.stride, fine_map.stride
+    p = f.copy()
+    p[:, 1:] = np.floor_divide(f[:, 1:], ts_c) * ts_c
+    d = (f[:, 1:] - p[:, 1:]) // ts_f
+    tap = d[:, 0] + 2 * (d[:, 1] + 2 * d[:, 2])
+    rows = in_map._me.lookup(p)
+    nbr = np.full((8, len(f)), -1, np.int32)
+    nbr[tap, np.arange(len(f))] = rows
+    nbr = torch.from_numpy(nbr)
+    return (nbr, None) if ordered else nbr
+
+
+# ---- entry points ------------------------------------------------------------------------------------------------------
+def _rows(n, out_rows):
+    return out_rows.long() if out_rows is not None else torch.arange(n)
+
+
+def cg3d_spconv_simt(**a):
+    x, W, out = a["in"], a["W"], a["out"]
+    n_out, Cin, Cout, K = a["n_out"], a["Cin"], a["Cout"], a["K"]
+    assert x.shape[1] == Cin and out.shape == (n_out, Cout) and a["ldi"] == x.stride(0) and a["ldo"] == out.stride(0)
+    assert a["tile_row0"] is None and a["n_tiles"] == 0
+    W = W.reshape(K, Cin, Cout)
+    xin = _ACT[a["in_act"]](x)
+    acc = torch.zeros((n_out, Cout), dtype=x.dtype)
+    rows = _rows(n_out, a["out_rows"])
+    for k in range(K):
+        if a["nbr"] is None:
+            acc[rows] += xin[torch.arange(n_out)] @ W[k]
+            continue
+        assert a["nbr"].shape == (K, max(n_out, 1))
+        src = a["nbr"][k, :n_out].long()
+        hit = src >= 0
+        acc.index_add_(0, rows[hit], xin[src[hit]] @ W[k])
+    if a["scale"] is not None:
+        acc = acc * a["scale"]
+    if a["shift"] is not None:
+        acc = acc + a["shift"]
+    if a["residual"] is not None:
+        acc = acc + a["residual"]
+    out.copy_(_ACT[a["act"]](acc))
+
+
+def cg3d_affine_act(**a):
+    x, out = a["x"], a["out"]
+    assert x.shape == (a["n"], a["C"]) and out.shape == x.shape
+    v = x
+    if a["scale"] is not None:
+        v = v * a["scale"]
+    if a["shift"] is not None:
+        v = v + a["shift"]
+    if a["add"] is not None:
+        v = v + a["add"]
+    out.copy_(_ACT[a["act"]](v))
+
+
+def cg3d_table_transpose(**a):
+    nbr, T = a["nbr"], a["nbrT"]
+    assert nbr.shape == (a["K"], a["n_cols"]) and T.shape[0] == a["K"] and T.shape[1] >= a["n_in"]
+    rows = a["out_rows"].numpy() if a["out_rows"] is not None else None
+    T[:, :a["n_in"]] = torch.from_numpy(Bk.table_transpose(nbr.numpy(), a["n_in"], rows).astype(np.int32))
+
+
+def cg3d_transpose_weights(**a):
+    W, Wt = a["W"], a["Wt"]
+    Wt.copy_(W.reshape(a["n_mats"], a["Cin"], a["Cout"]).transpose(1, 2).reshape(Wt.shape))
+
+
+def cg3d_spconv_wgrad(**a):
+    x, dy, dW = a["x"], a["dy"], a["dW"]
+    K, Cin, Cout = a["K"], a["Cin"], a["Cout"]
+    assert x.shape[1] == Cin and dy.shape[1] == Cout and dW.shape == (K, Cin, Cout)
+    assert a["slabs"] is None or a["slabs"].numel() >= K * Cin * Cout
+    xin = _ACT[a["in_act"]](x)
+    cols = torch.arange(a["col0"], a["col1"])
+    rows = a["out_rows"].long()[cols] if a["out_rows"] is not None else cols
+    for k in range(K):
+        src = a["nbr"][k, cols].long() if a["nbr"] is not None else cols
+        hit = src >= 0
+        dW[k] = xin[src[hit]].T @ dy[rows[hit]]
+
+
+def cg3d_bn_train_stats(**a):
+    x, n = a["x"], a["n"]
+    assert x.shape == (n, a["C"])
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + a["eps"])
+    a["mean"].copy_(mean)
+    a["rstd"].copy_(rstd)
+    g = a["gamma"] if a["gamma"] is not None else torch.ones_like(mean)
+    b = a["beta"] if a["beta"] is not None else torch.zeros_like(mean)
+    if a["scale"] is not None:
+        a["scale"].copy_(g * rstd)
+    if a["shift"] is not None:
+        a["shift"].copy_(b - mean * g * rstd)
+    mom = a["momentum"]
+    if a["running_mean"] is not None:
+        a["running_mean"].mul_(1 - mom).add_(mom * mean)
+    if a["running_var"] is not None:
+        a["running_var"].mul_(1 - mom).add_(mom * (x.var(0, unbiased=True) if n > 1 else var))
+
+
+def cg3d_bn_train_backward(**a):
+    x, dy, n = a["x"], a["dy"], a["n"]
+    if a["y_mask"] is not None:
+        dy = torch.where(a["y_mask"] > 0, dy, torch.zeros_like(dy))
+    xh = (x - a["mean"]) * a["rstd"]
+    dbeta, dgamma = dy.sum(0), (dy * xh).sum(0)
+    g = a["gamma"] if a["gamma"] is not None else torch.ones_like(dbeta)
+    a["dx"].copy_(g * a["rstd"] * (dy - dbeta / n - xh * dgamma / n))
+    a["dgamma"].copy_(dgamma)
+    a["dbeta"].copy_(dbeta)
+    if a["dres"] is not None:
+        a["dres"].copy_(dy)
+
+
+def cg3d_interp_trilinear(**a):
+    src = _me_of_keys(a["keys"])
+    q = a["query"].numpy().astype(np.int64)[:a["nq"]]
+    rows, w = Bk.interp_corners(src, q)
+    out = a["base"].clone() if a["base"] is not None else torch.zeros((a["nq"], a["C"]), dtype=a["feats"].dtype)
+    for c in range(8):
+        hit = np.nonzero(rows[:, c] >= 0)[0]
+        if len(hit):
+            out[torch.from_numpy(hit)] += a["feats"][torch.from_numpy(rows[hit, c])] * torch.from_numpy(w[hit, c]).to(out.dtype)[:, None]
+    a["out"].copy_(out)
+
+
+def cg3d_interp_trilinear_backward(**a):
+    qm = _me_of_keys(a["qkeys"])
+    assert qm.stride == a["tq"] and a["ts"] % a["tq"] == 0
+    srcm = me.CoordMap(a["src_coords"].numpy().astype(np.int64)[:a["n_src"]], a["ts"])
+    rows, w = Bk.interp_corners(srcm, qm.coords)
+    a["dF"].copy_(Bk.interp_backward(a["dOut"], rows, w, a["n_src"]).to(a["dF"].dtype))
+
+
+def _window(oc, ic, half):
+    d = (ic[None, :, 1:] - oc[:, None, 1:]).abs().max(-1).values
+    return ((d <= half) & (ic[None, :, 0] == oc[:, None, 0])).float()
+
+
+def cg3d_avgpool_window(**a):
+    M = _window(a["out_coords"][:a["n_out"]].long(), a["in_coords"][:a["n_in"]].long(), a["half"]).to(a["feats"].dtype)
+    a["out"].copy_((M @ a["feats"]) / M.sum(1, keepdim=True).clamp(min=1))
+
+
+def cg3d_avgpool_window_backward(**a):
+    M = _window(a["out_coords"][:a["n_out"]].long(), a["in_coords"][:a["n_in"]].long(), a["half"]).to(a["dOut"].dtype)
+    cnt = M.sum(1)
+    a["counts"][:a["n_out"]] = cnt
+    a["dIn"].copy_(M.T @ (a["dOut"] / cnt[:, None]))
+
+
+def cg3d_act_backward(**a):
+    dy, y = a["dy"], a["y"]
+    if a["act"] == 1:
+        d = torch.where(y > 0, dy, torch.zeros_like(dy))
+    elif a["act"] == 2:
+        d = torch.where(y > 0, dy, dy * (y + 1))
+    else:
+        d = dy
+    a["dx"].copy_(d)
+
+
+def cg3d_segment_mean_backward(**a):
+    inv = a["inverse"].long()
+    a["dIn"].copy_(a["dOut"][inv] / a["counts"][inv][:, None])
+
+
+def cg3d_assign(**a):
+    from oracle import train_oracle as T
+    offs = a["cls_offsets"].tolist()
+    pts = [a["locs"][offs[c]:offs[c + 1]] for c in range(a["n_cls"])]
+    ct, bt, lb = T.assign(pts, a["gt_boxes"], a["gt_labels"].long(), a["topk"])
+    a["centerness"].copy_(torch.nan_to_num(ct))
+    a["box_targets"].copy_(bt)
+    a["labels"].copy_(lb)
+    if a["box_index"] is not None:
+        a["box_index"].fill_(-1)
+
+
+def cg3d_assign_semantic(**a):
+    from oracle import train_oracle as T
+    sl, il = T.assign_semantic(a["points"], a["gt_boxes"], a["gt_labels"].long())
+    a["labels"].copy_(sl)
+    a["ins_labels"].copy_(il)
+
+
+def cg3d_focal_loss(**a):
+    from oracle import train_oracle as T
+    p = a["pred"].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = T.focal_loss(p, a["labels"], a["avg_factor"], a["gamma"], a["alpha"])
+    a["loss"][0] = float(loss)
+    if a["grad"] is not None:
+        a["grad"].copy_(torch.autograd.grad(loss, p)[0])
+
+
+def cg3d_bce_loss(**a):
+    from oracle import train_oracle as T
+    p = a["pred"].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = T.bce_loss(p, a["target"], a["avg_factor"])
+    a["loss"][0] = float(loss)
+    if a["grad"] is not None:
+        a["grad"].copy_(torch.autograd.grad(loss, p)[0])
+
+
+def cg3d_iou_loss_aa(**a):
+    from oracle import train_oracle as T
+    p = a["pred"].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = T.axis_aligned_iou_loss(p[:, :6], a["target"][:, :6], a["weight"], a["avg_factor"])
+    a["loss"][0] = float(loss)
+    if a["grad"] is not None:
+        a["grad"].copy_(torch.autograd.grad(loss, p)[0])
+
+
+def cg3d_smooth_l1_loss(**a):
+    from oracle import train_oracle as T
+    p = a["pred"].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = T.smooth_l1_sum(p, a["target"], a["weight"], a["beta"])
+    a["loss"][0] = float(loss)
+    if a["grad"] is not None:
+        a["grad"].copy_(torch.autograd.grad(loss, p)[0])
+
+
+def install(monkeypatch):
+    """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
+    from cagroup3d_b200 import _lib, sparse as S
+    names = _param_names()
+    table = {k: v for k, v in globals().items() if k.startswith("cg3d_")}
+    calls = []
+
+    def call(name, *args):
+        if name not in table:
+            raise NotImplementedError(f"{name} is not emulated")
+        params = names[name]
+        assert len(args) == len(params), (name, len(args), params)
+        calls.append(name)
+        table[name](**dict(zip(params, args)))
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(S, "strided_map", _strided_map)
+    monkeypatch.setattr(S, "neighbor_table", _neighbor_table)
+    monkeypatch.setattr(S, "transpose_table", _transpose_table)
+    return calls

@@ -1,0 +1,128 @@
+"""Host logic of the TRAINING path on the CPU: cagroup3d_b200/autograd.py, backbone_train.py and train_targets.py run
+against tests/cabi_emulator.py (a torch restatement of each C-ABI entry point's contract, arguments bound by the
+parameter names of include/cagroup3d_b200.h) and are compared with autograd through the fp64 oracle.  Checks argument
+order, shapes, which gradient goes where and the layer wiring -- not the CUDA code (that is tests/test_zz_gpu_*.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cagroup3d_oracle as O
+from oracle import me_cpu as me
+from oracle import train_oracle as T
+from tests import cabi_emulator as E
+
+
+def _rel(got, want):
+    return float((got.double() - want).norm()) / (float(want.norm()) + 1e-30)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride", [(16, 24, 3, 1), (16, 8, 3, 2), (8, 8, 1, 1), (8, 12, 1, 2)])
+def test_conv_autograd_wiring(monkeypatch, cin, cout, k, stride):
+    from cagroup3d_b200 import autograd as A, sparse as S
+    E.install(monkeypatch)
+    rng = np.random.default_rng(k * 10 + stride)
+    c = me.unique_first(np.concatenate([rng.integers(0, 2, (900, 1)), rng.integers(-12, 12, (900, 3))], 1))[0]
+    ox = me.SparseTensor(torch.from_numpy(rng.standard_normal((len(c), cin))), me.CoordMap(c, 1), me.Manager())
+    ox.mgr.by_stride[1] = ox.cmap
+    Wd = torch.from_numpy(rng.standard_normal((k ** 3, cin, cout)) / 5).requires_grad_(True)
+    Xd = ox.F.clone().requires_grad_(True)
+    y = me.conv(ox.with_F(Xd), Wd[0] if (k == 1 and stride == 1) else Wd, k, stride)
+    dY = torch.from_numpy(rng.standard_normal(tuple(y.F.shape)))
+    (y.F * dY).sum().backward()
+    mgr = S.Manager()
+    cm = E.cpu_map(c, 1, mgr)
+    mgr.by_stride[1] = cm
+    X = ox.F.float().requires_grad_(True)
+    W = (Wd.detach()[0] if (k == 1 and stride == 1) else Wd.detach()).float().contiguous().requires_grad_(True)
+    out = A.conv(S.SparseTensor(X, cm, mgr), W, k, stride, impl="simt")
+    assert np.array_equal(out.C.numpy(), y.C)
+    assert _rel(out.F.detach(), y.F.detach()) < 1e-5
+    out.F.backward(dY.float())
+    assert _rel(X.grad, Xd.grad) < 1e-5 and _rel(W.grad.reshape(Wd.shape), Wd.grad) < 1e-5
+
+
+def test_backbone_training_wiring_vs_oracle(monkeypatch):
+    """run_train on the emulated C ABI == the oracle's training-mode BiResNet: features and the gradient of all 168
+    backbone parameters (fp32 emulation vs fp64 oracle)."""
+    from cagroup3d_b200 import backbone_train as BT, model_init, sparse as S, synthetic
+    calls = E.install(monkeypatch)
+    B = 2
+    batch = synthetic.make_batch(B, target_voxels=700, config=11)
+    model = model_init.seeded_model(18, False, seed=2)
+    pts = torch.from_numpy(batch["points"])
+    orc = O.Oracle(model.state_dict(), O.default_cfg(18, False), dtype=torch.float64)
+    names = [k for k in orc.p if k.startswith("backbone_3d.") and k.endswith(("kernel", "bn.weight", "bn.bias"))]
+    for k in names:
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    orc.train_bn = True
+    res = orc.forward(pts, B, stages="backbone")
+    dY = torch.randn(tuple(res["bb_feats"].shape), generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    (res["bb_feats"] * dY).sum().backward()
+
+    bb = model.backbone_3d.train()
+    mgr = S.Manager()
+    cm = E.cpu_map(res["vox_coords"], 1, mgr)
+    mgr.by_stride[1] = cm
+    out = BT.run_train(bb, S.SparseTensor(res["vox_feats"].float().contiguous(), cm, mgr), impl="simt")
+    assert np.array_equal(out.C.numpy(), res["bb_coords"])
+    assert (out.F.detach().double() - res["bb_feats"].detach()).abs().max().item() < 1e-3
+    out.F.backward(dY.float())
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
+                 / (float(orc.p[k].grad.norm()) + 1e-5 * G), k) for k in names)
+    assert worst[0] < 5e-3, worst
+    assert int(bb.conv1[1].bn.num_batches_tracked) == 1
+    used = set(calls)
+    assert {"cg3d_spconv_simt", "cg3d_spconv_wgrad", "cg3d_table_transpose", "cg3d_transpose_weights", "cg3d_bn_train_stats",
+            "cg3d_bn_train_backward", "cg3d_affine_act", "cg3d_interp_trilinear", "cg3d_interp_trilinear_backward",
+            "cg3d_avgpool_window", "cg3d_avgpool_window_backward", "cg3d_act_backward"} <= used, used
+
+
+def test_targets_and_losses_wiring(monkeypatch):
+    from cagroup3d_b200 import train_targets as TT
+    with pytest.raises(RuntimeError, match="no CPU"):
+        TT.FocalLoss()(torch.zeros((2, 3)), torch.zeros((2,), dtype=torch.long), avg_factor=1.0)
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    g = torch.Generator().manual_seed(3)
+    ncls, m = 4, 9
+    boxes = torch.cat([(torch.rand((m, 3), generator=g) - 0.5) * 4, torch.rand((m, 3), generator=g) * 1.5 + 0.3, torch.zeros((m, 1))], 1)
+    labels = torch.randint(0, ncls - 1, (m,), generator=g)
+    pts = [(torch.rand((int(n), 3), generator=g) - 0.5) * 5 for n in (60, 200, 90, 33)]
+    ct, bt, lb = T.assign(pts, boxes, labels, 18)
+    gc, gb, gl = TT.CAGroup3DAssigner({"TOPK": 18}).assign(pts, boxes, labels)
+    assert torch.equal(gl, lb) and torch.equal(gb, bt) and gc.shape == ct.shape
+    sl, il = TT.CAGroup3DAssigner.assign_semantic(torch.cat(pts), boxes, labels, ncls)
+    assert torch.equal(sl, T.assign_semantic(torch.cat(pts), boxes, labels)[0])
+    N = len(lb)
+    pred = torch.randn((N, ncls), generator=g).requires_grad_(True)
+    loss = TT.FocalLoss()(pred, lb, avg_factor=7.0)
+    (3.0 * loss).backward()
+    pd = pred.detach().double().requires_grad_(True)
+    want = T.focal_loss(pd, lb, 7.0)
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-5 and _rel(pred.grad, 3.0 * pd.grad) < 1e-5
+    # box loss through a column slice of a wider prediction (the head passes decoded boxes with a yaw column)
+    P = 50
+    tgt = torch.cat([torch.randn((P, 3), generator=g), torch.rand((P, 3), generator=g) + 0.3, torch.zeros((P, 1))], 1)
+    pb = (tgt + torch.randn((P, 7), generator=g) * 0.2)
+    pb[:, 3:6] = pb[:, 3:6].abs() + 0.05
+    pb.requires_grad_(True)
+    w = torch.rand((P,), generator=g)
+    lbx = TT.IoU3DLoss(with_yaw=False)(pb, tgt, weight=w, avg_factor=float(w.sum()))
+    lbx.backward()
+    pdb = pb.detach().double().requires_grad_(True)
+    T.axis_aligned_iou_loss(pdb[:, :6], tgt[:, :6].double(), w.double(), float(w.sum())).backward()
+    assert _rel(pb.grad, pdb.grad) < 1e-5 and float(pb.grad[:, 6].abs().max()) == 0
+    x = torch.randn((P, 1), generator=g, requires_grad=True)
+    t = torch.rand((P, 1), generator=g)
+    TT.CrossEntropy(use_sigmoid=True)(x, t, avg_factor=11.0).backward()
+    xd = x.detach().double().requires_grad_(True)
+    T.bce_loss(xd, t.double(), 11.0).backward()
+    assert _rel(x.grad, xd.grad) < 1e-5
+    p3, t3, w3 = torch.randn((P, 3), generator=g, requires_grad=True), torch.randn((P, 3), generator=g), torch.rand((P, 3), generator=g)
+    TT.SmoothL1Loss(beta=0.04, reduction="sum")(p3, t3, weight=w3).backward()
+    pd3 = p3.detach().double().requires_grad_(True)
+    T.smooth_l1_sum(pd3, t3.double(), w3.double()).backward()
+    assert _rel(p3.grad, pd3.grad) < 1e-5
