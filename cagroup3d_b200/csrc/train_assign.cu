@@ -295,3 +295,108 @@ int cg3d_focal_loss(const float* pred, const long long* labels, long long n, int
 }
 
 }  // extern "C"
+
+// ---- vote targets from the per-point instance / semantic masks (cagroup_head.py:454-496, ScanNet branch) ----------------
+// The reference loops over torch.unique(instance ids) in Python (nonzero + min/max + cdist + argmin per instance) and
+// builds (instances x k x points) tensors for a k = 1 vote.  Here: one pass of integer atomics for the per-instance
+// bounding box and first point (min / max are order independent: bit-repeatable), one thread per instance for the
+// matched ground-truth centre, one thread per voxel for the target.
+namespace {
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+// ws: i32[n_inst][8] = (min x, y, z, max x, y, z, first point, unused)
+__global__ void vote_instance_init_kernel(int* __restrict__ ws, int n_inst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inst * 8) return;
+    const int f = i & 7;
+    ws[i] = f < 3 ? 0x7FFFFFFF : (f < 6 ? (int)0x80000000 : 0x7FFFFFFF);
+}
+
+__global__ void vote_instance_reduce_kernel(const float* __restrict__ pts, int ld, const long long* __restrict__ ins, int n,
+                                            int n_inst, int* __restrict__ ws) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long id = __ldg(ins + i);
+    if (id < 0 || id >= n_inst) return;
+    int* w = ws + id * 8;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int o = float_to_ordered(__ldg(pts + (size_t)i * ld + a));
+        atomicMin(w + a, o);
+        atomicMax(w + 3 + a, o);
+    }
+    atomicMin(w + 6, i);
+}
+
+// centers: f32[n_inst][3]: the matched ground-truth centre, -10000 for background instances, 0 for unused ids
+__global__ void vote_instance_center_kernel(const int* __restrict__ ws, int n_inst, const long long* __restrict__ sem,
+                                            int n_classes, const float* __restrict__ gt_boxes, int m, float* __restrict__ centers) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inst) return;
+    const int* w = ws + (size_t)i * 8;
+    float c[3] = {0.f, 0.f, 0.f};
+    if (w[6] != 0x7FFFFFFF) {
+        if (__ldg(sem + w[6]) < n_classes && m > 0) {
+            float ctr[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) ctr[a] = 0.5f * (ordered_to_float(w[a]) + ordered_to_float(w[3 + a]));
+            float best = 3.0e38f;
+            int bj = 0;
+            for (int j = 0; j < m; ++j) {
+                const float dx = ctr[0] - __ldg(gt_boxes + 7 * (size_t)j), dy = ctr[1] - __ldg(gt_boxes + 7 * (size_t)j + 1),
+                            dz = ctr[2] - __ldg(gt_boxes + 7 * (size_t)j + 2);
+                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                if (d < best) { best = d; bj = j; }          // torch.argmin: the first minimal index
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) c[a] = __ldg(gt_boxes + 7 * (size_t)bj + a);
+        } else {
+            c[0] = c[1] = c[2] = -10000.f;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) centers[(size_t)i * 3 + a] = c[a];
+}
+
+__global__ void vote_targets_kernel(const float* __restrict__ vox, int nv, const int* __restrict__ nearest,
+                                    const long long* __restrict__ ins, int n_inst, const float* __restrict__ centers,
+                                    float* __restrict__ targets, float* __restrict__ mask) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    const long long id = __ldg(ins + __ldg(nearest + v));
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float cc = (id >= 0 && id < n_inst) ? __ldg(centers + (size_t)id * 3 + a) : 0.f;
+        float t = cc - __ldg(vox + (size_t)v * 3 + a);
+        if (t < -100.f) { ok = false; t = 0.f; }
+        targets[(size_t)v * 3 + a] = t;
+    }
+    mask[v] = ok ? 1.f : 0.f;
+}
+
+}  // namespace
+
+extern "C" int cg3d_vote_targets(const float* scene_points, int ld, const long long* sem_mask, const long long* ins_mask, int n,
+                                 int n_inst, int n_classes, const float* gt_boxes, int m, const float* voxel_points,
+                                 const int* nearest, int nv, int* workspace, float* centers, float* targets, float* mask,
+                                 void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nv == 0) return 0;
+    if (n_inst <= 0 || n <= 0) return -1;
+    vote_instance_init_kernel<<<cg3d_div_up((long long)n_inst * 8, 256), 256, 0, st>>>(workspace, n_inst);
+    CG3D_LAUNCH_CHECK();
+    vote_instance_reduce_kernel<<<cg3d_div_up(n, 256), 256, 0, st>>>(scene_points, ld, ins_mask, n, n_inst, workspace);
+    CG3D_LAUNCH_CHECK();
+    vote_instance_center_kernel<<<cg3d_div_up(n_inst, 128), 128, 0, st>>>(workspace, n_inst, sem_mask, n_classes, gt_boxes, m,
+                                                                          centers);
+    CG3D_LAUNCH_CHECK();
+    vote_targets_kernel<<<cg3d_div_up(nv, 256), 256, 0, st>>>(voxel_points, nv, nearest, ins_mask, n_inst, centers, targets, mask);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}

@@ -176,3 +176,77 @@ class SmoothL1Loss(torch.nn.Module):
         t, w = target.detach().float().contiguous(), weight.detach().float().contiguous()
         fn = lambda p, loss, grad, ws: S._call("cg3d_smooth_l1_loss", p, t, w, n, C, float(self.beta), ws, loss, grad)
         return self.loss_weight * _RowLossFunction.apply(pred, fn, n * C)
+
+
+# ---- vote targets and the five first-stage loss terms of one sample ------------------------------------------------------
+def vote_targets(scene_points: torch.Tensor, voxel_points: torch.Tensor, gt_bboxes: torch.Tensor, pts_semantic_mask: torch.Tensor,
+                 pts_instance_mask: torch.Tensor, n_classes: int):
+    """cagroup_head.py:454-496 (ScanNet branch, k = 1): -> (offset targets (nv, 3), mask (nv,) float).
+    One host read (the number of instance ids), as in the reference (`pts_instance_mask.max() + 1` sizes a tensor)."""
+    from . import ops
+    _require_cuda(scene_points)
+    dev = scene_points.device
+    sp = scene_points.float().contiguous()
+    vp = voxel_points[:, :3].float().contiguous()
+    n, nv = sp.shape[0], vp.shape[0]
+    n_inst = int(pts_instance_mask.max()) + 1
+    nearest = ops.knn(1, sp[None, :, :3].contiguous(), vp[None])[0, 0].contiguous()            # (nv,) int32
+    ws = torch.empty((n_inst * 8,), dtype=torch.int32, device=dev)
+    centers = torch.empty((n_inst, 3), dtype=torch.float32, device=dev)
+    targets = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((nv,), dtype=torch.float32, device=dev)
+    boxes = gt_bboxes[:, :7].float().contiguous()
+    S._call("cg3d_vote_targets", sp, sp.stride(0), pts_semantic_mask.long().contiguous(), pts_instance_mask.long().contiguous(), n,
+            n_inst, int(n_classes), boxes, boxes.shape[0], vp, nearest, nv, ws, centers, targets, mask)
+    return targets, mask
+
+
+def bbox_pred_to_bbox(points: torch.Tensor, bbox_pred: torch.Tensor) -> torch.Tensor:
+    """cagroup_head.py:654-670, 6 outputs (no yaw): face distances -> (x, y, z, dx, dy, dz).  Index glue on the positive
+    rows only (differentiable torch ops; the fused decode of the inference path, cg3d_head_decode, has no backward)."""
+    if bbox_pred.shape[0] == 0:
+        return bbox_pred
+    c = points[:, :3] + (bbox_pred[:, 1:6:2] - bbox_pred[:, 0:6:2]) / 2
+    return torch.cat([c, bbox_pred[:, 0:6:2] + bbox_pred[:, 1:6:2]], 1)
+
+
+class FirstStageLoss:
+    """CAGroup3DHead._loss_single (cagroup_head.py:399-555) for WITH_YAW False, on the kernels above; the argument list
+    is the reference's.  `reduce_mean` is dist.reduce_mean (identity in a single process)."""
+
+    def __init__(self, n_classes: int, assigner_cfg=None):
+        self.n_classes = n_classes
+        self.assigner = CAGroup3DAssigner(assigner_cfg or {"LIMIT": 27, "TOPK": 18, "N_SCALES": 4})
+        self.loss_centerness = CrossEntropy(use_sigmoid=True, loss_weight=1.0)
+        self.loss_bbox = IoU3DLoss(with_yaw=False, loss_weight=1.0)
+        self.loss_cls = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
+        self.loss_sem = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
+        self.loss_offset = SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0)
+
+    def loss_single(self, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, original_points, semantic_scores,
+                    semantic_points, img_meta, gt_bboxes, gt_labels, scene_points, pts_semantic_mask, pts_instance_mask):
+        from .dist import reduce_mean
+        with torch.no_grad():
+            semantic_labels, _ = self.assigner.assign_semantic(semantic_points, gt_bboxes, gt_labels, self.n_classes)
+            centerness_targets, bbox_targets, labels = self.assigner.assign(points, gt_bboxes, gt_labels)
+            offset_targets, offset_masks = vote_targets(scene_points, original_points, gt_bboxes, pts_semantic_mask,
+                                                        pts_instance_mask, self.n_classes)
+        centerness, bbox_preds, cls_scores, points = (torch.cat(centernesses), torch.cat(bbox_preds), torch.cat(cls_scores),
+                                                      torch.cat(points))
+        w = (offset_masks.float() / torch.ones_like(offset_masks).float().sum() + 1e-6).unsqueeze(1).repeat(1, 3)
+        loss_offset = self.loss_offset(voxel_offset_preds, offset_targets, weight=w)
+        sem_n_pos = max(float(reduce_mean((semantic_labels >= 0).sum().float())), 1.)
+        loss_sem = self.loss_sem(semantic_scores, semantic_labels, avg_factor=sem_n_pos)
+        pos_inds = torch.nonzero(labels >= 0).squeeze(1)
+        n_pos = max(float(reduce_mean(torch.tensor(float(len(pos_inds)), device=centerness.device))), 1.)
+        loss_cls = self.loss_cls(cls_scores, labels, avg_factor=n_pos)
+        pos_centerness, pos_bbox_preds = centerness[pos_inds], bbox_preds[pos_inds]
+        pos_centerness_targets = centerness_targets[pos_inds].unsqueeze(1)
+        centerness_denorm = max(float(reduce_mean(pos_centerness_targets.sum().detach())), 1e-6)
+        if len(pos_inds) > 0:
+            loss_centerness = self.loss_centerness(pos_centerness, pos_centerness_targets, avg_factor=n_pos)
+            loss_bbox = self.loss_bbox(bbox_pred_to_bbox(points[pos_inds], pos_bbox_preds), bbox_targets[pos_inds],
+                                       weight=pos_centerness_targets.squeeze(1), avg_factor=centerness_denorm)
+        else:
+            loss_centerness, loss_bbox = pos_centerness.sum(), pos_bbox_preds.sum()
+        return loss_centerness, loss_bbox, loss_cls, loss_sem, loss_offset

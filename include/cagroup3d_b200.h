@@ -428,6 +428,16 @@ int cg3d_iou_loss_aa(const float* pred, int ldp, const float* target, int ldt, c
 int cg3d_smooth_l1_loss(const float* pred, const float* target, const float* weight, long long n, int C, float beta,
                         float* workspace, float* loss, float* grad, void* stream);
 
+/* Vote targets from the per-point masks (cagroup_head.py:454-496, ScanNet branch).  scene_points: f32[n][ld] (xyz first);
+ * sem_mask / ins_mask: i64[n]; instance ids in [0, n_inst); an instance whose FIRST point has a semantic label < n_classes
+ * votes for the centre of the gt box (f32[m][7]) nearest to the centre of its own axis-aligned bounding box.  voxel_points:
+ * f32[nv][3]; nearest: i32[nv], the k = 1 neighbour of every voxel among the scene points (cg3d_knn).  workspace: i32[n_inst * 8];
+ * centers: f32[n_inst][3] (output: matched centre, -10000 for background, 0 for unused ids); targets: f32[nv][3] =
+ * centre - voxel with components < -100 set to 0; mask: f32[nv] = 1 where no component was below -100. */
+int cg3d_vote_targets(const float* scene_points, int ld, const long long* sem_mask, const long long* ins_mask, int n,
+                      int n_inst, int n_classes, const float* gt_boxes, int m, const float* voxel_points, const int* nearest,
+                      int nv, int* workspace, float* centers, float* targets, float* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

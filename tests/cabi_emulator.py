@@ -304,6 +304,30 @@ def cg3d_smooth_l1_loss(**a):
         a["grad"].copy_(torch.autograd.grad(loss, p)[0])
 
 
+def cg3d_knn(**a):
+    assert a["xyz"].shape == (a["b"], a["n"], 3) and a["query"].shape == (a["b"], a["m"], 3) and a["k"] == 1
+    d = torch.cdist(a["query"].double(), a["xyz"].double())
+    a["idx"].copy_(d.argmin(2, keepdim=True).int())
+    a["dist2"].copy_((d.min(2, keepdim=True).values ** 2).float())
+
+
+def cg3d_vote_targets(**a):
+    sp, ins, sem = a["scene_points"][:, :3], a["ins_mask"], a["sem_mask"]
+    assert sp.shape[0] == a["n"] and a["ld"] == a["scene_points"].stride(0) and a["workspace"].numel() >= 8 * a["n_inst"]
+    centers = torch.zeros((a["n_inst"], 3))
+    for i in torch.unique(ins):
+        idx = torch.nonzero(ins == i).squeeze(1)
+        if sem[idx[0]] < a["n_classes"]:
+            c = 0.5 * (sp[idx].min(0)[0] + sp[idx].max(0)[0])
+            centers[i] = a["gt_boxes"][torch.argmin(torch.cdist(c.view(1, 3), a["gt_boxes"][:, :3]).view(-1)), :3]
+        else:
+            centers[i] = -10000.0
+    a["centers"].copy_(centers)
+    t = centers[ins[a["nearest"].long()]] - a["voxel_points"]
+    a["mask"].copy_((t >= -100.0).all(1).float())
+    a["targets"].copy_(torch.where(t < -100.0, torch.zeros_like(t), t))
+
+
 def install(monkeypatch):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
     from cagroup3d_b200 import _lib, sparse as S

@@ -126,3 +126,49 @@ def test_targets_and_losses_wiring(monkeypatch):
     pd3 = p3.detach().double().requires_grad_(True)
     T.smooth_l1_sum(pd3, t3.double(), w3.double()).backward()
     assert _rel(p3.grad, pd3.grad) < 1e-5
+
+
+def test_first_stage_loss_single_wiring(monkeypatch):
+    """train_targets.FirstStageLoss.loss_single (the reference's _loss_single argument list) == the oracle's five terms,
+    with gradients reaching every prediction tensor."""
+    from cagroup3d_b200 import ops, train_targets as TT
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+    g = torch.Generator().manual_seed(12)
+    ncls, m = 5, 8
+    boxes = torch.cat([(torch.rand((m, 3), generator=g) - 0.5) * 4, torch.rand((m, 3), generator=g) * 1.5 + 0.4, torch.zeros((m, 1))], 1)
+    gtl = torch.randint(0, ncls, (m,), generator=g)
+    # scene points: some on every box (instance 5 + j, class of the box), some background (instances 0..2, class ncls)
+    sp, sem, ins = [], [], []
+    for j in range(m):
+        q = boxes[j, :3] + (torch.rand((150, 3), generator=g) - 0.5) * boxes[j, 3:6]
+        sp.append(q); sem.append(torch.full((150,), int(gtl[j]))); ins.append(torch.full((150,), 5 + j))
+    q = (torch.rand((600, 3), generator=g) - 0.5) * 6
+    sp.append(q); sem.append(torch.full((600,), ncls)); ins.append(torch.randint(0, 3, (600,), generator=g))
+    sp, sem, ins = torch.cat(sp), torch.cat(sem), torch.cat(ins)
+    vox = sp[torch.randperm(len(sp), generator=g)[:700]] + 0.01
+    pts = [torch.cat([boxes[gtl == c][:, :3].repeat(12, 1) + (torch.rand((12 * int((gtl == c).sum()), 3), generator=g) - 0.5) * 0.6,
+                      (torch.rand((40, 3), generator=g) - 0.5) * 6]) for c in range(ncls)]
+    N = sum(len(p) for p in pts)
+    mk = lambda *shape: (torch.randn(shape, generator=g) * 0.5).requires_grad_(True)
+    ctr, cls, sems, offs = mk(N, 1), mk(N, ncls), mk(len(vox), ncls), (torch.randn((len(vox), 3), generator=g) * 0.1).requires_grad_(True)
+    reg = (torch.rand((N, 6), generator=g) * 0.6 + 0.1).requires_grad_(True)
+    sizes = [len(p) for p in pts]
+    split = lambda t: list(torch.split(t, sizes))
+    L = TT.FirstStageLoss(ncls)
+    got = L.loss_single(split(ctr), split(reg), split(cls), pts, offs, vox, sems, vox, None, boxes, gtl, sp, sem, ins)
+    sum(got).backward()
+    # oracle
+    ct_t, box_t, lab = T.assign(pts, boxes, gtl, 18)
+    assert (lab >= 0).sum() > 10
+    sem_l, _ = T.assign_semantic(vox, boxes, gtl)
+    off_t, off_m = T.vote_targets_from_masks(sp, vox, boxes, sem, ins, ncls)
+    d = {k: v.detach().double().requires_grad_(True) for k, v in dict(ctr=ctr, reg=reg, cls=cls, sems=sems, offs=offs).items()}
+    want = T.head_loss_terms(d["ctr"], O.bbox_pred_to_bbox(torch.cat(pts).double(), d["reg"]), d["cls"], ct_t.double(), box_t.double(), lab,
+                             d["sems"], sem_l, d["offs"], off_t.double(), off_m.double())
+    sum(want).backward()
+    for a, b in zip(got, want):
+        assert abs(float(a.detach()) - float(b.detach())) < 2e-5 * max(1.0, abs(float(b.detach())))
+    for k, t in dict(ctr=ctr, reg=reg, cls=cls, sems=sems, offs=offs).items():
+        assert t.grad is not None and _rel(t.grad, d[k].grad) < 1e-4, k

@@ -420,3 +420,22 @@ def test_centerness_iou_vote_losses_vs_oracle(lib):
     gs.backward()
     assert abs(gs.item() - ws_.item()) <= 1e-5 * max(1.0, abs(ws_.item()))
     _close(pg2.grad, pd2.grad, 1e-6)
+
+
+def test_vote_targets_vs_oracle(lib):
+    """cg3d_vote_targets (+ cg3d_knn, k = 1) against oracle/train_oracle.vote_targets_from_masks on a synthetic scene with
+    the per-point masks of the training golden (instances 0..4 = floor / walls, 5.. = boxes)."""
+    from cagroup3d_b200 import synthetic
+    from cagroup3d_b200.train_targets import vote_targets
+    from oracle import train_oracle as T
+    pts, boxes, sem, ins = synthetic.make_scene(1000 * 7 + 1, 3000, n_classes=18, return_masks=True)
+    sp = torch.from_numpy(pts[:, :3]).float()
+    gtb = torch.from_numpy(boxes[:, :7]).float()
+    sem_t, ins_t = torch.from_numpy(sem), torch.from_numpy(ins)
+    vox = torch.unique(torch.floor(sp / 0.04), dim=0) * 0.04
+    want_t, want_m = T.vote_targets_from_masks(sp, vox, gtb, sem_t, ins_t, 18)
+    got_t, got_m = vote_targets(sp.to(DEV), vox.to(DEV), gtb.to(DEV), sem_t.to(DEV), ins_t.to(DEV), 18)
+    # a voxel whose two nearest scene points are equally far (to the last bit) may take either instance
+    same = (got_m.cpu() == want_m) & ((got_t.cpu() - want_t).abs().max(1).values <= 1e-5)
+    assert same.float().mean().item() >= 0.999, same.float().mean().item()
+    assert 0.05 < want_m.mean().item() < 0.95
