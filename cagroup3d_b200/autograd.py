@@ -245,3 +245,25 @@ class AvgPoolFunction(torch.autograd.Function):
 def avg_pool(x: S.SparseTensor, k: int, stride: int) -> S.SparseTensor:
     omap = S.strided_map(x.cmap, x.mgr, stride)
     return S.SparseTensor(AvgPoolFunction.apply(x.F, x.cmap, omap, (k // 2) * x.cmap.stride), omap, x.mgr)
+
+
+class BiasFunction(torch.autograd.Function):
+    """F + bias (a MinkowskiConvolution's `bias` of shape (1, C)); d bias = column sums of dY (cg3d_column_sum)."""
+
+    @staticmethod
+    def forward(ctx, X, bias):
+        ctx.bias_shape = bias.shape
+        return S.affine_act(X.detach(), shift=bias.detach().reshape(-1).contiguous())
+
+    @staticmethod
+    def backward(ctx, dY):
+        dY = dY.contiguous()
+        n, C = dY.shape
+        db = torch.empty((C,), dtype=torch.float32, device=dY.device)
+        ws = torch.empty((_lib.host("cg3d_bn_train_workspace", n, C),), dtype=torch.float32, device=dY.device)
+        S._call("cg3d_column_sum", dY, dY.stride(0), n, C, ws, db)
+        return dY, db.reshape(ctx.bias_shape)
+
+
+def add_bias(F: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    return BiasFunction.apply(F, bias)

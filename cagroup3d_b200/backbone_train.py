@@ -34,7 +34,11 @@ def _bn(m, F: torch.Tensor, act=None, residual=None) -> torch.Tensor:
 
 
 def conv_bn(x: S.SparseTensor, conv, bn, act=None, residual=None, impl: Optional[str] = None) -> S.SparseTensor:
+    """conv -> training-mode BatchNorm (+ residual) -> activation.  ReLU is fused into the normalisation pass; ELU (the
+    head's blocks) is a second pass, its backward needs the activation's own output."""
     y = A.conv(x, conv.kernel, conv.kernel_size, conv.stride, impl=impl)
+    if act == "elu":
+        return y.with_F(A.elu(_bn(bn, y.F, None, residual)))
     return y.with_F(_bn(bn, y.F, act, residual))
 
 

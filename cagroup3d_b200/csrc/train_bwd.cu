@@ -291,6 +291,33 @@ __global__ void act_backward_kernel(const float* __restrict__ dy, int ldy, const
     }
 }
 
+// out[c] = sum over rows of x[r][c]: (row chunk, 32 channels) partial sums added in chunk order (the bias gradient)
+__global__ void __launch_bounds__(BN_NT) colsum_partial_kernel(const float* __restrict__ x, int ldx, long long n, int C,
+                                                                long long chunk, float* __restrict__ part) {
+    __shared__ float s1s[BN_LANES][BN_CH];
+    const int tx = threadIdx.x % BN_CH, ty = threadIdx.x / BN_CH;
+    const int c = blockIdx.y * BN_CH + tx, s = blockIdx.x;
+    const long long p0 = s * chunk, p1 = min(n, p0 + chunk);
+    float s1 = 0.f;
+    if (c < C)
+        for (long long r = p0 + ty; r < p1; r += BN_LANES) s1 += __ldg(x + (size_t)r * ldx + c);
+    s1s[ty][tx] = s1;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int l = 1; l < BN_LANES; ++l) s1 += s1s[l][tx];
+        part[(size_t)s * C + c] = s1;
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float* __restrict__ part, int C, int S, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += part[(size_t)s * C + c];
+    out[c] = a;
+}
+
 inline int flat_blocks(long long work, int nt) {
     long long b = (work + nt - 1) / nt;
     const long long cap = 148LL * 16;
@@ -378,6 +405,20 @@ int cg3d_act_backward(const float* dy, int ldy, const float* y, int ldyy, long l
     if (n == 0 || C == 0) return 0;
     if (act != CG3D_ACT_NONE && act != CG3D_ACT_RELU && act != CG3D_ACT_ELU) return -1;
     act_backward_kernel<<<flat_blocks(n * C, 256), 256, 0, (cudaStream_t)stream>>>(dy, ldy, y, ldyy, n, C, act, dx, lddx);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_column_sum(const float* x, int ldx, long long n, int C, float* workspace, float* out, void* stream) {
+    if (C <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return (int)cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, st);
+    const int S = bn_chunks(n, C);
+    const long long chunk = (n + S - 1) / S;
+    dim3 grid(S, cg3d_div_up(C, BN_CH));
+    colsum_partial_kernel<<<grid, BN_NT, 0, st>>>(x, ldx, n, C, chunk, workspace);
+    CG3D_LAUNCH_CHECK();
+    colsum_finalize_kernel<<<cg3d_div_up(C, 128), 128, 0, st>>>(workspace, C, S, out);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

@@ -438,6 +438,10 @@ int cg3d_vote_targets(const float* scene_points, int ld, const long long* sem_ma
                       int n_inst, int n_classes, const float* gt_boxes, int m, const float* voxel_points, const int* nearest,
                       int nv, int* workspace, float* centers, float* targets, float* mask, void* stream);
 
+/* out[c] = sum over the n rows of x[r][c] (row stride ldx): the gradient of a conv bias (semantic_conv / cls_conv,
+ * cagroup_head.py:167,176).  workspace: cg3d_bn_train_workspace(n, C) floats; chunk partial sums added in order. */
+int cg3d_column_sum(const float* x, int ldx, long long n, int C, float* workspace, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

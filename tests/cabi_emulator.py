@@ -328,6 +328,11 @@ def cg3d_vote_targets(**a):
     a["targets"].copy_(torch.where(t < -100.0, torch.zeros_like(t), t))
 
 
+def cg3d_column_sum(**a):
+    assert a["x"].shape == (a["n"], a["C"]) and a["ldx"] == a["x"].stride(0)
+    a["out"].copy_(a["x"].sum(0))
+
+
 def install(monkeypatch):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
     from cagroup3d_b200 import _lib, sparse as S

@@ -172,3 +172,63 @@ def test_first_stage_loss_single_wiring(monkeypatch):
         assert abs(float(a.detach()) - float(b.detach())) < 2e-5 * max(1.0, abs(float(b.detach())))
     for k, t in dict(ctr=ctr, reg=reg, cls=cls, sems=sems, offs=offs).items():
         assert t.grad is not None and _rel(t.grad, d[k].grad) < 1e-4, k
+
+
+def test_partial_training_step_wiring_vs_oracle(monkeypatch):
+    """backbone (training mode) -> shared part of the head -> semantic + vote loss -> backward, on the emulated C ABI,
+    against the same two terms computed from the oracle's training-mode forward: loss values and the gradient of every
+    parameter the two terms reach (backbone, semantic_conv, offset_block)."""
+    from cagroup3d_b200 import backbone_train as BT, head_train as HT, model_init, ops, sparse as S, synthetic, train_targets as TT
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 7 + i, 600, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    pts = torch.from_numpy(batch["points"])
+    model = model_init.seeded_model(ncls, False, seed=4)
+    with torch.no_grad():
+        model.dense_head.semantic_conv.bias.fill_(-1.0)          # some foreground probability, so the focal term has signal
+    gtb = [torch.from_numpy(b[:, :7]).float() for _, b, _, _ in scenes]
+    gtl = [torch.from_numpy(b[:, 7]).long() for _, b, _, _ in scenes]
+    sp = [torch.from_numpy(p[:, :3]).float() for p, _, _, _ in scenes]
+    semm = [torch.from_numpy(s) for _, _, s, _ in scenes]
+    insm = [torch.from_numpy(m) for _, _, _, m in scenes]
+
+    orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, False), dtype=torch.float64)
+    reach = ("backbone_3d.", "dense_head.semantic_conv", "dense_head.offset_block")
+    names = [k for k in orc.p if k.startswith(reach) and k.endswith(("kernel", "bn.weight", "bn.bias", "conv.bias"))]
+    for k in names:
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    orc.train_bn = True
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+    hi, Cc = res["head"], torch.from_numpy(res["bb_coords"])
+    want_sem, want_vote = [], []
+    for b in range(B):
+        rows = torch.nonzero(Cc[:, 0] == b).squeeze(1)
+        vox = Cc[rows, 1:].float() * 0.02
+        sl, _ = T.assign_semantic(vox, gtb[b], gtl[b])
+        ot, om = T.vote_targets_from_masks(sp[b], vox, gtb[b], semm[b], insm[b], ncls)
+        w = (om / torch.ones_like(om).sum() + 1e-6)[:, None].repeat(1, 3).double()
+        want_vote.append(T.smooth_l1_sum(hi["offsets"][rows], ot.double(), w))
+        want_sem.append(T.focal_loss(hi["sem"][rows], sl, max(float((sl >= 0).sum()), 1.0)))
+    want = (torch.stack(want_sem).mean(), torch.stack(want_vote).mean())
+    (want[0] + want[1]).backward()
+
+    model.train()
+    mgr = S.Manager()
+    cm = E.cpu_map(res["vox_coords"], 1, mgr)
+    mgr.by_stride[1] = cm
+    out = BT.run_train(model.backbone_3d, S.SparseTensor(res["vox_feats"].float().contiguous(), cm, mgr), impl="simt")
+    sem, offs, offF = HT.shared_part(model.dense_head, out, impl="simt")
+    assert offF.shape == (out.cmap.n, 64)
+    got = HT.semantic_and_vote_loss(model.dense_head, out, sem, offs, B, gtb, gtl, sp, semm, insm)
+    (got[0] + got[1]).backward()
+    for a, b in zip(got, want):
+        assert abs(float(a.detach()) - float(b.detach())) < 1e-4 * max(1.0, abs(float(b.detach()))), (a, b)
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    assert G > 0
+    worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
+                 / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
+    assert worst[0] < 1e-2, worst
