@@ -1,0 +1,54 @@
+"""One training step of what the CUDA path can differentiate so far (BASELINE config 4): BiResNet in
+training mode, the shared part of the head, the semantic and vote terms of CAGroup3DHead.loss, backward, the DDP
+gradient all-reduce and the optimizer step -- tools/train_utils/train_utils.py:42-75 (train_one_epoch's inner loop)
+restricted to those two loss terms.  The per-class grouping branch and the RoI stage are not differentiable here yet
+(DESIGN.md section 9), so this is NOT the reference's full loss; `CAGroup3D.forward` keeps refusing training mode until
+it is.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import backbone_train as BT
+from . import head_train as HT
+from .detector import voxelize
+
+
+def partial_training_step(model, batch_dict: dict, optimizer: Optional[torch.optim.Optimizer] = None, reducer=None,
+                          impl: Optional[str] = None) -> dict:
+    """batch_dict as the reference's training loader builds it (cagroup3d.py:27-40, scannet_dataset.py:68-76):
+    `points` (N, 7) [b, x, y, z, r, g, b] with colours 0..255 (divided by 255 IN PLACE, like the reference), `batch_size`,
+    `gt_boxes` (B, M, 8) zero-padded, class id in the last column, `semantic_mask` / `instance_mask` lists of
+    per-point int64 arrays.  reducer: dist.GradientAllReducer (or None in a single process).  Returns the tb_dict."""
+    B = batch_dict["batch_size"]
+    pts = batch_dict["points"]
+    pts[:, -3:] = pts[:, -3:] / 255.
+    head = model.dense_head
+    if reducer is not None:
+        reducer.zero_grad()
+    elif optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    x = voxelize(pts, model.voxel_size)
+    out = BT.run_train(model.backbone_3d, x, impl=impl)
+    sem, offs, _ = HT.shared_part(head, out, impl=impl)
+    gtb, gtl, scene, semm, insm = [], [], [], [], []
+    for b in range(B):
+        g = batch_dict["gt_boxes"][b]
+        g = g[~(g == 0.).all(1)]                                           # zero padding rows (cagroup_head.py:305-308)
+        gtb.append(g[:, :7].float().contiguous())
+        gtl.append(g[:, 7].long())
+        scene.append(pts[pts[:, 0] == b][:, 1:4].contiguous())
+        semm.append(torch.as_tensor(batch_dict["semantic_mask"][b], device=pts.device).long())
+        insm.append(torch.as_tensor(batch_dict["instance_mask"][b], device=pts.device).long())
+    loss_sem, loss_vote = HT.semantic_and_vote_loss(head, out, sem, offs, B, gtb, gtl, scene, semm, insm)
+    loss = loss_sem + loss_vote
+    loss.backward()
+    if reducer is not None:
+        reducer.reduce()
+    if optimizer is not None:
+        optimizer.step()
+    if hasattr(model, "update_global_step"):
+        model.update_global_step()
+    return {"loss": float(loss.detach()), "loss_sem": float(loss_sem.detach()), "loss_vote": float(loss_vote.detach())}

@@ -232,3 +232,39 @@ def test_partial_training_step_wiring_vs_oracle(monkeypatch):
     worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
                  / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
     assert worst[0] < 1e-2, worst
+
+
+def test_partial_training_step_driver(monkeypatch):
+    """train_step.partial_training_step: batch_dict in, gradients reduced, optimizer stepped, loss decreasing over a few
+    steps on a fixed batch (emulated C ABI; the voxelisation comes from the oracle)."""
+    from cagroup3d_b200 import dist as D, model_init, ops, sparse as S, synthetic, train_step as TS, train_targets as TT
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+
+    def voxelize_cpu(points, voxel_size):
+        c = points[:, :4].clone()
+        c[:, 1:] /= voxel_size
+        ox = me.from_points(c, points[:, 4:])
+        mgr = S.Manager()
+        cm = E.cpu_map(ox.C, 1, mgr)
+        mgr.by_stride[1] = cm
+        return S.SparseTensor(ox.F.float().contiguous(), cm, mgr)
+    monkeypatch.setattr(TS, "voxelize", voxelize_cpu)
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 7 + i, 400, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    model = model_init.seeded_model(ncls, False, seed=4).train()
+    params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head.semantic_conv", "dense_head.offset_block"))]
+    opt = torch.optim.AdamW(params, lr=2e-3)
+    red = D.GradientAllReducer(params, bucket_mb=8)
+    losses = []
+    for _ in range(4):
+        bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
+              "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+        tb = TS.partial_training_step(model, bd, opt, red, impl="simt")
+        assert set(tb) == {"loss", "loss_sem", "loss_vote"} and np.isfinite(tb["loss"])
+        losses.append(tb["loss"])
+    assert losses[-1] < losses[0], losses
+    assert int(model.global_step) == 4
+    assert all(p.grad is not None and p.grad.data_ptr() == red._view(p).data_ptr() for p in params)

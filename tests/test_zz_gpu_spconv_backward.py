@@ -439,3 +439,48 @@ def test_vote_targets_vs_oracle(lib):
     same = (got_m.cpu() == want_m) & ((got_t.cpu() - want_t).abs().max(1).values <= 1e-5)
     assert same.float().mean().item() >= 0.999, same.float().mean().item()
     assert 0.05 < want_m.mean().item() < 0.95
+
+
+def test_partial_training_step_on_device(lib):
+    """train_step.partial_training_step on cuda:0: the first step's two loss terms equal the oracle's training-mode
+    forward (batch-statistics BatchNorm) on the same batch, and a few AdamW steps on the fixed batch lower the loss."""
+    from cagroup3d_b200 import dist as D, model_init, synthetic, train_step as TS
+    from oracle import cagroup3d_oracle as O, train_oracle as T
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 7 + i, 1500, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    model = model_init.seeded_model(ncls, False, seed=4)
+    with torch.no_grad():
+        model.dense_head.semantic_conv.bias.fill_(-1.0)
+    pts = torch.from_numpy(batch["points"])
+    orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, False))
+    orc.train_bn = True
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+    hi, Cc = res["head"], torch.from_numpy(res["bb_coords"])
+    ws, wv = [], []
+    for b in range(B):
+        rows = torch.nonzero(Cc[:, 0] == b).squeeze(1)
+        vox = Cc[rows, 1:].float() * 0.02
+        gtb, gtl = torch.from_numpy(scenes[b][1][:, :7]).float(), torch.from_numpy(scenes[b][1][:, 7]).long()
+        sl, _ = T.assign_semantic(vox, gtb, gtl)
+        ot, om = T.vote_targets_from_masks(torch.from_numpy(scenes[b][0][:, :3]).float(), vox, gtb, torch.from_numpy(scenes[b][2]),
+                                           torch.from_numpy(scenes[b][3]), ncls)
+        w = (om / torch.ones_like(om).sum() + 1e-6)[:, None].repeat(1, 3)
+        wv.append(T.smooth_l1_sum(hi["offsets"][rows], ot, w))
+        ws.append(T.focal_loss(hi["sem"][rows], sl, max(float((sl >= 0).sum()), 1.0)))
+    want_sem, want_vote = float(torch.stack(ws).mean()), float(torch.stack(wv).mean())
+
+    model = model.to(DEV).train()
+    params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head.semantic_conv", "dense_head.offset_block"))]
+    opt = torch.optim.AdamW(params, lr=2e-3)
+    red = D.GradientAllReducer(params)
+    losses = []
+    for step in range(4):
+        bd = {"points": pts.clone().to(DEV), "batch_size": B, "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float().to(DEV),
+              "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+        tb = TS.partial_training_step(model, bd, opt, red)
+        if step == 0:
+            assert abs(tb["loss_sem"] - want_sem) <= 2e-3 * max(1.0, abs(want_sem)), (tb, want_sem)
+            assert abs(tb["loss_vote"] - want_vote) <= 2e-3 * max(1.0, abs(want_vote)), (tb, want_vote)
+        losses.append(tb["loss"])
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
