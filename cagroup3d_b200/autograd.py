@@ -267,3 +267,69 @@ class BiasFunction(torch.autograd.Function):
 
 def add_bias(F: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     return BiasFunction.apply(F, bias)
+
+
+# ---- grouped convolution (one weight group per class, cagroup_head.py:227-282 batched over the classes) ------------------
+class GroupedConvFunction(torch.autograd.Function):
+    """Y[row(j)] = sum_k X[nbr[k][j]] @ W[g(j)][k] where the positions j of weight group g are the contiguous range
+    [pos_off[g], pos_off[g+1]) of the (positional) table and its input rows the range [in_off[g], in_off[g+1]) -- the
+    class-batched layout of head.CAGroup3DHead.class_maps (class index folded into the batch index, rows class-major).
+    forward / dX: ONE grouped launch each (tile -> group table); dW: one cg3d_spconv_wgrad per group over its columns."""
+
+    @staticmethod
+    def forward(ctx, X, W, nbr, out_rows, n_out, K, pos_off, in_off, impl):
+        tile = 128 if (impl or S.get_conv_impl()) == "tc" and S.tc_supported(W.shape[-2], W.shape[-1], K) else 64
+        ctx.save_for_backward(X, W)
+        ctx.nbr, ctx.out_rows, ctx.K, ctx.pos_off, ctx.in_off, ctx.impl = nbr, out_rows, K, list(pos_off), list(in_off), impl
+        Y = torch.zeros((n_out, W.shape[-1]), dtype=torch.float32, device=X.device)
+        return S.gemm_rows(X.detach(), nbr, W.detach().contiguous(), n_out, K, tiles=S.make_tiles(list(pos_off), X.device, tile),
+                           out=Y, out_rows=out_rows, impl=impl)
+
+    @staticmethod
+    def backward(ctx, dY):
+        X, W = ctx.saved_tensors
+        dY = dY.contiguous()
+        G, K, Cin, Cout = W.shape[0], ctx.K, W.shape[-2], W.shape[-1]
+        dX = dW = None
+        if ctx.needs_input_grad[0]:
+            Wt = transpose_weights(W.detach().reshape(G, K, Cin, Cout))
+            nbrT = table_transpose(ctx.nbr, X.shape[0], ctx.out_rows)
+            tile = 128 if (ctx.impl or S.get_conv_impl()) == "tc" and S.tc_supported(Cout, Cin, K) else 64
+            dX = torch.zeros((X.shape[0], Cin), dtype=torch.float32, device=X.device)
+            S.gemm_rows(dY, nbrT, Wt, X.shape[0], K, tiles=S.make_tiles(ctx.in_off, X.device, tile), out=dX, impl=ctx.impl)
+        if ctx.needs_input_grad[1]:
+            dW = torch.stack([wgrad(X.detach(), ctx.nbr, dY, K, ctx.out_rows, cols=(ctx.pos_off[g], ctx.pos_off[g + 1]))
+                              for g in range(G)]).reshape(W.shape)
+        return dX, dW, None, None, None, None, None, None, None
+
+
+def grouped_conv(X: torch.Tensor, W: torch.Tensor, nbr: torch.Tensor, out_rows, n_out: int, K: int, pos_off, in_off,
+                 impl: Optional[str] = None) -> torch.Tensor:
+    """W: [G, K, Cin, Cout] (torch.stack of the per-class kernels, which keeps the autograd link to the parameters)."""
+    return GroupedConvFunction.apply(X, W, nbr, out_rows, n_out, K, pos_off, in_off, impl)
+
+
+class SegmentMeanFunction(torch.autograd.Function):
+    """UNWEIGHTED_AVERAGE quantisation of point features (cagroup_head.py:257-271): out[u] = mean of the rows p with
+    inverse[p] == u."""
+
+    @staticmethod
+    def forward(ctx, P, inverse, n_unique):
+        Pd = P.detach().contiguous()
+        n, C = Pd.shape
+        dev = Pd.device
+        out = torch.empty((n_unique, C), dtype=torch.float32, device=dev)
+        cnt = torch.empty((max(n_unique, 1),), dtype=torch.float32, device=dev)
+        ws = torch.empty((max(n_unique, 1) * C,), dtype=torch.int64, device=dev)
+        S._call("cg3d_segment_mean", Pd, C, None, 0, None, inverse, n, n_unique, C, out, cnt, ws)
+        ctx.save_for_backward(inverse, cnt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        inverse, cnt = ctx.saved_tensors
+        return segment_mean_backward(dOut, inverse, cnt), None, None
+
+
+def segment_mean(P: torch.Tensor, inverse: torch.Tensor, n_unique: int) -> torch.Tensor:
+    return SegmentMeanFunction.apply(P, inverse, n_unique)

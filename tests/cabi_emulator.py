@@ -97,26 +97,34 @@ def cg3d_spconv_simt(**a):
     x, W, out = a["in"], a["W"], a["out"]
     n_out, Cin, Cout, K = a["n_out"], a["Cin"], a["Cout"], a["K"]
     assert x.shape[1] == Cin and out.shape == (n_out, Cout) and a["ldi"] == x.stride(0) and a["ldo"] == out.stride(0)
-    assert a["tile_row0"] is None and a["n_tiles"] == 0
-    W = W.reshape(K, Cin, Cout)
+    W = W.reshape(-1, K, Cin, Cout)
     xin = _ACT[a["in_act"]](x)
-    acc = torch.zeros((n_out, Cout), dtype=x.dtype)
-    rows = _rows(n_out, a["out_rows"])
-    for k in range(K):
-        if a["nbr"] is None:
-            acc[rows] += xin[torch.arange(n_out)] @ W[k]
-            continue
-        assert a["nbr"].shape == (K, max(n_out, 1))
-        src = a["nbr"][k, :n_out].long()
-        hit = src >= 0
-        acc.index_add_(0, rows[hit], xin[src[hit]] @ W[k])
-    if a["scale"] is not None:
-        acc = acc * a["scale"]
-    if a["shift"] is not None:
-        acc = acc + a["shift"]
-    if a["residual"] is not None:
-        acc = acc + a["residual"]
-    out.copy_(_ACT[a["act"]](acc))
+    if a["tile_row0"] is None:
+        assert a["n_tiles"] == 0 and W.shape[0] == 1
+        tiles = [(0, n_out, 0)]
+    else:                                   # grouped mode: only the positions covered by a tile are written
+        assert len(a["tile_row0"]) == len(a["tile_rows"]) == len(a["tile_group"]) == a["n_tiles"]
+        assert int(a["tile_rows"].max()) <= 64, "the SIMT kernel's tile holds 64 rows"
+        tiles = list(zip(a["tile_row0"].tolist(), a["tile_rows"].tolist(), a["tile_group"].tolist()))
+    for p0, np_, g in tiles:
+        pos = torch.arange(p0, p0 + np_)
+        rows = a["out_rows"].long()[pos] if a["out_rows"] is not None else pos
+        acc = torch.zeros((np_, Cout), dtype=x.dtype)
+        for k in range(K):
+            if a["nbr"] is None:
+                acc += xin[rows] @ W[g, k]
+                continue
+            assert a["nbr"].shape == (K, max(n_out, 1))
+            src = a["nbr"][k, pos].long()
+            hit = src >= 0
+            acc[hit] += xin[src[hit]] @ W[g, k]
+        if a["scale"] is not None:
+            acc = acc * a["scale"].reshape(-1, Cout)[g]
+        if a["shift"] is not None:
+            acc = acc + a["shift"].reshape(-1, Cout)[g]
+        if a["residual"] is not None:
+            acc = acc + a["residual"][rows]
+        out[rows] = _ACT[a["act"]](acc)
 
 
 def cg3d_affine_act(**a):
@@ -331,6 +339,15 @@ def cg3d_vote_targets(**a):
 def cg3d_column_sum(**a):
     assert a["x"].shape == (a["n"], a["C"]) and a["ldx"] == a["x"].stride(0)
     a["out"].copy_(a["x"].sum(0))
+
+
+def cg3d_segment_mean(**a):
+    assert a["ref"] is None and a["srcB"] is None, "only the plain (ref == NULL) form is emulated"
+    src, inv, U, C = a["srcA"], a["inverse"].long(), a["n_unique"], a["C"]
+    assert src.shape == (a["n"], C) and a["ldA"] == src.stride(0) and a["workspace"].numel() >= U * C
+    cnt = torch.bincount(inv, minlength=U).to(src.dtype)
+    a["counts"][:U] = cnt
+    a["out"].copy_(torch.zeros((U, C), dtype=src.dtype).index_add_(0, inv, src) / cnt[:, None])
 
 
 def install(monkeypatch):

@@ -268,3 +268,49 @@ def test_partial_training_step_driver(monkeypatch):
     assert losses[-1] < losses[0], losses
     assert int(model.global_step) == 4
     assert all(p.grad is not None and p.grad.data_ptr() == red._view(p).data_ptr() for p in params)
+
+
+def test_grouped_conv_and_segment_mean_wiring(monkeypatch):
+    """GroupedConvFunction in the class-batched layout of the head (class folded into the batch index, rows class-major,
+    one weight group per class) and SegmentMeanFunction, against autograd through per-class oracle convolutions."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    E.install(monkeypatch)
+    rng = np.random.default_rng(8)
+    G, Bs, Cin, Cout, k = 3, 2, 8, 12, 3
+    coords, off = [], [0]
+    for g_ in range(G):
+        c = np.concatenate([rng.integers(0, Bs, (150 + 90 * g_, 1)) + g_ * Bs, rng.integers(-5, 5, (150 + 90 * g_, 3))], 1)
+        c = me.unique_first(c)[0]
+        coords.append(c)
+        off.append(off[-1] + len(c))
+    coords = np.concatenate(coords)
+    n = len(coords)
+    Wd = torch.from_numpy(rng.standard_normal((G, k ** 3, Cin, Cout)) / 4).requires_grad_(True)
+    # point features -> quantise-average onto the voxels -> grouped conv
+    inv = np.concatenate([np.arange(n), rng.integers(0, n, 2 * n)])
+    Pd = torch.from_numpy(rng.standard_normal((len(inv), Cin))).requires_grad_(True)
+    invt = torch.from_numpy(inv)
+    Xd = torch.zeros((n, Cin), dtype=torch.float64).index_add_(0, invt, Pd) / torch.bincount(invt, minlength=n).double()[:, None]
+    cm_o = me.CoordMap(coords, 1)
+    rules = me.kernel_map(cm_o, coords, k, 1)
+    Yd = torch.zeros((n, Cout), dtype=torch.float64)
+    for g_ in range(G):
+        sel = [(i[(o >= off[g_]) & (o < off[g_ + 1])], o[(o >= off[g_]) & (o < off[g_ + 1])]) for i, o in rules]
+        Yd = Yd + me._apply_rules(Xd, Wd[g_], sel, n)
+    dY = torch.from_numpy(rng.standard_normal((n, Cout)))
+    (Yd * dY).sum().backward()
+
+    mgr = S.Manager()
+    cm = E.cpu_map(coords, 1, mgr)
+    nbr, order = S.neighbor_table(cm, cm, k, mgr, ordered=True)
+    # the head keeps positions class-major: order the emulator's random permutation by class
+    cls_of = torch.from_numpy(np.searchsorted(np.array(off), order.numpy(), side="right") - 1)
+    perm = torch.argsort(cls_of, stable=True)
+    nbr, order = nbr[:, perm].contiguous(), order[perm].contiguous()
+    P = Pd.detach().float().requires_grad_(True)
+    W = Wd.detach().float().requires_grad_(True)
+    X = A.segment_mean(P, invt.int(), n)
+    Y = A.grouped_conv(X, W, nbr, order, n, k ** 3, off, off, impl="simt")
+    assert _rel(Y.detach(), Yd.detach()) < 1e-5
+    Y.backward(dY.float())
+    assert _rel(P.grad, Pd.grad) < 1e-5 and _rel(W.grad, Wd.grad) < 1e-5

@@ -484,3 +484,45 @@ def test_partial_training_step_on_device(lib):
             assert abs(tb["loss_vote"] - want_vote) <= 2e-3 * max(1.0, abs(want_vote)), (tb, want_vote)
         losses.append(tb["loss"])
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("impl,cin,cout,k", [("simt", 8, 12, 3), ("tc", 64, 64, 3), ("tc", 64, 64, 5)])
+def test_grouped_conv_and_segment_mean_backward(lib, impl, cin, cout, k):
+    """GroupedConvFunction (one weight group per class, class folded into the batch index: the layout of
+    head.class_maps) + SegmentMeanFunction against autograd through per-class oracle convolutions."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    rng = np.random.default_rng(8)
+    G, Bs = 3, 2
+    coords, off = [], [0]
+    for g_ in range(G):
+        c = np.concatenate([rng.integers(0, Bs, (900 + 300 * g_, 1)) + g_ * Bs, rng.integers(-8, 8, (900 + 300 * g_, 3))], 1)
+        c = me.unique_first(c)[0]
+        coords.append(c)
+        off.append(off[-1] + len(c))
+    coords = np.concatenate(coords)
+    n = len(coords)
+    Wd = torch.from_numpy(rng.standard_normal((G, k ** 3, cin, cout)) / np.sqrt(cin * 8)).requires_grad_(True)
+    inv = np.concatenate([np.arange(n), rng.integers(0, n, 2 * n)])
+    Pd = torch.from_numpy(rng.standard_normal((len(inv), cin))).requires_grad_(True)
+    invt = torch.from_numpy(inv)
+    Xd = torch.zeros((n, cin), dtype=torch.float64).index_add_(0, invt, Pd) / torch.bincount(invt, minlength=n).double()[:, None]
+    rules = me.kernel_map(me.CoordMap(coords, 1), coords, k, 1)
+    Yd = torch.zeros((n, cout), dtype=torch.float64)
+    for g_ in range(G):
+        sel = [(i[(o >= off[g_]) & (o < off[g_ + 1])], o[(o >= off[g_]) & (o < off[g_ + 1])]) for i, o in rules]
+        Yd = Yd + me._apply_rules(Xd, Wd[g_], sel, n)
+    dY = torch.from_numpy(rng.standard_normal((n, cout)))
+    (Yd * dY).sum().backward()
+
+    mgr = S.Manager(batch_bits=max(1, (G * Bs - 1).bit_length()))
+    cm = S.build_map(torch.from_numpy(coords.astype(np.int32)).to(DEV), 1, mgr)
+    nbr, order = S.neighbor_table(cm, cm, k, mgr, ordered=True, group_div=Bs)
+    P = Pd.detach().float().to(DEV).requires_grad_(True)
+    W = Wd.detach().float().to(DEV).requires_grad_(True)
+    X = A.segment_mean(P, invt.int().to(DEV), n)
+    Y = A.grouped_conv(X, W, nbr, order, n, k ** 3, off, off, impl=impl)
+    _close(Y.detach(), Yd.detach(), 2e-4)
+    Y.backward(dY.float().to(DEV))
+    torch.cuda.synchronize()
+    _close(P.grad, Pd.grad, 2e-4)
+    _close(W.grad, Wd.grad, 2e-4)
