@@ -293,7 +293,7 @@ class GroupedConvFunction(torch.autograd.Function):
         dX = dW = None
         if ctx.needs_input_grad[0]:
             Wt = transpose_weights(W.detach().reshape(G, K, Cin, Cout))
-            nbrT = table_transpose(ctx.nbr, X.shape[0], ctx.out_rows)
+            nbrT = table_transpose(ctx.nbr, X.shape[0], ctx.out_rows) if ctx.nbr is not None else None     # K == 1: identity rows
             tile = 128 if (ctx.impl or S.get_conv_impl()) == "tc" and S.tc_supported(Cout, Cin, K) else 64
             dX = torch.zeros((X.shape[0], Cin), dtype=torch.float32, device=X.device)
             S.gemm_rows(dY, nbrT, Wt, X.shape[0], K, tiles=S.make_tiles(ctx.in_off, X.device, tile), out=dX, impl=ctx.impl)

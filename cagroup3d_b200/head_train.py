@@ -57,3 +57,86 @@ def semantic_and_vote_loss(head, out: S.SparseTensor, sem: torch.Tensor, offs: t
         n_pos = max(float(reduce_mean((sem_labels >= 0).sum().float())), 1.)
         sems.append(focal(sem[rows], sem_labels, avg_factor=n_pos))
     return torch.mean(torch.stack(sems)), torch.mean(torch.stack(votes))
+
+
+# ---- the per-class grouping branch (cagroup_head.py:227-282, 627-652) in training mode -------------------------------------
+def coordinate_phase(head, out: S.SparseTensor, sem: torch.Tensor, offs: torch.Tensor, B: int) -> dict:
+    """Everything of head.CAGroup3DHead.class_maps that depends on coordinates and on the (detached) semantic scores /
+    vote offsets only: threshold selection, voted points, class voxels at both sizes with their point -> voxel maps.
+    No gradient flows through it (voxel indices are floors).  Same kernels, same class-batched layout (row batch index =
+    cls * B + b, rows class-major) as the inference plan."""
+    dev = out.F.device
+    N, ncls, nv = out.cmap.n, head.n_classes, (3 if head.with_yaw else 1)
+    vsA = torch.tensor(head.voxel_size_list, dtype=torch.float32, device=dev)
+    vsE = (vsA * head.expand).contiguous()
+    semd, offd = sem.detach().contiguous(), offs.detach().contiguous()
+    i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+    pad_rows = i32(B)
+    S._call("cg3d_first_rows", out.C, N, B, pad_rows)
+    mm = i32(6)
+    S._call("cg3d_coord_bounds", out.C, N, mm)
+    voted = torch.empty((N, nv, 3), dtype=torch.float32, device=dev)
+    S._call("cg3d_vote_points", out.C, offd, N, nv, float(head.voxel_size), out.cmap.stride, mm, voted)
+    flags = i32(ncls * N)
+    S._call("cg3d_semantic_flags", semd, N, ncls, float(head.semantic_threshold), flags)
+    pos, total = S.exclusive_scan(flags)
+    bounds = torch.cat([pos[::N][:ncls], total]).cpu().tolist()
+    sel_rows = i32(max(bounds[-1], 1))
+    S._call("cg3d_compact_rows", flags, pos, N, ncls, sel_rows)
+    fused = [0]
+    for c in range(ncls):
+        fused.append(fused[-1] + (nv + 1) * (bounds[c + 1] - bounds[c] + B))
+    nf = fused[-1]
+    meta = torch.tensor([bounds, fused], dtype=torch.int32).to(dev)
+    coordsA, coordsE, ref = i32(nf, 4), i32(nf, 4), i32(nf, 2)
+    S._call("cg3d_class_points", out.C, voted, sel_rows, meta[0], meta[1], pad_rows, vsA, vsE, ncls, B, nv, head.expand, nf,
+            float(head.voxel_size), coordsA, coordsE, ref)
+    mgr = S.Manager(batch_bits=max(1, (ncls * B - 1).bit_length()))
+    mapA, _, invA = S.unique_first(coordsA, 1, mgr, want_inverse=True)
+    mapE, _, invE = S.unique_first(coordsE, head.expand, mgr, want_inverse=True)
+    starts = meta[1][:ncls].long()
+    offA = invA[starts].cpu().tolist() + [mapA.n]
+    offE = invE[starts].cpu().tolist() + [mapE.n]
+    return dict(ref=ref, invA=invA, invE=invE, mapA=mapA, mapE=mapE, offA=offA, offE=offE, mgr=mgr, vsA=vsA)
+
+
+def _class_bn_elu(F: torch.Tensor, bns, off) -> torch.Tensor:
+    """every class has its own BatchNorm: batch statistics over the class's row range, then ELU"""
+    parts = [BT._bn(bn, F[off[c]:off[c + 1]]) for c, bn in enumerate(bns)]
+    return A.elu(torch.cat(parts))
+
+
+def class_branch(head, out: S.SparseTensor, offF: torch.Tensor, art: dict, B: int, impl: Optional[str] = None) -> dict:
+    """cagroup_head.py:227-282 + forward_single for all classes at once, differentiable.  -> dict(coords (V, 4) int32 with
+    batch index cls * B + b, class_off, feat (V, C), centerness (V, 1), cls (V, n_classes), reg (V, n_reg), bbox_pred (V, n_reg)
+    = exp(scale_c * reg[:, :6]) | reg[:, 6:])."""
+    C, ncls, nv = head.out_channels, head.n_classes, (3 if head.with_yaw else 1)
+    mapA, mapE, offA, offE, mgr = art["mapA"], art["mapE"], art["offA"], art["offE"], art["mgr"]
+    N = out.cmap.n
+    row, kind = art["ref"][:, 0].long(), art["ref"][:, 1].long()
+    # point features: the voted copy (kind >= 0) carries its slice of the offset features, the original copy the backbone's
+    P = torch.where((kind >= 0).unsqueeze(1), offF.view(N, nv, C)[row, kind.clamp(min=0)], out.F[row])
+    FA = A.segment_mean(P, art["invA"], mapA.n)
+    FE = A.segment_mean(P, art["invE"], mapE.n)
+    st = lambda ts: torch.stack(list(ts))
+    nbrE, ordE = S.neighbor_table(mapE, mapE, 5, mgr, ordered=True, group_div=B)
+    EF = A.grouped_conv(FE, st(m[0].kernel for m in head.cls_individual_expand_out), nbrE, ordE, mapE.n, 125, offE, offE, impl)
+    EF = _class_bn_elu(EF, [m[1] for m in head.cls_individual_expand_out], offE)
+    nbrU, ordU = S.transpose_table(mapE, mapA, head.expand, mgr, ordered=True, group_div=B)
+    UP = A.grouped_conv(EF, st(m[0].kernel for m in head.cls_individual_up), nbrU, ordU, mapA.n, head.expand ** 3, offA, offE, impl)
+    UP = _class_bn_elu(UP, [m[1][0] for m in head.cls_individual_up], offA)
+    nbrA, ordA = S.neighbor_table(mapA, mapA, head.cls_kernel, mgr, ordered=True, group_div=B)
+    OA = A.grouped_conv(FA, st(m[0].kernel for m in head.cls_individual_out), nbrA, ordA, mapA.n, head.cls_kernel ** 3, offA, offA, impl)
+    OA = _class_bn_elu(OA, [m[1] for m in head.cls_individual_out], offA)
+    Wf = st(m[0].kernel.unsqueeze(0) for m in head.cls_individual_fuse)                       # [G, 1, 2C, C]
+    O = A.grouped_conv(torch.cat([UP, OA], 1), Wf, None, None, mapA.n, 1, offA, offA, impl)
+    O = _class_bn_elu(O, [m[1] for m in head.cls_individual_fuse], offA)
+    x = S.SparseTensor(O, mapA, mgr)
+    ctr = A.conv(x, head.centerness_conv.kernel, 1, 1, impl=impl).F
+    cls = A.add_bias(A.conv(x, head.cls_conv.kernel, 1, 1, impl=impl).F, head.cls_conv.bias)
+    reg = A.conv(x, head.reg_conv.kernel, 1, 1, impl=impl).F
+    # Scale + exp (cagroup_head.py:639-645): row-wise scale of the row's class; glue on (V, 6) values
+    scale_rows = torch.cat([head.scales[c].scale.reshape(1).expand(offA[c + 1] - offA[c]) for c in range(ncls)])
+    bbox_pred = torch.cat([torch.exp(reg[:, :6] * scale_rows.unsqueeze(1)), reg[:, 6:]], 1)
+    head.fold.clear()
+    return dict(coords=mapA.coords, class_off=offA, feat=O, centerness=ctr, cls=cls, reg=reg, bbox_pred=bbox_pred)

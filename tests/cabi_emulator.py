@@ -68,12 +68,27 @@ def _neighbor_table(in_map, out_map, k, mgr, ordered=False, **kw):
     nbr = torch.from_numpy(Bk.rules_to_table(rules, max(out_map.n, 1)).astype(np.int32))
     if not ordered:
         return nbr
-    # a positional table in a non-trivial order, so the out_rows plumbing is exercised
-    perm = torch.from_numpy(np.random.default_rng(out_map.n + k).permutation(out_map.n).astype(np.int32))
+    # a positional table in a non-trivial order, so the out_rows plumbing is exercised; with group_div (grouped convs:
+    # the class is batch // group_div) positions stay class-major, as the real tile orders keep them
+    perm = np.random.default_rng(out_map.n + k).permutation(out_map.n)
+    if kw.get("group_div"):
+        perm = perm[np.argsort(out_map._me.coords[perm, 0] // kw["group_div"], kind="stable")]
+    perm = torch.from_numpy(perm.astype(np.int32))
     return nbr[:, perm.long()].contiguous(), perm
 
 
 def _transpose_table(in_map, fine_map, k, mgr, ordered=False, **kw):
+    if k == 3:          # generative k3 s3 onto given coordinates (A13), the oracle's child <-> tap assignment
+        f = fine_map._me.coords
+        r = np.mod(f[:, 1:], 3)
+        off = np.where(r == 0, 0, np.where(r == 1, 1, -1))
+        c = f.copy()
+        c[:, 1:] = f[:, 1:] - off
+        tap = (off[:, 0] + 1) + 3 * ((off[:, 1] + 1) + 3 * (off[:, 2] + 1))
+        nbr = np.full((27, max(len(f), 1)), -1, np.int32)
+        nbr[tap, np.arange(len(f))] = in_map._me.lookup(c)
+        nbr = torch.from_numpy(nbr)
+        return (nbr, None) if ordered else nbr
     assert k == 2
     f = fine_map._me.coords
     ts_c, ts_f = in_map.stride, fine_map.stride

@@ -314,3 +314,101 @@ def test_grouped_conv_and_segment_mean_wiring(monkeypatch):
     assert _rel(Y.detach(), Yd.detach()) < 1e-5
     Y.backward(dY.float())
     assert _rel(P.grad, Pd.grad) < 1e-5 and _rel(W.grad, Wd.grad) < 1e-5
+
+
+def _oracle_class_artifacts(res, thr, B, cfg, mgr):
+    """the class-batched coordinate artifacts of head_train.coordinate_phase, rebuilt from the oracle's training-mode
+    forward exactly as its per-class loop forms them (cagroup3d_oracle.Oracle.head), class folded into the batch index."""
+    from cagroup3d_b200 import sparse as S
+    hi = res["head"]
+    ncls, vs, ex = cfg["n_classes"], cfg["voxel_size"], cfg["expand"]
+    Cc = torch.from_numpy(res["bb_coords"])
+    Cf = Cc.float()
+    pad_id = np.array([np.nonzero(res["bb_coords"][:, 0] == b)[0][0] for b in range(B)], dtype=np.int64)
+    sizes = O.class_voxel_sizes(ncls)
+    qa_all, qe_all, ref = [], [], []
+    for cls in range(ncls):
+        s = torch.sigmoid(hi["sem"][:, cls])
+        sel = torch.cat([torch.nonzero(s > thr).squeeze(1), torch.from_numpy(pad_id)])
+        vc = Cf[sel].view(-1, 1, 4).repeat(1, 1, 1)
+        vc[:, :, 1:4] = hi["voted"][sel]
+        oc = Cf[sel].clone()
+        oc[:, 1:4] *= vs
+        fuse_c = torch.cat([vc.reshape(-1, 4), oc], 0)
+        vsz = torch.tensor(sizes[cls], dtype=torch.float32)
+        qa, qe = fuse_c.clone(), fuse_c.clone()
+        qa[:, 1:] = torch.floor(fuse_c[:, 1:] / vsz)
+        qe[:, 1:] = torch.floor(fuse_c[:, 1:] / (vsz * ex)) * ex
+        qa[:, 0] += cls * B
+        qe[:, 0] += cls * B
+        qa_all.append(qa.long().numpy()); qe_all.append(qe.long().numpy())
+        ref.append(torch.cat([torch.stack([sel, torch.zeros_like(sel)], 1), torch.stack([sel, -torch.ones_like(sel)], 1)]))
+    qa_all, qe_all, ref = np.concatenate(qa_all), np.concatenate(qe_all), torch.cat(ref).int()
+    ua, inva, _ = me.unique_first(qa_all)
+    ue, inve, _ = me.unique_first(qe_all)
+    mapA, mapE = E.cpu_map(ua, 1, mgr), E.cpu_map(ue, ex, mgr)
+    cls_rows = lambda u: [0] + np.cumsum(np.bincount(u[:, 0] // B, minlength=ncls)).tolist()
+    return dict(ref=ref, invA=torch.from_numpy(inva).int(), invE=torch.from_numpy(inve).int(), mapA=mapA, mapE=mapE,
+                offA=cls_rows(ua), offE=cls_rows(ue), mgr=mgr, vsA=torch.tensor(sizes))
+
+
+def test_class_branch_training_wiring_vs_oracle(monkeypatch):
+    """head_train.class_branch (per-class grouping branch, all classes in grouped launches, per-class batch-statistics
+    BatchNorm) on the emulated C ABI against the oracle's per-class loop in training mode: features, the three prediction
+    maps and the gradients of every parameter of the branch and of the backbone features."""
+    from cagroup3d_b200 import head_train as HT, model_init, sparse as S, synthetic
+    E.install(monkeypatch)
+    B, ncls = 2, 18
+    batch = synthetic.make_batch(B, target_voxels=500, config=12)
+    model = model_init.seeded_model(ncls, False, seed=6)
+    pts = torch.from_numpy(batch["points"])
+    cfg = O.default_cfg(ncls, False)
+    orc0 = O.Oracle(model.state_dict(), cfg)
+    orc0.train_bn = True
+    model_init.calibrate_semantic_bias(model, orc0.forward(pts, B, stages="backbone")["bb_feats"], 0.10)
+    orc = O.Oracle(model.state_dict(), cfg, dtype=torch.float64)
+    branch = ("dense_head.cls_individual", "dense_head.centerness_conv", "dense_head.cls_conv", "dense_head.reg_conv",
+              "dense_head.scales", "dense_head.feature_offset")
+    names = [k for k in orc.p if k.startswith(branch) and k.endswith(("kernel", "bn.weight", "bn.bias", "conv.bias", "scale"))]
+    for k in names + ["backbone_3d.out.4.bn.bias"]:              # the last one puts the backbone features on the tape
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    orc.train_bn = True
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+    res["bb_feats"].retain_grad()
+    maps = res["head"]["maps"]
+    g = torch.Generator().manual_seed(1)
+    loss, dys = 0.0, []
+    for m in maps:
+        d = [torch.randn(tuple(m[k].shape), generator=g, dtype=torch.float64) for k in ("ctr", "cls", "bbox")]
+        dys.append(d)
+        loss = loss + (m["ctr"] * d[0]).sum() + (m["cls"] * d[1]).sum() + (m["bbox"] * d[2]).sum()
+    loss.backward()
+
+    model.train()
+    head = model.dense_head
+    head.semantic_threshold = 0.05
+    mgr = S.Manager()
+    cm = E.cpu_map(res["bb_coords"], 2, mgr)
+    mgr.by_stride[2] = cm
+    outF = res["bb_feats"].detach().float().contiguous().requires_grad_(True)
+    out = S.SparseTensor(outF, cm, mgr)
+    sem, offs, offF = HT.shared_part(head, out, impl="simt")
+    assert (offF.detach().double() - res["head"]["offset_feat"].detach().reshape(offF.shape)).abs().max().item() < 1e-3
+    art = _oracle_class_artifacts(res, 0.05, B, cfg, S.Manager())
+    got = HT.class_branch(head, out, offF, art, B, impl="simt")
+    want_coords = np.concatenate([np.concatenate([m["coords"][:, :1] + c * B, m["coords"][:, 1:]], 1) for c, m in enumerate(maps)])
+    assert np.array_equal(got["coords"].numpy(), want_coords)
+    cat = lambda k: torch.cat([m[k] for m in maps]).detach()
+    assert sum(len(m["coords"]) for m in maps) > 10 * ncls
+    for k_got, k_want in (("feat", "feat"), ("centerness", "ctr"), ("cls", "cls"), ("reg", "reg"), ("bbox_pred", "bbox")):
+        assert (got[k_got].detach().double() - cat(k_want)).abs().max().item() < 2e-3, k_got
+    dctr, dcls, dbox = (torch.cat([d[i] for d in dys]).float() for i in range(3))
+    ((got["centerness"] * dctr).sum() + (got["cls"] * dcls).sum() + (got["bbox_pred"] * dbox).sum()).backward()
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
+                 / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
+    assert worst[0] < 2e-3, worst
+    # gradient reaching the backbone features: directly (the un-voted copy of every selected voxel) and through the
+    # offset features
+    assert _rel(outF.grad, res["bb_feats"].grad) < 2e-3
