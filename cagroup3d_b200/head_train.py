@@ -140,3 +140,41 @@ def class_branch(head, out: S.SparseTensor, offF: torch.Tensor, art: dict, B: in
     bbox_pred = torch.cat([torch.exp(reg[:, :6] * scale_rows.unsqueeze(1)), reg[:, 6:]], 1)
     head.fold.clear()
     return dict(coords=mapA.coords, class_off=offA, feat=O, centerness=ctr, cls=cls, reg=reg, bbox_pred=bbox_pred)
+
+
+# ---- the whole first-stage loss (CAGroup3DHead.loss, cagroup_head.py:322-398) -----------------------------------------------
+def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_labels, scene_points, pts_semantic_mask,
+                     pts_instance_mask, impl: Optional[str] = None, art: Optional[dict] = None):
+    """shared part -> coordinate phase -> per-class branch -> the five loss terms per sample -> batch means.
+    Returns (loss, tb_dict) like the reference (`one_stage_loss` = the sum).  `art`: precomputed coordinate artifacts
+    (tests teacher-force them); WITH_YAW False only."""
+    assert not head.with_yaw
+    B = batch_size
+    sem, offs, offF = shared_part(head, out, impl=impl)
+    if art is None:
+        with torch.no_grad():
+            art = coordinate_phase(head, out, sem, offs, B)
+    br = class_branch(head, out, offF, art, B, impl=impl)
+    crit = TT.FirstStageLoss(head.n_classes)
+    coords, vs = br["coords"], art["vsA"]
+    C = out.C
+    terms = []
+    for b in range(B):
+        ctrs, boxes, clss, pts = [], [], [], []
+        for c in range(head.n_classes):
+            lo, hi = br["class_off"][c], br["class_off"][c + 1]
+            r = lo + torch.nonzero(coords[lo:hi, 0] == c * B + b).squeeze(1)
+            ctrs.append(br["centerness"][r])
+            boxes.append(br["bbox_pred"][r])
+            clss.append(br["cls"][r])
+            pts.append(coords[r, 1:].float() * vs[c])
+        rows = torch.nonzero(C[:, 0] == b).squeeze(1)
+        vox = C[rows, 1:].float() * head.voxel_size
+        terms.append(crit.loss_single(ctrs, boxes, clss, pts, offs[rows], vox, sem[rows], vox, None, gt_bboxes[b], gt_labels[b],
+                                      scene_points[b], pts_semantic_mask[b], pts_instance_mask[b]))
+    names = ("loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote")
+    means = [torch.mean(torch.stack([t[i] for t in terms])) for i in range(5)]
+    loss = sum(means)
+    tb = {n: float(m.detach()) for n, m in zip(names, means)}
+    tb["one_stage_loss"] = float(loss.detach())
+    return loss, tb

@@ -1,9 +1,14 @@
-"""One training step of what the CUDA path can differentiate so far (BASELINE config 4): BiResNet in
-training mode, the shared part of the head, the semantic and vote terms of CAGroup3DHead.loss, backward, the DDP
-gradient all-reduce and the optimizer step -- tools/train_utils/train_utils.py:42-75 (train_one_epoch's inner loop)
-restricted to those two loss terms.  The per-class grouping branch and the RoI stage are not differentiable here yet
-(DESIGN.md section 9), so this is NOT the reference's full loss; `CAGroup3D.forward` keeps refusing training mode until
-it is.
+"""Training steps of what the CUDA path can differentiate so far (BASELINE config 4):
+tools/train_utils/train_utils.py:42-75 (train_one_epoch's inner loop: forward, loss, backward, optimizer step), with
+the DDP gradient average done by dist.GradientAllReducer.
+
+  first_stage_training_step   BiResNet in training mode + the whole CAGroup3DHead in training mode + all five terms of
+                              CAGroup3DHead.loss (`one_stage_loss` of the reference's tb_dict)
+  partial_training_step       the same restricted to the semantic and vote terms (no per-class branch)
+
+The RoI stage (proposal target layer + RoI losses, cagroup_roi_head.py:512-615) is not differentiable here yet
+(DESIGN.md section 9), so neither is the reference's full two-stage loss; `CAGroup3D.forward` keeps refusing training mode
+until it is.
 """
 from __future__ import annotations
 
@@ -14,6 +19,45 @@ import torch
 from . import backbone_train as BT
 from . import head_train as HT
 from .detector import voxelize
+
+
+def _targets_of(batch_dict: dict, pts: torch.Tensor, B: int):
+    gtb, gtl, scene, semm, insm = [], [], [], [], []
+    for b in range(B):
+        g = batch_dict["gt_boxes"][b]
+        g = g[~(g == 0.).all(1)]                                           # zero padding rows (cagroup_head.py:305-308)
+        gtb.append(g[:, :7].float().contiguous())
+        gtl.append(g[:, 7].long())
+        scene.append(pts[pts[:, 0] == b][:, 1:4].contiguous())
+        semm.append(torch.as_tensor(batch_dict["semantic_mask"][b], device=pts.device).long())
+        insm.append(torch.as_tensor(batch_dict["instance_mask"][b], device=pts.device).long())
+    return gtb, gtl, scene, semm, insm
+
+
+def first_stage_training_step(model, batch_dict: dict, optimizer: Optional[torch.optim.Optimizer] = None, reducer=None,
+                              impl: Optional[str] = None) -> dict:
+    """batch_dict as for partial_training_step plus `cur_epoch` (the semantic threshold schedule, cagroup3d.py:29-31).
+    Returns the reference's first-stage tb_dict (loss_centerness, loss_bbox, loss_cls, loss_sem, loss_vote, one_stage_loss)."""
+    B = batch_dict["batch_size"]
+    pts = batch_dict["points"]
+    pts[:, -3:] = pts[:, -3:] / 255.
+    head = model.dense_head
+    head.semantic_threshold = max(model.semantic_value - int(batch_dict["cur_epoch"]) * model.semantic_iter_value,
+                                  model.semantic_min_threshold)
+    if reducer is not None:
+        reducer.zero_grad()
+    elif optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    out = BT.run_train(model.backbone_3d, voxelize(pts, model.voxel_size), impl=impl)
+    loss, tb = HT.first_stage_loss(head, out, B, *_targets_of(batch_dict, pts, B), impl=impl)
+    loss.backward()
+    if reducer is not None:
+        reducer.reduce()
+    if optimizer is not None:
+        optimizer.step()
+    if hasattr(model, "update_global_step"):
+        model.update_global_step()
+    return tb
 
 
 def partial_training_step(model, batch_dict: dict, optimizer: Optional[torch.optim.Optimizer] = None, reducer=None,
@@ -33,16 +77,7 @@ def partial_training_step(model, batch_dict: dict, optimizer: Optional[torch.opt
     x = voxelize(pts, model.voxel_size)
     out = BT.run_train(model.backbone_3d, x, impl=impl)
     sem, offs, _ = HT.shared_part(head, out, impl=impl)
-    gtb, gtl, scene, semm, insm = [], [], [], [], []
-    for b in range(B):
-        g = batch_dict["gt_boxes"][b]
-        g = g[~(g == 0.).all(1)]                                           # zero padding rows (cagroup_head.py:305-308)
-        gtb.append(g[:, :7].float().contiguous())
-        gtl.append(g[:, 7].long())
-        scene.append(pts[pts[:, 0] == b][:, 1:4].contiguous())
-        semm.append(torch.as_tensor(batch_dict["semantic_mask"][b], device=pts.device).long())
-        insm.append(torch.as_tensor(batch_dict["instance_mask"][b], device=pts.device).long())
-    loss_sem, loss_vote = HT.semantic_and_vote_loss(head, out, sem, offs, B, gtb, gtl, scene, semm, insm)
+    loss_sem, loss_vote = HT.semantic_and_vote_loss(head, out, sem, offs, B, *_targets_of(batch_dict, pts, B))
     loss = loss_sem + loss_vote
     loss.backward()
     if reducer is not None:

@@ -412,3 +412,100 @@ def test_class_branch_training_wiring_vs_oracle(monkeypatch):
     # gradient reaching the backbone features: directly (the un-voted copy of every selected voxel) and through the
     # offset features
     assert _rel(outF.grad, res["bb_feats"].grad) < 2e-3
+
+
+def test_first_stage_loss_wiring_vs_training_oracle(monkeypatch):
+    """head_train.first_stage_loss (all five terms of CAGroup3DHead.loss) on the emulated C ABI == oracle/train_oracle.
+    first_stage_loss (which reproduces the REFERENCE's training step, tests/test_train_oracle.py) on the same batch, and
+    its backward reaches the backbone features and every head parameter."""
+    from cagroup3d_b200 import head_train as HT, model_init, ops, sparse as S, synthetic, train_targets as TT
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 7 + i, 500, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    pts = torch.from_numpy(batch["points"])
+    model = model_init.seeded_model(ncls, False, seed=3)
+    cfg = O.default_cfg(ncls, False)
+    orc = O.Oracle(model.state_dict(), cfg)
+    orc.train_bn = True
+    model_init.calibrate_semantic_bias(model, orc.forward(pts, B, stages="backbone")["bb_feats"], 0.10)
+    with torch.no_grad():
+        model.dense_head.cls_conv.bias.fill_(-2.0)
+    gtb = [torch.from_numpy(b[:, :7]).float() for _, b, _, _ in scenes]
+    gtl = [torch.from_numpy(b[:, 7]).long() for _, b, _, _ in scenes]
+    semm = [torch.from_numpy(s) for _, _, s, _ in scenes]
+    insm = [torch.from_numpy(m) for _, _, _, m in scenes]
+    orc = O.Oracle(model.state_dict(), cfg)
+    want = T.first_stage_loss(orc, pts, B, gtb, gtl, semm, insm, cur_epoch=10)
+    orc.train_bn = True
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+
+    model.train()
+    head = model.dense_head
+    head.semantic_threshold = 0.05
+    mgr = S.Manager()
+    cm = E.cpu_map(res["bb_coords"], 2, mgr)
+    mgr.by_stride[2] = cm
+    outF = res["bb_feats"].detach().float().contiguous().requires_grad_(True)
+    art = _oracle_class_artifacts(res, 0.05, B, cfg, S.Manager())
+    sp = [pts[pts[:, 0] == b][:, 1:4].contiguous() for b in range(B)]
+    loss, tb = HT.first_stage_loss(head, S.SparseTensor(outF, cm, mgr), B, gtb, gtl, sp, semm, insm, impl="simt", art=art)
+    for k in ("loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote", "one_stage_loss"):
+        assert abs(tb[k] - want[k]) <= 2e-4 * max(1.0, abs(want[k])), (k, tb[k], want[k])
+    assert want["loss_bbox"] > 0 and want["loss_centerness"] > 0
+    loss.backward()
+    assert outF.grad is not None and float(outF.grad.abs().max()) > 0
+    missing = [n for n, p in head.named_parameters() if p.grad is None]
+    assert missing == [], missing
+
+
+def test_first_stage_training_step_driver(monkeypatch):
+    """train_step.first_stage_training_step end to end on the emulated C ABI, with the coordinate phase served by the
+    oracle-backed artifact builder: tb_dict keys of the reference, gradients in the reducer's buckets, loss going down."""
+    from cagroup3d_b200 import dist as D, head_train as HT, model_init, ops, sparse as S, synthetic, train_step as TS, train_targets as TT
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+    B, ncls = 2, 18
+    cfg = O.default_cfg(ncls, False)
+
+    def voxelize_cpu(points, voxel_size):
+        c = points[:, :4].clone()
+        c[:, 1:] /= voxel_size
+        ox = me.from_points(c, points[:, 4:])
+        mgr = S.Manager()
+        cm = E.cpu_map(ox.C, 1, mgr)
+        mgr.by_stride[1] = cm
+        return S.SparseTensor(ox.F.float().contiguous(), cm, mgr)
+
+    def coordinate_phase_cpu(head, out, sem, offs, Bn):
+        Cc = out.C.long()
+        ts, vs = out.cmap.stride, head.voxel_size
+        mx = ((Cc[:, 1:].max(0)[0] + ts) * vs).float()
+        mn = ((Cc[:, 1:].min(0)[0] - ts) * vs).float()
+        voted = (Cc[:, 1:].float() * vs).view(-1, 1, 3) + offs.detach().float().view(-1, 1, 3)
+        voted = torch.maximum(torch.minimum(voted, mx.view(1, 1, 3)), mn.view(1, 1, 3))
+        res = dict(bb_coords=out.C.numpy().astype(np.int64), head=dict(sem=sem.detach(), voted=voted))
+        return _oracle_class_artifacts(res, head.semantic_threshold, Bn, cfg, S.Manager())
+    monkeypatch.setattr(TS, "voxelize", voxelize_cpu)
+    monkeypatch.setattr(HT, "coordinate_phase", coordinate_phase_cpu)
+    scenes = [synthetic.make_scene(1000 * 7 + i, 200, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    model = model_init.seeded_model(ncls, False, seed=3).train()
+    with torch.no_grad():
+        model.dense_head.semantic_conv.bias.fill_(-2.5)
+    params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head."))]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    red = D.GradientAllReducer(params, bucket_mb=64)
+    losses = []
+    for _ in range(2):
+        bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "cur_epoch": 10,
+              "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
+              "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+        tb = TS.first_stage_training_step(model, bd, opt, red, impl="simt")
+        assert set(tb) == {"loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote", "one_stage_loss"}
+        losses.append(tb["one_stage_loss"])
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+    assert all(p.grad.data_ptr() == red._view(p).data_ptr() for p in params)

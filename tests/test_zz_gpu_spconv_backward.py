@@ -526,3 +526,43 @@ def test_grouped_conv_and_segment_mean_backward(lib, impl, cin, cout, k):
     torch.cuda.synchronize()
     _close(P.grad, Pd.grad, 2e-4)
     _close(W.grad, Wd.grad, 2e-4)
+
+
+def test_first_stage_training_step_on_device(lib):
+    """train_step.first_stage_training_step on cuda:0 (free running: selection, class voxels and rule maps all on the
+    device): the first step's five loss terms against oracle/train_oracle.first_stage_loss (pinned to the REFERENCE's
+    training step by tests/golden/scannet_train_small.npz), then a few AdamW steps lower the loss.  A selected voxel on the
+    threshold or a voted point on a cell boundary may fall differently in fp32, hence 1e-2 on the class-branch terms."""
+    from cagroup3d_b200 import dist as D, model_init, synthetic, train_step as TS
+    from oracle import cagroup3d_oracle as O, train_oracle as T
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 7 + i, 1500, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    pts = torch.from_numpy(batch["points"])
+    model = model_init.seeded_model(ncls, False, seed=3)
+    cfg = O.default_cfg(ncls, False)
+    orc = O.Oracle(model.state_dict(), cfg)
+    orc.train_bn = True
+    model_init.calibrate_semantic_bias(model, orc.forward(pts, B, stages="backbone")["bb_feats"], 0.10)
+    with torch.no_grad():
+        model.dense_head.cls_conv.bias.fill_(-2.0)
+    gtb = [torch.from_numpy(b[:, :7]).float() for _, b, _, _ in scenes]
+    gtl = [torch.from_numpy(b[:, 7]).long() for _, b, _, _ in scenes]
+    want = T.first_stage_loss(O.Oracle(model.state_dict(), cfg), pts, B, gtb, gtl, [torch.from_numpy(s) for _, _, s, _ in scenes],
+                              [torch.from_numpy(m) for _, _, _, m in scenes], cur_epoch=10)
+    model = model.to(DEV).train()
+    params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head."))]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    red = D.GradientAllReducer(params)
+    losses = []
+    for step in range(3):
+        bd = {"points": pts.clone().to(DEV), "batch_size": B, "cur_epoch": 10, "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float().to(DEV),
+              "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+        tb = TS.first_stage_training_step(model, bd, opt, red)
+        if step == 0:
+            for k in ("loss_sem", "loss_vote"):
+                assert abs(tb[k] - want[k]) <= 2e-3 * max(1.0, abs(want[k])), (k, tb, want)
+            for k in ("loss_centerness", "loss_bbox", "loss_cls"):
+                assert abs(tb[k] - want[k]) <= 1e-2 * max(1.0, abs(want[k])), (k, tb, want)
+        losses.append(tb["one_stage_loss"])
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
