@@ -63,7 +63,7 @@ class CAGroup3D(nn.Module):
 
     def forward(self, batch_dict):
         if self.training:
-            raise NotImplementedError("the B200 path covers inference (eval mode); call model.eval()")
+            return self.forward_train(batch_dict)
         cur_epoch = batch_dict["cur_epoch"]
         assert cur_epoch is not None
         thr = max(self.semantic_value - int(cur_epoch) * self.semantic_iter_value, self.semantic_min_threshold)
@@ -74,6 +74,32 @@ class CAGroup3D(nn.Module):
         for m in self.module_list:
             batch_dict.update(m(batch_dict))
         return self.post_processing(batch_dict)
+
+    def forward_train(self, batch_dict):
+        """cagroup3d.py:41-47,99-158 in training mode: -> (ret_dict{'loss'}, tb_dict, disp_dict{..., 'cur_semantic_value'}),
+        what tools/train_utils/train_utils.py:56-58 consumes.  Differentiable so far: BiResNet, the whole dense head and
+        its five loss terms (`one_stage_loss`).  The RoI stage's target layer and losses (cagroup_roi_head.py:512-615) are
+        not built on the CUDA path, so a model WITH a RoI head refuses to train instead of silently dropping
+        `loss_two_stage`; a first-stage-only model (no ROI_HEAD in the config) trains."""
+        if self.roi_head is not None:
+            raise NotImplementedError("training the RoI stage is not on the B200 path yet (first-stage-only models train; "
+                                      "call model.eval() for inference)")
+        from . import backbone_train as BT, head_train as HT
+        from .train_step import _targets_of
+        cur_epoch = batch_dict["cur_epoch"]
+        assert cur_epoch is not None
+        thr = max(self.semantic_value - int(cur_epoch) * self.semantic_iter_value, self.semantic_min_threshold)
+        self.dense_head.semantic_threshold = thr
+        pts = batch_dict["points"]
+        pts[:, -3:] = pts[:, -3:] / 255.
+        B = batch_dict["batch_size"]
+        out = BT.run_train(self.backbone_3d, voxelize(pts, self.voxel_size))
+        batch_dict["sp_tensor"] = out
+        loss, tb_dict = HT.first_stage_loss(self.dense_head, out, B, *_targets_of(batch_dict, pts, B))
+        disp_dict = dict(tb_dict)
+        tb_dict = {"loss_all": float(loss.detach()), **tb_dict}
+        disp_dict["cur_semantic_value"] = thr
+        return {"loss": loss}, tb_dict, disp_dict
 
     def post_processing(self, batch_dict):
         """cagroup3d.py:52-88: package per-sample dicts; recall_dict keeps its zero-initialised keys."""

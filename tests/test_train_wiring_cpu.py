@@ -509,3 +509,17 @@ def test_first_stage_training_step_driver(monkeypatch):
         losses.append(tb["one_stage_loss"])
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
     assert all(p.grad.data_ptr() == red._view(p).data_ptr() for p in params)
+    # the pcdet-style call of the train loop (train_utils.py:56-58) on a first-stage-only model
+    from cagroup3d_b200 import detector as DT
+    monkeypatch.setattr(DT, "voxelize", voxelize_cpu)
+    monkeypatch.setitem(S._CONV_IMPL, "name", "simt")            # the emulation covers the fp32 conv entry point
+    bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "cur_epoch": 3,
+          "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
+          "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+    with pytest.raises(NotImplementedError, match="RoI stage"):
+        model(dict(bd, points=bd["points"].clone()))
+    model.roi_head, model.module_list = None, model.module_list[:2]
+    ret, tb, disp = model(bd)
+    assert ret["loss"].requires_grad and abs(tb["loss_all"] - tb["one_stage_loss"]) < 1e-6
+    assert abs(disp.pop("cur_semantic_value") - max(0.15 - 3 * 0.02, 0.05)) < 1e-9 and set(disp) == set(tb) - {"loss_all"}
+    ret["loss"].backward()
