@@ -14,7 +14,9 @@ from tests.util import to_gpu_sparse
 # hardware.  The file sorts last and its tests are non-strict xfail, so that the outcome of this first hardware run is
 # recorded (XPASS = the kernel is right, XFAIL = it is not) without `pytest -x` hiding the rest of the training tests
 # behind the first failure or colouring the hardware-verified inference suite.  Remove the xfail mark once they have run.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="training kernels: first hardware run pending")]
+# The timeout (pytest-timeout, thread method: the process exits) bounds a kernel that would never finish on its first run.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="training kernels: first hardware run pending"),
+              pytest.mark.timeout(900, method="thread")]
 DEV = "cuda"
 
 
