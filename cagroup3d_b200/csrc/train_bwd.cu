@@ -318,6 +318,35 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int C, in
     out[c] = a;
 }
 
+// out[u] = sum of src[order[j]] over j in [seg_off[u], seg_off[u+1]) in that order: the scatter-add of a gather whose index
+// map is not injective (RoI pooling contraction backward), made deterministic by a stable sort of the point ids by target row
+__global__ void segment_sum_sorted_kernel(const float* __restrict__ src, const int* __restrict__ order,
+                                          const int* __restrict__ seg_off, int n_seg, int C, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int u = warp; u < n_seg; u += nwarps) {
+        const int j0 = __ldg(seg_off + u), j1 = __ldg(seg_off + u + 1);
+        for (int ch0 = 0; ch0 < C; ch0 += 32 * IB_CPL) {
+            float acc[IB_CPL];
+#pragma unroll
+            for (int q = 0; q < IB_CPL; ++q) acc[q] = 0.f;
+            for (int j = j0; j < j1; ++j) {
+                const float* row = src + (size_t)__ldg(order + j) * C;
+#pragma unroll
+                for (int q = 0; q < IB_CPL; ++q) {
+                    const int ch = ch0 + q * 32 + lane;
+                    if (ch < C) acc[q] += __ldg(row + ch);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < IB_CPL; ++q) {
+                const int ch = ch0 + q * 32 + lane;
+                if (ch < C) out[(size_t)u * C + ch] = acc[q];
+            }
+        }
+    }
+}
+
 inline int flat_blocks(long long work, int nt) {
     long long b = (work + nt - 1) / nt;
     const long long cap = 148LL * 16;
@@ -419,6 +448,14 @@ int cg3d_column_sum(const float* x, int ldx, long long n, int C, float* workspac
     colsum_partial_kernel<<<grid, BN_NT, 0, st>>>(x, ldx, n, C, chunk, workspace);
     CG3D_LAUNCH_CHECK();
     colsum_finalize_kernel<<<cg3d_div_up(C, 128), 128, 0, st>>>(workspace, C, S, out);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_segment_sum_sorted(const float* src, const int* order, const int* seg_off, int n_seg, int C, float* out, void* stream) {
+    if (n_seg == 0 || C == 0) return 0;
+    segment_sum_sorted_kernel<<<flat_blocks((long long)n_seg * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, order, seg_off, n_seg,
+                                                                                                         C, out);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

@@ -442,6 +442,12 @@ int cg3d_vote_targets(const float* scene_points, int ld, const long long* sem_ma
  * cagroup_head.py:167,176).  workspace: cg3d_bn_train_workspace(n, C) floats; chunk partial sums added in order. */
 int cg3d_column_sum(const float* x, int ldx, long long n, int C, float* workspace, float* out, void* stream);
 
+/* out[u] = src[order[j]] summed over j in [seg_off[u], seg_off[u+1]) IN THAT ORDER (f32[n_seg][C]): the scatter-add of a
+ * gather whose index map is not injective -- the dX of the RoI pooling contraction (cagroup_roi_head.py:72-90: two RoIs
+ * can reach the same unique grid voxel at the same tap) -- with `order` a stable sort of the point ids by target row
+ * (cg3d_sort_pairs) and seg_off the exclusive scan of cg3d_histogram_i32 of the targets.  No atomics. */
+int cg3d_segment_sum_sorted(const float* src, const int* order, const int* seg_off, int n_seg, int C, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

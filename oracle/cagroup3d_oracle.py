@@ -275,7 +275,7 @@ class Oracle:
         x = pooled
         for li, bi in ((0, 1), (4, 5)):
             x = x @ self.W(r + f"reg_fc_layers.{li}.weight").t()
-            x = torch.relu(me.batchnorm(x, self.p, r + f"reg_fc_layers.{bi}."))
+            x = torch.relu(me.batchnorm(x, self.p, r + f"reg_fc_layers.{bi}.", train=self.train_bn))
         reg = x @ self.W(r + "reg_pred_layer.weight").t() + self.W(r + "reg_pred_layer.bias")
         # decode (cagroup_roi_head.py:477-510)
         cs = cfg["code_size"]

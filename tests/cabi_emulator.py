@@ -365,6 +365,38 @@ def cg3d_segment_mean(**a):
     a["out"].copy_(torch.zeros((U, C), dtype=src.dtype).index_add_(0, inv, src) / cnt[:, None])
 
 
+def cg3d_sort_pairs(**a):
+    n, b0, b1 = a["n"], a["begin_bit"], a["end_bit"]
+    k = a["keys"][:n]
+    sub = (k >> b0) & ((1 << (b1 - b0)) - 1) if b1 - b0 < 63 else k
+    perm = torch.argsort(sub, stable=True)
+    a["keys"][:n] = k[perm]
+    a["vals"][:n] = a["vals"][:n][perm]
+
+
+def cg3d_histogram_i32(**a):
+    ids = a["ids"][:a["n"]].long()
+    a["counts"][:a["nseg"]] = torch.bincount(ids, minlength=a["nseg"])[:a["nseg"]].int()
+
+
+def cg3d_exclusive_scan_i32(**a):
+    params = list(a)
+    flags, n = a[params[0]], a[params[1]]
+    out, total = a[params[2]], a[params[-1]]
+    c = torch.cumsum(flags[:n].long(), 0)
+    out[:n] = (c - flags[:n].long()).int()
+    total[0] = int(c[-1]) if n else 0
+
+
+def cg3d_segment_sum_sorted(**a):
+    src, order, off = a["src"], a["order"].long(), a["seg_off"].tolist()
+    out = torch.zeros((a["n_seg"], a["C"]), dtype=src.dtype)
+    for u in range(a["n_seg"]):
+        if off[u + 1] > off[u]:
+            out[u] = src[order[off[u]:off[u + 1]]].sum(0)
+    a["out"].copy_(out)
+
+
 def install(monkeypatch):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
     from cagroup3d_b200 import _lib, sparse as S

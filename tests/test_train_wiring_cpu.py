@@ -523,3 +523,69 @@ def test_first_stage_training_step_driver(monkeypatch):
     assert ret["loss"].requires_grad and abs(tb["loss_all"] - tb["one_stage_loss"]) < 1e-6
     assert abs(disp.pop("cur_semantic_value") - max(0.15 - 3 * 0.02, 0.05)) < 1e-9 and set(disp) == set(tb) - {"loss_all"}
     ret["loss"].backward()
+
+
+def test_roi_branch_training_wiring_vs_oracle(monkeypatch):
+    """roi_train.roi_branch (5^3 grid conv at the RoI grid voxels, 7^3 pooling contraction with its non-injective table,
+    batch-statistics BatchNorm, regression MLP) on the emulated C ABI against the oracle's RoI head run with batch
+    statistics: pooled features, rcnn_reg, gradients of every RoI-head parameter and of the backbone features."""
+    from cagroup3d_b200 import model_init, roi_train as RT, sparse as S, synthetic
+    E.install(monkeypatch)
+    B, ncls = 2, 18
+    scenes = [synthetic.make_scene(1000 * 9 + i, 700, n_classes=ncls) for i in range(B)]
+    batch = synthetic.collate_batch(scenes)
+    pts = torch.from_numpy(batch["points"])
+    model = model_init.seeded_model(ncls, False, seed=5)
+    cfg = O.default_cfg(ncls, False)
+    orc = O.Oracle(model.state_dict(), cfg, dtype=torch.float64)
+    names = [k for k in orc.p if k.startswith("roi_head.") and k.endswith(("kernel", "weight", "bias")) and "running" not in k]
+    for k in names:
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    res = orc.forward(pts, B, stages="backbone")
+    g = torch.Generator().manual_seed(2)
+    R = 9
+    pred_list = []
+    for b in range(B):
+        gt = torch.from_numpy(scenes[b][1][:R, :7]).double()
+        bx = torch.cat([gt[:, :3] + torch.randn((R, 3), generator=g).double() * 0.05, gt[:, 3:6] * 1.1, torch.zeros((R, 1), dtype=torch.float64)], 1)
+        bx[-1] = bx[0]                                            # two identical RoIs: the pooling table repeats (tap, voxel) pairs
+        pred_list.append((bx, torch.rand((R,), generator=g).double(), torch.randint(0, ncls, (R,), generator=g)))
+    Fb = res["bb_feats"].detach().double().requires_grad_(True)
+    omgr = me.Manager()
+    ocm = me.CoordMap(res["bb_coords"], 2)
+    omgr.by_stride[2] = ocm
+    orc.train_bn = True
+    _, inter = orc.roi_head(me.SparseTensor(Fb, ocm, omgr), pred_list, B)
+    d1 = torch.randn(tuple(inter["pooled"].shape), generator=g, dtype=torch.float64)
+    d2 = torch.randn(tuple(inter["rcnn_reg"].shape), generator=g, dtype=torch.float64)
+    ((inter["pooled"] * d1).sum() + (inter["rcnn_reg"] * d2).sum()).backward()
+
+    # coordinate artifacts from the oracle's intermediate results
+    gsz = cfg["grid"]
+    uq, inv, _ = me.unique_first(np.concatenate([inter["grid_coords"][:, :1], inter["grid_coords"][:, 1:] * cfg["coord_key"]], 1))
+    assert np.array_equal(uq, inter["uniq"])
+    nr = B * R
+    ii, jj, kk = np.meshgrid(np.arange(gsz), np.arange(gsz), np.arange(gsz), indexing="ij")
+    tap = (ii + gsz * jj + gsz * gsz * kk).ravel()
+    ptab = np.zeros((gsz ** 3, nr), np.int32)
+    ptab[tap[None, :].repeat(nr, 0), np.arange(nr)[:, None].repeat(gsz ** 3, 1)] = inv.reshape(nr, gsz ** 3)
+    assert len(np.unique(ptab[:, [0, R - 1]], axis=1).T) == 1                   # the duplicated RoI: a non-injective table
+    mgr = S.Manager()
+    cm = E.cpu_map(res["bb_coords"], 2, mgr)
+    mgr.by_stride[2] = cm
+    umap = E.cpu_map(uq, 2, mgr)
+    nbr, order = S.neighbor_table(cm, umap, cfg["roi_kernel"], mgr, ordered=True)
+    art = dict(umap=umap, nbr=nbr, order=order, ptab=torch.from_numpy(ptab), nr=nr)
+    model.train()
+    F = res["bb_feats"].detach().float().contiguous().requires_grad_(True)
+    rois = inter["rois"].float()
+    pooled, reg, _ = RT.roi_branch(model.roi_head, S.SparseTensor(F, cm, mgr), rois, B, R, impl="simt", dropout=False, art=art)
+    assert (pooled.detach().double() - inter["pooled"].detach()).abs().max().item() < 1e-3
+    assert (reg.detach().double() - inter["rcnn_reg"].detach()).abs().max().item() < 1e-3
+    ((pooled * d1.float()).sum() + (reg * d2.float()).sum()).backward()
+    assert _rel(F.grad, Fb.grad) < 2e-3
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
+                 / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
+    assert worst[0] < 5e-3, worst

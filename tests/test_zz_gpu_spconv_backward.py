@@ -572,3 +572,52 @@ def test_first_stage_training_step_on_device(lib):
                 assert abs(tb[k] - want[k]) <= 1e-2 * max(1.0, abs(want[k])), (k, tb, want)
         losses.append(tb["one_stage_loss"])
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_roi_branch_training_on_device(lib):
+    """roi_train.roi_branch on cuda:0 (coordinate phase on the device) against the oracle's RoI head with batch statistics:
+    pooled features, rcnn_reg, gradients of every RoI-head parameter and of the backbone features.  Two identical RoIs
+    make the pooling table repeat (tap, voxel) pairs -- the case cg3d_segment_sum_sorted exists for."""
+    from cagroup3d_b200 import model_init, roi_train as RT, synthetic
+    from oracle import cagroup3d_oracle as O
+    B, ncls, R = 2, 18, 9
+    scenes = [synthetic.make_scene(1000 * 9 + i, 1500, n_classes=ncls) for i in range(B)]
+    pts = torch.from_numpy(synthetic.collate_batch(scenes)["points"])
+    model = model_init.seeded_model(ncls, False, seed=5)
+    cfg = O.default_cfg(ncls, False)
+    orc = O.Oracle(model.state_dict(), cfg, dtype=torch.float64)
+    names = [k for k in orc.p if k.startswith("roi_head.") and k.endswith(("kernel", "weight", "bias")) and "running" not in k]
+    for k in names:
+        orc.p[k] = orc.p[k].double().requires_grad_(True)
+    res = orc.forward(pts, B, stages="backbone")
+    g = torch.Generator().manual_seed(2)
+    pred_list = []
+    for b in range(B):
+        gt = torch.from_numpy(scenes[b][1][:R, :7]).double()
+        bx = torch.cat([gt[:, :3] + torch.randn((R, 3), generator=g).double() * 0.05, gt[:, 3:6] * 1.1, torch.zeros((R, 1), dtype=torch.float64)], 1)
+        bx[-1] = bx[0]
+        pred_list.append((bx, torch.rand((R,), generator=g).double(), torch.randint(0, ncls, (R,), generator=g)))
+    Fb = res["bb_feats"].detach().double().requires_grad_(True)
+    omgr, ocm = me.Manager(), me.CoordMap(res["bb_coords"], 2)
+    omgr.by_stride[2] = ocm
+    orc.train_bn = True
+    _, inter = orc.roi_head(me.SparseTensor(Fb, ocm, omgr), pred_list, B)
+    d1 = torch.randn(tuple(inter["pooled"].shape), generator=g, dtype=torch.float64)
+    d2 = torch.randn(tuple(inter["rcnn_reg"].shape), generator=g, dtype=torch.float64)
+    ((inter["pooled"] * d1).sum() + (inter["rcnn_reg"] * d2).sum()).backward()
+
+    model = model.to(DEV).train()
+    sp = to_gpu_sparse(res["bb_coords"], res["bb_feats"], 2)
+    F = sp.F.clone().requires_grad_(True)
+    pooled, reg, art = RT.roi_branch(model.roi_head, sp.with_F(F), inter["rois"].float().to(DEV), B, R, dropout=False)
+    assert np.array_equal(art["umap"].coords.cpu().numpy(), inter["uniq"])
+    _close(pooled.detach(), inter["pooled"].detach(), 1e-3)
+    _close(reg.detach(), inter["rcnn_reg"].detach(), 1e-3)
+    ((pooled * d1.float().to(DEV)).sum() + (reg * d2.float().to(DEV)).sum()).backward()
+    torch.cuda.synchronize()
+    _close(F.grad, Fb.grad, 2e-3)
+    params = dict(model.named_parameters())
+    G = max(float(orc.p[k].grad.norm()) for k in names)
+    worst = max((float((params[k].grad.double().cpu().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
+                 / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
+    assert worst[0] < 2e-2, worst
