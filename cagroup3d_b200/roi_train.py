@@ -105,3 +105,182 @@ def roi_branch(roi_head, sp: S.SparseTensor, rois: torch.Tensor, B: int, rmax: i
     reg = A.add_bias(A.SparseConvFunction.apply(x, pred.weight.t().contiguous(), None, None, x.shape[0], 1, impl), pred.bias)
     roi_head.fold.clear()
     return pooled, reg, art
+
+
+# ---- proposal targets and the RoI loss (cagroup_proposal_target_layer.py, cagroup_roi_head.py:262-320,512-615) -----------
+class ProposalTargetLayer:
+    """Samples `roi_per_image` RoIs per sample (foreground by IoU with a same-class gt box, hard / easy background) and
+    attaches their targets; the reference's sampling rules and random draws (numpy permutation for the foreground,
+    torch.randint for the background, both on the host generators, so a seeded run draws the same RoIs as the reference).
+    Host-side index logic on device tensors; the IoU matrix comes from cg3d_boxes_pairwise_bev (ops.boxes_iou3d_gpu)."""
+
+    def __init__(self, roi_per_image=128, fg_ratio=0.5, reg_fg_thresh=0.3, cls_fg_thresh=0.55, cls_bg_thresh=0.15,
+                 cls_bg_thresh_l0=0.1, hard_bg_ratio=0.8):
+        self.roi_per_image, self.fg_ratio, self.reg_fg_thresh = roi_per_image, fg_ratio, reg_fg_thresh
+        self.cls_fg_thresh, self.cls_bg_thresh, self.cls_bg_thresh_l0 = cls_fg_thresh, cls_bg_thresh, cls_bg_thresh_l0
+        self.hard_bg_ratio = hard_bg_ratio
+
+    def __call__(self, batch_dict: dict) -> dict:
+        rois, gt_of_rois, gt_labels, ious, scores, labels = self.sample_rois_for_rcnn(batch_dict)
+        reg_valid_mask = (ious > self.reg_fg_thresh).long()
+        fg, bg = ious > self.cls_fg_thresh, ious < self.cls_bg_thresh
+        interval = ~fg & ~bg
+        cls_labels = fg.float()
+        cls_labels[interval] = (ious[interval] - self.cls_bg_thresh) / (self.cls_fg_thresh - self.cls_bg_thresh)
+        return {"rois": rois, "gt_of_rois": gt_of_rois, "gt_label_of_rois": gt_labels, "gt_iou_of_rois": ious, "roi_scores": scores,
+                "roi_labels": labels, "reg_valid_mask": reg_valid_mask, "rcnn_cls_labels": cls_labels}
+
+    def sample_rois_for_rcnn(self, batch_dict: dict):
+        B, rois, roi_scores, roi_labels = batch_dict["batch_size"], batch_dict["rois"], batch_dict["roi_scores"], batch_dict["roi_labels"]
+        gt_boxes, gt_labels = batch_dict["gt_bboxes_3d"], batch_dict["gt_labels_3d"]
+        n, cs = self.roi_per_image, rois.shape[-1]
+        out_rois, out_gt = rois.new_zeros(B, n, cs), rois.new_zeros(B, n, gt_boxes[0].shape[-1])
+        out_gt_lab, out_iou, out_sc = rois.new_zeros(B, n), rois.new_zeros(B, n), rois.new_zeros(B, n)
+        out_lab = rois.new_zeros((B, n), dtype=torch.long)
+        for b in range(B):
+            cur_gt = gt_boxes[b].clone()
+            cur_gt[..., 6] *= -1
+            cur_gt = cur_gt.new_zeros((1, cur_gt.shape[1])) if len(cur_gt) == 0 else cur_gt
+            cur_labels = gt_labels[b]
+            max_overlaps, assignment = self.get_max_iou_with_same_class(rois[b], roi_labels[b], cur_gt[:, 0:7], cur_labels.long())
+            idx = self.subsample_rois(max_overlaps)
+            out_rois[b], out_lab[b], out_iou[b], out_sc[b] = rois[b][idx], roi_labels[b][idx], max_overlaps[idx], roi_scores[b][idx]
+            out_gt[b] = cur_gt[assignment[idx]]
+            out_gt_lab[b] = cur_labels[assignment[idx]]
+        return out_rois, out_gt, out_gt_lab, out_iou, out_sc, out_lab
+
+    def subsample_rois(self, max_overlaps: torch.Tensor) -> torch.Tensor:
+        import numpy as np
+        fg_per_image = int(np.round(self.fg_ratio * self.roi_per_image))
+        fg_thresh = min(self.reg_fg_thresh, self.cls_fg_thresh)
+        fg = (max_overlaps >= fg_thresh).nonzero().view(-1)
+        easy = (max_overlaps < self.cls_bg_thresh_l0).nonzero().view(-1)
+        hard = ((max_overlaps < self.reg_fg_thresh) & (max_overlaps >= self.cls_bg_thresh_l0)).nonzero().view(-1)
+        n_fg, n_bg = fg.numel(), hard.numel() + easy.numel()
+        dev = max_overlaps.device
+        if n_fg > 0 and n_bg > 0:
+            k = min(fg_per_image, n_fg)
+            fg = fg[torch.from_numpy(np.random.permutation(n_fg)).long().to(dev)[:k]]
+            bg = self.sample_bg_inds(hard, easy, self.roi_per_image - k, self.hard_bg_ratio)
+        elif n_fg > 0:
+            r = torch.from_numpy(np.floor(np.random.rand(self.roi_per_image) * n_fg)).long().to(dev)
+            fg = fg[r]
+            bg = fg[fg < 0]
+        elif n_bg > 0:
+            bg = self.sample_bg_inds(hard, easy, self.roi_per_image, self.hard_bg_ratio)
+        else:
+            raise NotImplementedError("no foreground and no background RoI")
+        return torch.cat((fg, bg), dim=0)
+
+    @staticmethod
+    def sample_bg_inds(hard, easy, n_bg, hard_bg_ratio):
+        pick = lambda inds, k: inds[torch.randint(low=0, high=inds.numel(), size=(k,)).long().to(inds.device)]
+        if hard.numel() > 0 and easy.numel() > 0:
+            n_hard = min(int(n_bg * hard_bg_ratio), len(hard))
+            return torch.cat([pick(hard, n_hard), pick(easy, n_bg - n_hard)], dim=0)
+        if hard.numel() > 0:
+            return pick(hard, n_bg)
+        if easy.numel() > 0:
+            return pick(easy, n_bg)
+        raise NotImplementedError
+
+    @staticmethod
+    def get_max_iou_with_same_class(rois, roi_labels, gt_boxes, gt_labels):
+        from . import ops
+        max_overlaps = rois.new_zeros(rois.shape[0])
+        assignment = roi_labels.new_zeros(roi_labels.shape[0])
+        for k in range(int(gt_labels.min()), int(gt_labels.max()) + 1):
+            rm, gm = roi_labels == k, gt_labels == k
+            if rm.sum() > 0 and gm.sum() > 0:
+                iou = ops.boxes_iou3d_gpu(rois[rm].contiguous(), gt_boxes[gm].contiguous())
+                best, arg = torch.max(iou, dim=1)
+                max_overlaps[rm] = best
+                assignment[rm] = gm.nonzero().view(-1)[arg]
+        return max_overlaps, assignment
+
+
+def reorder_rois(pred_boxes_3d, enlarge_ratio=False):
+    """reoder_rois_for_refining (cagroup_roi_head.py:328-362): pad the per-sample detections, flip the heading sign."""
+    B = len(pred_boxes_3d)
+    rmax = max(1, max(len(p[0]) for p in pred_boxes_3d))
+    ref = pred_boxes_3d[0][0]
+    rois, scores = ref.new_zeros((B, rmax, ref.shape[-1])), ref.new_zeros((B, rmax))
+    labels = ref.new_zeros((B, rmax)).long()
+    for b, (bx, sc, lb) in enumerate(pred_boxes_3d):
+        rois[b, :len(bx)], scores[b, :len(bx)], labels[b, :len(bx)] = bx, sc, lb
+    rois[..., 6] *= -1
+    if enlarge_ratio:
+        rois[..., 3:6] *= enlarge_ratio
+    return rois, scores, labels
+
+
+def assign_targets(target_layer: ProposalTargetLayer, input_dict: dict, code_size: int) -> dict:
+    """cagroup_roi_head.py:288-326: sampled RoIs + their gt boxes in the RoI's canonical frame."""
+    import numpy as np
+    from pcdet.utils import common_utils
+    with torch.no_grad():
+        t = target_layer(input_dict)
+    B = input_dict["batch_size"]
+    rois, gt = t["rois"], t["gt_of_rois"]
+    t["gt_of_rois_src"] = gt.clone().detach()
+    roi_ry = rois[:, :, 6] % (2 * np.pi)
+    gt[:, :, 6] = gt[:, :, 6] % (2 * np.pi)
+    gt[:, :, 0:3] = gt[:, :, 0:3] - rois[:, :, 0:3]
+    gt[:, :, 6] = gt[:, :, 6] - roi_ry
+    if code_size > 6:
+        gt = common_utils.rotate_points_along_z(points=gt.view(-1, 1, gt.shape[-1]), angle=-roi_ry.view(-1)).view(B, -1, gt.shape[-1])
+        h = gt[:, :, 6] % (2 * np.pi)
+        opp = (h > np.pi * 0.5) & (h < np.pi * 1.5)
+        h[opp] = (h[opp] + np.pi) % (2 * np.pi)
+        h[h > np.pi] = h[h > np.pi] - np.pi * 2
+        gt[:, :, 6] = torch.clamp(h, min=-np.pi / 2, max=np.pi / 2)
+    t["gt_of_rois"] = gt
+    return t
+
+
+def encode_residuals(boxes: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:
+    """CAGroupResidualCoder.encode_torch for code_size 6 (cagroup_utils.py:99-145): centres by the anchor's BEV diagonal /
+    height, sizes as log ratios."""
+    a, g = anchors.clone(), boxes.clone()
+    a[:, 3:6], g[:, 3:6] = torch.clamp_min(a[:, 3:6], min=1e-5), torch.clamp_min(g[:, 3:6], min=1e-5)
+    diag = torch.sqrt(a[:, 3:4] ** 2 + a[:, 4:5] ** 2)
+    return torch.cat([(g[:, 0:1] - a[:, 0:1]) / diag, (g[:, 1:2] - a[:, 1:2]) / diag, (g[:, 2:3] - a[:, 2:3]) / a[:, 5:6],
+                      torch.log(g[:, 3:6] / a[:, 3:6])], dim=-1)
+
+
+def roi_reg_loss(rcnn_reg: torch.Tensor, targets: dict, code_size: int, code_weights, reg_weight: float = 1.0):
+    """get_box_reg_layer_loss (cagroup_roi_head.py:547-575), 'smooth-l1', code_size 6, no IoU loss: WeightedSmoothL1Loss
+    (beta 1/9, loss_utils.py:76-138) of the residual-coded targets, summed over the foreground RoIs / max(#foreground, 1).
+    The sum and its gradient are one cg3d_smooth_l1_loss call (the code weights scale prediction and target alike)."""
+    from . import train_targets as TT
+    assert code_size == 6, "the yaw / sin-cos codes of SUN RGB-D are not on the CUDA training path yet"
+    fg = targets["reg_valid_mask"].view(-1) > 0
+    fg_sum = int(fg.long().sum())
+    n = rcnn_reg.shape[0]
+    anchors = targets["rois"][..., 0:code_size].clone().detach().view(-1, code_size)
+    anchors[:, 0:3] = 0
+    tgt = encode_residuals(targets["gt_of_rois"][..., 0:code_size].reshape(n, code_size), anchors)
+    cw = torch.as_tensor(code_weights, dtype=torch.float32, device=rcnn_reg.device).view(1, -1)
+    pred = rcnn_reg.view(n, -1) * cw
+    tgt = torch.where(torch.isnan(tgt), rcnn_reg.detach().view(n, -1), tgt) * cw
+    w = (fg.float() / max(fg_sum, 1)).unsqueeze(1).repeat(1, code_size)
+    loss = TT.SmoothL1Loss(beta=1.0 / 9.0, reduction="sum")(pred, tgt, weight=w) * reg_weight
+    return loss, {"rcnn_loss_reg": float(loss.detach()), "loss_two_stage": float(loss.detach())}
+
+
+def roi_stage_loss(roi_head, sp: S.SparseTensor, pred_bbox_list, gt_bboxes, gt_labels, impl: Optional[str] = None,
+                   dropout: bool = True, cfg: Optional[dict] = None):
+    """CAGroup3DRoIHead.forward_train + .loss (cagroup_roi_head.py:262-286,512-529): pad the stage-1 detections, sample
+    and assign RoIs, pool, regress, smooth-L1 on the foreground.  cfg: the ROI_HEAD section (defaults of the ScanNet yaml)."""
+    cfg = cfg or {}
+    g = cfg.get
+    layer = ProposalTargetLayer(roi_per_image=g("ROI_PER_IMAGE", 128), fg_ratio=g("ROI_FG_RATIO", 0.9), reg_fg_thresh=g("REG_FG_THRESH", 0.3))
+    rois, scores, labels = reorder_rois([(b.detach(), s.detach(), l) for b, s, l in pred_bbox_list], g("ENLARGE_RATIO", False))
+    B = len(pred_bbox_list)
+    inp = dict(batch_size=B, rois=rois, roi_scores=scores, roi_labels=labels, gt_bboxes_3d=gt_bboxes, gt_labels_3d=gt_labels)
+    targets = assign_targets(layer, inp, roi_head.code_size)
+    pooled, reg, _ = roi_branch(roi_head, sp, targets["rois"], B, layer.roi_per_image, impl=impl, dropout=dropout)
+    lw = g("LOSS_WEIGHTS", {}) or {}
+    loss, tb = roi_reg_loss(reg, targets, roi_head.code_size, lw.get("CODE_WEIGHT", [1.0] * roi_head.code_size),
+                            lw.get("RCNN_REG_WEIGHT", 1.0))
+    return loss, tb, targets

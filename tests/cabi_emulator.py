@@ -397,6 +397,12 @@ def cg3d_segment_sum_sorted(**a):
     a["out"].copy_(out)
 
 
+def cg3d_boxes_pairwise_bev(**a):
+    from oracle import iou3d_oracle
+    assert a["boxes_a"].shape == (a["na"], 7) and a["boxes_b"].shape == (a["nb"], 7)
+    a["out"].copy_(iou3d_oracle.pairwise(a["boxes_a"], a["boxes_b"], {0: "overlap", 1: "iou", 2: "iou_normal"}[a["mode"]]))
+
+
 def install(monkeypatch):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
     from cagroup3d_b200 import _lib, sparse as S

@@ -589,3 +589,35 @@ def test_roi_branch_training_wiring_vs_oracle(monkeypatch):
     worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
                  / (float(orc.p[k].grad.norm()) + 1e-4 * G), k) for k in names)
     assert worst[0] < 5e-3, worst
+
+
+def test_roi_targets_and_loss_equal_the_reference(monkeypatch):
+    """roi_train.reorder_rois / ProposalTargetLayer / assign_targets / roi_reg_loss on the seeded inputs of
+    tests/golden/roi_train_parts.npz -- produced by the REFERENCE's own ProposalTargetLayer, CAGroup3DRoIHead.assign_targets
+    and get_box_reg_layer_loss (tests/golden/make_roi_train_golden.py) -- with the same host generator seeds: the same
+    sampled RoIs, targets, masks and loss."""
+    import os
+    from cagroup3d_b200 import ops, roi_train as RT, train_targets as TT
+    from tests.golden import make_roi_train_golden as MK
+    E.install(monkeypatch)
+    monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
+    monkeypatch.setattr(ops, "_chk", lambda *ts: None)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_train_parts.npz"))
+    gtb, gtl, preds = MK.inputs()
+    rois, scores, labels = RT.reorder_rois(preds)
+    assert np.array_equal(rois.numpy(), z["padded_rois"]) and np.array_equal(labels.numpy(), z["padded_labels"])
+    inp = dict(batch_size=2, rois=rois, roi_scores=scores, roi_labels=labels, gt_bboxes_3d=[b.clone() for b in gtb], gt_labels_3d=gtl)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    t = RT.assign_targets(RT.ProposalTargetLayer(roi_per_image=128, fg_ratio=0.9, reg_fg_thresh=0.3), inp, 6)
+    assert np.array_equal(t["rois"].numpy(), z["rois"]) and np.array_equal(t["roi_labels"].numpy(), z["roi_labels"])
+    assert np.array_equal(t["reg_valid_mask"].numpy(), z["reg_valid_mask"]) and int((t["reg_valid_mask"] > 0).sum()) == int(z["n_fg"])
+    assert np.abs(t["gt_iou_of_rois"].numpy() - z["gt_iou_of_rois"]).max() < 1e-5
+    for k in ("gt_of_rois", "gt_of_rois_src", "gt_label_of_rois", "rcnn_cls_labels", "roi_scores"):
+        assert np.abs(t[k].numpy() - z[k]).max() < 1e-5, k
+    reg = torch.from_numpy(z["rcnn_reg"]).requires_grad_(True)
+    loss, tb = RT.roi_reg_loss(reg, t, 6, [1.0] * 6)
+    assert abs(float(loss.detach()) - float(z["rcnn_loss_reg"])) < 1e-5 and tb["loss_two_stage"] == tb["rcnn_loss_reg"]
+    loss.backward()
+    fg = torch.from_numpy(z["reg_valid_mask"]).view(-1) > 0
+    assert float(reg.grad[~fg].abs().max()) == 0 and float(reg.grad[fg].abs().max()) > 0
