@@ -77,27 +77,17 @@ class CAGroup3D(nn.Module):
 
     def forward_train(self, batch_dict):
         """cagroup3d.py:41-47,99-158 in training mode: -> (ret_dict{'loss'}, tb_dict, disp_dict{..., 'cur_semantic_value'}),
-        what tools/train_utils/train_utils.py:56-58 consumes.  Differentiable so far: BiResNet, the whole dense head and
-        its five loss terms (`one_stage_loss`).  The RoI stage's target layer and losses (cagroup_roi_head.py:512-615) are
-        not built on the CUDA path, so a model WITH a RoI head refuses to train instead of silently dropping
-        `loss_two_stage`; a first-stage-only model (no ROI_HEAD in the config) trains."""
-        if self.roi_head is not None:
-            raise NotImplementedError("training the RoI stage is not on the B200 path yet (first-stage-only models train; "
-                                      "call model.eval() for inference)")
-        from . import backbone_train as BT, head_train as HT
-        from .train_step import _targets_of
+        what tools/train_utils/train_utils.py:56-58 consumes: BiResNet and both heads with batch-statistics BatchNorm,
+        the five first-stage loss terms and the RoI regression loss (train_step.two_stage_loss).  WITH_YAW False only."""
+        from .train_step import two_stage_loss
         cur_epoch = batch_dict["cur_epoch"]
         assert cur_epoch is not None
         thr = max(self.semantic_value - int(cur_epoch) * self.semantic_iter_value, self.semantic_min_threshold)
         self.dense_head.semantic_threshold = thr
         pts = batch_dict["points"]
         pts[:, -3:] = pts[:, -3:] / 255.
-        B = batch_dict["batch_size"]
-        out = BT.run_train(self.backbone_3d, voxelize(pts, self.voxel_size))
-        batch_dict["sp_tensor"] = out
-        loss, tb_dict = HT.first_stage_loss(self.dense_head, out, B, *_targets_of(batch_dict, pts, B))
-        disp_dict = dict(tb_dict)
-        tb_dict = {"loss_all": float(loss.detach()), **tb_dict}
+        loss, tb_dict = two_stage_loss(self, batch_dict)
+        disp_dict = {k: v for k, v in tb_dict.items() if k != "loss_all"}
         disp_dict["cur_semantic_value"] = thr
         return {"loss": loss}, tb_dict, disp_dict
 

@@ -144,7 +144,7 @@ def class_branch(head, out: S.SparseTensor, offF: torch.Tensor, art: dict, B: in
 
 # ---- the whole first-stage loss (CAGroup3DHead.loss, cagroup_head.py:322-398) -----------------------------------------------
 def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_labels, scene_points, pts_semantic_mask,
-                     pts_instance_mask, impl: Optional[str] = None, art: Optional[dict] = None):
+                     pts_instance_mask, impl: Optional[str] = None, art: Optional[dict] = None, return_branch: bool = False):
     """shared part -> coordinate phase -> per-class branch -> the five loss terms per sample -> batch means.
     Returns (loss, tb_dict) like the reference (`one_stage_loss` = the sum).  `art`: precomputed coordinate artifacts
     (tests teacher-force them); WITH_YAW False only."""
@@ -177,4 +177,15 @@ def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_l
     loss = sum(means)
     tb = {n: float(m.detach()) for n, m in zip(names, means)}
     tb["one_stage_loss"] = float(loss.detach())
+    if return_branch:
+        return loss, tb, br
     return loss, tb
+
+
+def stage1_proposals(head, br: dict, B: int):
+    """get_bboxes on the training-mode predictions (cagroup_head.py:296-297, detached): the inference plan's device-resident
+    decode / top-k / NMS (head.CAGroup3DHead.proposals) on [centerness | cls | reg] -> per-sample (boxes, scores, labels)."""
+    with torch.no_grad():
+        cm = dict(pred=torch.cat([br["centerness"], br["cls"], br["reg"]], 1).detach().contiguous(), coords=br["coords"])
+        det_boxes, det_scores, det_labels, off, _ = head.proposals(cm, B)
+    return [(det_boxes[off[b]:off[b + 1]], det_scores[off[b]:off[b + 1]], det_labels[off[b]:off[b + 1]].long()) for b in range(B)]

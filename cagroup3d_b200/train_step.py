@@ -2,13 +2,13 @@
 tools/train_utils/train_utils.py:42-75 (train_one_epoch's inner loop: forward, loss, backward, optimizer step), with
 the DDP gradient average done by dist.GradientAllReducer.
 
+  training_step               the reference's whole step for WITH_YAW False: both stages' losses (`loss_all`)
   first_stage_training_step   BiResNet in training mode + the whole CAGroup3DHead in training mode + all five terms of
                               CAGroup3DHead.loss (`one_stage_loss` of the reference's tb_dict)
   partial_training_step       the same restricted to the semantic and vote terms (no per-class branch)
 
-The RoI stage (proposal target layer + RoI losses, cagroup_roi_head.py:512-615) is not differentiable here yet
-(DESIGN.md section 9), so neither is the reference's full two-stage loss; `CAGroup3D.forward` keeps refusing training mode
-until it is.
+The SUN RGB-D branches (yaw: rotated IoU loss, sin-cos / yaw residual codes, 3 votes per seed) are not on the CUDA
+training path yet.
 """
 from __future__ import annotations
 
@@ -53,6 +53,51 @@ def first_stage_training_step(model, batch_dict: dict, optimizer: Optional[torch
     loss.backward()
     if reducer is not None:
         reducer.reduce()
+    if optimizer is not None:
+        optimizer.step()
+    if hasattr(model, "update_global_step"):
+        model.update_global_step()
+    return tb
+
+
+def two_stage_loss(model, batch_dict: dict, impl: Optional[str] = None, dropout: bool = True):
+    """CAGroup3D.get_training_loss (cagroup3d.py:99-158): first-stage loss + RoI-stage loss of a batch, WITH_YAW False.
+    -> (loss_all, tb_dict with the reference's keys).  batch_dict["points"] must already be normalised / on the device."""
+    from . import roi_train as RT
+    B = batch_dict["batch_size"]
+    pts = batch_dict["points"]
+    head = model.dense_head
+    out = BT.run_train(model.backbone_3d, voxelize(pts, model.voxel_size), impl=impl)
+    gtb, gtl, scene, semm, insm = _targets_of(batch_dict, pts, B)
+    loss1, tb, br = HT.first_stage_loss(head, out, B, gtb, gtl, scene, semm, insm, impl=impl, return_branch=True)
+    if model.roi_head is None:
+        return loss1, {"loss_all": float(loss1.detach()), **tb}
+    proposals = HT.stage1_proposals(head, br, B)
+    loss2, tb2, _ = RT.roi_stage_loss(model.roi_head, out, proposals, gtb, gtl, impl=impl, dropout=dropout,
+                                      cfg=model.model_cfg.get("ROI_HEAD", None))
+    tb.update(tb2)
+    loss = loss1 + loss2
+    return loss, {"loss_all": float(loss.detach()), **tb}
+
+
+def training_step(model, batch_dict: dict, optimizer: Optional[torch.optim.Optimizer] = None, reducer=None,
+                  impl: Optional[str] = None, grad_norm_clip: Optional[float] = None) -> dict:
+    """train_utils.py:48-72 for one batch: zero_grad, forward + both losses, backward, gradient average over the ranks,
+    clip_grad_norm_ (OPTIMIZATION.GRAD_NORM_CLIP), optimizer step.  Returns the reference's tb_dict."""
+    pts = batch_dict["points"]
+    pts[:, -3:] = pts[:, -3:] / 255.
+    model.dense_head.semantic_threshold = max(model.semantic_value - int(batch_dict["cur_epoch"]) * model.semantic_iter_value,
+                                              model.semantic_min_threshold)
+    if reducer is not None:
+        reducer.zero_grad()
+    elif optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    loss, tb = two_stage_loss(model, batch_dict, impl=impl)
+    loss.backward()
+    if reducer is not None:
+        reducer.reduce()
+    if grad_norm_clip:
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.grad is not None], grad_norm_clip)
     if optimizer is not None:
         optimizer.step()
     if hasattr(model, "update_global_step"):

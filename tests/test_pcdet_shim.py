@@ -119,11 +119,11 @@ def test_collate_layout_and_prediction_dicts():
     assert len(annos[1]["name"]) == 0 and annos[1]["frame_id"] == 1
 
 
-def test_forward_refuses_training_mode_and_cpu_tensors():
+def test_forward_refuses_cpu_tensors_in_both_modes():
     from cagroup3d_b200 import model_init
     m = model_init.seeded_model(18, False)
     with pytest.raises(AssertionError):
         m({"points": torch.zeros((10, 7)), "batch_size": 1, "cur_epoch": 10})     # CPU tensor: no CPU fallback
     m.train()
-    with pytest.raises(NotImplementedError):
-        m({"points": torch.zeros((10, 7)), "batch_size": 1, "cur_epoch": 10})
+    with pytest.raises(AssertionError):                                            # training mode: CUDA tensors only as well
+        m({"points": torch.zeros((10, 7)), "batch_size": 1, "cur_epoch": 10, "gt_boxes": torch.zeros((1, 1, 8))})

@@ -491,7 +491,7 @@ def test_first_stage_training_step_driver(monkeypatch):
         return _oracle_class_artifacts(res, head.semantic_threshold, Bn, cfg, S.Manager())
     monkeypatch.setattr(TS, "voxelize", voxelize_cpu)
     monkeypatch.setattr(HT, "coordinate_phase", coordinate_phase_cpu)
-    scenes = [synthetic.make_scene(1000 * 7 + i, 200, n_classes=ncls, return_masks=True) for i in range(B)]
+    scenes = [synthetic.make_scene(1000 * 7 + i, 150, n_classes=ncls, return_masks=True) for i in range(B)]
     batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
     model = model_init.seeded_model(ncls, False, seed=3).train()
     with torch.no_grad():
@@ -509,20 +509,53 @@ def test_first_stage_training_step_driver(monkeypatch):
         losses.append(tb["one_stage_loss"])
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
     assert all(p.grad.data_ptr() == red._view(p).data_ptr() for p in params)
-    # the pcdet-style call of the train loop (train_utils.py:56-58) on a first-stage-only model
-    from cagroup3d_b200 import detector as DT
+    # the pcdet-style call of the train loop (train_utils.py:56-58): both stages, then a first-stage-only model
+    from cagroup3d_b200 import detector as DT, roi_train as RT
     monkeypatch.setattr(DT, "voxelize", voxelize_cpu)
     monkeypatch.setitem(S._CONV_IMPL, "name", "simt")            # the emulation covers the fp32 conv entry point
+    gtb = [torch.from_numpy(b[:, :7]).float() for _, b, _, _ in scenes]
+    gtl = [torch.from_numpy(b[:, 7]).long() for _, b, _, _ in scenes]
+
+    def proposals_cpu(head, br, Bn):                             # stage-1 detections near the gt boxes (the NMS kernels are not emulated)
+        g = torch.Generator().manual_seed(0)
+        return [(torch.cat([gtb[b][:, :3] + torch.randn((len(gtb[b]), 3), generator=g) * 0.05, gtb[b][:, 3:6], torch.zeros((len(gtb[b]), 1))], 1),
+                 torch.rand((len(gtb[b]),), generator=g), gtl[b].clone()) for b in range(Bn)]
+
+    def roi_coordinate_phase_cpu(roi_head, sp, rois, Bn, rmax):
+        orc = O.Oracle(model.state_dict(), cfg)
+        omgr, ocm = me.Manager(), me.CoordMap(sp.C.numpy().astype(np.int64), 2)
+        omgr.by_stride[2] = ocm
+        pl = [(rois[b].detach().clone() * torch.tensor([1, 1, 1, 1, 1, 1, -1.0]), torch.ones(rmax), torch.zeros(rmax, dtype=torch.long)) for b in range(Bn)]
+        _, inter = orc.roi_head(me.SparseTensor(sp.F.detach().clone(), ocm, omgr), pl, Bn)
+        return _roi_artifacts(inter, cfg, sp, Bn * rmax)
+    monkeypatch.setattr(HT, "stage1_proposals", proposals_cpu)
+    monkeypatch.setattr(RT, "coordinate_phase", roi_coordinate_phase_cpu)
     bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "cur_epoch": 3,
           "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
           "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
-    with pytest.raises(NotImplementedError, match="RoI stage"):
-        model(dict(bd, points=bd["points"].clone()))
-    model.roi_head, model.module_list = None, model.module_list[:2]
-    ret, tb, disp = model(bd)
-    assert ret["loss"].requires_grad and abs(tb["loss_all"] - tb["one_stage_loss"]) < 1e-6
+    np.random.seed(0)
+    ret, tb, disp = model(dict(bd, points=bd["points"].clone()))
+    assert {"loss_all", "one_stage_loss", "rcnn_loss_reg", "loss_two_stage"} <= set(tb) and tb["rcnn_loss_reg"] > 0
+    assert abs(tb["loss_all"] - tb["one_stage_loss"] - tb["loss_two_stage"]) < 1e-4
     assert abs(disp.pop("cur_semantic_value") - max(0.15 - 3 * 0.02, 0.05)) < 1e-9 and set(disp) == set(tb) - {"loss_all"}
     ret["loss"].backward()
+    assert [n for n, p in model.named_parameters() if p.grad is None] == []
+    tb2 = TS.training_step(model, dict(bd, points=bd["points"].clone()), opt, red, impl="simt", grad_norm_clip=10.0)
+    assert set(tb2) == set(tb)
+
+
+def _roi_artifacts(inter, cfg, sp, nr):
+    """coordinate artifacts of roi_train.coordinate_phase from the oracle's RoI-head intermediates"""
+    from cagroup3d_b200 import sparse as S
+    gsz = cfg["grid"]
+    uq, inv, _ = me.unique_first(np.concatenate([inter["grid_coords"][:, :1], inter["grid_coords"][:, 1:] * cfg["coord_key"]], 1))
+    ii, jj, kk = np.meshgrid(np.arange(gsz), np.arange(gsz), np.arange(gsz), indexing="ij")
+    tap = (ii + gsz * jj + gsz * gsz * kk).ravel()
+    ptab = np.zeros((gsz ** 3, nr), np.int32)
+    ptab[tap[None, :].repeat(nr, 0), np.arange(nr)[:, None].repeat(gsz ** 3, 1)] = inv.reshape(nr, gsz ** 3)
+    umap = E.cpu_map(uq, 2, sp.mgr)
+    nbr, order = S.neighbor_table(sp.cmap, umap, cfg["roi_kernel"], sp.mgr, ordered=True)
+    return dict(umap=umap, nbr=nbr, order=order, ptab=torch.from_numpy(ptab), nr=nr)
 
 
 def test_roi_branch_training_wiring_vs_oracle(monkeypatch):
