@@ -1,5 +1,5 @@
-"""Per-kernel device times of one first-stage TRAINING step (development aid for BASELINE config 4: ScanNet training, batch
-4 per GPU; not the bench).  Forward + loss + backward through train_step.first_stage_training_step on synthetic scenes with
+"""Per-kernel device times of one whole (two-stage) TRAINING step (development aid for BASELINE config 4: ScanNet training, batch
+4 per GPU; not the bench).  Forward + both losses + backward + optimizer through train_step.training_step on synthetic scenes with
 per-point masks; prints ms per step and the C-ABI entry points ranked by device time.
 
     python tools/train_times.py [--batch 4] [--voxels 50000] [--steps 3] [--conv tc|simt]
@@ -40,7 +40,9 @@ def main():
     with torch.no_grad():
         out = BT.run_train(model.backbone_3d, voxelize(p, 0.02))
     model_init.calibrate_semantic_bias(model, out.F.detach(), a.p_sel)
-    params = [q for n, q in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head."))]
+    with torch.no_grad():
+        model.dense_head.cls_conv.bias.fill_(-2.0)            # stage-1 detections for the RoI stage
+    params = list(model.parameters())
     opt = torch.optim.AdamW(params, lr=1e-3)
     red = D.GradientAllReducer(params)
     print(f"setup {time.time() - t0:.1f}s  points {tuple(pts.shape)}  parameters {sum(q.numel() for q in params) / 1e6:.1f} M "
@@ -49,7 +51,7 @@ def main():
     def step():
         bd = {"points": pts.clone(), "batch_size": a.batch, "cur_epoch": 10, "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float().to(dev),
               "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
-        return TS.first_stage_training_step(model, bd, opt, red)
+        return TS.training_step(model, bd, opt, red, grad_norm_clip=10.0)
 
     for _ in range(2):
         tb = step()
@@ -62,7 +64,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
-    print(f"first-stage training step {ms:.2f} ms -> {a.batch / ms * 1e3:.1f} scenes/s per GPU")
+    print(f"training step {ms:.2f} ms -> {a.batch / ms * 1e3:.1f} scenes/s per GPU")
     S.Profile.active = []
     S.Profile.stage = "train"
     step()
