@@ -40,6 +40,10 @@ class SyntheticIndoorDataset(Dataset):
         return self.n_scenes
 
     def __getitem__(self, i):
+        if self.training:               # scannet_dataset.py:68-76: training items carry the per-point masks
+            pts, boxes, sem, ins = synthetic.make_scene(1000 * self.seed_group + i, self.target_voxels, n_classes=len(self.class_names),
+                                                        sunrgbd=self.sunrgbd, n_points=self.n_points, return_masks=True)
+            return {"points": pts, "gt_boxes": boxes, "frame_id": i, "semantic_mask": sem, "instance_mask": ins}
         pts, boxes = synthetic.make_scene(1000 * self.seed_group + i, self.target_voxels, n_classes=len(self.class_names),
                                           sunrgbd=self.sunrgbd, n_points=self.n_points)
         return {"points": pts, "gt_boxes": boxes, "frame_id": i}
@@ -51,8 +55,12 @@ class SyntheticIndoorDataset(Dataset):
         gt = np.zeros((len(batch_list), m, 8), np.float32)
         for i, d in enumerate(batch_list):
             gt[i, :len(d["gt_boxes"])] = d["gt_boxes"]
-        return {"points": np.concatenate(pts, 0), "gt_boxes": gt, "frame_id": np.array([d["frame_id"] for d in batch_list]),
-                "batch_size": len(batch_list)}
+        out = {"points": np.concatenate(pts, 0), "gt_boxes": gt, "frame_id": np.array([d["frame_id"] for d in batch_list]),
+               "batch_size": len(batch_list)}
+        for k in ("semantic_mask", "instance_mask"):        # kept as per-sample lists (dataset.py:207-210)
+            if k in batch_list[0]:
+                out[k] = [d[k] for d in batch_list]
+        return out
 
     @staticmethod
     def generate_prediction_dicts(batch_dict, pred_dicts, class_names, output_path=None):

@@ -127,3 +127,20 @@ def test_forward_refuses_cpu_tensors_in_both_modes():
     m.train()
     with pytest.raises(AssertionError):                                            # training mode: CUDA tensors only as well
         m({"points": torch.zeros((10, 7)), "batch_size": 1, "cur_epoch": 10, "gt_boxes": torch.zeros((1, 1, 8))})
+
+
+def test_training_loader_items_carry_masks():
+    """build_dataloader(training=True): batches in the layout CAGroup3D.get_training_loss reads (cagroup3d.py:99-135) --
+    zero-padded gt_boxes (B, M, 8) and per-sample semantic / instance mask lists aligned with the points."""
+    from pcdet.datasets import build_dataloader
+    cfg = load_cfg(ROOT, "scannet")
+    cfg.DATA_CONFIG["SYNTHETIC"] = {"NUM_SCENES": 3, "VOXELS": 800}
+    ds, loader, _ = build_dataloader(cfg.DATA_CONFIG, cfg.CLASS_NAMES, batch_size=2, dist=False, workers=0, training=True)
+    b = next(iter(loader))
+    assert b["batch_size"] == 2 and b["gt_boxes"].shape[0] == 2 and b["gt_boxes"].shape[2] == 8
+    assert len(b["semantic_mask"]) == len(b["instance_mask"]) == 2
+    for i in range(2):
+        n = int((b["points"][:, 0] == i).sum())
+        assert len(b["semantic_mask"][i]) == len(b["instance_mask"][i]) == n
+        fg = b["semantic_mask"][i] < len(cfg.CLASS_NAMES)
+        assert fg.any() and (b["instance_mask"][i][fg] >= 5).all() and (b["instance_mask"][i][~fg] < 5).all()
