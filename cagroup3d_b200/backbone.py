@@ -259,6 +259,12 @@ class BiResNet(nn.Module):
         self.fold.clear()
         return super()._load_from_state_dict(*a, **k)
 
+    def train(self, mode: bool = True):
+        """switching between training and evaluation drops the folded / stacked copies of the parameters (an optimizer
+        step or new running statistics made them stale)"""
+        self.fold.clear()
+        return super().train(mode)
+
     def run(self, x: S.SparseTensor) -> S.SparseTensor:
         """biresnet.py:358-406.  The high-resolution branch (layer3_/4_/5_, 128 channels at stride 4) and the
         low-resolution branch (layer3/4/5 + DAPPM, few rows, many small launches) are independent between their

@@ -83,6 +83,12 @@ class CAGroup3DRoIHead(nn.Module):
         self.fold.clear()
         return super()._load_from_state_dict(*a, **k)
 
+    def train(self, mode: bool = True):
+        """switching between training and evaluation drops the folded / stacked copies of the parameters (an optimizer
+        step or new running statistics made them stale)"""
+        self.fold.clear()
+        return super().train(mode)
+
     def _apply(self, fn, *a, **k):
         self.fold.clear()
         return super()._apply(fn, *a, **k)

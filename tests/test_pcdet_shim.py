@@ -144,3 +144,18 @@ def test_training_loader_items_carry_masks():
         assert len(b["semantic_mask"][i]) == len(b["instance_mask"][i]) == n
         fg = b["semantic_mask"][i] < len(cfg.CLASS_NAMES)
         assert fg.any() and (b["instance_mask"][i][fg] >= 5).all() and (b["instance_mask"][i][~fg] < 5).all()
+
+
+def test_mode_switch_drops_folded_parameter_copies():
+    """model.eval() after training steps must not evaluate with folded BatchNorms / stacked class weights made before the
+    last optimizer step."""
+    from cagroup3d_b200 import model_init
+    m = model_init.seeded_model(18, False)
+    for mod in (m.backbone_3d, m.dense_head, m.roi_head):
+        mod.fold.get("probe", lambda: 1)
+        assert mod.fold._c
+    m.train()
+    assert not m.backbone_3d.fold._c and not m.dense_head.fold._c and not m.roi_head.fold._c
+    m.dense_head.fold.get("probe", lambda: 1)
+    m.eval()
+    assert not m.dense_head.fold._c
