@@ -403,9 +403,19 @@ def cg3d_boxes_pairwise_bev(**a):
     a["out"].copy_(iou3d_oracle.pairwise(a["boxes_a"], a["boxes_b"], {0: "overlap", 1: "iou", 2: "iou_normal"}[a["mode"]]))
 
 
-def install(monkeypatch):
-    """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test)."""
+class _Setter:
+    """monkeypatch stand-in for a process that ends with the test (spawned gloo workers)"""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def install(monkeypatch=None):
+    """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test;
+    monkeypatch=None: for the rest of the process)."""
     from cagroup3d_b200 import _lib, sparse as S
+    monkeypatch = monkeypatch or _Setter
     names = _param_names()
     table = {k: v for k, v in globals().items() if k.startswith("cg3d_")}
     calls = []

@@ -142,3 +142,67 @@ def test_gradient_reducer_single_process():
     assert D.reduce_mean(t) is t
     red.zero_grad()
     assert all(float(p.grad.abs().max()) == 0 for p in red.params)
+
+
+# ---- the training step under two ranks: every rank its own scene, gradients averaged through the flat buckets -------------
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from cagroup3d_b200 import model_init, ops, sparse as S, synthetic, train_step as TS, train_targets as TT
+    from oracle import me_cpu as me
+    from tests import cabi_emulator as E
+    E.install()                                                   # C ABI emulated on the CPU (tests/cabi_emulator.py)
+    TT._require_cuda = lambda t: None
+    ops._chk = lambda *ts: None
+
+    def voxelize_cpu(points, voxel_size):
+        c = points[:, :4].clone()
+        c[:, 1:] /= voxel_size
+        ox = me.from_points(c, points[:, 4:])
+        mgr = S.Manager()
+        cm = E.cpu_map(ox.C, 1, mgr)
+        mgr.by_stride[1] = cm
+        return S.SparseTensor(ox.F.float().contiguous(), cm, mgr)
+    TS.voxelize = voxelize_cpu
+
+    def batch_of(scene_index):
+        p, b, s, m = synthetic.make_scene(1000 * 7 + scene_index, 250, n_classes=18, return_masks=True)
+        bt = synthetic.collate_batch([(p, b)])
+        return {"points": torch.from_numpy(bt["points"]).clone(), "batch_size": 1, "gt_boxes": torch.from_numpy(bt["gt_boxes"]).float(),
+                "semantic_mask": [s], "instance_mask": [m]}
+
+    def grads_of(scene_index, reducer_on):
+        model = model_init.seeded_model(18, False, seed=4).train()
+        params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head.semantic_conv", "dense_head.offset_block"))]
+        red = D.GradientAllReducer(params, bucket_mb=16) if reducer_on else None
+        tb = TS.partial_training_step(model, batch_of(scene_index), None, red, impl="simt")
+        return [p.grad.clone() for p in params], tb
+
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    got, tb = grads_of(rank, True)                                # my scene, gradients averaged over the ranks
+    mine, _ = grads_of(rank, False)                               # the same step without the reducer ...
+    flat = torch.cat([g.reshape(-1) for g in mine])
+    parts = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)                                  # ... averaged by the test itself
+    want = sum(parts) / world
+    have = torch.cat([g.reshape(-1) for g in got])
+    worst = float((have - want).norm()) / (float(want.norm()) + 1e-12)
+    differs = float((have - flat).norm()) / (float(flat.norm()) + 1e-12)          # and it is not just my own gradient
+    ok = bool(np.isfinite(tb["loss"])) and worst < 1e-4 and differs > 1e-2
+    q.put((rank, bool(ok), worst, differs))
+    dist.destroy_process_group()
+
+
+def test_training_step_gradients_averaged_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=600) for _ in ps)
+    [p.join(60) for p in ps]
+    assert [r[:2] for r in res] == [(0, True), (1, True)], res
