@@ -217,7 +217,6 @@ def reorder_rois(pred_boxes_3d, enlarge_ratio=False):
 def assign_targets(target_layer: ProposalTargetLayer, input_dict: dict, code_size: int) -> dict:
     """cagroup_roi_head.py:288-326: sampled RoIs + their gt boxes in the RoI's canonical frame."""
     import numpy as np
-    from pcdet.utils import common_utils
     with torch.no_grad():
         t = target_layer(input_dict)
     B = input_dict["batch_size"]
@@ -228,6 +227,7 @@ def assign_targets(target_layer: ProposalTargetLayer, input_dict: dict, code_siz
     gt[:, :, 0:3] = gt[:, :, 0:3] - rois[:, :, 0:3]
     gt[:, :, 6] = gt[:, :, 6] - roi_ry
     if code_size > 6:
+        from pcdet.utils import common_utils
         gt = common_utils.rotate_points_along_z(points=gt.view(-1, 1, gt.shape[-1]), angle=-roi_ry.view(-1)).view(B, -1, gt.shape[-1])
         h = gt[:, :, 6] % (2 * np.pi)
         opp = (h > np.pi * 0.5) & (h < np.pi * 1.5)
