@@ -57,14 +57,15 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 
 def test_product_never_imports_oracle():
-    """the oracle is test infrastructure: nothing under cagroup3d_b200/, pcdet/ or tools/ may import it."""
+    """the oracle and the C-ABI emulator (tests/cabi_emulator.py) are test infrastructure: nothing under cagroup3d_b200/,
+    pcdet/ or tools/ may import them."""
     bad = []
     for top in ("cagroup3d_b200", "pcdet", "tools"):
         for dp, _, files in os.walk(os.path.join(ROOT, top)):
             for f in files:
                 if f.endswith(".py"):
                     s = open(os.path.join(dp, f)).read()
-                    if re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M) or "tests.golden" in s:
+                    if re.search(r"^\s*(from|import)\s+(oracle|tests)\b", s, flags=re.M) or "tests.golden" in s or "cabi_emulator" in s:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
 
