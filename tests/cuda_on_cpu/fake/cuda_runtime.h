@@ -1,0 +1,147 @@
+// TEST INFRASTRUCTURE: a minimal stand-in for the CUDA runtime + device builtins, so that the .cu sources of the TRAINING
+// kernels (written without access to a GPU) can be compiled with g++ and executed on the CPU: one std::thread per CUDA
+// thread, blocks one after the other, __syncthreads / warp shuffles / ballots as real barriers.  It checks the kernels'
+// SOURCE (indexing, reductions, barrier placement, launch arithmetic) against the same oracles as the GPU tests; it says
+// nothing about performance and does not replace the run on hardware.  See tests/cuda_on_cpu/build.py.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+using std::max;
+using std::min;
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct float4 { float x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+#define cudaFuncSetAttribute(...) ((void)0)
+
+namespace cpu_cuda {
+struct Barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, waiting = 0;
+    unsigned long gen = 0;
+    void reset(int n_) { n = n_; waiting = 0; }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        unsigned long g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+struct Warp {
+    Barrier bar;
+    unsigned long long buf[32];
+};
+extern Barrier block_barrier;
+extern std::vector<Warp>* warps;
+extern dim3 g_blockDim, g_gridDim;
+extern char* dyn_smem;
+extern thread_local dim3 t_threadIdx, t_blockIdx;
+extern thread_local int t_linear;
+
+template <class T>
+inline unsigned long long to_bits(T v) { unsigned long long b = 0; memcpy(&b, &v, sizeof(T)); return b; }
+template <class T>
+inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+
+template <class T>
+inline T warp_read(T v, int src_lane) {
+    Warp& w = (*warps)[t_linear >> 5];
+    w.buf[t_linear & 31] = to_bits(v);
+    w.bar.wait();
+    T r = from_bits<T>(w.buf[src_lane & 31]);
+    w.bar.wait();
+    return r;
+}
+
+template <class K, class... A>
+void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A... args) {
+    const int nt = (int)(block.x * block.y * block.z);
+    g_blockDim = block;
+    g_gridDim = grid;
+    std::vector<char> dyn(smem + 16);
+    dyn_smem = dyn.data();
+    std::vector<Warp> ws((nt + 31) / 32);
+    warps = &ws;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                block_barrier.reset(nt);
+                for (int w = 0; w < (int)ws.size(); ++w) ws[w].bar.reset(std::min(32, nt - 32 * w));
+                std::vector<std::thread> th;
+                th.reserve(nt);
+                for (int t = 0; t < nt; ++t)
+                    th.emplace_back([=] {
+                        t_linear = t;
+                        t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                        t_blockIdx = dim3(bx, by, bz);
+                        kernel(args...);
+                    });
+                for (auto& x : th) x.join();
+            }
+}
+}  // namespace cpu_cuda
+
+#define threadIdx cpu_cuda::t_threadIdx
+#define blockIdx cpu_cuda::t_blockIdx
+#define blockDim cpu_cuda::g_blockDim
+#define gridDim cpu_cuda::g_gridDim
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline void __syncthreads() { cpu_cuda::block_barrier.wait(); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) { return cpu_cuda::warp_read(v, src); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return cpu_cuda::warp_read(v, (cpu_cuda::t_linear & 31) ^ lane_mask); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    cpu_cuda::Warp& w = (*cpu_cuda::warps)[cpu_cuda::t_linear >> 5];
+    w.buf[cpu_cuda::t_linear & 31] = pred ? 1 : 0;
+    w.bar.wait();
+    unsigned r = 0;
+    for (int l = 0; l < w.bar.n; ++l) r |= (unsigned)(w.buf[l] & 1) << l;
+    w.bar.wait();
+    return r;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int atomicMin(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int atomicMax(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}

@@ -1,0 +1,250 @@
+"""The TRAINING kernels' CUDA sources executed on the CPU (tests/cuda_on_cpu: g++ build of the unmodified .cu files over a
+thread-per-CUDA-thread shim with real barriers / warp exchanges) against the oracles the GPU tests use.  These kernels were
+written without access to a GPU; this checks their source -- indexing, reductions, barrier placement, launch arithmetic --
+until tests/test_zz_gpu_spconv_backward.py has run on hardware.  The product path never loads this library."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import backward_oracle as Bk
+from oracle import me_cpu as me
+from oracle import train_oracle as T
+
+f32, i32, i64 = np.float32, np.int32, np.int64
+
+
+@pytest.fixture(scope="module")
+def K():
+    from cagroup3d_b200 import _lib
+    from tests.cuda_on_cpu import build
+    lib = build.load()
+    protos = _lib.parse_header()
+
+    def call(name, *args):
+        fn = getattr(lib, name)
+        types = protos[name]
+        stream = [] if name in _lib._host_only else [None]
+        assert len(args) + len(stream) == len(types), (name, len(args), len(types))
+        fn.argtypes, fn.restype = types, ctypes.c_int
+        conv = [a.ctypes.data if isinstance(a, np.ndarray) else a for a in args]
+        rc = fn(*conv, *stream)
+        assert rc == 0 or name in _lib._host_only, (name, rc)
+        return rc
+    return call
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def test_wgrad_transpose_kernels(K):
+    rng = np.random.default_rng(0)
+    n_in, n, Kt, Cin, Cout = 900, 2500, 3, 40, 24
+    nbr = rng.integers(-1, n_in, (Kt, n)).astype(i32)
+    nbr[:, rng.random(n) < 0.3] = -1
+    X, dY = rng.standard_normal((n_in, Cin)).astype(f32), rng.standard_normal((n, Cout)).astype(f32)
+    perm = rng.permutation(n).astype(i32)
+    for out_rows, c0, c1, act in ((None, 0, n, 0), (perm, 0, n, 1), (perm, 700, 1900, 0)):
+        S = K("cg3d_spconv_wgrad_slabs", c1 - c0, Cin, Cout, Kt)
+        slabs = np.zeros((S * Kt * Cin * Cout,), f32)
+        dW = np.full((Kt, Cin, Cout), np.nan, f32)
+        K("cg3d_spconv_wgrad", X, Cin, act, nbr, dY, Cout, n, c0, c1, Cin, Cout, Kt, out_rows, slabs if S > 1 else None, dW)
+        masked = nbr.copy()
+        masked[:, :c0] = -1
+        masked[:, c1:] = -1
+        Xa = np.maximum(X, 0) if act else X
+        _, want = Bk.conv_backward(torch.from_numpy(Xa).double(), torch.zeros((Kt, Cin, Cout), dtype=torch.float64), masked,
+                                   torch.from_numpy(dY).double(), out_rows=out_rows)
+        assert _rel(dW, want.numpy()) < 1e-5, (S, c0, c1)
+    assert K("cg3d_spconv_wgrad_slabs", 2500, Cin, Cout, Kt) > 1            # the slab path was exercised
+    # identity rows (1x1 conv / Linear)
+    dW1 = np.zeros((1, Cin, Cout), f32)
+    K("cg3d_spconv_wgrad", X[:800], Cin, 0, None, dY[:800], Cout, 800, 0, 800, Cin, Cout, 1, None, None, dW1)
+    assert _rel(dW1[0], X[:800].astype(np.float64).T @ dY[:800].astype(np.float64)) < 1e-5
+    # transposed table of an injective rule map, positional
+    inj = np.full((Kt, n), -1, i32)
+    for k in range(Kt):
+        cols = rng.permutation(n)[:n_in // 2]
+        inj[k, cols] = rng.permutation(n_in)[:n_in // 2]
+    T_ = np.zeros((Kt, n_in), i32)
+    K("cg3d_table_transpose", inj, Kt, n, perm, n_in, T_)
+    assert np.array_equal(T_, Bk.table_transpose(inj, n_in, perm))
+    W = rng.standard_normal((5, Cin, Cout)).astype(f32)
+    Wt = np.zeros((5, Cout, Cin), f32)
+    K("cg3d_transpose_weights", W, 5, Cin, Cout, Wt)
+    assert np.array_equal(Wt, W.transpose(0, 2, 1))
+
+
+def test_batchnorm_and_rowwise_kernels(K):
+    rng = np.random.default_rng(1)
+    n, C = 3000, 40
+    X = (rng.standard_normal((n, C)) * 3 + rng.standard_normal(C) * 5).astype(f32)
+    gamma, beta, dY = (rng.random(C) + 0.5).astype(f32), rng.standard_normal(C).astype(f32), rng.standard_normal((n, C)).astype(f32)
+    ws = np.zeros((K("cg3d_bn_train_workspace", n, C),), f32)
+    mean, rstd, scale, shift = (np.zeros(C, f32) for _ in range(4))
+    rm, rv = np.zeros(C, f32), np.ones(C, f32)
+    K("cg3d_bn_train_stats", X, C, n, C, 1e-5, 0.1, gamma, beta, ws, mean, rstd, scale, shift, rm, rv)
+    Xd = X.astype(np.float64)
+    assert _rel(mean, Xd.mean(0)) < 1e-6 and _rel(rstd, 1 / np.sqrt(Xd.var(0) + 1e-5)) < 1e-5
+    assert _rel(rm, 0.1 * Xd.mean(0)) < 1e-6 and _rel(rv, 0.9 + 0.1 * Xd.var(0, ddof=1)) < 1e-5
+    Y = np.maximum(X * scale + shift, 0).astype(f32)
+    want_y = np.maximum((Xd - Xd.mean(0)) / np.sqrt(Xd.var(0) + 1e-5) * gamma + beta, 0)
+    assert _rel(Y, want_y) < 1e-5
+    dx, dres, dg, db = np.zeros((n, C), f32), np.zeros((n, C), f32), np.zeros(C, f32), np.zeros(C, f32)
+    K("cg3d_bn_train_backward", X, C, dY, C, Y, C, n, C, mean, rstd, gamma, ws, dx, C, dres, C, dg, db)
+    dy_eff = np.where(Y > 0, dY, 0)
+    wdx, wdg, wdb = Bk.batchnorm_train_backward(torch.from_numpy(Xd), torch.from_numpy(gamma).double(), torch.from_numpy(dy_eff).double())
+    assert _rel(dx, wdx.numpy()) < 2e-5 and _rel(dg, wdg.numpy()) < 2e-5 and _rel(db, wdb.numpy()) < 2e-5
+    assert np.array_equal(dres, dy_eff.astype(f32))
+    cs = np.zeros(C, f32)
+    K("cg3d_column_sum", dY, C, n, C, ws, cs)
+    assert _rel(cs, dY.astype(np.float64).sum(0)) < 1e-5
+    for act, fn in ((1, lambda v: np.maximum(v, 0)), (2, lambda v: np.where(v > 0, v, np.expm1(v)))):
+        y = fn(X / 4).astype(f32)
+        d = np.zeros((n, C), f32)
+        K("cg3d_act_backward", dY, C, y, C, n, C, act, d, C)
+        want = np.where(y > 0, dY, 0 if act == 1 else dY * (y + 1))
+        assert _rel(d, want) < 1e-6
+    U = 500
+    inv = rng.integers(0, U, n).astype(i32)
+    inv[:U] = np.arange(U)
+    dO = rng.standard_normal((U, C)).astype(f32)
+    cnt = np.bincount(inv, minlength=U).astype(f32)
+    dIn = np.zeros((n, C), f32)
+    K("cg3d_segment_mean_backward", dO, inv, cnt, n, C, dIn, C)
+    assert _rel(dIn, Bk.segment_mean_backward(torch.from_numpy(dO).double(), inv, n).numpy()) < 1e-6
+    order = np.argsort(inv, kind="stable").astype(i32)
+    off = np.concatenate([[0], np.cumsum(np.bincount(inv, minlength=U))]).astype(i32)
+    out = np.zeros((U, C), f32)
+    K("cg3d_segment_sum_sorted", dY, order, off, U, C, out)
+    want = np.zeros((U, C))
+    np.add.at(want, inv, dY.astype(np.float64))
+    assert _rel(out, want) < 1e-5
+
+
+def _hash_table(coords):
+    """the library's open-addressing table (common.cuh: cg3d_pack / cg3d_hash, linear probing)"""
+    M = (1 << 64) - 1
+
+    def h(k):
+        k ^= k >> 33; k = (k * 0xff51afd7ed558ccd) & M; k ^= k >> 33; k = (k * 0xc4ceb9fe1a85ec53) & M; k ^= k >> 33
+        return k & 0xFFFFFFFF
+    cap = 1
+    while cap < 2 * len(coords):
+        cap *= 2
+    keys = np.full(cap, M, np.uint64)
+    vals = np.full(cap, -1, i32)
+    for r, c in enumerate(coords):
+        k = ((int(c[0]) & 0xFFFF) << 48) | (((int(c[1]) + 32768) & 0xFFFF) << 32) | (((int(c[2]) + 32768) & 0xFFFF) << 16) | ((int(c[3]) + 32768) & 0xFFFF)
+        s = h(k) & (cap - 1)
+        while keys[s] != M:
+            s = (s + 1) & (cap - 1)
+        keys[s], vals[s] = k, r
+    return keys, vals, cap
+
+
+def test_interp_and_avgpool_backward_kernels(K):
+    rng = np.random.default_rng(2)
+    ts, tq, C = 4, 1, 40
+    q = np.unique(np.concatenate([rng.integers(0, 2, (700, 1)), rng.integers(-12, 12, (700, 3)) * tq], 1), axis=0)
+    src = q.copy()
+    src[:, 1:] = np.floor_divide(src[:, 1:], ts) * ts
+    src = np.unique(src, axis=0)
+    src = src[rng.random(len(src)) < 0.7]
+    dOut = rng.standard_normal((len(q), C)).astype(f32)
+    rows, w = Bk.interp_corners(me.CoordMap(src.astype(i64), ts), q.astype(i64))
+    want = Bk.interp_backward(torch.from_numpy(dOut).double(), rows, w, len(src)).numpy()
+    keys, vals, cap = _hash_table(q)
+    dF = np.full((len(src), C), np.nan, f32)
+    K("cg3d_interp_trilinear_backward", src.astype(i32), len(src), ts, keys, vals, cap, tq, dOut, C, dF)
+    assert _rel(dF, want) < 1e-5
+    # average pooling backward: coarse outputs over a window of inputs
+    ic = np.unique(np.concatenate([rng.integers(0, 2, (300, 1)), rng.integers(-6, 6, (300, 3)) * 2], 1), axis=0).astype(i32)
+    oc = ic.copy()
+    oc[:, 1:] = np.floor_divide(oc[:, 1:], 4) * 4
+    oc = np.unique(oc, axis=0).astype(i32)
+    half = 4
+    m = (np.abs(ic[None, :, 1:] - oc[:, None, 1:]).max(-1) <= half) & (ic[None, :, 0] == oc[:, None, 0])
+    dO = rng.standard_normal((len(oc), C)).astype(f32)
+    cnt, dIn = np.zeros(len(oc), f32), np.zeros((len(ic), C), f32)
+    K("cg3d_avgpool_window_backward", oc, len(oc), ic, len(ic), half, dO, C, cnt, dIn)
+    assert np.array_equal(cnt, m.sum(1).astype(f32))
+    assert _rel(dIn, m.T.astype(np.float64) @ (dO / m.sum(1)[:, None])) < 1e-5
+
+
+def test_assigner_and_loss_kernels(K):
+    from tests.test_zz_gpu_spconv_backward import _assign_case
+    for yaw in (False, True):
+        pts, boxes, labels, ncls = _assign_case(yaw)
+        pts = [p[:400] for p in pts]
+        locs = np.ascontiguousarray(torch.cat(pts).numpy(), f32)
+        offs = np.cumsum([0] + [len(p) for p in pts]).astype(i32)
+        n, m = len(locs), len(boxes)
+        b, l = np.ascontiguousarray(boxes.numpy(), f32), labels.numpy().astype(i32)
+        for topk in (18, 3):
+            ct, bt, lb = T.assign(pts, boxes, labels, topk)
+            kth, c, bx, lab, idx = np.zeros(m, f32), np.zeros(n, f32), np.zeros((n, 7), f32), np.zeros(n, i64), np.zeros(n, i32)
+            K("cg3d_assign", locs, n, offs, ncls, b, l, m, topk, kth, c, bx, lab, idx)
+            same = lab == lb.numpy()
+            assert (~same).mean() <= (0.0 if not yaw else 2e-3)
+            pos = same & (lb.numpy() >= 0)
+            assert pos.sum() > 10 and np.array_equal(bx[pos], bt.numpy()[pos]) and np.abs(c[pos] - ct.numpy()[pos]).max() < 1e-5
+        sl, il = T.assign_semantic(torch.from_numpy(locs), boxes, labels)
+        gs, gi = np.zeros(n, i64), np.zeros(n, i64)
+        K("cg3d_assign_semantic", locs, n, b, l, m, gs, gi)
+        assert ((gs != sl.numpy()) | (gi != il.numpy())).mean() <= (0.0 if not yaw else 2e-3)
+    rng = np.random.default_rng(3)
+    n, C = 700, 18
+    pred, lab = (rng.standard_normal((n, C)) * 3).astype(f32), rng.integers(-1, C, n).astype(i64)
+    pd = torch.from_numpy(pred).double().requires_grad_(True)
+    want = T.focal_loss(pd, torch.from_numpy(lab), 37.0)
+    want.backward()
+    ws, loss, grad = np.zeros(max(K("cg3d_focal_loss_workspace", n, C), K("cg3d_loss_workspace", n * C)), f32), np.zeros(1, f32), np.zeros((n, C), f32)
+    K("cg3d_focal_loss", pred, lab, n, C, 2.0, 0.25, 37.0, ws, loss, grad)
+    assert abs(loss[0] - float(want)) < 1e-5 * max(1, abs(float(want))) and _rel(grad, pd.grad.numpy()) < 1e-5
+    P = 600
+    tgt = np.concatenate([rng.standard_normal((P, 3)), rng.random((P, 3)) + 0.3], 1).astype(f32)
+    pb = (tgt + rng.standard_normal((P, 6)) * 0.3).astype(f32)
+    pb[:, 3:] = np.abs(pb[:, 3:]) + 0.05
+    pb[:30, :3] += 5
+    w = rng.random(P).astype(f32)
+    pdb = torch.from_numpy(pb).double().requires_grad_(True)
+    wl = T.axis_aligned_iou_loss(pdb, torch.from_numpy(tgt).double(), torch.from_numpy(w).double(), float(w.sum()))
+    wl.backward()
+    g6 = np.zeros((P, 6), f32)
+    K("cg3d_iou_loss_aa", pb, 6, tgt, 6, w, P, float(w.sum()), ws, loss, g6, 6)
+    assert abs(loss[0] - float(wl)) < 1e-5 and _rel(g6, pdb.grad.numpy()) < 2e-5
+    x, t = (rng.standard_normal(P) * 2).astype(f32), rng.random(P).astype(f32)
+    xd = torch.from_numpy(x).double().requires_grad_(True)
+    wb = T.bce_loss(xd, torch.from_numpy(t).double(), 37.0)
+    wb.backward()
+    g1 = np.zeros(P, f32)
+    K("cg3d_bce_loss", x, t, P, 37.0, ws, loss, g1)
+    assert abs(loss[0] - float(wb)) < 1e-5 * max(1, abs(float(wb))) and _rel(g1, xd.grad.numpy()) < 1e-6
+    p3, t3, w3 = (rng.standard_normal((P, 3)) * 0.1).astype(f32), (rng.standard_normal((P, 3)) * 0.1).astype(f32), rng.random((P, 3)).astype(f32)
+    pd3 = torch.from_numpy(p3).double().requires_grad_(True)
+    wsl = T.smooth_l1_sum(pd3, torch.from_numpy(t3).double(), torch.from_numpy(w3).double())
+    wsl.backward()
+    g3 = np.zeros((P, 3), f32)
+    K("cg3d_smooth_l1_loss", p3, t3, w3, P, 3, 0.04, ws, loss, g3)
+    assert abs(loss[0] - float(wsl)) < 1e-5 * max(1, abs(float(wsl))) and _rel(g3, pd3.grad.numpy()) < 1e-6
+
+
+def test_vote_targets_kernel(K):
+    from cagroup3d_b200 import synthetic
+    pts, boxes, sem, ins = synthetic.make_scene(1000 * 7 + 1, 600, n_classes=18, return_masks=True)
+    sp = np.ascontiguousarray(pts[:, :3], f32)
+    gtb = np.ascontiguousarray(boxes[:, :7], f32)
+    vox = np.unique(np.floor(sp / 0.04), axis=0).astype(f32) * f32(0.04)
+    spt, vt = torch.from_numpy(sp), torch.from_numpy(vox)
+    want_t, want_m = T.vote_targets_from_masks(spt, vt, torch.from_numpy(gtb), torch.from_numpy(sem), torch.from_numpy(ins), 18)
+    nearest = torch.cdist(vt, spt).argmin(1).numpy().astype(i32)
+    n_inst = int(ins.max()) + 1
+    ws, centers = np.zeros(n_inst * 8, i32), np.zeros((n_inst, 3), f32)
+    tg, mk = np.zeros((len(vox), 3), f32), np.zeros(len(vox), f32)
+    K("cg3d_vote_targets", sp, 3, sem.astype(i64), ins.astype(i64), len(sp), n_inst, 18, gtb, len(gtb), vox, nearest, len(vox), ws, centers,
+      tg, mk)
+    assert np.array_equal(mk, want_m.numpy()) and np.abs(tg - want_t.numpy()).max() < 1e-5
