@@ -411,21 +411,40 @@ class _Setter:
         setattr(obj, name, value)
 
 
-def install(monkeypatch=None):
+def install(monkeypatch=None, compiled: bool = False):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test;
-    monkeypatch=None: for the rest of the process)."""
+    monkeypatch=None: for the rest of the process).
+
+    compiled=True: the entry points of the training kernels are NOT emulated but served by their own CUDA sources compiled
+    for the CPU (tests/cuda_on_cpu), called exactly as _lib.call calls the GPU library -- raw data pointers, sizes and
+    strides as passed -- so a wrong stride / a non-contiguous view / a wrong dtype handed over by the Python side shows up
+    as a wrong result here instead of on the device."""
     from cagroup3d_b200 import _lib, sparse as S
     monkeypatch = monkeypatch or _Setter
+    native, protos = None, None
+    if compiled:
+        import ctypes
+        from tests.cuda_on_cpu import build as cpu_build
+        native, protos = cpu_build.load(), _lib.parse_header()
     names = _param_names()
     table = {k: v for k, v in globals().items() if k.startswith("cg3d_")}
     calls = []
 
     def call(name, *args):
-        if name not in table:
-            raise NotImplementedError(f"{name} is not emulated")
         params = names[name]
         assert len(args) == len(params), (name, len(args), params)
         calls.append(name)
+        # (the interpolation backward probes the query map's REAL hash table, which cpu_map() does not build: stays emulated)
+        if native is not None and hasattr(native, name) and name != "cg3d_interp_trilinear_backward":
+            fn = getattr(native, name)
+            fn.argtypes, fn.restype = protos[name], ctypes.c_int
+            for a in args:
+                assert not isinstance(a, torch.Tensor) or a.device.type == "cpu"
+            rc = fn(*[a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args], None)
+            assert rc == 0, (name, rc)
+            return
+        if name not in table:
+            raise NotImplementedError(f"{name} is not emulated")
         table[name](**dict(zip(params, args)))
 
     monkeypatch.setattr(_lib, "call", call)

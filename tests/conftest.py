@@ -10,6 +10,16 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: minutes of CPU time (CUDA sources on CPU threads); runs only with CG3D_SLOW_TESTS=1")
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get("CG3D_SLOW_TESTS", "0") == "1":
+        return
+    skip = pytest.mark.skip(reason="slow: set CG3D_SLOW_TESTS=1")
+    for it in items:
+        if "slow" in it.keywords:
+            it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

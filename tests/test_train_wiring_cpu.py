@@ -16,10 +16,11 @@ def _rel(got, want):
     return float((got.double() - want).norm()) / (float(want.norm()) + 1e-30)
 
 
+@pytest.mark.parametrize("compiled", [False, True])
 @pytest.mark.parametrize("cin,cout,k,stride", [(16, 24, 3, 1), (16, 8, 3, 2), (8, 8, 1, 1), (8, 12, 1, 2)])
-def test_conv_autograd_wiring(monkeypatch, cin, cout, k, stride):
+def test_conv_autograd_wiring(monkeypatch, cin, cout, k, stride, compiled):
     from cagroup3d_b200 import autograd as A, sparse as S
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     rng = np.random.default_rng(k * 10 + stride)
     c = me.unique_first(np.concatenate([rng.integers(0, 2, (900, 1)), rng.integers(-12, 12, (900, 3))], 1))[0]
     ox = me.SparseTensor(torch.from_numpy(rng.standard_normal((len(c), cin))), me.CoordMap(c, 1), me.Manager())
@@ -79,11 +80,12 @@ def test_backbone_training_wiring_vs_oracle(monkeypatch):
             "cg3d_avgpool_window", "cg3d_avgpool_window_backward", "cg3d_act_backward"} <= used, used
 
 
-def test_targets_and_losses_wiring(monkeypatch):
+@pytest.mark.parametrize("compiled", [False, True])
+def test_targets_and_losses_wiring(monkeypatch, compiled):
     from cagroup3d_b200 import train_targets as TT
     with pytest.raises(RuntimeError, match="no CPU"):
         TT.FocalLoss()(torch.zeros((2, 3)), torch.zeros((2,), dtype=torch.long), avg_factor=1.0)
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
     g = torch.Generator().manual_seed(3)
     ncls, m = 4, 9
@@ -128,11 +130,12 @@ def test_targets_and_losses_wiring(monkeypatch):
     assert _rel(p3.grad, pd3.grad) < 1e-5
 
 
-def test_first_stage_loss_single_wiring(monkeypatch):
+@pytest.mark.parametrize("compiled", [False, True])
+def test_first_stage_loss_single_wiring(monkeypatch, compiled):
     """train_targets.FirstStageLoss.loss_single (the reference's _loss_single argument list) == the oracle's five terms,
     with gradients reaching every prediction tensor."""
     from cagroup3d_b200 import ops, train_targets as TT
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
     monkeypatch.setattr(ops, "_chk", lambda *ts: None)
     g = torch.Generator().manual_seed(12)
@@ -270,11 +273,12 @@ def test_partial_training_step_driver(monkeypatch):
     assert all(p.grad is not None and p.grad.data_ptr() == red._view(p).data_ptr() for p in params)
 
 
-def test_grouped_conv_and_segment_mean_wiring(monkeypatch):
+@pytest.mark.parametrize("compiled", [False, True])
+def test_grouped_conv_and_segment_mean_wiring(monkeypatch, compiled):
     """GroupedConvFunction in the class-batched layout of the head (class folded into the batch index, rows class-major,
     one weight group per class) and SegmentMeanFunction, against autograd through per-class oracle convolutions."""
     from cagroup3d_b200 import autograd as A, sparse as S
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     rng = np.random.default_rng(8)
     G, Bs, Cin, Cout, k = 3, 2, 8, 12, 3
     coords, off = [], [0]
@@ -557,12 +561,13 @@ def _roi_artifacts(inter, cfg, sp, nr):
     return dict(umap=umap, nbr=nbr, order=order, ptab=torch.from_numpy(ptab), nr=nr)
 
 
-def test_roi_branch_training_wiring_vs_oracle(monkeypatch):
+@pytest.mark.parametrize("compiled", [False, pytest.param(True, marks=pytest.mark.slow)])       # compiled: 4 minutes, passes
+def test_roi_branch_training_wiring_vs_oracle(monkeypatch, compiled):
     """roi_train.roi_branch (5^3 grid conv at the RoI grid voxels, 7^3 pooling contraction with its non-injective table,
     batch-statistics BatchNorm, regression MLP) on the emulated C ABI against the oracle's RoI head run with batch
     statistics: pooled features, rcnn_reg, gradients of every RoI-head parameter and of the backbone features."""
     from cagroup3d_b200 import model_init, roi_train as RT, sparse as S, synthetic
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     B, ncls = 2, 18
     scenes = [synthetic.make_scene(1000 * 9 + i, 700, n_classes=ncls) for i in range(B)]
     batch = synthetic.collate_batch(scenes)
@@ -623,7 +628,8 @@ def test_roi_branch_training_wiring_vs_oracle(monkeypatch):
     assert worst[0] < 5e-3, worst
 
 
-def test_roi_targets_and_loss_equal_the_reference(monkeypatch):
+@pytest.mark.parametrize("compiled", [False, True])
+def test_roi_targets_and_loss_equal_the_reference(monkeypatch, compiled):
     """roi_train.reorder_rois / ProposalTargetLayer / assign_targets / roi_reg_loss on the seeded inputs of
     tests/golden/roi_train_parts.npz -- produced by the REFERENCE's own ProposalTargetLayer, CAGroup3DRoIHead.assign_targets
     and get_box_reg_layer_loss (tests/golden/make_roi_train_golden.py) -- with the same host generator seeds: the same
@@ -631,7 +637,7 @@ def test_roi_targets_and_loss_equal_the_reference(monkeypatch):
     import os
     from cagroup3d_b200 import ops, roi_train as RT, train_targets as TT
     from tests.golden import make_roi_train_golden as MK
-    E.install(monkeypatch)
+    E.install(monkeypatch, compiled=compiled)
     monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
     monkeypatch.setattr(ops, "_chk", lambda *ts: None)
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_train_parts.npz"))
@@ -653,3 +659,52 @@ def test_roi_targets_and_loss_equal_the_reference(monkeypatch):
     loss.backward()
     fg = torch.from_numpy(z["reg_valid_mask"]).view(-1) > 0
     assert float(reg.grad[~fg].abs().max()) == 0 and float(reg.grad[fg].abs().max()) > 0
+
+
+def test_autograd_bricks_through_the_compiled_kernels(monkeypatch):
+    """BatchNorm (+ residual + ReLU) on a ROW SLICE of a wider matrix, ReLU / ELU, bias and the average pool, with the
+    training kernels' own CUDA sources (compiled for the CPU) behind the Python glue: pointers, strides and sizes exactly as
+    autograd.py hands them to the library."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    E.install(monkeypatch, compiled=True)
+    g = torch.Generator().manual_seed(0)
+    n, C = 700, 40
+    big = (torch.randn((n + 300, C), generator=g) * 2 + 1)
+    R, gamma, beta, dY = torch.randn((n, C), generator=g), torch.rand((C,), generator=g) + 0.5, torch.randn((C,), generator=g), torch.randn((n, C), generator=g)
+    Xd, Rd, gd, bd = (t.double().requires_grad_(True) for t in (big, R, gamma, beta))
+    want = torch.relu(torch.nn.functional.batch_norm(Xd[200:200 + n], None, None, gd, bd, training=True) + Rd)
+    (want * dY.double()).sum().backward()
+    X, Rg, gg, bg = (t.clone().requires_grad_(True) for t in (big, R, gamma, beta))
+    rm, rv = torch.zeros(C), torch.ones(C)
+    Y = A.batch_norm_train(X[200:200 + n], gg, bg, rm, rv, act="relu", residual=Rg)
+    assert _rel(Y.detach(), want.detach()) < 1e-5
+    Y.backward(dY)
+    assert _rel(X.grad, Xd.grad) < 1e-4 and _rel(Rg.grad, Rd.grad) < 1e-6 and _rel(gg.grad, gd.grad) < 1e-4 and _rel(bg.grad, bd.grad) < 1e-4
+    assert float(X.grad[:200].abs().max()) == 0 and float(X.grad[200 + n:].abs().max()) == 0
+    assert _rel(rm, 0.1 * big[200:200 + n].double().mean(0)) < 1e-5
+    for name, fn, op in (("relu", torch.relu, A.relu), ("elu", torch.nn.functional.elu, A.elu)):
+        xd = R.double().requires_grad_(True)
+        (fn(xd) * dY.double()).sum().backward()
+        xg = R.clone().requires_grad_(True)
+        op(xg).backward(dY)
+        assert _rel(xg.grad, xd.grad) < 1e-6, name
+    b = torch.randn((1, C), generator=g).requires_grad_(True)
+    xg = R.clone().requires_grad_(True)
+    A.add_bias(xg, b).backward(dY)
+    assert _rel(b.grad, dY.double().sum(0, keepdim=True)) < 1e-5 and torch.equal(xg.grad, dY)
+    rng = np.random.default_rng(1)
+    c = me.unique_first(np.concatenate([rng.integers(0, 2, (300, 1)), rng.integers(-6, 6, (300, 3)) * 2], 1))[0]
+    omgr = me.Manager()
+    ox = me.SparseTensor(torch.from_numpy(rng.standard_normal((len(c), 16))).requires_grad_(True), me.CoordMap(c, 2), omgr)
+    omgr.by_stride[2] = ox.cmap
+    wantp = me.avg_pool(ox, 5, 2)
+    dO = torch.from_numpy(rng.standard_normal(tuple(wantp.F.shape)))
+    (wantp.F * dO).sum().backward()
+    mgr = S.Manager()
+    cm = E.cpu_map(c, 2, mgr)
+    mgr.by_stride[2] = cm
+    Fg = ox.F.detach().float().requires_grad_(True)
+    y = A.avg_pool(S.SparseTensor(Fg, cm, mgr), 5, 2)
+    assert np.array_equal(y.C.numpy(), wantp.C) and _rel(y.F.detach(), wantp.F.detach()) < 1e-5
+    y.F.backward(dO.float())
+    assert _rel(Fg.grad, ox.F.grad) < 1e-5
