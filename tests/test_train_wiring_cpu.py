@@ -72,7 +72,13 @@ def test_backbone_training_wiring_vs_oracle(monkeypatch):
     G = max(float(orc.p[k].grad.norm()) for k in names)
     worst = max((float((params[k].grad.double().reshape(orc.p[k].grad.shape) - orc.p[k].grad).norm())
                  / (float(orc.p[k].grad.norm()) + 1e-5 * G), k) for k in names)
-    assert worst[0] < 5e-3, worst
+    # bound derived from the measured forward error: ReLU-mask flips, see the GPU twin of this test
+    # (tests/test_zz_gpu_spconv_backward.py::test_backbone_training_forward_backward_vs_oracle)
+    ref = res["bb_feats"].detach()
+    eps_f = float(((out.F.detach().double() - ref).abs() / ref.std(0, keepdim=True))[ref > 0].median())
+    bound = 3.0 * float(np.sqrt(48 * 0.8 * eps_f))
+    print("eps_f %.3e bound %.3e worst %.3e %s" % (eps_f, bound, worst[0], worst[1]))
+    assert eps_f < 2e-6 and worst[0] < bound, (worst, eps_f, bound)
     assert int(bb.conv1[1].bn.num_batches_tracked) == 1
     used = set(calls)
     assert {"cg3d_spconv_simt", "cg3d_spconv_wgrad", "cg3d_table_transpose", "cg3d_transpose_weights", "cg3d_bn_train_stats",
