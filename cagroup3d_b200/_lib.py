@@ -20,26 +20,52 @@ _lib = None
 _host_only = set()          # entry points without a trailing `void* stream`
 
 
+# pointee type of a pointer parameter -> tensor dtypes it may point at (None: untyped, e.g. `void*`)
+_POINTEE = {
+    "float": (torch.float32,),
+    "int": (torch.int32,),
+    "unsigned": (torch.int32,),
+    "unsigned int": (torch.int32,),
+    "unsigned short": (torch.int16, torch.bfloat16, torch.float16, torch.uint16),
+    "unsigned char": (torch.uint8, torch.int8, torch.bool),
+    "long long": (torch.int64,),
+    "unsigned long long": (torch.int64,),
+    "void": None,
+}
+_pointees = {}              # name -> [dtype tuple | None | "scalar"] per parameter
+
+
 def parse_header(path: str = HEADER_PATH):
-    """-> {name: [ctypes types]} for every `int cg3d_*(...)` prototype."""
+    """-> {name: [ctypes types]} for every `int cg3d_*(...)` prototype.  The pointee type of every pointer parameter is
+    kept as well (`_pointees`): call() checks device, dtype and unit inner stride of each tensor against it."""
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     protos = {}
     for m in re.finditer(r"\bint\s+(cg3d_\w+)\s*\(([^)]*)\)\s*;", src):
         name, args = m.group(1), m.group(2)
-        types = []
+        types, pts = [], []
         for a in [x.strip() for x in args.split(",") if x.strip()]:
+            if a == "void":
+                continue
             if "*" in a:
                 types.append(ctypes.c_void_p)
+                base = re.sub(r"\bconst\b", "", a.split("*")[0]).strip()
+                if base not in _POINTEE:
+                    raise RuntimeError(f"unparsed pointee '{base}' of {name}")
+                pts.append(_POINTEE[base])
             elif a.startswith("float"):
                 types.append(ctypes.c_float)
+                pts.append("scalar")
             elif a.startswith("long long"):
                 types.append(ctypes.c_longlong)
+                pts.append("scalar")
             elif a.startswith("int"):
                 types.append(ctypes.c_int)
+                pts.append("scalar")
             else:
                 raise RuntimeError(f"unparsed parameter '{a}' of {name}")
         protos[name] = types
+        _pointees[name] = pts
         if not args.strip().endswith("stream"):
             _host_only.add(name)
     return protos
@@ -61,10 +87,19 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
-def _arg(a):
+def _arg(a, name="", i=0, want=None):
     if a is None:
         return None
     if isinstance(a, torch.Tensor):
+        # a wrong device / dtype / stride would be a silent out-of-bounds access on the GPU, not an error
+        if not a.is_cuda:
+            raise TypeError(f"{name}: argument {i} is a {a.device} tensor; the C ABI takes device pointers")
+        if want == "scalar":
+            raise TypeError(f"{name}: argument {i} is a tensor where the header declares a scalar")
+        if want is not None and a.dtype not in want:
+            raise TypeError(f"{name}: argument {i} has dtype {a.dtype}, the header declares {want}")
+        if a.numel() > 1 and a.dim() >= 1 and a.stride(-1) != 1 and a.shape[-1] != 1:
+            raise TypeError(f"{name}: argument {i} has inner stride {a.stride(-1)}; rows must be contiguous")
         return a.data_ptr()
     return a
 
@@ -76,7 +111,8 @@ def stream_ptr() -> int:
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point on the current CUDA stream; raise on a non-zero status."""
     fn = getattr(load(), name)
-    rc = fn(*[_arg(a) for a in args], stream_ptr())
+    pts = _pointees.get(name, ())
+    rc = fn(*[_arg(a, name, i, pts[i] if i < len(pts) else None) for i, a in enumerate(args)], stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed with status {rc}")
 

@@ -328,6 +328,17 @@ class Tiles:
     rows: torch.Tensor
     group: torch.Tensor
     n: int
+    offsets: Optional[list] = None        # the per-group row ranges the tiling was cut from
+    tile: int = 0
+    alt: Dict[int, "Tiles"] = field(default_factory=dict)
+
+    def with_tile(self, tile: int) -> "Tiles":
+        """the same row ranges cut into tiles of another height (the pair-compacted kernel's 448 rows); cached"""
+        if tile == self.tile:
+            return self
+        if tile not in self.alt:
+            self.alt[tile] = make_tiles(self.offsets, self.row0.device, tile)
+        return self.alt[tile]
 
 
 def make_tiles(seg_offsets, device, tile=64) -> Tiles:
@@ -338,7 +349,7 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
         for s in range(a, b, tile):
             r0.append(s); rn.append(min(tile, b - s)); gg.append(g)
     t = torch.tensor([r0, rn, gg], dtype=torch.int32).to(device, non_blocking=True)
-    return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), len(r0))
+    return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), len(r0), list(seg_offsets), tile)
 
 
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
@@ -374,8 +385,11 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
         if split_out is not None and Cout % 32 == 0 and out.stride(0) == Cout:
             So = torch.empty((n_out, 2 * Cout), dtype=torch.int16, device=out.device)
             out._cg3d_split = {(out.data_ptr(), out._version, out.stride(0), 1 if split_out == "relu" else 0): So}
-        if nbr is not None and K >= PAIRS_MIN_K and _PAIRS["on"] and Cin == 64:
-            # wide kernel over a thinly occupied map: GEMM over compacted rule pairs (spconv_pairs.cu)
+        if pairs_route(nbr, Cin, Cout, K):
+            # a (row tile, tap) holds a fraction of the tile's rows: GEMM over compacted rule pairs (spconv_pairs.cu)
+            if tiles is not None:
+                pt = tiles.with_tile(pairs_tile_rows())
+                targs = (pt.row0, pt.rows, pt.group, pt.n, out_rows)
             _call("cg3d_spconv_pairs", split_rows(Fin, in_act), nbr, weight_image(W, pairs=True), out, out.stride(0), n_out,
                   Cin, Cout, K, scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
         else:
@@ -412,11 +426,23 @@ def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
     return cache[key]
 
 
-# CG3D_PAIRS=1 sends rule maps with at least this many taps to the pair-compacted kernel (spconv_pairs.cu).  It is
-# parity-tested but OFF by default: on B200 its per-stage role overhead (~1500 clk per (tile, tap) at ~17 pairs) is
-# above the row-stationary kernel's (~1170 clk), see profiles/r1_pairs_kernel.md.
-PAIRS_MIN_K = 64
+# CG3D_PAIRS=1 sends the rule maps of 64 -> 64 channel layers with at least PAIRS_MIN_K taps to the pair-compacted kernel
+# (spconv_pairs.cu v2: 352-row tiles, <= 64 pairs per stage, weights as the M operand).  Parity-tested, OFF by default: on
+# B200 it is still behind the row-stationary kernel (9^3 class conv 7.7 vs 6.8 ms, 3^3 64-channel layers 0.25-0.45 vs
+# 0.17-0.20 ms): 12 MMAs per (tap, <= 64 pairs) at >= 52 clk each and ~1000 shared-memory wavefronts per stage
+# (profiles/r2_pairs_v2.md has the role-by-role numbers).
+PAIRS_MIN_K = int(os.environ.get("CG3D_PAIRS_MIN_K", "27"))
+PAIRS_MAX_COUT = int(os.environ.get("CG3D_PAIRS_MAX_COUT", "64"))
 _PAIRS = {"on": os.environ.get("CG3D_PAIRS", "0") == "1"}
+
+
+def pairs_route(nbr, Cin: int, Cout: int, K: int) -> bool:
+    return (nbr is not None and _PAIRS["on"] and K >= PAIRS_MIN_K and Cin == 64 and Cout % 64 == 0
+            and Cout <= PAIRS_MAX_COUT)
+
+
+def pairs_tile_rows() -> int:
+    return _lib.host("cg3d_spconv_pairs_tile_rows")
 
 
 def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:

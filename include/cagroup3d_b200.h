@@ -151,14 +151,18 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
                    int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
                    const int* out_rows, unsigned short* out_split, int out_split_relu, float* splitk_ws, void* stream);
 
-/* Same contraction for WIDE kernels over thinly occupied maps (Cin == 64, Cout % 64 == 0, 1 < K <= 729): the 9^3 / 5^3
- * per-class convolutions of cagroup_head.py:255-266 and the 5^3 RoI grid convolution of cagroup_roi_head.py:69, where a
- * 128-row tile reaches most taps but each (tile, tap) holds only 3-13 % of the rows.  tcgen05 GEMM over the COMPACTED rule
- * pairs of one tap (weights = M operand, pairs = N operand, 16..128), results scattered into a shared-memory accumulator;
- * MMA work is proportional to the number of pairs instead of rows x taps.  Same arguments, precision (bf16 hi/lo split,
- * all four products, fp32 accumulation), tiling (<= 128 rows per tile) and determinism as cg3d_spconv_tc; the weight
- * image has its own layout (cg3d_spconv_pairs_prepare, same byte count as the fp32 weights). */
+/* Same contraction as a GEMM over the COMPACTED rule pairs (Cin == 64, Cout % 64 == 0, 1 < K <= 729): the 9^3 / 5^3
+ * per-class convolutions of cagroup_head.py:255-266, the 64-channel 3^3 layers of biresnet.py:246-266 and
+ * cagroup_head.py:166 -- layers where a (row tile, tap) holds only 3-25 % of the tile's rows, so the row-stationary
+ * kernel spends its shared-memory and L2 -> SM bandwidth on zero rows and on re-streaming the tap's weights every 128
+ * rows.  Operand roles swapped: the tap's weights are the M = 64 operand, the tap's compacted pairs of a
+ * cg3d_spconv_pairs_tile_rows() = 448-row tile the N operand (8..64 per stage), results scattered into a shared-memory
+ * accumulator with ONE owner thread per word.  MMA work is proportional to the number of pairs instead of rows x taps.
+ * Same arguments, precision (bf16 hi/lo split, three products, fp32 accumulation) and determinism as cg3d_spconv_tc;
+ * grouped launches pass tiles of at most cg3d_spconv_pairs_tile_rows() rows; the weight image has its own layout
+ * (cg3d_spconv_pairs_prepare, same byte count as the fp32 weights). */
 int cg3d_spconv_pairs_supported(int Cin, int Cout, int K);
+int cg3d_spconv_pairs_tile_rows(void);
 int cg3d_spconv_pairs_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
 int cg3d_spconv_pairs(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo,
                       int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,

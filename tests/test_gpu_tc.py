@@ -95,7 +95,7 @@ def test_split_rows_layout(lib):
         assert ((hi + lo) - want).abs().max().item() <= 2 ** -16 * want.abs().max().item()
 
 
-@pytest.mark.parametrize("k,cout,grouped", [(5, 64, False), (5, 128, False), (9, 64, True), (7, 64, False)])
+@pytest.mark.parametrize("k,cout,grouped", [(5, 64, False), (5, 128, False), (9, 64, True), (7, 64, False), (3, 64, False)])
 def test_spconv_pairs_vs_simt_and_oracle(lib, monkeypatch, k, cout, grouped):
     """pair-compacted tcgen05 kernel (wide kernels over thin maps) == exact fp32 SIMT kernel == CPU oracle, incl. grouped
     per-class weights, a ragged last tile, residual + ELU epilogue, the split-bf16 second output and rows without any pair."""
@@ -118,6 +118,8 @@ def test_spconv_pairs_vs_simt_and_oracle(lib, monkeypatch, k, cout, grouped):
     kw = dict(scale=sc, shift=sh, residual=res.to(DEV), act="elu", in_act="relu")
     assert lib.cg3d_spconv_pairs_supported(64, cout, k ** 3) == 1 and k ** 3 >= S.PAIRS_MIN_K
     monkeypatch.setitem(S._PAIRS, "on", True)
+    monkeypatch.setattr(S, "PAIRS_MAX_COUT", 128)          # also the two-slice launch (not routed by default)
+    assert S.pairs_route(nbr, 64, cout, k ** 3)
     got = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 128) if grouped else None, impl="tc",
                       split_out="relu", **kw)
     want = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 64) if grouped else None, impl="simt", **kw)
@@ -145,6 +147,7 @@ def test_spconv_pairs_at_query_coordinates(lib, monkeypatch):
     """conv evaluated at foreign query coordinates (RoI grid conv, A12): most queries have few or no neighbours."""
     from cagroup3d_b200 import sparse as S
     monkeypatch.setitem(S._PAIRS, "on", True)
+    monkeypatch.setattr(S, "PAIRS_MAX_COUT", 128)
     ox = oracle_tensor(33, 64, n=1500)
     x = to_gpu_sparse(ox.C, ox.F, 1)
     g = torch.Generator().manual_seed(8)

@@ -1,0 +1,35 @@
+"""Times the 9^3 class conv / a 64-channel 3^3 layer alone (development aid): python tools/conv_probe2.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from cagroup3d_b200 import sparse as S
+from tools.stage_times import setup
+
+def main():
+    S.set_conv_impl("tc")
+    model, pts, n1, n2 = setup(8, 50000)
+    rec = []
+    orig = S._call
+    def spy(name, *args, meta=None):
+        if name in ("cg3d_spconv_pairs", "cg3d_spconv_tc") and args[2 if name == "cg3d_spconv_pairs" else 2] is not None:
+            rec.append((name, args))
+        return orig(name, *args, meta=meta)
+    S._call = spy
+    model({"points": pts.clone(), "batch_size": 8, "cur_epoch": 10})
+    S._call = orig
+    torch.cuda.synchronize()
+    for name, args in rec:
+        if name != "cg3d_spconv_pairs":
+            continue
+        K = args[8]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        orig(name, *args)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            orig(name, *args)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{name} K={K} n_out={args[5]} {e0.elapsed_time(e1) / 3:.3f} ms")
+
+main()
