@@ -1,6 +1,15 @@
 """Benchmark of the CAGroup3D inference hot path (BASELINE.json: scenes/s at ~50k voxels/scene).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--conv simt|tc]
+                    [--workload scannet|sunrgbd|sweep|train] [--voxel-size 0.02]
+
+--workload (default scannet = BASELINE.json configs[1], the configuration the metric is quoted on):
+    sunrgbd   configs[2]: SUN RGB-D-shaped inference, batch 16 per GPU, 10 classes, 100 000 points / scene, yaw boxes and
+              rotated-BEV NMS, voxel 0.02 m (tools/cfgs/sunrgbd_models/CAGroup3D.yaml:9; --voxel-size 0.01 = BASELINE's figure)
+    sweep     configs[4]: the scannet workload at 10k / 20k / 50k / 100k / 200k active voxels per scene (batch 8 per GPU =
+              64 scenes on 8 GPUs); the line's value is the 50k point, config.sweep holds every density
+    train     configs[3]: ScanNet-shaped TRAINING step (forward, both stages' losses, backward, bucketed gradient
+              all-reduce, AdamW), 4 scenes per GPU, fp32
 
 One "step" = one forward of the whole detector (voxelise -> BiResNet -> class-aware grouping head ->
 RoI-Conv pooling -> NMS) over one batch of 8 synthetic ScanNet-shaped scenes (~50k active voxels each;
@@ -32,6 +41,18 @@ import torch  # noqa: E402
 METRIC = "scenes_per_sec_at_50k_voxels_per_scene"
 WORKLOAD = "ScanNetV2-shaped CAGroup3D inference, batch 8 per GPU, voxel 0.02 m, ~50k active voxels/scene, 18 classes"
 P_SEL, P_BOX = 1.0 / 18, 0.002
+# name -> (description, metric, n_classes, with_yaw, batch per GPU, voxel target of the generator, points per scene, seed config)
+WORKLOADS = {
+    "scannet": (WORKLOAD, METRIC, 18, False, 8, 50000, None, 2),
+    "sunrgbd": ("SUN RGB-D-shaped CAGroup3D inference, batch 16 per GPU, 10 classes, 100000 points/scene, yaw boxes + rotated-BEV NMS",
+                "scenes_per_sec_sunrgbd_100k_points_per_scene", 10, True, 16, 50000, 100000, 3),
+    "sweep": ("density sweep of the ScanNetV2-shaped inference workload, batch 8 per GPU, 10k -> 200k active voxels/scene",
+              METRIC, 18, False, 8, 50000, None, 5),
+    "train": ("ScanNetV2-shaped CAGroup3D TRAINING step (forward + both stages' losses + backward + gradient all-reduce + AdamW), "
+              "4 scenes per GPU, voxel 0.02 m, ~50k active voxels/scene, 18 classes, fp32 master weights",
+              "train_scenes_per_sec_at_50k_voxels_per_scene", 18, False, 4, 50000, None, 4),
+}
+SWEEP_VOXELS = (10000, 20000, 50000, 100000, 200000)
 
 
 def env_int(name, default):
@@ -128,59 +149,87 @@ def conv_bytes(meta, P):
     return b
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--voxels", type=int, default=50000)
-    ap.add_argument("--conv", default=os.environ.get("CG3D_CONV", "auto"))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--layers-json", default=None, help="write the per-layer roofline table here")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    from cagroup3d_b200 import _lib, model_init, sparse as S, synthetic
+def setup_inference(wl, voxels, voxel_size, rank, conv):
+    """model + synthetic batch of one rank, head-occupancy knobs calibrated (untimed)."""
+    from cagroup3d_b200 import model_init, sparse as S, synthetic
     from cagroup3d_b200.detector import voxelize
-    _lib.load()
-    conv = args.conv
-    if conv == "auto":
-        conv = "tc" if hasattr(_lib.load(), "cg3d_spconv_tc") else "simt"
+    _, _, ncls, yaw, B, _, n_points, cfg = WORKLOADS[wl]
     S.set_conv_impl(conv)
-
-    B = args.batch
-    data = synthetic.make_batch(B, target_voxels=args.voxels, config=2, first_scene=rank * B)
+    data = synthetic.make_batch(B, target_voxels=voxels, config=cfg, n_classes=ncls, sunrgbd=yaw, first_scene=rank * B,
+                                n_points=n_points)
     host_pts = torch.from_numpy(data["points"]).pin_memory()
     dev_pts = host_pts.cuda()
-    model = model_init.seeded_model(18, False, seed=0).cuda()
+    model = model_init.seeded_model(ncls, yaw, seed=0)
+    if voxel_size != 0.02:
+        model.voxel_size = voxel_size
+        model.dense_head.voxel_size = voxel_size
+        if model.roi_head is not None and hasattr(model.roi_head, "voxel_size"):
+            model.roi_head.voxel_size = voxel_size
+    model = model.cuda()
     # declared head-occupancy knobs (model_init.py): not timed
     p = dev_pts.clone()
     p[:, -3:] /= 255.
-    x = voxelize(p, 0.02)
+    x = voxelize(p, voxel_size)
     out = model.backbone_3d.run(x)
     n_vox, n_vox2 = x.cmap.n, out.cmap.n
-    model_init.calibrate_semantic_bias(model, out.F, P_SEL)
+    model_init.calibrate_semantic_bias(model, out.F, 1.0 / ncls)
     model.dense_head.semantic_threshold = 0.05
     cm = model.dense_head.class_maps(out, B)
     model_init.calibrate_cls_bias(model, cm["pred"], P_BOX)
-    del p, x, out, cm
+    return model, host_pts, dev_pts, B, n_vox, n_vox2
+
+
+class Timer:
+    """W warm-up steps, then K steps between barrier + synchronize on both sides, CUDA events, max over ranks."""
+
+    def __init__(self, dist, sampler):
+        self.dist, self.sampler = dist, sampler
+
+    def __call__(self, fn, steps, warmup, profile_convs=False):
+        from cagroup3d_b200 import sparse as S
+        dist = self.dist
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        self.sampler.enabled = True
+        S.LaunchCounter.n = 0
+        if profile_convs:
+            S.Profile.active = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        self.sampler.enabled = False
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        rec, S.Profile.active = S.Profile.active, None
+        return ms.item(), S.LaunchCounter.n, rec
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def bench_inference(args, wl, voxels, rank, world, timed, conv, with_e2e=True):
+    """value / roofline / e2e of one inference workload at one density -> dict of the JSON line's pieces."""
+    from cagroup3d_b200 import sparse as S
+    from cagroup3d_b200 import dist as D
+    model, host_pts, dev_pts, B, n_vox, n_vox2 = setup_inference(wl, voxels, args.voxel_size, rank, conv)
 
     def step_resident():
         return model({"points": dev_pts.clone(), "batch_size": B, "cur_epoch": 10})
-
-    from cagroup3d_b200 import dist as D
 
     def step_e2e():
         """the user-facing call: pinned host points -> device -> model(batch_dict) -> (N > 1: gather of all ranks'
@@ -189,8 +238,7 @@ def main():
         pred, _ = model({"points": pts, "batch_size": B, "cur_epoch": 10})
         if world > 1:
             pred = D.gather_detections(pred, world * B)
-        outs = [(d["pred_boxes"].cpu(), d["pred_scores"].cpu(), d["pred_labels"].cpu()) for d in pred]
-        return outs
+        return [(d["pred_boxes"].cpu(), d["pred_scores"].cpu(), d["pred_labels"].cpu()) for d in pred]
 
     # ---- instrumented pass: per-launch algorithmic bytes of the sparse-conv kernel (untimed) ----
     S.Profile.active = []
@@ -200,6 +248,7 @@ def main():
     rec, S.Profile.active = S.Profile.active, None
     convs = [(name, meta) for name, _, meta, _, _ in rec if meta is not None and name.startswith("cg3d_spconv")]
     conv_info = []
+
     def active_tile_taps(meta):
         """(128-row tile, tap) pairs the tensor-core kernel actually runs: a tap is skipped when no row of the tile has
         a neighbour for it.  Counted from the rule map the launch got (positional = tile order), untimed."""
@@ -213,48 +262,17 @@ def main():
             m = torch.cat([m, torch.zeros((m.shape[0], pad), dtype=torch.bool, device=m.device)], 1)
         return int(m.view(m.shape[0], tiles, 128).any(-1).sum().item())
 
+    n_backbone_convs = 56
     for name, meta in convs:
         P = S.count_rules(meta["nbr"]) if meta["nbr"] is not None else meta["n_out"]
-        tt = active_tile_taps(meta) if (name == "cg3d_spconv_tc" and len(conv_info) < 56) else None
+        tt = active_tile_taps(meta) if (name == "cg3d_spconv_tc" and len(conv_info) < n_backbone_convs) else None
         conv_info.append(dict(kernel=name, K=meta["K"], Cin=meta["Cin"], Cout=meta["Cout"], n_in=meta["n_in"],
                               n_out=meta["n_out"], P=P, bytes=conv_bytes(meta, P), flops=2.0 * P * meta["Cin"] * meta["Cout"],
                               tile_taps=tt,
                               mma_flops=(3 * 2.0 * tt * 128 * meta["Cin"] * meta["Cout"]) if tt is not None else None))
-    n_backbone_convs = 56
     del rec, convs
     n_det = sum(len(d["pred_boxes"]) for d in pred)
     d2h_bytes = sum(d["pred_boxes"].numel() * 4 + d["pred_scores"].numel() * 4 + d["pred_labels"].numel() * 8 for d in pred)
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-
-    def timed(fn, steps, warmup, profile_convs=False):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler.enabled = True
-        S.LaunchCounter.n = 0
-        if profile_convs:
-            S.Profile.active = []
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler.enabled = False
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if dist:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        rec, S.Profile.active = S.Profile.active, None
-        return ms.item(), S.LaunchCounter.n, rec
 
     # value: inputs resident in HBM
     ms_total, launches, _ = timed(step_resident, args.steps, args.warmup)
@@ -286,33 +304,37 @@ def main():
         ci["ms"] = t
         ci["GBps"] = ci["bytes"] / t / 1e6 if t > 0 else None
         ci["TFLOPs"] = ci["flops"] / t / 1e9 if t > 0 else None
-    try:
-        peaks_hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
-    except Exception:
-        peaks_hbm = 6650.0
+    peaks = load_peaks()
+    peak = peaks.get("hbm_gbs", 6650.0)
     bb = conv_info[:n_backbone_convs]
     bb_bytes, bb_ms, bb_flops = sum(c["bytes"] for c in bb), sum(c["ms"] for c in bb), sum(c["flops"] for c in bb)
-    all_ms = sum(c["ms"] for c in conv_info)
+    all_ms, all_bytes = sum(c["ms"] for c in conv_info), sum(c["bytes"] for c in conv_info)
     # the 64-channel stride-1/2 layers are the HBM-bound part of the backbone (SURVEY 8d "sanity"); reported apart
     hb = [c for c in bb if c["Cin"] <= 64 and c["Cout"] <= 128]
     hbm_layers = {"launches": len(hb), "ms": sum(c["ms"] for c in hb),
                   "achieved": sum(c["bytes"] for c in hb) / max(sum(c["ms"] for c in hb), 1e-9) / 1e6, "unit": "GB/s"}
-    hbm_layers["frac"] = hbm_layers["achieved"] / peaks_hbm
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_layers["frac"] = hbm_layers["achieved"] / peak
+    # every sparse-conv launch of the step (backbone + head incl. the 9^3 class conv + RoI stage), so that the headline
+    # fraction cannot hide the most expensive launch
+    rest = conv_info[n_backbone_convs:]
+    worst = max(conv_info, key=lambda c: c["ms"])
+    all_convs = {"launches": len(conv_info), "ms": all_ms, "achieved": all_bytes / max(all_ms, 1e-9) / 1e6, "unit": "GB/s",
+                 "frac": all_bytes / max(all_ms, 1e-9) / 1e6 / peak,
+                 "head_roi": {"launches": len(rest), "ms": sum(c["ms"] for c in rest),
+                              "achieved": sum(c["bytes"] for c in rest) / max(sum(c["ms"] for c in rest), 1e-9) / 1e6},
+                 "slowest_launch": {k: worst[k] for k in ("kernel", "K", "Cin", "Cout", "n_out", "P", "ms", "GBps", "TFLOPs")}}
     achieved = bb_bytes / bb_ms / 1e6
     # DRAM traffic per launch of the same 56 launches: from the committed ncu --set full capture (it cannot be measured
     # live: a number taken under a profiler is never a bench value, and the bench never runs under one)
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_spconv_traffic.json")))
-        traffic, traffic_src = tj["traffic_bytes_per_launch_avg"], f"profiles/r1_spconv_traffic.json ({tj['launches']} launches, {tj['metric']})"
-    except Exception:
-        pass
+    if wl == "scannet" and voxels == 50000:
+        for f in ("r2_spconv_traffic.json", "r1_spconv_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", f)))
+                traffic, traffic_src = tj["traffic_bytes_per_launch_avg"], f"profiles/{f} ({tj['launches']} launches, {tj['metric']})"
+                break
+            except Exception:
+                pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "kernel": f"cg3d_spconv_{conv} (56 backbone launches per step, algorithmic bytes = SURVEY 8d formula)",
@@ -322,7 +344,7 @@ def main():
                 "spconv_share_of_step": all_ms / (ms_serial / args.steps), "split_pass_ms_per_step": split_ms,
                 "timed_in": "separate pass of the same steps, single stream, CUDA events around each launch "
                             f"({ms_serial / args.steps:.2f} ms/step)",
-                "hbm_bound_layers": hbm_layers}
+                "hbm_bound_layers": hbm_layers, "all_spconv_launches": all_convs}
     # the same launches read against the TENSOR roof: bf16 MMA work the kernel executes (3 products of the bf16x3 split x
     # 128-row tiles x the taps a tile does not skip) / measured sustained cuBLAS bf16 rate
     tcl = [c for c in bb if c.get("mma_flops")]
@@ -338,38 +360,200 @@ def main():
                                                         "achieved": sum(c["mma_flops"] for c in big) / max(sum(c["ms"] for c in big), 1e-9) / 1e9}}
         roofline["tensor"]["k27_layers_cin_ge_128"]["frac"] = roofline["tensor"]["k27_layers_cin_ge_128"]["achieved"] / peaks["bf16_tflops_sustained"]
 
-    # e2e: pinned host inputs -> device -> forward -> host outputs
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    e2e = None
+    if with_e2e:
+        # e2e: pinned host inputs -> device -> forward -> host outputs
+        ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": int(host_pts.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes)}
+    info = {"batch_per_gpu": B, "voxels_per_scene": n_vox // B, "stride2_voxels_per_scene": n_vox2 // B,
+            "points_per_batch": int(host_pts.shape[0]), "detections_per_batch": n_det,
+            "backbone_streams": 2 if two else 1, "coordinate_stream": bool(coord)}
+    del model
+    torch.cuda.empty_cache()
+    return dict(value=value, ms_step=ms_step, launches=launches, roofline=roofline, e2e=e2e, info=info, conv_info=conv_info)
+
+
+def bench_train(args, rank, world, timed, conv, dist):
+    """BASELINE configs[3]: one training step = train_step.training_step (tools/train_utils/train_utils.py:48-72)."""
+    from cagroup3d_b200 import backbone_train as BT, dist as D, model_init, sparse as S, synthetic, train_step as TS
+    from cagroup3d_b200.detector import voxelize
+    _, _, ncls, yaw, B, voxels, _, cfg = WORKLOADS["train"]
+    B = args.batch or B
+    voxels = args.voxels
+    S.set_conv_impl(conv)
+    dev = "cuda"
+    scenes = [synthetic.make_scene(1000 * cfg + rank * B + i, voxels, n_classes=ncls, return_masks=True) for i in range(B)]
+    batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
+    model = model_init.seeded_model(ncls, yaw, seed=0).to(dev).train()
+    host_pts = torch.from_numpy(batch["points"]).pin_memory()
+    pts = host_pts.to(dev)
+    p = pts.clone()
+    p[:, -3:] /= 255.
+    with torch.no_grad():
+        out = BT.run_train(model.backbone_3d, voxelize(p, 0.02))
+    n_vox2 = out.cmap.n
+    model_init.calibrate_semantic_bias(model, out.F.detach(), P_SEL)
+    with torch.no_grad():
+        model.dense_head.cls_conv.bias.fill_(-2.0)            # stage-1 detections for the RoI stage (random init has none)
+    del out, p
+    params = list(model.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    red = D.GradientAllReducer(params)
+    gt = torch.from_numpy(batch["gt_boxes"]).float()
+    sem, ins = [s for _, _, s, _ in scenes], [m for _, _, _, m in scenes]
+    last = {}
+
+    def step_resident():
+        bd = {"points": pts.clone(), "batch_size": B, "cur_epoch": 10, "gt_boxes": gt.to(dev), "semantic_mask": sem, "instance_mask": ins}
+        last["tb"] = TS.training_step(model, bd, opt, red, grad_norm_clip=10.0)
+
+    def step_e2e():
+        bd = {"points": host_pts.to(dev, non_blocking=True), "batch_size": B, "cur_epoch": 10, "gt_boxes": gt.to(dev, non_blocking=True),
+              "semantic_mask": sem, "instance_mask": ins}
+        last["tb"] = TS.training_step(model, bd, opt, red, grad_norm_clip=10.0)      # tb_dict: python floats = D2H of the losses
+
+    ms_total, launches, _ = timed(step_resident, args.steps, args.warmup)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    # per-kernel table of one step (CUDA events around every C-ABI call) + the collective's share
+    S.Profile.active = []
+    S.Profile.stage = "train"
+    t_red = {"ms": 0.0}
+    orig_reduce = red.reduce
+
+    def timed_reduce():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        n = orig_reduce()
+        b.record()
+        t_red["ev"] = (a, b)
+        return n
+    red.reduce = timed_reduce
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    red.reduce = orig_reduce
+    rec, S.Profile.active = S.Profile.active, None
+    per = {}
+    for name, _, _, a0, a1 in rec:
+        c = per.setdefault(name, [0, 0.0])
+        c[0] += 1
+        c[1] += a0.elapsed_time(a1)
+    kernel_ms = sum(v[1] for v in per.values())
+    top = sorted(per.items(), key=lambda kv: -kv[1][1])[:14]
+    ar_ms = t_red["ev"][0].elapsed_time(t_red["ev"][1]) if "ev" in t_red else 0.0
+    # roofline of the dominant kernel of the step (weight gradient): algorithmic bytes = X rows + dY rows read once per tap
+    # that has pairs ... reported as its share; the forward / dX convs reuse the inference kernel (see the scannet line)
+    peaks = load_peaks()
+    dom = top[0]
+    roofline = {"bound": "tensor" if dom[0].startswith("cg3d_spconv") else "hbm", "kernel": dom[0], "calls_per_step": dom[1][0],
+                "ms_per_step": dom[1][1], "share_of_kernel_time": dom[1][1] / max(kernel_ms, 1e-9),
+                "achieved": None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": None, "traffic": None,
+                "note": "training step: per-kernel device times below; the conv forward / dX launches are the inference kernel "
+                        "(roofline in the scannet workload's line)"}
+    table = [{"kernel": k, "calls": v[0], "ms": v[1], "share": v[1] / max(kernel_ms, 1e-9)} for k, v in top]
+    info = {"batch_per_gpu": B, "stride2_voxels_per_scene": n_vox2 // B, "points_per_batch": int(host_pts.shape[0]),
+            "iters_per_sec": 1e3 / ms_step, "parameters_M": sum(q.numel() for q in params) / 1e6,
+            "gradient_bucket_MB": red.nbytes / 1e6, "optimizer": "AdamW fp32, grad-norm clip 10",
+            "allreduce_ms_per_step": ar_ms, "allreduce_share_of_step": ar_ms / max(e0.elapsed_time(e1), 1e-9),
+            "kernel_ms_per_step": kernel_ms, "instrumented_step_ms": e0.elapsed_time(e1), "kernels": table,
+            "losses": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in last.get("tb", {}).items()}}
+    e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
+           "h2d_bytes_per_step": int(host_pts.numel() * 4 + gt.numel() * 4), "d2h_bytes_per_step": 8 * len(last.get("tb", {}))}
+    return dict(value=value, ms_step=ms_step, launches=launches, roofline=roofline, e2e=e2e, info=info, conv_info=[])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="scannet", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="scenes per GPU (default: the workload's)")
+    ap.add_argument("--voxels", type=int, default=50000)
+    ap.add_argument("--voxel-size", type=float, default=0.02)
+    ap.add_argument("--conv", default=os.environ.get("CG3D_CONV", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-json", default=None, help="write the per-layer roofline table here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    wl = args.workload
+    desc, metric = WORKLOADS[wl][0], WORKLOADS[wl][1]
+    if args.batch:
+        WORKLOADS[wl] = WORKLOADS[wl][:4] + (args.batch,) + WORKLOADS[wl][5:]
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from cagroup3d_b200 import _lib
+    _lib.load()
+    conv = args.conv
+    if conv == "auto":
+        conv = "tc" if hasattr(_lib.load(), "cg3d_spconv_tc") else "simt"
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timed = Timer(dist, sampler)
+
+    extra = {}
+    if wl == "train":
+        r = bench_train(args, rank, world, timed, conv, dist)
+    elif wl == "sweep":
+        pts_ = []
+        r = None
+        for v in SWEEP_VOXELS:
+            rv = bench_inference(args, wl, v, rank, world, timed, conv)
+            rl = rv["roofline"]
+            pts_.append({"target_voxels": v, "voxels_per_scene": rv["info"]["voxels_per_scene"], "scenes_per_sec": rv["value"],
+                         "ms_per_step": rv["ms_step"], "e2e_scenes_per_sec": rv["e2e"]["value"],
+                         "backbone_GBps": rl["achieved"], "backbone_frac": rl["frac"],
+                         "hbm_bound_layers_GBps": rl["hbm_bound_layers"]["achieved"], "hbm_bound_layers_frac": rl["hbm_bound_layers"]["frac"],
+                         "all_spconv_GBps": rl["all_spconv_launches"]["achieved"]})
+            if v == 50000:
+                r = rv
+        extra["sweep"] = pts_
+    else:
+        r = bench_inference(args, wl, args.voxels, rank, world, timed, conv)
     sampler.stop_flag = True
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt = time_cpu_oracle(args.voxels, 1, 0)
         cpu = {"value": v, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"1 scene of the workload (~{args.voxels} voxels), full forward, {dt:.1f} s; torch CPU fp32 "
-                         "gather->sgemm->scatter per kernel offset (the ME CPU algorithm; ME is not installable offline)"}
+               "sample": f"1 ScanNet-shaped scene (~{args.voxels} voxels), full inference forward, {dt:.1f} s; torch CPU fp32 "
+                         "gather->sgemm->scatter per kernel offset (the ME CPU algorithm; ME is not installable offline)"
+                         + ("" if wl in ("scannet", "sweep") else "; the oracle has no timed arm for this workload, the scannet scene is the sample")}
 
     if rank == 0:
+        cfg = {"workload": desc, **r["info"], "conv_impl": conv, "voxel_size_m": args.voxel_size, "p_sel": 1.0 / WORKLOADS[wl][2],
+               "p_box": P_BOX, "weights": "seed-0 random init (no checkpoint offline)" + ("" if wl == "train" else ", eval-mode BatchNorm"),
+               "l2": "working set > L2: ~0.5 GB of weights (+ images) and the activations are re-streamed every step, no flush needed",
+               **extra}
         line = {
-            "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": metric, "value": r["value"], "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if conv == "simt" else "f32 (bf16x3 split on tcgen05, fp32 accumulate)",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "voxels_per_scene": n_vox // B,
-                       "stride2_voxels_per_scene": n_vox2 // B, "points_per_batch": int(host_pts.shape[0]),
-                       "conv_impl": conv, "backbone_streams": 2 if two else 1, "coordinate_stream": bool(coord), "p_sel": P_SEL, "p_box": P_BOX, "detections_per_batch": n_det,
-                       "weights": "seed-0 random init (no checkpoint offline), eval-mode BatchNorm",
-                       "l2": "working set > L2: 506 MB of weights + activations re-streamed every step, no flush needed"},
-            "e2e": {"value": e2e_value, "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(host_pts.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes)},
-            "gpu_launches": launches, "gpu_launches_note": "C-ABI calls in the timed region; each launches >= 1 kernel",
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+            "data": "synthetic", "config": cfg, "e2e": r["e2e"],
+            "gpu_launches": r["launches"], "gpu_launches_note": "C-ABI calls in the timed region; each launches >= 1 kernel",
+            "roofline": r["roofline"], "cpu_baseline": cpu, "clocks": sampler.summary(),
         }
         print(json.dumps(line))
         if args.layers_json:
             with open(args.layers_json, "w") as f:
-                json.dump({"ms_per_step": ms_step, "layers": conv_info}, f, indent=1)
+                json.dump({"ms_per_step": r["ms_step"], "layers": r["conv_info"]}, f, indent=1)
     if dist:
         dist.destroy_process_group()
 
