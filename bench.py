@@ -237,8 +237,8 @@ def bench_inference(args, wl, voxels, rank, world, timed, conv, with_e2e=True):
         pts = host_pts.cuda(non_blocking=True)
         pred, _ = model({"points": pts, "batch_size": B, "cur_epoch": 10})
         if world > 1:
-            pred = D.gather_detections(pred, world * B)
-        return [(d["pred_boxes"].cpu(), d["pred_scores"].cpu(), d["pred_labels"].cpu()) for d in pred]
+            return D.gather_detections(pred, world * B, to_host=True)
+        return D.detections_to_host(pred)
 
     # ---- instrumented pass: per-launch algorithmic bytes of the sparse-conv kernel (untimed) ----
     S.Profile.active = []

@@ -127,3 +127,23 @@ class CAGroup3D(nn.Module):
             for k in missing:
                 logger.info("Not updated weight %s: %s", k, str(tuple(own[k].shape)))
         return missing
+
+    def load_params_with_optimizer(self, filename, to_cpu=False, optimizer=None, logger=None):
+        """detector3d_template.py:389-419: resume -- strict state-dict load, optimizer state from the checkpoint (or its
+        `_optim` side file), -> (it, epoch)."""
+        if not os.path.isfile(filename):
+            raise FileNotFoundError(filename)
+        loc = torch.device("cpu") if to_cpu else None
+        ckpt = torch.load(filename, map_location=loc, weights_only=False)
+        self.load_state_dict(ckpt["model_state"], strict=True)
+        if optimizer is not None:
+            if ckpt.get("optimizer_state") is not None:
+                optimizer.load_state_dict(ckpt["optimizer_state"])
+            else:
+                side = "%s_optim.%s" % (filename[:-4], filename[-3:])
+                if os.path.exists(side):
+                    optimizer.load_state_dict(torch.load(side, map_location=loc, weights_only=False)["optimizer_state"])
+        if logger is not None:
+            logger.info("==> Loaded checkpoint %s (epoch %s, it %s, version %s)", filename, ckpt.get("epoch", -1), ckpt.get("it", 0),
+                        ckpt.get("version", "none"))
+        return ckpt.get("it", 0.0), ckpt.get("epoch", -1)

@@ -158,7 +158,7 @@ def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_l
     crit = TT.FirstStageLoss(head.n_classes)
     coords, vs = br["coords"], art["vsA"]
     C = out.C
-    terms = []
+    samples = []
     for b in range(B):
         ctrs, boxes, clss, pts = [], [], [], []
         for c in range(head.n_classes):
@@ -170,8 +170,11 @@ def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_l
             pts.append(coords[r, 1:].float() * vs[c])
         rows = torch.nonzero(C[:, 0] == b).squeeze(1)
         vox = C[rows, 1:].float() * head.voxel_size
-        terms.append(crit.loss_single(ctrs, boxes, clss, pts, offs[rows], vox, sem[rows], vox, None, gt_bboxes[b], gt_labels[b],
-                                      scene_points[b], pts_semantic_mask[b], pts_instance_mask[b]))
+        samples.append(dict(centernesses=ctrs, bbox_preds=boxes, cls_scores=clss, points=pts, voxel_offset_preds=offs[rows],
+                            original_points=vox, semantic_scores=sem[rows], semantic_points=vox, gt_bboxes=gt_bboxes[b],
+                            gt_labels=gt_labels[b], scene_points=scene_points[b], pts_semantic_mask=pts_semantic_mask[b],
+                            pts_instance_mask=pts_instance_mask[b]))
+    terms = crit.loss_batch(samples)                 # one rank-average for all 3 B normalisers
     names = ("loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote")
     means = [torch.mean(torch.stack([t[i] for t in terms])) for i in range(5)]
     loss = sum(means)

@@ -223,30 +223,58 @@ class FirstStageLoss:
         self.loss_sem = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
         self.loss_offset = SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0)
 
-    def loss_single(self, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, original_points, semantic_scores,
-                    semantic_points, img_meta, gt_bboxes, gt_labels, scene_points, pts_semantic_mask, pts_instance_mask):
-        from .dist import reduce_mean
+    def _targets(self, points, original_points, semantic_points, gt_bboxes, gt_labels, scene_points, pts_semantic_mask,
+                 pts_instance_mask):
+        """targets of one sample (points: the per-class list of locations) + its three LOCAL loss normalisers (device scalars: positive semantic voxels, positive
+        locations, sum of positive centerness targets)."""
         with torch.no_grad():
             semantic_labels, _ = self.assigner.assign_semantic(semantic_points, gt_bboxes, gt_labels, self.n_classes)
             centerness_targets, bbox_targets, labels = self.assigner.assign(points, gt_bboxes, gt_labels)
             offset_targets, offset_masks = vote_targets(scene_points, original_points, gt_bboxes, pts_semantic_mask,
                                                         pts_instance_mask, self.n_classes)
+            pos = labels >= 0
+            local = torch.stack([(semantic_labels >= 0).sum().float(), pos.sum().float(),
+                                 centerness_targets[pos].sum()])            # (targets of unassigned locations may be NaN)
+        return dict(semantic_labels=semantic_labels, centerness_targets=centerness_targets, bbox_targets=bbox_targets,
+                    labels=labels, offset_targets=offset_targets, offset_masks=offset_masks, local=local)
+
+    def _terms(self, t, norm, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, semantic_scores):
+        """the five loss terms of one sample given its targets and its (rank-averaged) normalisers (3 python floats)."""
         centerness, bbox_preds, cls_scores, points = (torch.cat(centernesses), torch.cat(bbox_preds), torch.cat(cls_scores),
                                                       torch.cat(points))
+        offset_masks = t["offset_masks"]
         w = (offset_masks.float() / torch.ones_like(offset_masks).float().sum() + 1e-6).unsqueeze(1).repeat(1, 3)
-        loss_offset = self.loss_offset(voxel_offset_preds, offset_targets, weight=w)
-        sem_n_pos = max(float(reduce_mean((semantic_labels >= 0).sum().float())), 1.)
-        loss_sem = self.loss_sem(semantic_scores, semantic_labels, avg_factor=sem_n_pos)
+        loss_offset = self.loss_offset(voxel_offset_preds, t["offset_targets"], weight=w)
+        sem_n_pos, n_pos, centerness_denorm = max(norm[0], 1.), max(norm[1], 1.), max(norm[2], 1e-6)
+        loss_sem = self.loss_sem(semantic_scores, t["semantic_labels"], avg_factor=sem_n_pos)
+        labels = t["labels"]
         pos_inds = torch.nonzero(labels >= 0).squeeze(1)
-        n_pos = max(float(reduce_mean(torch.tensor(float(len(pos_inds)), device=centerness.device))), 1.)
         loss_cls = self.loss_cls(cls_scores, labels, avg_factor=n_pos)
         pos_centerness, pos_bbox_preds = centerness[pos_inds], bbox_preds[pos_inds]
-        pos_centerness_targets = centerness_targets[pos_inds].unsqueeze(1)
-        centerness_denorm = max(float(reduce_mean(pos_centerness_targets.sum().detach())), 1e-6)
+        pos_centerness_targets = t["centerness_targets"][pos_inds].unsqueeze(1)
         if len(pos_inds) > 0:
             loss_centerness = self.loss_centerness(pos_centerness, pos_centerness_targets, avg_factor=n_pos)
-            loss_bbox = self.loss_bbox(bbox_pred_to_bbox(points[pos_inds], pos_bbox_preds), bbox_targets[pos_inds],
+            loss_bbox = self.loss_bbox(bbox_pred_to_bbox(points[pos_inds], pos_bbox_preds), t["bbox_targets"][pos_inds],
                                        weight=pos_centerness_targets.squeeze(1), avg_factor=centerness_denorm)
         else:
             loss_centerness, loss_bbox = pos_centerness.sum(), pos_bbox_preds.sum()
         return loss_centerness, loss_bbox, loss_cls, loss_sem, loss_offset
+
+    def loss_single(self, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, original_points, semantic_scores,
+                    semantic_points, img_meta, gt_bboxes, gt_labels, scene_points, pts_semantic_mask, pts_instance_mask):
+        from .dist import reduce_mean
+        t = self._targets(points, original_points, semantic_points, gt_bboxes, gt_labels, scene_points,
+                          pts_semantic_mask, pts_instance_mask)
+        norm = reduce_mean(t["local"]).cpu().tolist()                       # one collective + one read for the three
+        return self._terms(t, norm, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, semantic_scores)
+
+    def loss_batch(self, samples):
+        """loss_single over the samples of a batch with ONE reduce_mean for all 3 B normalisers (the reference issues 3 B
+        scalar all-reduces per step, each with a host read: cagroup_head.py:523,530,538 inside the per-sample loop).
+        samples: list of dicts with loss_single's argument names -> list of five-term tuples."""
+        from .dist import reduce_mean
+        ts = [self._targets(a["points"], a["original_points"], a["semantic_points"], a["gt_bboxes"], a["gt_labels"],
+                            a["scene_points"], a["pts_semantic_mask"], a["pts_instance_mask"]) for a in samples]
+        norms = reduce_mean(torch.stack([t["local"] for t in ts])).cpu().tolist()
+        return [self._terms(t, n, a["centernesses"], a["bbox_preds"], a["cls_scores"], a["points"], a["voxel_offset_preds"],
+                            a["semantic_scores"]) for t, n, a in zip(ts, norms, samples)]

@@ -10,8 +10,9 @@ positive (eval.py:90-188); AP = area under the monotone precision envelope (eval
 
 The one non-numpy piece of the reference is `rotate_iou_gpu_eval(..., criterion=2)` (numba-CUDA BEV intersection area,
 eval.py:38-42).  Here the BEV intersection comes from `bev_overlap_fn(boxes (n,7), qboxes (m,7)) -> (n, m)`:
-  * default: the C-ABI op cg3d_boxes_pairwise_bev mode 0 on the GPU (cagroup3d_b200.ops.boxes_overlap_bev, the same
-    rotated-rectangle clipping the reference's iou3d_nms uses) -- there is no CPU fallback for rotated boxes;
+  * default: the C-ABI op cg3d_boxes_pairwise_bev mode 0 on the GPU (cagroup3d_b200.ops.boxes_overlap_bev, the
+    rotated-rectangle clipping of iou3d_nms, called with NEGATED headings: rotate_iou.py rotates corners clockwise) --
+    there is no CPU fallback for rotated boxes;
   * `axis_aligned_bev_overlap` (numpy, exact) may be passed for heading-free boxes (ScanNet) and is what the CPU tests
     use to compare with the reference's own eval.py.
 The height overlap and the 3-D IoU (eval.py:6-36) are numpy.
@@ -37,8 +38,12 @@ def _gpu_bev_overlap(boxes: np.ndarray, qboxes: np.ndarray) -> np.ndarray:
     if not torch.cuda.is_available():
         raise RuntimeError("rotated BEV overlap runs on the CUDA op (cg3d_boxes_pairwise_bev); pass "
                            "bev_overlap_fn=axis_aligned_bev_overlap for heading-free boxes on a box without a GPU")
+    # rotate_iou.py:216-242 (rbbox_to_corners) turns the corners CLOCKWISE by the heading, the iou3d_nms convention of
+    # cg3d_boxes_pairwise_bev counter-clockwise: the same rectangles are reached with the heading negated on both sides
     a = torch.from_numpy(np.ascontiguousarray(boxes, np.float32)).cuda()
     b = torch.from_numpy(np.ascontiguousarray(qboxes, np.float32)).cuda()
+    a[:, 6] = -a[:, 6]
+    b[:, 6] = -b[:, 6]
     return ops.boxes_overlap_bev(a, b).cpu().numpy().astype(np.float64)
 
 

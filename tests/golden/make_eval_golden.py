@@ -7,8 +7,8 @@ they do not exist offline:
   * terminaltables.AsciiTable (printing only) -> a stub;
   * pcdet.datasets.kitti.kitti_object_eval_python.rotate_iou.rotate_iou_gpu_eval (numba-CUDA BEV intersection area,
     criterion 2) -> case "scannet": the exact axis-aligned intersection (the boxes have no heading);
-                    case "rotated": intersection recovered from the reference's compiled CPU IoU
-                    (oracle/_ref iou3d boxes_iou_bev_cpu): inter = iou (a1 + a2) / (1 + iou).
+                    case "rotated": oracle/rotate_iou_oracle.py, a float32 CPU restatement of rotate_iou.py itself
+                    (clockwise corner rotation, :216-242).
 The fixture stores the seeded inputs and the reference's result dict.
 """
 import importlib.util
@@ -79,11 +79,7 @@ def load_reference_eval(rinc_fn):
 
 
 def main():
-    import torch
-    from oracle import build_ref
     from pcdet_shim_path import indoor_eval_module          # our implementation, loaded by path (see below)
-    build_ref.build()
-    ref_iou = build_ref.load("iou3d_nms_cuda")
 
     def rinc_axis(b, q, criterion):
         assert criterion == 2
@@ -92,14 +88,11 @@ def main():
             np.concatenate([q[:, :2], np.zeros((len(q), 1)), q[:, 2:4], np.ones((len(q), 1))], 1)).astype(np.float32)
 
     def rinc_rot(b, q, criterion):
-        assert criterion == 2
-        full = lambda x: torch.from_numpy(np.concatenate([x[:, :2], np.zeros((len(x), 1), np.float32), x[:, 2:4],
-                                                          np.ones((len(x), 1), np.float32), x[:, 4:5]], 1).astype(np.float32)).contiguous()
-        iou = torch.zeros((len(b), len(q)), dtype=torch.float32)
-        ref_iou.boxes_iou_bev_cpu(full(b), full(q), iou)
-        iou = iou.numpy().astype(np.float64)
-        area = (b[:, 2] * b[:, 3])[:, None] + (q[:, 2] * q[:, 3])[None, :]
-        return (iou * area / (1.0 + iou)).astype(np.float32)
+        # the numba-CUDA kernel itself restated on the CPU, function by function (oracle/rotate_iou_oracle.py): corners
+        # rotated CLOCKWISE as rbbox_to_corners does -- NOT the iou3d_nms convention, which a first version of this
+        # fixture used and which made the rotated test circular
+        from oracle import rotate_iou_oracle
+        return rotate_iou_oracle.rotate_iou_eval(b, q, criterion)
 
     out = {}
     for name, rotated, fn in (("scannet", False, rinc_axis), ("rotated", True, rinc_rot)):

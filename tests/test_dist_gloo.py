@@ -29,8 +29,12 @@ def _worker(rank, world, port, n_scenes, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = [_fake_dets(i) for i in D.shard_indices(n_scenes, rank, world)]
+    D._GATHER_CAP["rows"] = 2                             # the fixed-capacity buffer overflows: every rank grows it alike
     merged = D.gather_detections(mine, n_scenes)
-    ok = len(merged) == n_scenes
+    ok0 = D._GATHER_CAP["rows"] >= max(sum(len(d["pred_boxes"]) for d in mine), 2)
+    again = D.gather_detections(mine, n_scenes, to_host=True)           # second call: one collective, no retry
+    ok0 &= all(torch.equal(a["pred_boxes"], b["pred_boxes"]) for a, b in zip(merged, again))
+    ok = ok0 and len(merged) == n_scenes
     for i, d in enumerate(merged):
         w = _fake_dets(i)
         wb = w["pred_boxes"] if w["pred_boxes"].shape[1] == 7 else torch.cat([w["pred_boxes"], torch.zeros((len(w["pred_boxes"]), 1))], 1)
@@ -47,7 +51,7 @@ def test_gather_detections_world2_gloo():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    for n_scenes in (5,):
+    for n_scenes in (5, 12):
         ps = [ctx.Process(target=_worker, args=(r, 2, port, n_scenes, q)) for r in range(2)]
         [p.start() for p in ps]
         res = sorted(q.get(timeout=120) for _ in ps)
@@ -55,9 +59,16 @@ def test_gather_detections_world2_gloo():
         assert res == [(0, True), (1, True)]
 
 
-def test_gather_single_process_is_identity():
-    d = [_fake_dets(i) for i in range(3)]
-    assert D.gather_detections(d, 3) is not None and len(D.gather_detections(d, 2)) == 2
+def test_gather_single_process_normalises_like_the_collective():
+    """world size 1: no collective, but the same output format as with N ranks (7-wide boxes, int64 labels)."""
+    d = [_fake_dets(i) for i in range(4)]
+    out = D.gather_detections(d, 4)
+    assert len(out) == 4 and len(D.gather_detections(d, 2)) == 2
+    for a, b in zip(out, d):
+        assert a["pred_boxes"].shape == (len(b["pred_boxes"]), 7) and a["pred_labels"].dtype == torch.int64
+        assert torch.equal(a["pred_boxes"][:, :b["pred_boxes"].shape[1]], b["pred_boxes"]) and torch.equal(a["pred_scores"], b["pred_scores"])
+    host = D.detections_to_host(d)
+    assert all(torch.equal(h["pred_labels"], b["pred_labels"]) for h, b in zip(host, d))
 
 
 # ---- training collectives: gradient all-reduce in flat buckets, reduce_mean -------------------------------------

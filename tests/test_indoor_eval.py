@@ -68,3 +68,36 @@ def test_rotated_boxes_on_the_cuda_overlap_op(lib):
     gts, dts = make_case(c["seed"], c["n_scenes"], c["n_cls"], True)
     got = IE.indoor_eval(gts, dts, [0.25, 0.5], {i: f"c{i}" for i in range(6)})
     _close(got, c["result"], 1e-4)
+
+
+def test_rotate_iou_oracle_known_answers():
+    """oracle/rotate_iou_oracle.py (restatement of the reference's rotate_iou.py) on answers derivable by hand, and the
+    pair on which the clockwise convention of rbbox_to_corners and the counter-clockwise one of iou3d_nms disagree."""
+    from oracle import rotate_iou_oracle as R
+    sq = np.array([[0, 0, 2, 2, 0]], np.float32)
+    assert R.rotate_iou_eval(sq, sq, 2)[0, 0] == 4.0 and R.rotate_iou_eval(sq, sq, -1)[0, 0] == 1.0
+    assert abs(R.rotate_iou_eval(sq, np.array([[0.5, 0, 2, 2, 0]], np.float32), -1)[0, 0] - 0.6) < 1e-6
+    bar = np.array([[0, 0, 2, 1, 0]], np.float32)
+    assert abs(R.rotate_iou_eval(bar, np.array([[0, 0, 2, 1, np.pi / 2]], np.float32), 2)[0, 0] - 1.0) < 1e-5
+    A, B = np.array([[0, 0, 2, 1, .5]], np.float32), np.array([[.3, .4, 1.8, 1.1, .3]], np.float32)
+    cw = R.rotate_iou_eval(A, B, -1)[0, 0]
+    An, Bn = A.copy(), B.copy()
+    An[:, 4], Bn[:, 4] = -A[:, 4], -B[:, 4]
+    ccw = R.rotate_iou_eval(An, Bn, -1)[0, 0]
+    assert abs(cw - 0.331) < 2e-3 and abs(ccw - 0.431) < 2e-3                # distinct centres: the sign matters
+    # a heading turns the long axis of a bar at the origin towards -y for x > 0 (clockwise)
+    c = R.rbbox_to_corners(np.array([0, 0, 2, 0.2, 0.3], np.float32)).reshape(4, 2)
+    assert c[2, 0] > 0 and c[2, 1] < 0.2
+
+
+@pytest.mark.gpu
+def test_cuda_bev_overlap_follows_rotate_iou_convention(lib):
+    """the product's BEV intersection == the rotate_iou restatement on random yawed boxes with distinct centres."""
+    from oracle import rotate_iou_oracle as R
+    rng = np.random.default_rng(3)
+    mk = lambda n: np.concatenate([rng.uniform(-1.5, 1.5, (n, 3)), rng.uniform(0.4, 2.0, (n, 3)), rng.uniform(-1.5, 1.5, (n, 1))], 1).astype(np.float32)
+    a, b = mk(40), mk(30)
+    got = IE._gpu_bev_overlap(a, b)
+    want = R.rotate_iou_eval(a[:, [0, 1, 3, 4, 6]], b[:, [0, 1, 3, 4, 6]], 2)
+    assert np.abs(got - want).max() <= 2e-4 * max(1.0, want.max()), np.abs(got - want).max()
+    assert (want > 0.05).sum() > 50
