@@ -99,5 +99,13 @@ def test_cuda_bev_overlap_follows_rotate_iou_convention(lib):
     a, b = mk(40), mk(30)
     got = IE._gpu_bev_overlap(a, b)
     want = R.rotate_iou_eval(a[:, [0, 1, 3, 4, 6]], b[:, [0, 1, 3, 4, 6]], 2)
-    assert np.abs(got - want).max() <= 2e-4 * max(1.0, want.max()), np.abs(got - want).max()
+    an, bn = a.copy(), b.copy()
+    an[:, 6], bn[:, 6] = -a[:, 6], -b[:, 6]
+    wrong = R.rotate_iou_eval(an[:, [0, 1, 3, 4, 6]], bn[:, [0, 1, 3, 4, 6]], 2)          # the counter-clockwise reading
+    err, err_wrong = np.abs(got - want), np.abs(got - wrong)
+    print("max / mean |CUDA - rotate_iou|: %.2e / %.2e   against the other sign: %.2e / %.2e" % (err.max(), err.mean(), err_wrong.max(), err_wrong.mean()))
+    # the two implementations clip differently at the edges (iou3d_nms tests corners with a 1e-2 margin,
+    # iou3d_nms_kernel.cu:35-49), so areas agree to ~1e-2, far below the effect of the sign (tenths of a square metre)
+    assert err.max() <= 3e-2 and err.mean() <= 2e-3, (err.max(), err.mean())
+    assert err_wrong.mean() > 20 * err.mean() and err_wrong.max() > 0.2
     assert (want > 0.05).sum() > 50
