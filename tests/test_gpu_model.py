@@ -17,26 +17,28 @@ DEV = "cuda"
 TOL = 1e-3
 
 
-@pytest.fixture(scope="module", params=[(18, False), (10, True)], ids=["scannet18", "sunrgbd10"])
+# third case: ONE scene of the bench generator at the BASELINE density (config 2, ~50 k voxels): every stage test below
+# then also runs at the size the headline number is quoted on (~40 s of CPU oracle)
+@pytest.fixture(scope="module", params=[(18, False, 2500, 2, 7), (10, True, 2500, 2, 7), (18, False, 50000, 1, 2)],
+                ids=["scannet18", "sunrgbd10", "scannet18-50k"])
 def setup(request, lib):
     from cagroup3d_b200 import model_init, synthetic, sparse as S
-    ncls, yaw = request.param
-    B = 2
+    ncls, yaw, voxels, B, config = request.param
     # the test scenes are small: lower the row threshold so that the tap-pattern / coarse-block tile orders of the bench
     # configuration are part of what is compared with the oracle
     old_min = S.MASK_MIN_ROWS
     S.MASK_MIN_ROWS = 256
     request.addfinalizer(lambda: setattr(S, "MASK_MIN_ROWS", old_min))
-    batch = synthetic.make_batch(B, target_voxels=2500, n_classes=ncls, sunrgbd=yaw, config=7)
+    batch = synthetic.make_batch(B, target_voxels=voxels, n_classes=ncls, sunrgbd=yaw, config=config)
     model = model_init.seeded_model(ncls, yaw, seed=3)
     pts = torch.from_numpy(batch["points"])
     orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
     bb = orc.forward(pts, B, stages="backbone")
-    model_init.calibrate_semantic_bias(model, bb["bb_feats"], 0.08)
+    model_init.calibrate_semantic_bias(model, bb["bb_feats"], 0.08 if voxels < 10000 else 1.0 / ncls)   # bench: p_sel = 1 / n_cls
     orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
     res = orc.forward(pts, B, cur_epoch=10)
     pred = torch.cat([torch.cat([m["ctr"], m["cls"], m["reg"]], 1) for m in res["head"]["maps"]])
-    model_init.calibrate_cls_bias(model, pred, 0.02)
+    model_init.calibrate_cls_bias(model, pred, 0.02 if voxels < 10000 else 0.002)                        # bench: p_box
     orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
     res = orc.forward(pts, B, cur_epoch=10)
     return dict(model=model.to(DEV), orc=orc, res=res, pts=pts, B=B, ncls=ncls, yaw=yaw)
@@ -158,22 +160,54 @@ def test_roi_head_teacher_forced(setup):
         _cmp_dets((fb[foff[b]:foff[b + 1]], fs[foff[b]:foff[b + 1]], fl[foff[b]:foff[b + 1]]), s["res"]["final"][b])
 
 
+def _match(pred, want, tag):
+    """one-to-one matching of detection lists: fraction of the oracle's (box | score) rows reproduced within TOL."""
+    gb, gs = pred["pred_boxes"].cpu(), pred["pred_scores"].cpu()
+    wb, ws, _ = want
+    if len(wb) == 0:
+        return 1.0, len(gb), 0
+    d = torch.cdist(torch.cat([gb, gs[:, None]], 1), torch.cat([wb.float(), ws.float()[:, None]], 1), p=float("inf"))
+    near = d.min(0).values
+    matched = (near <= TOL).float().mean().item()
+    print("%s: %d detections (oracle %d), matched within %g: %.4f, max |delta| on the matched ones %.2e, worst %.2e"
+          % (tag, len(gb), len(wb), TOL, matched, float(near[near <= TOL].max()) if matched > 0 else float("nan"), float(near.max())))
+    return matched, len(gb), len(wb)
+
+
 def test_end_to_end_forward(setup):
-    """Whole forward through the pcdet-style API; every stage runs on its own (CUDA) inputs."""
+    """Whole forward through the pcdet-style API; every stage runs on its own (CUDA) inputs.
+
+    Two comparisons, both printed.  FREE-RUNNING against the oracle's own forward: the two fp32 implementations differ in
+    the last bits of the vote offsets, and a voted point that sits within that distance of a class-voxel boundary is
+    floored into the neighbouring voxel (cagroup_head.py:251) -- which moves the few detections fed by that voxel by
+    0.05-0.3 m.  First hardware run: 97.2 % ... 100 % of the detections matched within 1e-3 (profiles/r2_gpu_parity_e2e.log).
+    TEACHER-FORCED at the two discontinuities: the oracle re-run with the CUDA path's semantic logits and vote offsets
+    (its `force` argument: threshold select and floor() then take the same decisions) must reproduce the detections."""
     s = setup
     pts = s["pts"].clone().to(DEV)
-    pred_dicts, recall = s["model"]({"points": pts, "batch_size": s["B"], "cur_epoch": 10})
+    model = s["model"]
+    pred_dicts, recall = model({"points": pts, "batch_size": s["B"], "cur_epoch": 10})
     assert torch.allclose(pts[:, -3:].cpu(), s["pts"][:, -3:] / 255.)    # the in-place /255 of the reference
     assert len(pred_dicts) == s["B"] and "gt" in recall
     for b in range(s["B"]):
-        wb, ws, wl = s["res"]["final"][b]
-        gb, gs, gl = pred_dicts[b]["pred_boxes"], pred_dicts[b]["pred_scores"], pred_dicts[b]["pred_labels"]
+        gl, gb = pred_dicts[b]["pred_labels"], pred_dicts[b]["pred_boxes"]
         assert gl.dtype == torch.int64 and gb.shape[1] == 7
-        # free-running: a rounding-level difference may flip a discrete decision upstream, so match
-        # detections one to one instead of demanding identical lists
-        assert abs(len(gb) - len(wb)) <= max(2, len(wb) // 50), (len(gb), len(wb))
-        if len(wb) == 0:
-            continue
-        d = torch.cdist(torch.cat([gb.cpu(), gs.cpu()[:, None]], 1), torch.cat([wb.float(), ws.float()[:, None]], 1), p=float("inf"))
-        matched = (d.min(0).values <= TOL).float().mean().item()
-        assert matched >= 0.90, matched
+        m, ng, nw = _match(pred_dicts[b], s["res"]["final"][b], "free-running sample %d" % b)
+        assert abs(ng - nw) <= max(2, nw // 50), (ng, nw)
+        assert m >= 0.95, m
+    # the oracle forced with the CUDA path's values at the two discontinuities
+    from cagroup3d_b200.detector import voxelize
+    p = s["pts"].clone().to(DEV)
+    p[:, -3:] /= 255.
+    out = model.backbone_3d.run(voxelize(p, 0.02))
+    model.dense_head.semantic_threshold = 0.05
+    cm = model.dense_head.class_maps(out, s["B"])
+    pa, pb = assert_same_coord_set(out.C.cpu().numpy(), s["res"]["bb_coords"])
+    n = len(pa)
+    sem, offs = torch.empty((n, cm["sem"].shape[1])), torch.empty((n, cm["offsets"].shape[1]))
+    sem[pb], offs[pb] = cm["sem"].cpu()[pa], cm["offsets"].cpu()[pa]
+    forced = s["orc"].forward(s["pts"], s["B"], cur_epoch=10, force={"sem": sem, "offsets": offs})
+    for b in range(s["B"]):
+        m, ng, nw = _match(pred_dicts[b], forced["final"][b], "teacher-forced sample %d" % b)
+        assert abs(ng - nw) <= 1, (ng, nw)
+        assert m >= 0.995, m

@@ -127,7 +127,7 @@ def test_cuda_forward_vs_reference_python_golden(lib, name):
     assert np.abs(cm["sem"].cpu().numpy()[pa] - gold["sem"][pb]).max() <= 1e-3
     assert np.abs(cm["offsets"].cpu().numpy()[pa] - gold["offsets"][pb]).max() <= 1e-3
     # whole forward: detections of the reference matched one-to-one (a last-bit flip at a threshold / floor can move a
-    # few boxes, so 97 % of the reference's detections must be reproduced within 1e-3)
+    # few boxes; the matched fraction is printed: 97.5 % - 100 % on hardware)
     pred, _ = model({"points": torch.from_numpy(batch["points"]).to(DEV), "batch_size": B, "cur_epoch": 10})
     for b in range(B):
         want = gold[f"final_b{b}"]
@@ -138,7 +138,11 @@ def test_cuda_forward_vs_reference_python_golden(lib, name):
         d = torch.cdist(g, w, p=float("inf"))
         lab = pred[b]["pred_labels"].cpu()[:, None].double() == torch.from_numpy(want[:, -1])[None].double()
         d = torch.where(lab, d, torch.full_like(d, 1e9))
-        assert (d.min(0).values <= 1e-3).double().mean().item() >= 0.97
+        near = d.min(0).values
+        matched = (near <= 1e-3).double().mean().item()
+        print("sample %d: %d detections (reference %d), matched within 1e-3: %.4f, max |delta| on the matched ones %.2e"
+              % (b, len(g), len(w), matched, float(near[near <= 1e-3].max()) if matched > 0 else float("nan")))
+        assert matched >= 0.97, matched             # free-running (see tests/test_gpu_model.py::test_end_to_end_forward)
 
 
 def test_knn_vs_c_oracle_and_api(lib):
