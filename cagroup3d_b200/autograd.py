@@ -320,7 +320,7 @@ class SegmentMeanFunction(torch.autograd.Function):
         dev = Pd.device
         out = torch.empty((n_unique, C), dtype=torch.float32, device=dev)
         cnt = torch.empty((max(n_unique, 1),), dtype=torch.float32, device=dev)
-        ws = torch.empty((max(n_unique, 1) * C,), dtype=torch.int64, device=dev)
+        ws = torch.empty((_lib.host("cg3d_segment_mean_workspace", n, n_unique),), dtype=torch.int64, device=dev)
         S._call("cg3d_segment_mean", Pd, C, None, 0, None, inverse, n, n_unique, C, out, cnt, ws)
         ctx.save_for_backward(inverse, cnt)
         return out

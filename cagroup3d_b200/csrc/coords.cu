@@ -59,6 +59,48 @@ __global__ void flag_winner_kernel(const int* __restrict__ slot_of_row, const in
         flag[i] = (vals[slot_of_row[i]] == i) ? 1 : 0;
 }
 
+// ---- the same pipeline with the row count read from DEVICE memory (cg3d_unique_first_dev): the source rows are the
+// unique rows of another map whose size the host has not read back yet; launches are sized by the upper bound n_max ----
+__device__ __forceinline__ int4 strided_row(int4 c, int ts) {
+    return ts > 1 ? make_int4(c.x, cg3d_floordiv(c.y, ts) * ts, cg3d_floordiv(c.z, ts) * ts, cg3d_floordiv(c.w, ts) * ts) : c;
+}
+
+__global__ void hash_insert_dev_kernel(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int ts,
+                                       unsigned long long* keys, int* vals, unsigned mask, int* __restrict__ slot_of_row) {
+    const int n = min(*n_ptr, n_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = strided_row(coords[i], ts);
+        unsigned long long key = cg3d_pack(c.x, c.y, c.z, c.w);
+        unsigned slot = cg3d_hash(key) & mask;
+        while (true) {
+            unsigned long long prev = atomicCAS(keys + slot, CG3D_EMPTY_KEY, key);
+            if (prev == CG3D_EMPTY_KEY || prev == key) break;
+            slot = (slot + 1) & mask;
+        }
+        atomicMin(vals + slot, i);
+        slot_of_row[i] = (int)slot;
+    }
+}
+
+// flag[i] = 1 for the winner rows of the first n, 0 up to n_max (the scan below runs over the upper bound)
+__global__ void flag_winner_dev_kernel(const int* __restrict__ slot_of_row, const int* __restrict__ vals,
+                                       const int* __restrict__ n_ptr, int n_max, int* __restrict__ flag) {
+    const int n = min(*n_ptr, n_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_max; i += gridDim.x * blockDim.x)
+        flag[i] = (i < n && vals[slot_of_row[i]] == i) ? 1 : 0;
+}
+
+__global__ void unique_emit_dev_kernel(const int4* __restrict__ coords, const int* __restrict__ slot_of_row, int* vals,
+                                       const int* __restrict__ excl, const int* __restrict__ flag,
+                                       const int* __restrict__ n_ptr, int n_max, int ts, int4* __restrict__ out_coords) {
+    const int n = min(*n_ptr, n_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) {                               // winner: emit the row and relabel the table entry (key -> unique row)
+            out_coords[excl[i]] = strided_row(coords[i], ts);
+            vals[slot_of_row[i]] = excl[i];
+        }
+}
+
 // ---- exclusive scan of int32 (three small kernels; n up to a few million) ---------------------
 constexpr int kScanBlock = 1024;
 
@@ -367,6 +409,30 @@ int cg3d_unique_first(const int* coords, int n, unsigned long long* keys, int* v
     unique_emit_kernel<<<g, kThreads, 0, s>>>((const int4*)coords, slot, vals, excl, n, (int4*)out_coords,
                                               first_row, inverse);
     unique_relabel_kernel<<<g, kThreads, 0, s>>>(slot, vals, excl, flag, n);
+    CG3D_LAUNCH_CHECK();
+    return 0;
+}
+
+int cg3d_unique_first_dev(const int* coords, const int* n_rows, int n_max, int ts, unsigned long long* keys, int* vals,
+                          int capacity, int* out_coords, int* n_unique, int* workspace, void* stream) {
+    // workspace: 3*n_max + cg3d_scan_workspace_ints(n_max) ints  (slot_of_row | flag | excl | block sums)
+    cudaStream_t s = (cudaStream_t)stream;
+    if (capacity < 2 || (capacity & (capacity - 1))) return -1;
+    cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * (size_t)capacity, s);
+    cudaMemsetAsync(vals, 0x7F, sizeof(int) * (size_t)capacity, s);
+    if (n_max == 0) { cudaMemsetAsync(n_unique, 0, sizeof(int), s); return 0; }
+    int* slot = workspace;
+    int* flag = workspace + n_max;
+    int* excl = workspace + 2 * (size_t)n_max;
+    int* sums = workspace + 3 * (size_t)n_max;
+    const unsigned mask = (unsigned)capacity - 1;
+    const int g = grid_for(n_max);
+    hash_insert_dev_kernel<<<g, kThreads, 0, s>>>((const int4*)coords, n_rows, n_max, ts, keys, vals, mask, slot);
+    flag_winner_dev_kernel<<<g, kThreads, 0, s>>>(slot, vals, n_rows, n_max, flag);
+    int rc = cg3d_exclusive_scan_i32(flag, n_max, excl, sums, n_unique, stream);
+    if (rc) return rc;
+    unique_emit_dev_kernel<<<g, kThreads, 0, s>>>((const int4*)coords, slot, vals, excl, flag, n_rows, n_max, ts,
+                                                  (int4*)out_coords);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

@@ -83,36 +83,75 @@ __global__ void avgpool_kernel(const int4* __restrict__ oc, const int4* __restri
     (void)inv;
 }
 
-// sums[inverse[p], :] += feat(p); feat(p) = src[row(p)*ld + col_off(p) ...] with optional indirection
-__global__ void segment_accumulate_kernel(const float* __restrict__ srcA, int ldA, const float* __restrict__ srcB,
-                                          int ldB, const int2* __restrict__ ref, const int* __restrict__ inverse,
-                                          int n, int C, unsigned long long* __restrict__ sums,
-                                          float* __restrict__ counts) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int p = warp; p < n; p += nwarps) {
-        const float* src;
-        if (ref) {
-            int2 r = __ldg(ref + p);   // (row, kind): kind >= 0 -> slice `kind` of srcA, kind < 0 -> srcB
-            src = r.y >= 0 ? srcA + (size_t)r.x * ldA + (size_t)r.y * C : srcB + (size_t)r.x * ldB;
-        } else {
-            src = srcA + (size_t)p * ldA;
-        }
-        int u = __ldg(inverse + p);
-        // fixed point (2^-30 units, 64-bit integer atomics): the sum does not depend on the order in which the points of a
-        // voxel arrive, so the forward is bit-repeatable; float atomics made the class maps differ in the last bits
-        // from run to run.  |feature| < 2^21 and the 2^-31 rounding of tiny values are far inside the 1e-3 parity bar.
-        for (int ch = lane; ch < C; ch += 32)
-            atomicAdd(sums + (size_t)u * C + ch, (unsigned long long)__float2ll_rn(__ldg(src + ch) * 1073741824.f));
-        if (lane == 0) atomicAdd(counts + u, 1.f);
+// ---- UNWEIGHTED_AVERAGE quantisation: out[u] = mean of feat(p) over the points p with inverse[p] == u ----------------
+// Three passes without a 64-bit atomic: (1) histogram of `inverse` (int atomics) -> (2) exclusive scan = segment offsets ->
+// (3) every point takes the next free slot of its segment (int atomic cursor) -> (4) one warp per unique row adds its
+// points' features.  The sum is taken in 2^-30 FIXED POINT (64-bit integer adds in registers): integer addition is
+// associative, so the result does not depend on the order in which step (3) happened to fill the segment -- the forward
+// is bit-repeatable, and bit-identical to the earlier version that did one 64-bit atomicAdd per (point, channel) into a
+// n_unique x C table (1.34 ms for the two maps of the head; this form streams each feature row once).
+__global__ void segment_count_kernel(const int* __restrict__ inverse, int n, int* __restrict__ cnt) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) atomicAdd(cnt + __ldg(inverse + p), 1);
+}
+
+__global__ void segment_fill_kernel(const int* __restrict__ inverse, int n, const int* __restrict__ offs, int* __restrict__ cursor,
+                                    int* __restrict__ list) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int u = __ldg(inverse + p);
+        list[__ldg(offs + u) + atomicAdd(cursor + u, 1)] = p;
     }
 }
 
-__global__ void segment_divide_kernel(const unsigned long long* __restrict__ sums, const float* __restrict__ counts,
-                                      long long total, int C, float* __restrict__ out) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x)
-        out[i] = (float)((double)(long long)sums[i] * (1.0 / 1073741824.0) / (double)counts[i / C]);
+// feat(p) = src[row(p)*ld + col_off(p) ...] with optional indirection; |feature| < 2^21 and the 2^-31 rounding of tiny
+// values are far inside the 1e-3 parity bar
+__global__ void segment_reduce_kernel(const float* __restrict__ srcA, int ldA, const float* __restrict__ srcB, int ldB,
+                                      const int2* __restrict__ ref, const int* __restrict__ offs, const int* __restrict__ cnt,
+                                      const int* __restrict__ list, int n_unique, int C, float* __restrict__ out,
+                                      float* __restrict__ counts) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int u = warp; u < n_unique; u += nwarps) {
+        const int o = __ldg(offs + u), m = __ldg(cnt + u);
+        if (lane == 0) counts[u] = (float)m;
+        for (int c0 = 0; c0 < C; c0 += 128) {                          // up to 4 channels per lane per pass
+            long long acc[4] = {0, 0, 0, 0};
+            // four points per round: their index / reference / feature loads are independent, so a long segment (the 3x
+            // coarser map holds ~8 points per voxel) does not pay four dependent memory latencies per point
+            for (int j0 = 0; j0 < m; j0 += 4) {
+                const float* src[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    src[t] = nullptr;
+                    if (j0 + t < m) {
+                        const int p = __ldg(list + o + j0 + t);
+                        if (ref) {
+                            const int2 r = __ldg(ref + p);   // (row, kind): kind >= 0 -> slice `kind` of srcA, kind < 0 -> srcB
+                            src[t] = r.y >= 0 ? srcA + (size_t)r.x * ldA + (size_t)r.y * C : srcB + (size_t)r.x * ldB;
+                        } else {
+                            src[t] = srcA + (size_t)p * ldA;
+                        }
+                    }
+                }
+                float v[4][4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ch = c0 + lane + 32 * k;
+                        v[t][k] = (src[t] && ch < C) ? __ldg(src[t] + ch) : 0.f;
+                    }
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[k] += __float2ll_rn(v[t][k] * 1073741824.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ch = c0 + lane + 32 * k;
+                if (ch < C) out[(size_t)u * C + ch] = (float)((double)acc[k] * (1.0 / 1073741824.0) / (double)m);
+            }
+        }
+    }
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, int ld, int col0, const int* __restrict__ rows, int n,
@@ -157,18 +196,34 @@ int cg3d_avgpool_window(const int* out_coords, int n_out, const int* in_coords, 
     return 0;
 }
 
+/* workspace of cg3d_segment_mean in 64-bit words: counts | offsets | cursors (n_unique ints each) | point list (n) | scan */
+int cg3d_segment_mean_workspace(int n, int n_unique) {
+    const long long ints = 3LL * (n_unique + 1) + n + cg3d_scan_workspace_ints(n_unique + 1) + 8;
+    return (int)((ints + 1) / 2);
+}
+
 int cg3d_segment_mean(const float* srcA, int ldA, const float* srcB, int ldB, const int* ref, const int* inverse,
                       int n, int n_unique, int C, float* out, float* counts, long long* workspace, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_unique == 0) return 0;
-    unsigned long long* sums = reinterpret_cast<unsigned long long*>(workspace);
-    cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * (size_t)n_unique * C, s);
-    cudaMemsetAsync(counts, 0, sizeof(float) * (size_t)n_unique, s);
-    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_unique * C, s); return 0; }
-    segment_accumulate_kernel<<<flat_grid((long long)n * 32, 256), 256, 0, s>>>(srcA, ldA, srcB, ldB, (const int2*)ref,
-                                                                                 inverse, n, C, sums, counts);
-    segment_divide_kernel<<<flat_grid((long long)n_unique * C, 256), 256, 0, s>>>(sums, counts,
-                                                                                   (long long)n_unique * C, C, out);
+    if (n == 0) {
+        cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_unique * C, s);
+        cudaMemsetAsync(counts, 0, sizeof(float) * (size_t)n_unique, s);
+        return 0;
+    }
+    int* cnt = reinterpret_cast<int*>(workspace);
+    int* offs = cnt + (n_unique + 1);
+    int* cursor = offs + (n_unique + 1);
+    int* list = cursor + (n_unique + 1);
+    int* scan_ws = list + n;
+    cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_unique + 1), s);
+    cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)(n_unique + 1), s);
+    segment_count_kernel<<<flat_grid(n, 256), 256, 0, s>>>(inverse, n, cnt);
+    int rc = cg3d_exclusive_scan_i32(cnt, n_unique, offs, scan_ws + 1, scan_ws, stream);
+    if (rc) return rc;
+    segment_fill_kernel<<<flat_grid(n, 256), 256, 0, s>>>(inverse, n, offs, cursor, list);
+    segment_reduce_kernel<<<flat_grid((long long)n_unique * 32, 256), 256, 0, s>>>(srcA, ldA, srcB, ldB, (const int2*)ref, offs, cnt,
+                                                                                   list, n_unique, C, out, counts);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

@@ -22,19 +22,28 @@ DENSE_HEADS = {"CAGroup3DHead": CAGroup3DHead}
 ROI_HEADS = {"CAGroup3DRoIHead": CAGroup3DRoIHead}
 
 
-def voxelize(points: torch.Tensor, voxel_size: float) -> S.SparseTensor:
+def voxelize(points: torch.Tensor, voxel_size: float, pyramid: bool = True) -> S.SparseTensor:
     """CAGroup3D.voxelization (cagroup3d.py:18-25): floor(xyz / voxel_size), hash-unique, the first
-    point of every voxel gives its colour (ME RANDOM_SUBSAMPLE made deterministic)."""
+    point of every voxel gives its colour (ME RANDOM_SUBSAMPLE made deterministic).
+    pyramid: also build the strided maps BiResNet / DAPPM will ask for (strides 2 .. 512) right here, all sizes read back
+    in ONE host sync together with the voxel count (sparse.voxel_pyramid); False: they are built on demand."""
     assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous()
     n, ld = points.shape
     coords, err = S.quantize(points, ld, n, (voxel_size,) * 3)
     mgr = S.Manager()
-    cmap, first, _ = S.unique_first(coords, 1, mgr, want_first=True)
-    mgr.by_stride[1] = cmap
-    if int(err.item()):
+    if pyramid and _PYRAMID["on"]:
+        cmap, first, n_err = S.voxel_pyramid(coords, mgr, err=err)
+    else:
+        cmap, first, _ = S.unique_first(coords, 1, mgr, want_first=True)
+        mgr.by_stride[1] = cmap
+        n_err = int(err.item())
+    if n_err:
         raise ValueError("voxel index outside the 16-bit coordinate range of the hash key")
     F = S.gather_rows(points, 4, first, cmap.n, ld - 4)
     return S.SparseTensor(F, cmap, mgr)
+
+
+_PYRAMID = {"on": os.environ.get("CG3D_PYRAMID", "1") != "0"}
 
 
 class CAGroup3D(nn.Module):

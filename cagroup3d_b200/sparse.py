@@ -41,6 +41,7 @@ class Profile:
     active = None
     stage = ""
     conv_only = False
+    streams = None          # optional list: the CUDA stream of every recorded call (tools/timeline.py)
 
 
 def _call(name, *args, meta=None):
@@ -53,6 +54,8 @@ def _call(name, *args, meta=None):
     _lib.call(name, *args)
     e1.record()
     Profile.active.append((name, Profile.stage, meta, e0, e1))
+    if Profile.streams is not None:
+        Profile.streams.append(torch.cuda.current_stream().cuda_stream)
 
 
 def _i32(*shape, device):
@@ -136,6 +139,47 @@ def unique_first(coords: torch.Tensor, stride: int, mgr: Optional[Manager] = Non
     u = int(nu.item())
     cm = CoordMap(out[:u], stride, keys, vals, mgr.new_uid() if mgr else 0)
     return cm, (first[:u] if want_first else None), (inv[:n] if want_inverse else None)
+
+
+# BiResNet + DAPPM coordinate pyramid (biresnet.py:109-127,265-268): (tensor stride, tensor stride of the map it is made
+# from).  ME derives a strided map from the rows of the conv's / pool's INPUT map, so the DAPPM pools (strides 2 .. 16 on
+# the stride-32 tensor) all start from the stride-32 rows.
+BACKBONE_PYRAMID = ((2, 1), (4, 2), (8, 4), (16, 8), (32, 16), (64, 32), (128, 32), (256, 32), (512, 32))
+
+
+def voxel_pyramid(coords: torch.Tensor, mgr: Manager, plan=BACKBONE_PYRAMID, err: Optional[torch.Tensor] = None):
+    """The stride-1 map of `coords` (hash-unique, first occurrence) AND every strided map of `plan`, with ONE host
+    read-back for all their sizes: level l is made from the unique rows of its source level while that level's row count
+    still lives on the device (cg3d_unique_first_dev, launches sized by the upper bound).  Replaces 1 + len(plan) size
+    syncs spread over the backbone by one at its start.  -> (stride-1 map, first_row of its rows); the strided maps are
+    left in mgr.by_stride, where strided_map() finds them.  err: optional device counter read back with the sizes."""
+    dev, n = coords.device, coords.shape[0]
+    L = len(plan)
+    cap = _lib.hash_capacity(n)
+    cnt = torch.zeros((L + 2,), dtype=torch.int32, device=dev)
+    ws = _i32(3 * n + _lib.scan_workspace_ints(n), device=dev)
+    keys0 = torch.empty((cap,), dtype=torch.int64, device=dev)
+    vals0 = _i32(cap, device=dev)
+    out0 = _i32(max(n, 1), 4, device=dev)
+    first = _i32(max(n, 1), device=dev)
+    _call("cg3d_unique_first", coords, n, keys0, vals0, cap, out0, first, None, cnt[0:1], ws)
+    bufs = {1: (out0, keys0, vals0, cnt[0:1])}
+    for l, (ts, src) in enumerate(plan):
+        so, _, _, sn = bufs[src]
+        keys = torch.empty((cap,), dtype=torch.int64, device=dev)
+        vals = _i32(cap, device=dev)
+        out = _i32(max(n, 1), 4, device=dev)
+        _call("cg3d_unique_first_dev", so, sn, n, ts, keys, vals, cap, out, cnt[l + 1:l + 2], ws)
+        bufs[ts] = (out, keys, vals, cnt[l + 1:l + 2])
+    if err is not None:
+        cnt[L + 1:L + 2].copy_(err)
+    host = cnt.cpu().tolist()                                    # the one host sync of the backbone's coordinate maps
+    maps = {}
+    for i, ts in enumerate([1] + [p[0] for p in plan]):
+        out, keys, vals, _ = bufs[ts]
+        maps[ts] = CoordMap(out[:host[i]], ts, keys, vals, mgr.new_uid())
+        mgr.by_stride[ts] = maps[ts]
+    return maps[1], first[:host[0]], host[L + 1]
 
 
 def build_map(coords: torch.Tensor, stride: int, mgr: Optional[Manager] = None) -> CoordMap:
@@ -343,13 +387,15 @@ class Tiles:
 
 def make_tiles(seg_offsets, device, tile=64) -> Tiles:
     """seg_offsets: python list [g0_start, g1_start, ..., total] of contiguous per-group row ranges."""
-    r0, rn, gg = [], [], []
-    for g in range(len(seg_offsets) - 1):
-        a, b = seg_offsets[g], seg_offsets[g + 1]
-        for s in range(a, b, tile):
-            r0.append(s); rn.append(min(tile, b - s)); gg.append(g)
-    t = torch.tensor([r0, rn, gg], dtype=torch.int32).to(device, non_blocking=True)
-    return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), len(r0), list(seg_offsets), tile)
+    import numpy as np
+    off = np.asarray(seg_offsets, dtype=np.int64)
+    cnt = np.maximum(-(-(off[1:] - off[:-1]) // tile), 0)                     # tiles per group (vectorised: the head's maps
+    gg = np.repeat(np.arange(len(cnt)), cnt)                                   # have thousands of tiles)
+    first = np.cumsum(cnt) - cnt
+    r0 = off[:-1][gg] + (np.arange(int(cnt.sum())) - first[gg]) * tile
+    rn = np.minimum(tile, off[1:][gg] - r0)
+    t = torch.from_numpy(np.stack([r0, rn, gg]).astype(np.int32)).to(device, non_blocking=True)
+    return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), int(cnt.sum()), list(seg_offsets), tile)
 
 
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
@@ -522,7 +568,7 @@ def segment_mean(srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C) -> torch.Te
     dev = inverse.device
     out = _f32(n_unique, C, device=dev)
     cnt = _f32(max(n_unique, 1), device=dev)
-    ws = torch.empty((max(n_unique, 1) * C,), dtype=torch.int64, device=dev)
+    ws = torch.empty((_lib.host("cg3d_segment_mean_workspace", n, n_unique),), dtype=torch.int64, device=dev)
     _call("cg3d_segment_mean", srcA, ldA, srcB, ldB, ref, inverse, n, n_unique, C, out, cnt, ws)
     return out
 

@@ -55,6 +55,15 @@ int cg3d_exclusive_scan_i32(const int* in, int n, int* out, int* block_sums, int
 int cg3d_unique_first(const int* coords, int n, unsigned long long* keys, int* vals, int capacity, int* out_coords,
                       int* first_row, int* inverse, int* n_unique, int* workspace, void* stream);
 
+/* The same for a source whose row count still lives in DEVICE memory: rows 0 .. min(*n_rows, n_max) - 1 of `coords`
+ * are strided to tensor stride `ts` (ts <= 1: taken as they are) and hash-uniqued in first-occurrence order.  Launches are
+ * sized by the upper bound n_max, so a whole pyramid of strided maps (the stride 2 .. 512 maps of BiResNet and DAPPM,
+ * biresnet.py:109-127,265-268: each level made from the unique rows of another) is built without reading a size back; the
+ * host reads all counts once at the end.  capacity: power of two >= 2 * n_max; out_coords: n_max rows;
+ * workspace: 3 * n_max + cg3d_scan_workspace_ints(n_max) ints. */
+int cg3d_unique_first_dev(const int* coords, const int* n_rows, int n_max, int ts, unsigned long long* keys, int* vals,
+                          int capacity, int* out_coords, int* n_unique, int* workspace, void* stream);
+
 /* table over already-unique rows: key -> row index. */
 int cg3d_hash_build(const int* coords, int n, unsigned long long* keys, int* vals, int capacity, void* stream);
 
@@ -188,9 +197,11 @@ int cg3d_avgpool_window(const int* out_coords, int n_out, const int* in_coords, 
 
 /* UNWEIGHTED_AVERAGE quantisation (cagroup_head.py:257-271; A3): out[u] = mean over points p with
  * inverse[p] == u of feat(p); ref == NULL: feat(p) = srcA[p*ldA ..]; else ref[p] = (row, kind):
- * kind >= 0 -> srcA[row*ldA + kind*C ..], kind < 0 -> srcB[row*ldB ..].  counts: n_unique floats; workspace: n_unique * C
- * 64-bit integers (the sums are accumulated in 2^-30 fixed point so that the result does not depend on the order of
- * the atomics: bit-repeatable forward). */
+ * kind >= 0 -> srcA[row*ldA + kind*C ..], kind < 0 -> srcB[row*ldB ..].  counts: n_unique floats; workspace:
+ * cg3d_segment_mean_workspace(n, n_unique) 64-bit words.  Histogram -> scan -> segment fill -> one warp per unique row;
+ * the sums are taken in 2^-30 fixed point (integer adds), so the result does not depend on the order in which a
+ * segment was filled: bit-repeatable forward, no 64-bit atomics. */
+int cg3d_segment_mean_workspace(int n, int n_unique);
 int cg3d_segment_mean(const float* srcA, int ldA, const float* srcB, int ldB, const int* ref, const int* inverse,
                       int n, int n_unique, int C, float* out, float* counts, long long* workspace, void* stream);
 

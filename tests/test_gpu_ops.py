@@ -47,6 +47,35 @@ def test_quantize_unique_first_exact(lib):
     assert torch.equal(x.F.cpu(), ox.F)                       # the first point's colour, bit exact
 
 
+def test_voxel_pyramid_equals_on_demand_maps(lib):
+    """sparse.voxel_pyramid (all strided maps of BiResNet / DAPPM with device-side row counts, ONE size read-back) gives
+    exactly the maps the on-demand path builds one sync at a time: same rows in the same order, same table contents
+    (probed through a rule map), and the oracle's row sets."""
+    from cagroup3d_b200 import sparse as S
+    from cagroup3d_b200.detector import voxelize
+    pts = rand_cloud(5, n=60000, batch=3)
+    pts[:, 1:4] *= 4.0                                       # spread: the coarse levels keep more than a handful of rows
+    pts[:, 4:] /= 255.
+    a = voxelize(pts.to(DEV), 0.02, pyramid=True)
+    b = voxelize(pts.to(DEV), 0.02, pyramid=False)
+    assert torch.equal(a.C, b.C) and torch.equal(a.F, b.F)
+    assert sorted(a.mgr.by_stride) == [1] + [p[0] for p in S.BACKBONE_PYRAMID] and sorted(b.mgr.by_stride) == [1]
+    for ts, src in S.BACKBONE_PYRAMID:
+        want = S.strided_map(b.mgr.by_stride[src], b.mgr, ts // src)                 # one host sync each
+        got = S.strided_map(a.mgr.by_stride[src], a.mgr, ts // src)                  # cached: no work
+        assert got is a.mgr.by_stride[ts] and torch.equal(got.coords, want.coords), ts
+        if got.n:
+            ta = S.neighbor_table(a.mgr.by_stride[src], got, 3, a.mgr)
+            tb = S.neighbor_table(b.mgr.by_stride[src], want, 3, b.mgr)
+            assert torch.equal(ta, tb), ts
+    c = pts[:, :4].clone()
+    c[:, 1:] /= 0.02
+    ox = me.from_points(c, pts[:, 4:])
+    o2 = ox.mgr.strided(ox.cmap, 2)
+    assert (a.mgr.by_stride[2].coords.cpu().numpy() == o2.coords).all() or \
+        set(map(tuple, a.mgr.by_stride[2].coords.cpu().numpy())) == set(map(tuple, o2.coords))
+
+
 def test_negative_and_empty_inputs(lib):
     from cagroup3d_b200 import sparse as S
     pts = torch.tensor([[0, -0.001, 0.0, 0.019, 1, 2, 3], [0, -0.02, -0.0200001, 0.02, 4, 5, 6]], dtype=torch.float32)
