@@ -48,6 +48,12 @@
 #include "common.cuh"
 #include "../../include/cagroup3d_b200.h"
 
+// persistent schedule of the same contraction (spconv_tc4.cu)
+int cg3d_spconv_tc4_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
+                           int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
+                           const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
+                           unsigned short* out_split, int out_split_relu, int NT, void* stream);
+
 namespace {
 
 constexpr int TM = 128;            // output rows per CTA (UMMA M)
@@ -210,14 +216,19 @@ struct TcArgs {
 // TMAG: the A tile of a stage is fetched by the TMA engine (tile::gather4, one instruction per lane = 4 rows, one warp per
 // ring slot) instead of 1024 cp.async per stage: the gather warps were issue-bound (a handful of extra ALU instructions
 // per copy cost 10-15 % of the layer), the TMA path needs ~10 instructions per stage and no per-thread arrivals.
-template <int NT, int STAGES, bool STASH, bool STK, bool TMAG>
+// CPS (chunks per stage, plain variant only): a barrier phase carries CPS consecutive 32-channel sub-tiles [A | B], i.e. half
+// the producer -> MMA -> producer handshakes per tap at CPS = 2 for the same bytes in flight (the handshake costs 400-600 clk
+// per stage whatever the stage carries: profiles/r2_conv_skeleton_ablation.md).
+template <int NT, int STAGES, bool STASH, bool STK, bool TMAG, int CPS = 1>
 __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap) {
     static_assert(!STK || NT == 64, "the stacked-weights variant is the 64-column kernel");
     static_assert(!(STK && TMAG), "the stacked variant keeps the cp.async gather");
-    constexpr int KCH = STK ? 64 : KC;                    // channels per stage
+    static_assert(CPS == 1 || (!STK && !TMAG), "several sub-tiles per stage: plain variant only");
+    constexpr int KCH = STK ? 64 : KC * CPS;              // channels per stage
     constexpr int A_TILE = STK ? 2 * A_BYTES : A_BYTES;   // STK: hi tile + lo tile
-    constexpr int B_BYTES = STK ? 128 * 128 : NT * 128;   // bytes of the B tile of a stage
-    constexpr int STAGE_BYTES = A_TILE + B_BYTES;
+    constexpr int B_BYTES = STK ? 128 * 128 : NT * 128;   // bytes of the B tile of a (sub-)stage
+    constexpr int SUB_BYTES = A_TILE + B_BYTES;
+    constexpr int STAGE_BYTES = CPS * SUB_BYTES;
     constexpr int TCOLS = STK ? 128 : NT;                 // TMEM columns of the accumulator
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (a.nbr) {
+    if (a.nbr && !(a.debug & 4096)) {                     // 4096 (timing experiment): no rule-map scan
         constexpr int NW = NTHREADS / 32, UN = 4;         // 4 taps per warp per round, all loads issued before the votes
         for (int k0 = warp * UN; k0 < a.K; k0 += NW * UN) {
             int v[UN][TM / 32];
@@ -324,7 +335,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         return lo;
     };
     const int a0 = a.ksplit > 1 ? lower_bound_tap((int)(((long long)a.K * blockIdx.z) / a.ksplit)) : 0;
-    const int a1 = a.ksplit > 1 ? lower_bound_tap((int)(((long long)a.K * (blockIdx.z + 1)) / a.ksplit)) : n_active;
+    const int a1 = (a.debug & 2048) ? a0                                  // 2048 (timing experiment): no K loop
+                                    : (a.ksplit > 1 ? lower_bound_tap((int)(((long long)a.K * (blockIdx.z + 1)) / a.ksplit)) : n_active);
     const int n_iters = (a1 - a0) * nchunks;
     float* const outp = a.out + (size_t)blockIdx.z * a.zstride;
     const uint32_t tmem_base = tmem_slot;
@@ -424,21 +436,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
             const long long p1 = clock64();
             mbar_wait(empty_s, ph);
             if (t == 0) TC_PROF(8, clock64() - p1);
-            const unsigned long long src = src0 + (unsigned)((q % nchunks) * (STK ? 256 : 128));
             if (!(a.debug & 4)) {
+#pragma unroll
+              for (int u = 0; u < CPS; ++u) {
+                const unsigned long long src = src0 + (unsigned)(((q % nchunks) * CPS + u) * (STK ? 256 : 128));
 #pragma unroll
                 for (int i = 0; i < (STK ? RW / 2 : RW / 4); ++i) {
                     const int m = STK ? (i >> 1) : i;             // 4-row group; STK: copy i fills tile i & 1 (hi, lo)
                     const int tile = STK ? (i & 1) : 0;
                     const int idx = __shfl_sync(0xffffffffu, cur[m >> 3], 4 * (m & 7) + rsub);
                     const bool ok = idx >= 0;
-                    const uint32_t dst = dst0 + (uint32_t)(tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
+                    const uint32_t dst = dst0 + (uint32_t)(u * SUB_BYTES + tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
                     // rows without a neighbour get zeros from a plain 16-byte shared store, not from a 0-byte cp.async:
                     // an LDGSTS that mixes copying and zero-filling lanes costs extra shared-memory wavefronts (ncu:
                     // half of the LSU wavefronts of the K = 729 layer were such conflicts, profiles/r1_ncu_spconv_tc.md)
                     if (ok) cp_async16_full(dst, (src + (unsigned)(tile * 64)) + (unsigned long long)(unsigned)idx * row_bytes);
                     else st_shared_zero16(dst);
                 }
+              }
             }
             cp_async_arrive_noinc(full_s);
 #pragma unroll
@@ -480,6 +495,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         if (t == 0) { TC_PROF(5, e1 - t_main); TC_PROF(11, e1 - e0); }
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += C_BEGIN_STEP) {
+            if (a.debug & 256) break;                     // timing experiment: no epilogue
             uint32_t v[16], w[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
@@ -551,11 +567,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                     const int s = it % STAGES;
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    const size_t blk = (((size_t)g * a.K + k) * nchunks + c) * ntn + blockIdx.y;
                     const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)B_BYTES;
-                    mbar_expect_tx(full0 + 8 * s, nbytes);
-                    bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + A_TILE), a.wimg + blk * (size_t)B_BYTES, nbytes,
-                                  full0 + 8 * s);
+                    mbar_expect_tx(full0 + 8 * s, CPS * nbytes);
+#pragma unroll
+                    for (int u = 0; u < CPS; ++u) {
+                        const size_t blk = (((size_t)g * a.K + k) * (nchunks * CPS) + c * CPS + u) * ntn + blockIdx.y;
+                        bulk_copy_g2s(base + (uint32_t)(s * STAGE_BYTES + u * SUB_BYTES + A_TILE), a.wimg + blk * (size_t)B_BYTES, nbytes,
+                                      full0 + 8 * s);
+                    }
                 }
             }
         }
@@ -576,7 +595,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                 const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
                 // a 128-byte row holds [hi k0..31 | lo k0..31]: hi k-step kk at +32 kk bytes, lo at +64 + 32 kk bytes
                 const uint64_t da = make_desc(sa), db = make_desc(sa + A_TILE);
-                if constexpr (STK) {
+                if constexpr (CPS > 1) {
+#pragma unroll
+                    for (int u = 0; u < CPS; ++u) {
+                        const uint64_t dau = make_desc(sa + u * SUB_BYTES), dbu = make_desc(sa + u * SUB_BYTES + A_TILE);
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk) {
+                            if (a.debug & 16) break;
+                            const uint64_t hi = (uint64_t)(kk * 2), lo = (uint64_t)(4 + kk * 2);     // in 16-byte units
+                            umma_bf16(tmem_base, dau + hi, dbu + hi, IDESC, (it | u | kk) ? 1u : 0u);
+                            umma_bf16(tmem_base, dau + hi, dbu + lo, IDESC, 1u);
+                            umma_bf16(tmem_base, dau + lo, dbu + hi, IDESC, 1u);
+                        }
+                    }
+                } else if constexpr (STK) {
                     const uint64_t dal = make_desc(sa + A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < KCH / 16; ++kk) {
@@ -734,18 +766,18 @@ void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_ti
     }
 }
 
-template <int NT, int STAGES, bool STASH, bool STK = false, bool TMAG = false>
+template <int NT, int STAGES, bool STASH, bool STK = false, bool TMAG = false, int CPS = 1>
 int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t s) {
-    constexpr int smem = STAGES * (STK ? 3 * A_BYTES : A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
+    constexpr int smem = STAGES * (STK ? 3 * A_BYTES : CPS * (A_BYTES + NT * 128)) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT, a.ksplit);
-    spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG><<<grid, NTHREADS, smem, s>>>(a, tmap);
+    spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS><<<grid, NTHREADS, smem, s>>>(a, tmap);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -811,8 +843,8 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
         a.out = splitk_ws; a.ldo = Cout; a.scale = a.shift = a.residual = nullptr; a.act = 0; a.out_split = nullptr;
         a.ksplit = ks; a.zstride = (long long)n_out * Cout;
     }
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    int dbg = 0;                                       // timing experiments (development): read per call, tools/conv_probe2.py
+    { const char* e = getenv("CG3D_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     a.debug = dbg;
     if (tiles == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -856,7 +888,18 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return -4;
     }
+    static int cps2 = -1;
+    if (cps2 < 0) { const char* e = getenv("CG3D_TC_CPS"); cps2 = (e ? atoi(e) : 2) == 2 ? 1 : 0; }
     int rc;
+    // CG3D_TC_V4=1: launches without split-K go to the persistent kernel (spconv_tc4.cu: one CTA per SM, overlapped epilogue;
+    // same bits).  Opt-in: measured 10-25 % SLOWER than two CTAs per SM of the kernel below, which overlap one tile's
+    // prologue / epilogue with the other's K loop already and have twice the gather warps (profiles/r2_conv_skeleton_ablation.md)
+    static int v4 = -1;
+    if (v4 < 0) { const char* e = getenv("CG3D_TC_V4"); v4 = e ? atoi(e) : 0; }
+    if (v4 && ks == 1 && !stacked && !use_tma && !dense && !dbg && (NT != 64 || Cin % 64 == 0)) {
+        return cg3d_spconv_tc4_launch(in_split, nbr, wimg, out, ldo, n_out, Cin, Cout, K, scale, shift, residual, act, tile_row0,
+                                      tile_rows, tile_group, tiles, out_rows, out_split, out_split_relu, NT, stream);
+    }
     if (stacked)
         rc = stash ? launch_tc<64, 2, true, true>(a, tmap, tiles, s) : launch_tc<64, 2, false, true>(a, tmap, tiles, s);
     else if (use_tma || dense) {
@@ -866,6 +909,9 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
         else
             rc = NT == 256 ? launch_tc<256, 2, false, false, true>(a, tmap, tiles, s)
                            : (NT == 128 ? launch_tc<128, 3, false, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, false, false, true>(a, tmap, tiles, s));
+    } else if (NT == 64 && cps2 && Cin % 64 == 0) {
+        // 64-column tiles: two 32-channel sub-tiles per barrier phase (2 stages of 48 KB instead of 4 of 24 KB)
+        rc = stash ? launch_tc<64, 2, true, false, false, 2>(a, tmap, tiles, s) : launch_tc<64, 2, false, false, false, 2>(a, tmap, tiles, s);
     } else if (stash)
         rc = NT == 256 ? launch_tc<256, 2, true>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tmap, tiles, s) : launch_tc<64, 4, true>(a, tmap, tiles, s));
     else

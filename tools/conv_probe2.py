@@ -19,17 +19,25 @@ def main():
     S._call = orig
     torch.cuda.synchronize()
     for name, args in rec:
-        if name != "cg3d_spconv_pairs":
+        if name != ("cg3d_spconv_pairs" if os.environ.get("CG3D_PAIRS", "0") == "1" else "cg3d_spconv_tc"):
             continue
-        K = args[8]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        orig(name, *args)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
+        K = args[8] if name == "cg3d_spconv_pairs" else args[9]
+        if K < int(os.environ.get("PROBE_MIN_K", "27")):
+            continue
+        n_out = args[5] if name == "cg3d_spconv_pairs" else args[6]
+        line = f"{name} K={K} n_out={n_out} Cin={args[6] if name == 'cg3d_spconv_pairs' else args[7]}"
+        for dbg in os.environ.get("PROBE_DEBUGS", "0").split(","):
+            os.environ["CG3D_TC_DEBUG"] = dbg                 # timing ablations of the SAME launch (results are garbage for dbg != 0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             orig(name, *args)
-        e1.record()
-        torch.cuda.synchronize()
-        print(f"{name} K={K} n_out={args[5]} {e0.elapsed_time(e1) / 3:.3f} ms")
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                orig(name, *args)
+            e1.record()
+            torch.cuda.synchronize()
+            line += f"  dbg{dbg}: {e0.elapsed_time(e1) / 3:.3f} ms"
+        os.environ["CG3D_TC_DEBUG"] = "0"
+        print(line)
 
 main()
