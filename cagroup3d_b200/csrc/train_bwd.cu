@@ -320,12 +320,15 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ part, int C, in
 
 // out[u] = sum of src[order[j]] over j in [seg_off[u], seg_off[u+1]) in that order: the scatter-add of a gather whose index
 // map is not injective (RoI pooling contraction backward), made deterministic by a stable sort of the point ids by target row
+constexpr int SEG_LONG = 512;      // segments with more points than this get a whole CTA (segment_sum_long_kernel)
+
 __global__ void segment_sum_sorted_kernel(const float* __restrict__ src, const int* __restrict__ order,
                                           const int* __restrict__ seg_off, int n_seg, int C, float* __restrict__ out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int u = warp; u < n_seg; u += nwarps) {
         const int j0 = __ldg(seg_off + u), j1 = __ldg(seg_off + u + 1);
+        if (j1 - j0 > SEG_LONG) continue;
         for (int ch0 = 0; ch0 < C; ch0 += 32 * IB_CPL) {
             float acc[IB_CPL];
 #pragma unroll
@@ -344,6 +347,55 @@ __global__ void segment_sum_sorted_kernel(const float* __restrict__ src, const i
                 if (ch < C) out[(size_t)u * C + ch] = acc[q];
             }
         }
+    }
+}
+
+// A segment of tens of thousands of points (all grid points of the zero-padded / degenerate RoIs of a training batch fall
+// into ONE voxel: 43 218 of 175 616 points in the config-4 step, 21 ms on a single warp): one CTA per long segment, each of
+// its 8 warps adds a contiguous eighth of the points in order, the eight partial sums are added in warp order -- a fixed
+// association, so the result is bit-repeatable.  CTAs of short segments exit at once.
+__global__ void __launch_bounds__(256) segment_sum_long_kernel(const float* __restrict__ src, const int* __restrict__ order,
+                                                               const int* __restrict__ seg_off, int C, float* __restrict__ out) {
+    __shared__ float part[8][32 * IB_CPL];
+    const int u = blockIdx.x;
+    const int j0 = __ldg(seg_off + u), j1 = __ldg(seg_off + u + 1);
+    if (j1 - j0 <= SEG_LONG) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (j1 - j0 + 7) / 8, a0 = j0 + w * per, a1 = min(j1, a0 + per);
+    for (int ch0 = 0; ch0 < C; ch0 += 32 * IB_CPL) {
+        float acc[IB_CPL];
+#pragma unroll
+        for (int q = 0; q < IB_CPL; ++q) acc[q] = 0.f;
+        for (int jb = a0; jb < a1; jb += 8) {              // eight rows in flight per warp: the loads are independent,
+            float v[8][IB_CPL];                            // the additions stay in point order
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const bool ok = jb + t < a1;
+                const float* row = src + (size_t)(ok ? __ldg(order + jb + t) : 0) * C;
+#pragma unroll
+                for (int q = 0; q < IB_CPL; ++q) {
+                    const int ch = ch0 + q * 32 + lane;
+                    v[t][q] = (ok && ch < C) ? __ldg(row + ch) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+#pragma unroll
+                for (int q = 0; q < IB_CPL; ++q) acc[q] += v[t][q];
+        }
+#pragma unroll
+        for (int q = 0; q < IB_CPL; ++q) part[w][q * 32 + lane] = acc[q];
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int q = 0; q < IB_CPL; ++q) {
+                float t = part[0][q * 32 + lane];
+                for (int k = 1; k < 8; ++k) t += part[k][q * 32 + lane];
+                const int ch = ch0 + q * 32 + lane;
+                if (ch < C) out[(size_t)u * C + ch] = t;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -456,6 +508,7 @@ int cg3d_segment_sum_sorted(const float* src, const int* order, const int* seg_o
     if (n_seg == 0 || C == 0) return 0;
     segment_sum_sorted_kernel<<<flat_blocks((long long)n_seg * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, order, seg_off, n_seg,
                                                                                                          C, out);
+    segment_sum_long_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(src, order, seg_off, C, out);
     CG3D_LAUNCH_CHECK();
     return 0;
 }

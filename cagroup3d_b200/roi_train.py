@@ -16,6 +16,7 @@ The proposal target layer and the RoI losses (cagroup_proposal_target_layer.py, 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -59,6 +60,8 @@ class PoolTableConvFunction(torch.autograd.Function):
             S._call("cg3d_histogram_i32", tgt, npts, n_in, counts)
             seg_off, _ = S.exclusive_scan(counts)
             dX = torch.empty((n_in, Cin), dtype=torch.float32, device=dev)
+            if os.environ.get("CG3D_TRAIN_DEBUG"):
+                print(f"[pool dX] taps {T} rois {nr} points {npts} unique voxels {n_in} Cin {Cin} max segment {int(counts.max())}", flush=True)
             S._call("cg3d_segment_sum_sorted", G, order, seg_off, n_in, Cin, dX)
         if ctx.needs_input_grad[1]:
             dW = A.wgrad(X.detach(), table, dY, T).reshape(W.shape)

@@ -675,3 +675,29 @@ def test_two_stage_training_step_on_device(lib):
     red = D.GradientAllReducer(params)
     losses = [TS.training_step(model, mk(), opt, red, grad_norm_clip=10.0)["one_stage_loss"] for _ in range(4)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_segment_sum_sorted_long_segments(lib):
+    """cg3d_segment_sum_sorted with segments of tens of thousands of points (the zero-padded RoIs of a training batch all
+    reach ONE grid voxel): the long segments go to a CTA each; same sums as index_add in fp64, bit-repeatable."""
+    from cagroup3d_b200 import sparse as S
+    g = torch.Generator().manual_seed(4)
+    n_seg, npts, C = 3000, 120000, 128
+    tgt = torch.randint(0, n_seg, (npts,), generator=g, dtype=torch.int32)
+    tgt[:40000] = 7                                             # one segment of > 40 000 points
+    tgt[40000:41000] = 2999                                     # and one of ~1 000 (also above the per-warp limit)
+    Gm = torch.randn((npts, C), generator=g)
+    keys, order = tgt.to(torch.int64).to(DEV), torch.arange(npts, dtype=torch.int32, device=DEV)
+    S.sort_pairs(keys, order, npts, end_bit=12)
+    counts = torch.zeros((n_seg + 1,), dtype=torch.int32, device=DEV)
+    S._call("cg3d_histogram_i32", tgt.to(DEV), npts, n_seg, counts)
+    seg_off, _ = S.exclusive_scan(counts)
+    outs = []
+    for _ in range(2):
+        out = torch.empty((n_seg, C), device=DEV)
+        S._call("cg3d_segment_sum_sorted", Gm.to(DEV), order, seg_off, n_seg, C, out)
+        outs.append(out)
+    torch.cuda.synchronize()
+    want = torch.zeros((n_seg, C), dtype=torch.float64).index_add_(0, tgt.long(), Gm.double())
+    assert torch.equal(outs[0], outs[1])
+    _close(outs[0], want, 2e-6 * 200)                          # ~40 000 fp32 additions in the long segment
