@@ -54,6 +54,12 @@ int cg3d_spconv_tc4_launch(const unsigned short* in_split, const int* nbr, const
                            const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
                            unsigned short* out_split, int out_split_relu, int NT, void* stream);
 
+// 64-column tiles with the gathered operand in tensor memory (spconv_ts.cu)
+int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
+                          int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
+                          const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
+                          unsigned short* out_split, int out_split_relu, int ksplit, long long zstride, int debug, void* stream);
+
 namespace {
 
 constexpr int TM = 128;            // output rows per CTA (UMMA M)
@@ -424,15 +430,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                     else if (a.nbr) v = (a.debug & 64) ? row0 + r : __ldg(a.nbr + (size_t)k * a.n_out + row0 + r);
                     else v = a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
                 }
-                dst[j] = (a.debug & 2) ? -1 : v;
+                dst[j] = v;     // (no use of v here: the warp must not wait for the index load it has just issued)
             }
         };
         int cur[RW / 32], nxt[RW / 32];
         if (slot < n_iters) fetch(slot, cur);
         uint32_t ph = 1u;                              // parity to wait for on the slot's empty barrier
+        // A shared-memory position of the slot is always written by the same lane, so the lane knows what it left there:
+        // bit 4 (m & 7) of dirty[m >> 3] = "my piece of 4-row group m holds data" (initially: garbage).  Rows without a
+        // neighbour are zeroed only where the previous phase of the slot left data -- at 13 % occupancy (the 9^3 class
+        // conv) that drops ~3/4 of the zero stores, which were 30 % of the stage's shared-memory wavefronts.
+        uint32_t dirty[RW / 32];
+#pragma unroll
+        for (int j = 0; j < RW / 32; ++j) dirty[j] = 0x11111111u;
+        const bool lazy_zero = !(a.debug & 8192);      // 8192 (timing experiment): zero every empty row, as before
 #pragma unroll 1
         for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
             if (q + STAGES < n_iters) fetch(q + STAGES, nxt);
+            // rows of this stage with a neighbour as this lane's copies see them: lane 4 (m & 7) + rsub holds the rule-map
+            // entry of the row its copy of group m fills
+            uint32_t okm[RW / 32], zm[RW / 32];
+#pragma unroll
+            for (int j = 0; j < RW / 32; ++j) {
+                okm[j] = (__ballot_sync(0xffffffffu, cur[j] >= 0 && !(a.debug & 2)) >> rsub) & 0x11111111u;
+                zm[j] = lazy_zero ? (dirty[j] & ~okm[j]) : ~okm[j];
+                dirty[j] = okm[j];
+            }
             const long long p1 = clock64();
             mbar_wait(empty_s, ph);
             if (t == 0) TC_PROF(8, clock64() - p1);
@@ -445,13 +468,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                     const int m = STK ? (i >> 1) : i;             // 4-row group; STK: copy i fills tile i & 1 (hi, lo)
                     const int tile = STK ? (i & 1) : 0;
                     const int idx = __shfl_sync(0xffffffffu, cur[m >> 3], 4 * (m & 7) + rsub);
-                    const bool ok = idx >= 0;
+                    const bool ok = (okm[m >> 3] >> (4 * (m & 7))) & 1u;
+                    const bool zero = (zm[m >> 3] >> (4 * (m & 7))) & 1u;
                     const uint32_t dst = dst0 + (uint32_t)(u * SUB_BYTES + tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
                     // rows without a neighbour get zeros from a plain 16-byte shared store, not from a 0-byte cp.async:
                     // an LDGSTS that mixes copying and zero-filling lanes costs extra shared-memory wavefronts (ncu:
                     // half of the LSU wavefronts of the K = 729 layer were such conflicts, profiles/r1_ncu_spconv_tc.md)
                     if (ok) cp_async16_full(dst, (src + (unsigned)(tile * 64)) + (unsigned long long)(unsigned)idx * row_bytes);
-                    else st_shared_zero16(dst);
+                    else if (zero) st_shared_zero16(dst);
                 }
               }
             }
@@ -900,7 +924,14 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
         return cg3d_spconv_tc4_launch(in_split, nbr, wimg, out, ldo, n_out, Cin, Cout, K, scale, shift, residual, act, tile_row0,
                                       tile_rows, tile_group, tiles, out_rows, out_split, out_split_relu, NT, stream);
     }
-    if (stacked)
+    // 64-column tiles: the gathered operand lives in TMEM (spconv_ts.cu), CG3D_TC_TS=0 restores the shared-memory kernel
+    const char* ts_env = getenv("CG3D_TC_TS");
+    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && !stacked && !use_tma && !dense;
+    if (ts)
+        rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
+                                   a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,
+                                   a.ksplit, a.zstride, dbg, stream);
+    else if (stacked)
         rc = stash ? launch_tc<64, 2, true, true>(a, tmap, tiles, s) : launch_tc<64, 2, false, true>(a, tmap, tiles, s);
     else if (use_tma || dense) {
         if (stash)
