@@ -926,7 +926,9 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     }
     // 64-column tiles: the gathered operand lives in TMEM (spconv_ts.cu), CG3D_TC_TS=0 restores the shared-memory kernel
     const char* ts_env = getenv("CG3D_TC_TS");
-    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && !stacked && !use_tma && !dense;
+    // (split-K launches stay on the shared-memory kernel: few tiles of dense taps, where the per-thread row loads of the
+    // TMEM gather are L1-bound -- 7^3 RoI pooling contraction 0.31 vs 0.35 ms)
+    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && ks == 1 && !stacked && !use_tma && !dense;
     if (ts)
         rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
                                    a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,

@@ -33,17 +33,27 @@ namespace {
 constexpr int TM = 128;            // output rows per CTA (UMMA M) = TMEM lanes
 constexpr int NT = 64;             // output columns per CTA
 constexpr int KCH = 64;            // channels per stage
-constexpr int SA = 3;              // pipeline stages: A in TMEM, B (weights) in shared memory, one barrier pair per stage
-constexpr int SB = SA;
 constexpr int B_BYTES = NT * 128;  // one 32-channel weight sub-tile [n][hi 32 | lo 32]
 constexpr int STAGE_B = 2 * B_BYTES;
-constexpr int NGW = 8;             // gather / epilogue warps
-constexpr int NTHREADS = (NGW + 2) * 32;
 constexpr int STASH_K = 27;
 constexpr int MAX_TAPS = 729;
-constexpr int TCOLS = 256;         // accumulator 64 + 3 A stages of 64 columns (32 words hi/lo per 32-channel half)
-constexpr int EPI_BYTES = NGW * 32 * 36 * 4;
+constexpr int NEPI = 8;            // epilogue warps (the first eight gather warps)
+constexpr int EPI_BYTES = NEPI * 32 * 36 * 4;
+// Shape: NG = 2 gather warp groups of four warps (group g fills the stages q = g (mod NG)), 10 warps, two CTAs per SM (256
+// TMEM columns each: accumulator + 3 A stages), so the prologue / epilogue of one tile overlaps the K loop of the other and
+// every SM has two MMA-issuing and two weight-loading warps.  (A one-CTA-per-SM shape with four groups, two MMA warps and two
+// accumulators was built and measured: equal on the 9^3 conv, 7 % faster on the 5^3 one, 35 % slower on K = 27 layers, and
+// its two accumulators make a row's sum depend on which taps its tile skips -- dropped.)
+// A group that waits for a slot's previous use to be consumed filled its last stage NG stages ago, after the MMAs of the
+// stage NG + SA back had completed; with SA >= NG that covers the slot's use before last, so a parity wait is unambiguous.
+constexpr int NG = 2;
+constexpr int SA = 3;              // A stages in TMEM
+constexpr int SB = 5;              // weight stages in shared memory (own ring, see the barriers)
+constexpr int NGW = 4 * NG;        // gather warps
+constexpr int NTHREADS = (NGW + 2) * 32;
+constexpr int TCOLS = NT + SA * KCH;   // 256
 constexpr int RING_BYTES = SB * STAGE_B > EPI_BYTES ? SB * STAGE_B : EPI_BYTES;
+constexpr int A_COL0 = NT;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -59,11 +69,11 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+        : "r"(bar), "r"(parity), "r"(0x989680u)          // suspend-time hint: sleep in hardware until the phase flips instead of
+        : "memory");                                     // spinning (16 gather warps polling starve the loader / MMA warps of issue slots)
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -72,10 +82,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity))
         if (clock64() - t0 > 8000000000LL) __trap();     // ~4 s watchdog: a protocol bug must not hang the GPU
 }
+// called by all lanes of a converged warp, one elected lane issues (see umma_ts_bf16)
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -91,16 +111,78 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 // D[tmem] (+)= A[tmem] x B[smem]: A = 128 lanes x 8 columns (16 bf16 of the row, two per 32-bit column)
+// Called by ALL lanes of a converged warp; one elected lane issues.  (Issued from an `if (lane == 0)` branch, ptxas wraps every
+// tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes -- ~70 clk per instruction in the ncu source view, which
+// is what looked like an "issue floor" of one MMA per 52 - 59 clk per thread.)
 __device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+// The 12 MMAs of a 64-channel stage (2 halves x 2 k-steps x {hi*hi, hi*lo, lo*hi}) in ONE block with ONE election: issued one
+// by one from C++, every tcgen05.mma drags an ELECT, two VOTEU and 4 - 6 R2UR.BROADCAST along (~200 instructions per stage
+// on the issuing warp, which runs them in order: 75 % of its time in the ncu source view).
+//   a: TMEM column address of the stage's A tile ([hi 16 words | lo 16 words] per 32-channel half, a k-step = 8 words)
+//   b: shared-memory descriptor of the stage's first weight sub-tile (the second one B_BYTES further = +512 in 16-byte
+//      units; inside a 128-byte row: hi k-step kk at +2 kk, lo at +4 + 2 kk)
+__device__ __forceinline__ void umma_ts_stage(uint32_t tmem_d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t accum_first) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q, p;\n\t"
+        ".reg .b32 ta;\n\t"
+        ".reg .b64 tb;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.u32 ta, %1, 0;\n\t"
+        "add.u64 tb, %2, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "add.u32 ta, %1, 0;\n\t"
+        "add.u64 tb, %2, 4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 16;\n\t"
+        "add.u64 tb, %2, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 8;\n\t"
+        "add.u64 tb, %2, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 8;\n\t"
+        "add.u64 tb, %2, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 24;\n\t"
+        "add.u64 tb, %2, 2;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 32;\n\t"
+        "add.u64 tb, %2, 512;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 32;\n\t"
+        "add.u64 tb, %2, 516;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 48;\n\t"
+        "add.u64 tb, %2, 512;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 40;\n\t"
+        "add.u64 tb, %2, 514;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 40;\n\t"
+        "add.u64 tb, %2, 518;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "add.u32 ta, %1, 56;\n\t"
+        "add.u64 tb, %2, 514;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "r"(a), "l"(b), "r"(idesc), "r"(accum_first)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -118,6 +200,30 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint4& a, const 
           "r"(c.z), "r"(c.w), "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w)
         : "memory");
 }
+// the warp's 32 lanes x 64 consecutive columns in one instruction
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint4 (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, "
+        "%33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+        "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+        ::"r"(taddr),
+          "r"(v[0].x), "r"(v[0].y), "r"(v[0].z), "r"(v[0].w), "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w),
+          "r"(v[2].x), "r"(v[2].y), "r"(v[2].z), "r"(v[2].w), "r"(v[3].x), "r"(v[3].y), "r"(v[3].z), "r"(v[3].w),
+          "r"(v[4].x), "r"(v[4].y), "r"(v[4].z), "r"(v[4].w), "r"(v[5].x), "r"(v[5].y), "r"(v[5].z), "r"(v[5].w),
+          "r"(v[6].x), "r"(v[6].y), "r"(v[6].z), "r"(v[6].w), "r"(v[7].x), "r"(v[7].y), "r"(v[7].z), "r"(v[7].w),
+          "r"(v[8].x), "r"(v[8].y), "r"(v[8].z), "r"(v[8].w), "r"(v[9].x), "r"(v[9].y), "r"(v[9].z), "r"(v[9].w),
+          "r"(v[10].x), "r"(v[10].y), "r"(v[10].z), "r"(v[10].w), "r"(v[11].x), "r"(v[11].y), "r"(v[11].z), "r"(v[11].w),
+          "r"(v[12].x), "r"(v[12].y), "r"(v[12].z), "r"(v[12].w), "r"(v[13].x), "r"(v[13].y), "r"(v[13].z), "r"(v[13].w),
+          "r"(v[14].x), "r"(v[14].y), "r"(v[14].z), "r"(v[14].w), "r"(v[15].x), "r"(v[15].y), "r"(v[15].z), "r"(v[15].w)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
     uint4 v;
@@ -129,6 +235,7 @@ __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
 __device__ unsigned long long g_ts_prof[16];
 #define TS_PROF(i, v) do { if (PROF) atomicAdd(&g_ts_prof[i], (unsigned long long)(v)); } while (0)
 #define TS_CLK() (PROF ? clock64() : 0LL)
+#define TS_DBG(bit) (PROF && (a.debug & (bit)))
 
 struct TsArgs {
     const unsigned short* in_split;   // [rows][Cin/32][hi 32 | lo 32] bf16
@@ -161,11 +268,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
     unsigned char* const ring = smem_raw + (base - smem_u32(smem_raw));
     int* nbr_s = reinterpret_cast<int*>(ring + RING_BYTES);          // STASH: rule-map columns of this tile, [K][TM]
 
-    __shared__ __align__(8) unsigned long long bars[2 * SA + 1];
+    __shared__ __align__(8) unsigned long long bars[2 * SA + 2 * SB + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ unsigned short taps[KCAP];
     __shared__ unsigned char active[KCAP];
     __shared__ int n_active_s;
+    // K > 27: the rule-map entries a gather thread needs come through a private 3-deep cp.async ring (issued two of the
+    // thread's stages ahead).  A register load would be cheaper in instructions, but its scoreboard is shared with the
+    // row loads whose destination registers the next stage overwrites, and the warp then waits for the index it has just
+    // requested (720 clk per stage in the ncu source view of the first version).
+    __shared__ int idx_ring[STASH ? 1 : 3 * NGW * 32];
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     int row0, nrows, g = 0;
@@ -184,13 +296,24 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
     const int nchunks = a.Cin / KCH;
     const int ntn = a.Cout / NT;
 
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SA]), accum_bar = smem_u32(&bars[2 * SA]);
+    // The weight ring is DEEPER than the A ring and has its own barriers: a weight tile takes ~1500 clk from request to
+    // arrival; requested only when its A slot is released (one barrier pair for both, the first version) that latency sat
+    // in every slot's cycle and everybody waited for everybody (MMA warps, gather groups and loader each idle 25 - 50 %).
+    //   fullB[s]:  the copy's expect_tx + bytes                      -> MMA warp
+    //   emptyB[s]: ONE software arrival, by the gather warp that sees the A slot of the stage SA later released (the MMAs of
+    //              a stage read its A and its B slot; no second tcgen05.commit on the MMA thread, ~85 clk each)
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SA]), fullB0 = smem_u32(&bars[2 * SA]),
+                   emptyB0 = smem_u32(&bars[2 * SA + SB]), accum_bar = smem_u32(&bars[2 * SA + 2 * SB]);
 
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < SA; ++s) {
-            mbar_init(full0 + 8 * s, NGW / 2 + 1);       // one arrival per warp of the group that filled the stage + the
-            mbar_init(empty0 + 8 * s, 1);                // weight copy's expect_tx
+            mbar_init(full0 + 8 * s, 4);                 // one arrival per warp of the group that filled the stage
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(fullB0 + 8 * s, 1);
+            mbar_init(emptyB0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -258,42 +381,55 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
         // group grp (warps 4 grp .. 4 grp + 3) fills the stages q = grp, grp + 2, ...; stage q lives in A slot q % SA.
         // A slot's empty barrier cannot run two phases ahead of a waiting group: the group filled stage q - 2 only after the
         // MMAs of stage q - 5 (hence q - 6, the slot's phase before last) had completed.
-        const int grp = warp >> 2, lq = warp & 3;
+        const int grp = warp >> 2, lq = warp & 3;         // lq = the warp's TMEM lane quarter
         const int r = lq * 32 + lane;
         const uint32_t row_bytes = 4u * (uint32_t)a.Cin;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)NT;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)A_COL0;
         // stage q = (active tap ai, 64-channel chunk c), A / B slot s, barrier phase parity ph: all advanced incrementally
         // (a division per stage is real money in a loop that one warp runs in order)
-        auto fetch_idx = [&](int ai) {
-            int v = -1;
-            if (r < nrows) {
-                if (STASH) v = nbr_s[(int)taps[ai] * TM + r];
-                else if (a.nbr) v = (a.debug & 64) ? ((r & 7) ? -1 : row0 + r) : __ldg(a.nbr + (size_t)taps[ai] * a.n_out + row0 + r);
-                else v = a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
-            }
-            return v;           // (no use of v here: the warp must not wait for the index load it has just issued)
-        };
-        auto advance = [&](int& ai, int& c) {             // two stages on
-            c += 2;
+        const bool in_tile = r < nrows;
+        const int* const nbr_row = a.nbr ? a.nbr + row0 + r : nullptr;
+        const uint32_t ring0 = smem_u32(&idx_ring[STASH ? 0 : t * 3]);
+        auto advance = [&](int& ai, int& c) {             // NG stages on
+            c += NG;
             while (c >= nchunks) { c -= nchunks; ++ai; }
         };
-        const bool no_loads = (a.debug & 2) != 0;
+        // rule-map entry of (tap index ai, this row): STASH / no map -> value now; else request it into ring slot `slot`
+        auto request = [&](int ai, int slot, bool live) {
+            if (!STASH && a.nbr) {
+                if (live && in_tile) cp_async4(ring0 + 4 * slot, nbr_row + (size_t)taps[ai] * a.n_out);
+                cp_async_commit();
+            }
+        };
+        auto obtain = [&](int ai, int slot) {
+            if (!in_tile) return -1;
+            if (STASH) return nbr_s[(int)taps[ai] * TM + r];
+            if (a.nbr) return TS_DBG(64) ? ((r & 7) ? -1 : row0 + r) : idx_ring[t * 3 + slot];
+            return a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
+        };
         int ai = a0, c = grp;                             // stage q = grp
         while (c >= nchunks) { c -= nchunks; ++ai; }
-        int ai_n = ai, c_n = c;                           // stage q + 2
-        advance(ai_n, c_n);
-        int cur = grp < n_iters ? fetch_idx(ai) : -1;
-        int s = grp;                                      // SA = 3 > grp
+        int ai_1 = ai, c_1 = c;                           // stage q + NG
+        advance(ai_1, c_1);
+        int ai_2 = ai_1, c_2 = c_1;                       // stage q + 2 NG
+        advance(ai_2, c_2);
+        request(ai, 0, grp < n_iters);
+        request(ai_1, 1, grp + NG < n_iters);
+        int slot = 0;                                     // ring slot of stage q
+        int s = grp;                                      // SA > grp
+        int sb_rel = (grp - SA + 2 * SB) % SB;            // weight slot of stage q - SA
         uint32_t ph = 1u;                                 // parity to wait for on the slot's empty barrier
         long long g_wait = 0, g_st = 0, g_idx = 0, g_ld = 0;
         const long long g_t0 = TS_CLK();
 #pragma unroll 1
-        for (int q = grp; q < n_iters; q += 2) {
+        for (int q = grp; q < n_iters; q += NG) {
             const long long i0 = TS_CLK();
-            const int nxt = q + 2 < n_iters ? fetch_idx(ai_n) : -1;
+            if (!STASH && a.nbr) cp_async_wait<1>();       // the request of stage q has landed (q + NG's may be in flight)
+            const int cur = obtain(ai, slot);
+            request(ai_2, slot == 0 ? 2 : slot - 1, q + 2 * NG < n_iters);
             const long long i1 = TS_CLK();
             uint4 v[16];
-            if (cur >= 0 && !no_loads) {
+            if (cur >= 0 && !TS_DBG(2)) {
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(a.in_split) + (size_t)(unsigned)cur * row_bytes + (unsigned)(c * 256);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = ldg_nc16(src + 16 * j);
@@ -304,26 +440,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
             const long long w0 = TS_CLK();
             mbar_wait(empty0 + 8 * s, ph);
             tc_fence_after();
+            if (lq == 0 && lane == 0 && q >= SA) mbar_arrive(emptyB0 + 8 * sb_rel);      // stage q - SA has been consumed
             const long long w1 = TS_CLK();
-            const uint32_t ta = t_lane + (uint32_t)(s * KCH);
-            if (!(a.debug & 4)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) tmem_st16(ta + 16 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (!TS_DBG(4)) {
+                tmem_st64(t_lane + (uint32_t)(s * KCH), v);
                 tmem_st_wait();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);
-            cur = nxt;
-            c = c_n;
-            advance(ai_n, c_n);
-            s += 2;
+            ai = ai_1; c = c_1;
+            ai_1 = ai_2; c_1 = c_2;
+            advance(ai_2, c_2);
+            slot = slot == 2 ? 0 : slot + 1;
+            s += NG;
             if (s >= SA) { s -= SA; ph ^= 1u; }
+            sb_rel += NG;
+            if (sb_rel >= SB) sb_rel -= SB;
             if (PROF) { g_wait += w1 - w0; g_st += clock64() - w1; g_idx += i1 - i0; g_ld += w0 - i1; }
         }
+        if (!STASH && a.nbr) cp_async_wait<0>();
         if (t == 0) { TS_PROF(0, 1); TS_PROF(1, n_iters); TS_PROF(2, TS_CLK() - g_t0); TS_PROF(3, g_wait); TS_PROF(4, g_st); TS_PROF(10, g_idx); TS_PROF(11, g_ld); }
         // ================= epilogue: warp -> TMEM lane quarter (warp % 4), column half (warp / 4) =========
         // (as spconv_tc.cu: 32-column panels transposed through a private shared-memory patch, 128-byte row segments out)
+      if (warp < NEPI) {
         const int half = warp >> 2;
         const int prow = (r < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r) : -1;
         float* stg = reinterpret_cast<float*>(ring) + warp * (32 * 36);
@@ -345,7 +485,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
             mbar_wait(accum_bar, 0);                      // every MMA has completed: the weight ring is idle as well
             tc_fence_after();
         }
-        if (!(a.debug & 256)) {
+        if (!TS_DBG(256)) {
             uint32_t va[16], vb[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, va);
@@ -390,69 +530,65 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
                 }
             }
         }
+      }
         tc_fence_before();
     } else if (warp == NGW) {
         // ================= weight-tile loader (bulk async copy): two 32-channel sub-tiles per stage =================
-        if (lane == 0) {
-            int it = 0;
-            long long l_wait = 0;
+        {                                                 // the whole warp runs the loop, one elected lane issues
+            long long l_wait = 0, l_copy = 0;
             const long long l_t0 = TS_CLK();
+            // everything the loop needs is advanced incrementally: ~20 dependent instructions per stage instead of ~60
+            // (a single in-order warp pays 5 - 20 clk for each IMAD.WIDE / S2UR / R2UR of an address rebuilt from scratch)
+            const uint32_t nbytes = TS_DBG(1) ? 32u : (uint32_t)STAGE_B;
+            const size_t tap_stride = (size_t)(nchunks * 2) * ntn * B_BYTES;            // bytes between taps of the image
+            const unsigned char* const w_g = a.wimg + ((size_t)g * a.K * (nchunks * 2) * ntn + blockIdx.y) * (size_t)B_BYTES;
+            const size_t chunk_stride = (size_t)2 * ntn * B_BYTES;                      // one 64-channel stage further
+            int s = 0;
+            uint32_t ph = 1u;
+            uint32_t dst = base, fb = fullB0, eb = emptyB0;
             for (int ai = a0; ai < a1; ++ai) {
-                const int k = taps[ai];
-                for (int c = 0; c < nchunks; ++c, ++it) {
-                    const int s = it % SB;
+                const unsigned char* src = w_g + (size_t)taps[ai] * tap_stride;
+                for (int c = 0; c < nchunks; ++c, src += chunk_stride) {
                     const long long w0 = TS_CLK();
-                    mbar_wait(empty0 + 8 * s, (uint32_t)((it / SB) & 1) ^ 1u);
-                    l_wait += TS_CLK() - w0;
-                    const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)B_BYTES;
-                    const size_t blk = (((size_t)g * a.K + k) * (nchunks * 2) + c * 2) * ntn + blockIdx.y;
+                    mbar_wait(eb, ph);
+                    const long long w1 = TS_CLK();
+                    l_wait += w1 - w0;
+                    mbar_expect_tx_elect(fb, nbytes);
                     if (ntn == 1) {                       // the stage's two 32-channel sub-tiles are contiguous in the image
-                        mbar_expect_tx(full0 + 8 * s, 2 * nbytes);
-                        bulk_copy_g2s(base + (uint32_t)(s * STAGE_B), a.wimg + blk * (size_t)B_BYTES, 2 * nbytes, full0 + 8 * s);
+                        bulk_copy_g2s(dst, src, nbytes, fb);
                     } else {
-                        mbar_expect_tx(full0 + 8 * s, 2 * nbytes);
-#pragma unroll
-                        for (int u = 0; u < 2; ++u)
-                            bulk_copy_g2s(base + (uint32_t)(s * STAGE_B + u * B_BYTES), a.wimg + (blk + (size_t)u * ntn) * (size_t)B_BYTES,
-                                          nbytes, full0 + 8 * s);
+                        bulk_copy_g2s(dst, src, nbytes / 2, fb);
+                        bulk_copy_g2s(dst + B_BYTES, src + (size_t)ntn * B_BYTES, nbytes / 2, fb);
                     }
+                    l_copy += TS_CLK() - w1;
+                    if (++s == SB) { s = 0; ph ^= 1u; dst = base; fb = fullB0; eb = emptyB0; }
+                    else { dst += STAGE_B; fb += 8; eb += 8; }
                 }
             }
-            TS_PROF(5, l_wait); TS_PROF(6, TS_CLK() - l_t0);
+            if (lane == 0) { TS_PROF(5, l_wait); TS_PROF(6, TS_CLK() - l_t0); TS_PROF(12, l_copy); }
         }
         __syncwarp();
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            long long m_wb = 0, m_wa = 0, m_is = 0;
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+        {
+            long long m_wa = 0, m_is = 0;
+            int sa = 0, sb = 0;
+            uint32_t ph = 0u, phb = 0u;
             for (int it = 0; it < n_iters; ++it) {
-                const int sa = it % SA, sb = sa;
-                const long long m0 = TS_CLK();
-                const long long m1 = m0;
-                mbar_wait(full0 + 8 * sa, (uint32_t)(it / SA) & 1u);
+                const long long m1 = TS_CLK();
+                mbar_wait(fullB0 + 8 * sb, phb);
+                mbar_wait(full0 + 8 * sa, ph);
                 tc_fence_after();
                 const long long m2 = TS_CLK();
-                const uint32_t ta = tmem_base + (uint32_t)(NT + sa * KCH);
-                const uint32_t sbase = base + (uint32_t)(sb * STAGE_B);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    // TMEM columns of the 32-channel half u: [hi: 16 words | lo: 16 words]; a k-step is 8 words
-                    // shared-memory row of the weight sub-tile: [hi k0..31 | lo k0..31], k-step kk at +32 kk (+64) bytes
-                    const uint64_t db = make_desc(sbase + (uint32_t)(u * B_BYTES));
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        if (a.debug & 16) break;
-                        const uint32_t a_hi = ta + (uint32_t)(u * 32 + kk * 8), a_lo = a_hi + 16u;
-                        const uint64_t b_hi = db + (uint64_t)(kk * 2), b_lo = db + (uint64_t)(4 + kk * 2);   // 16-byte units
-                        umma_ts_bf16(tmem_base, a_hi, b_hi, IDESC, (it | u | kk) ? 1u : 0u);
-                        umma_ts_bf16(tmem_base, a_hi, b_lo, IDESC, 1u);
-                        umma_ts_bf16(tmem_base, a_lo, b_hi, IDESC, 1u);
-                    }
-                }
+                if (!TS_DBG(16))
+                    umma_ts_stage(tmem_base, tmem_base + (uint32_t)(A_COL0 + sa * KCH), make_desc(base + (uint32_t)(sb * STAGE_B)), IDESC,
+                                  it ? 1u : 0u);
                 umma_commit(empty0 + 8 * sa);
-                m_wb += m1 - m0; m_wa += m2 - m1; m_is += TS_CLK() - m2;
+                if (++sa == SA) { sa = 0; ph ^= 1u; }
+                if (++sb == SB) { sb = 0; phb ^= 1u; }
+                if (PROF) { m_wa += m2 - m1; m_is += clock64() - m2; }
             }
-            TS_PROF(7, m_wb); TS_PROF(8, m_wa); TS_PROF(9, m_is);
+            if (lane == 0) { TS_PROF(8, m_wa); TS_PROF(9, m_is); }
             if (n_iters > 0) umma_commit(accum_bar);
         }
         __syncwarp();
@@ -492,17 +628,18 @@ int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const 
              out_split_relu, n_out, Cin, Cout, K, act, ldo, ksplit, zstride, debug};
     const bool stash = nbr && K <= STASH_K;
     int rc;
-    if (debug & 8) rc = stash ? launch_ts<true, true>(a, tiles, (cudaStream_t)stream) : launch_ts<false, true>(a, tiles, (cudaStream_t)stream);
-    else rc = stash ? launch_ts<true, false>(a, tiles, (cudaStream_t)stream) : launch_ts<false, false>(a, tiles, (cudaStream_t)stream);
-    if (rc == 0 && (debug & 8)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (debug) rc = stash ? launch_ts<true, true>(a, tiles, st) : launch_ts<false, true>(a, tiles, st);
+    else rc = stash ? launch_ts<true, false>(a, tiles, st) : launch_ts<false, false>(a, tiles, st);
+    if (rc == 0 && (debug & 8)) {               // (any debug bit selects the instrumented build; 8 prints its counters)
         unsigned long long h[16], z[16] = {0};
         cudaStreamSynchronize((cudaStream_t)stream);
         cudaMemcpyFromSymbol(h, g_ts_prof, sizeof(h));
         cudaMemcpyToSymbol(g_ts_prof, z, sizeof(z));
         const double c = h[0] ? (double)h[0] : 1.0, n = h[1] ? (double)h[1] : 1.0;
         fprintf(stderr, "[ts prof] ctas=%llu stages/cta=%.1f | clk per STAGE: gather-group loop %.0f (index fetch %.0f, row loads %.0f, empty-wait %.0f, store+arrive %.0f; a group runs "
-                        "every other stage) | loader loop %.0f (empty-wait %.0f) | mma: wait-B %.0f wait-A %.0f issue %.0f\n",
-                h[0], n / c, h[2] / n, h[10] / n, h[11] / n, h[3] / n, h[4] / n, h[6] / n, h[5] / n, h[7] / n, h[8] / n, h[9] / n);
+                        "every other stage) | loader loop %.0f (empty-wait %.0f, expect_tx + copy issue %.0f) | mma: wait-B %.0f wait-A %.0f issue %.0f\n",
+                h[0], n / c, h[2] / n, h[10] / n, h[11] / n, h[3] / n, h[4] / n, h[6] / n, h[5] / n, h[12] / n, h[7] / n, h[8] / n, h[9] / n);
     }
     return rc;
 }
