@@ -37,7 +37,7 @@ def transpose_weights(W: torch.Tensor) -> torch.Tensor:
 
 
 def wgrad(X: torch.Tensor, nbr: Optional[torch.Tensor], dY: torch.Tensor, K: int, out_rows: Optional[torch.Tensor] = None,
-          in_act=None, cols=None) -> torch.Tensor:
+          in_act=None, cols=None, impl: Optional[str] = None) -> torch.Tensor:
     """dW [K, Cin, Cout] of Y[row(j)] = sum_k in_act(X[nbr[k][j]]) @ W[k] over the columns `cols` = (col0, col1) of the
     table (default: all)."""
     assert X.stride(1) == 1 and dY.stride(1) == 1 and X.dtype == dY.dtype == torch.float32
@@ -47,6 +47,14 @@ def wgrad(X: torch.Tensor, nbr: Optional[torch.Tensor], dY: torch.Tensor, K: int
     dW = torch.empty((K, Cin, Cout), dtype=torch.float32, device=X.device)
     ns = _lib.host("cg3d_spconv_wgrad_slabs", c1 - c0, Cin, Cout, K)
     slabs = torch.empty((ns * K * Cin * Cout,), dtype=torch.float32, device=X.device) if ns > 1 else None
+    name = impl or S.get_conv_impl()
+    if (name == "tc" and Cin % 64 == 0 and Cout % 64 == 0 and in_act in (None, "none", "relu") and X.shape[0] > 0
+            and dY.shape[0] > 0 and X.data_ptr() % 16 == 0 and dY.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0
+            and dY.stride(0) % 4 == 0):
+        # tensor cores: the operands are the split-bf16 copies the forward conv (of X) and the dX conv (of dY) use anyway
+        S._call("cg3d_spconv_wgrad_tc", S.split_rows(X, in_act), nbr, S.split_rows(dY), n_cols, c0, c1, Cin, Cout, K,
+                out_rows, slabs, dW)
+        return dW
     S._call("cg3d_spconv_wgrad", X, X.stride(0), S.ACT[in_act], nbr, dY, dY.stride(0), n_cols, c0, c1, Cin, Cout, K,
             out_rows, slabs, dW)
     return dW
@@ -69,7 +77,7 @@ def conv_backward(X: torch.Tensor, W: torch.Tensor, nbr: Optional[torch.Tensor],
                 nbrT = table_transpose(nbr, X.shape[0], out_rows)
             dX = S.gemm_rows(dY, nbrT, Wt, X.shape[0], K, impl=impl)
     if need_dw:
-        dW = wgrad(X.detach(), nbr, dY, K, out_rows).reshape(W.shape)
+        dW = wgrad(X.detach(), nbr, dY, K, out_rows, impl=impl).reshape(W.shape)
     return dX, dW
 
 
@@ -298,8 +306,8 @@ class GroupedConvFunction(torch.autograd.Function):
             dX = torch.zeros((X.shape[0], Cin), dtype=torch.float32, device=X.device)
             S.gemm_rows(dY, nbrT, Wt, X.shape[0], K, tiles=S.make_tiles(ctx.in_off, X.device, tile), out=dX, impl=ctx.impl)
         if ctx.needs_input_grad[1]:
-            dW = torch.stack([wgrad(X.detach(), ctx.nbr, dY, K, ctx.out_rows, cols=(ctx.pos_off[g], ctx.pos_off[g + 1]))
-                              for g in range(G)]).reshape(W.shape)
+            dW = torch.stack([wgrad(X.detach(), ctx.nbr, dY, K, ctx.out_rows, cols=(ctx.pos_off[g], ctx.pos_off[g + 1]),
+                                    impl=ctx.impl) for g in range(G)]).reshape(W.shape)
         return dX, dW, None, None, None, None, None, None, None
 
 

@@ -361,6 +361,13 @@ int cg3d_spconv_wgrad_slabs(int n_cols, int Cin, int Cout, int K);
 int cg3d_spconv_wgrad(const float* x, int ldx, int in_act, const int* nbr, const float* dy, int ldy, int n_cols, int col0,
                       int col1, int Cin, int Cout, int K, const int* out_rows, float* slabs, float* dW, void* stream);
 
+/* The same sums on the tensor cores (tcgen05, pair index = contraction dimension, both operands MN-major) for
+ * Cin % 64 == 0 and Cout % 64 == 0.  x_split / dy_split: the cg3d_split_bf16 images of in_act(x) (n_in rows, 2 Cin bf16) and
+ * of dy (2 Cout bf16) -- the forward's operand and the dX launch's operand, so no extra pass; every bf16 product
+ * (hi*hi, hi*lo, lo*hi, lo*lo) is accumulated in fp32.  slabs / dW / columns / determinism as cg3d_spconv_wgrad. */
+int cg3d_spconv_wgrad_tc(const unsigned short* x_split, const int* nbr, const unsigned short* dy_split, int n_cols, int col0,
+                         int col1, int Cin, int Cout, int K, const int* out_rows, float* slabs, float* dW, void* stream);
+
 /* ---- training-mode BatchNorm and the backward of the row-gather ops (training; MinkowskiBatchNorm = BatchNorm1d over
  * the rows of a sparse tensor, biresnet.py:8-103; features_at_coordinates backward, biresnet.py:182-197,376-394;
  * UNWEIGHTED_AVERAGE quantisation backward, cagroup_head.py:257-271).  No float atomics: bit-repeatable. ---------- */

@@ -121,6 +121,43 @@ def test_wgrad_column_ranges_relu_and_empty(lib):
     assert A.wgrad(x.F, nbr, dY.to(DEV), 27, cols=(5, 5)).abs().max().item() == 0
 
 
+@pytest.mark.parametrize("cin,cout,n", [(64, 64, 2500), (128, 64, 6000), (64, 128, 6000), (128, 256, 900), (256, 128, 20000)])
+def test_wgrad_tensor_core_vs_oracle_and_ffma(lib, cin, cout, n):
+    """cg3d_spconv_wgrad_tc (pair index = contraction dimension of a tcgen05.mma, MN-major split-bf16 operands): the fp64
+    oracle within fp32 rounding, the FFMA kernel's values, the same bits twice; row-ordered and positional tables, a
+    column range with ReLU'd input, identity rows (K = 1), an empty range."""
+    from cagroup3d_b200 import autograd as A, sparse as S
+    TOL = 1e-5        # of the largest |dW| entry: each operand is hi + lo = 16 mantissa bits (2^-17 relative), products summed in fp32
+    ox = oracle_tensor(40 + cin // 64, cin, n=n, batch=2)
+    x = to_gpu_sparse(ox.C, ox.F, 1)
+    m = x.cmap.n
+    nbr = S.neighbor_table(x.cmap, x.cmap, 3, x.mgr)
+    g = torch.Generator().manual_seed(cin + cout)
+    dY = torch.randn((m, cout), generator=g)
+    dYg = dY.to(DEV)
+    Z = torch.zeros((27, cin, cout), dtype=torch.float64)
+    _, want = Bk.conv_backward(ox.F.double(), Z, nbr.cpu().numpy(), dY.double())
+    got = A.wgrad(x.F, nbr, dYg, 27, impl="tc")
+    ffma = A.wgrad(x.F, nbr, dYg, 27, impl="simt")
+    _close(got, want, TOL)                                             # bf16 hi + lo keeps 16 mantissa bits per operand
+    _close(ffma, want, 5e-6)                                           # fp32 FFMA sums of up to ~10^4 products
+    assert torch.equal(got, A.wgrad(x.F, nbr, dYg, 27, impl="tc"))     # ordered slabs, no atomics
+    # positional (tap-pattern ordered) table
+    perm = torch.randperm(m, generator=g).to(torch.int32)
+    nbr_pos = nbr[:, perm.long().to(DEV)].contiguous()
+    _close(A.wgrad(x.F, nbr_pos, dYg, 27, out_rows=perm.to(DEV), impl="tc"), want, TOL)
+    # one weight group's columns, ReLU'd input
+    c0, c1 = m // 4, m // 4 + m // 3
+    masked = nbr.cpu().numpy().copy()
+    masked[:, :c0] = -1
+    masked[:, c1:] = -1
+    _, want_r = Bk.conv_backward(torch.relu(ox.F).double(), Z, masked, dY.double())
+    _close(A.wgrad(x.F, nbr, dYg, 27, in_act="relu", cols=(c0, c1), impl="tc"), want_r, TOL)
+    assert A.wgrad(x.F, nbr, dYg, 27, cols=(7, 7), impl="tc").abs().max().item() == 0
+    # identity rows (1x1 conv / Linear)
+    _close(A.wgrad(x.F, None, dYg, 1, impl="tc")[0], ox.F.double().T @ dY.double(), TOL)
+
+
 # ---- training-mode BatchNorm, interpolation / quantise-average backward (csrc/train_bwd.cu) -----------------------
 @pytest.mark.parametrize("n,C", [(5000, 64), (300, 7), (70000, 128), (1, 32), (257, 33)])
 def test_bn_train_forward_backward_vs_oracle(lib, n, C):
