@@ -158,19 +158,33 @@ def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_l
     crit = TT.FirstStageLoss(head.n_classes)
     coords, vs = br["coords"], art["vsA"]
     C = out.C
+    # Rows of the class-batched maps carry (class * B + sample) in column 0.  The reference walks samples and classes and
+    # picks each (sample, class) block with a boolean mask (B x n_classes selections, each a host sync here); one stable
+    # sort by (sample, class) puts every block into one contiguous slice with its rows in their original order, and ONE
+    # read-back of the block sizes gives the slice bounds.
+    ncls = head.n_classes
+    key = coords[:, 0].long()
+    blk = (key % B) * ncls + key // B
+    perm = torch.sort(blk, stable=True)[1]
+    cnt = torch.bincount(blk, minlength=B * ncls)
+    vs_rows = vs[key // B]                              # per-class voxel size: a scalar or a per-axis triple
+    if vs_rows.dim() == 1:
+        vs_rows = vs_rows.unsqueeze(1)
+    ctr_s, box_s, cls_s = br["centerness"][perm], br["bbox_pred"][perm], br["cls"][perm]
+    pts_s = (coords[:, 1:].float() * vs_rows)[perm]
+    Cb = C[:, 0].long()
+    vperm = torch.sort(Cb, stable=True)[1]
+    bounds = torch.cat([cnt, torch.bincount(Cb, minlength=B)]).cumsum(0).cpu().tolist()
+    off = [0] + bounds[:B * ncls]
+    voff = [0] + [v - bounds[B * ncls - 1] for v in bounds[B * ncls:]]
+    vox_all = C[:, 1:].float() * head.voxel_size
     samples = []
     for b in range(B):
-        ctrs, boxes, clss, pts = [], [], [], []
-        for c in range(head.n_classes):
-            lo, hi = br["class_off"][c], br["class_off"][c + 1]
-            r = lo + torch.nonzero(coords[lo:hi, 0] == c * B + b).squeeze(1)
-            ctrs.append(br["centerness"][r])
-            boxes.append(br["bbox_pred"][r])
-            clss.append(br["cls"][r])
-            pts.append(coords[r, 1:].float() * vs[c])
-        rows = torch.nonzero(C[:, 0] == b).squeeze(1)
-        vox = C[rows, 1:].float() * head.voxel_size
-        samples.append(dict(centernesses=ctrs, bbox_preds=boxes, cls_scores=clss, points=pts, voxel_offset_preds=offs[rows],
+        sl = [slice(off[b * ncls + c], off[b * ncls + c + 1]) for c in range(ncls)]
+        rows = vperm[voff[b]:voff[b + 1]]
+        vox = vox_all[rows]
+        samples.append(dict(centernesses=[ctr_s[q] for q in sl], bbox_preds=[box_s[q] for q in sl], cls_scores=[cls_s[q] for q in sl],
+                            points=[pts_s[q] for q in sl], voxel_offset_preds=offs[rows],
                             original_points=vox, semantic_scores=sem[rows], semantic_points=vox, gt_bboxes=gt_bboxes[b],
                             gt_labels=gt_labels[b], scene_points=scene_points[b], pts_semantic_mask=pts_semantic_mask[b],
                             pts_instance_mask=pts_instance_mask[b]))

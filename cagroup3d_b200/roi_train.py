@@ -189,17 +189,19 @@ class ProposalTargetLayer:
 
     @staticmethod
     def get_max_iou_with_same_class(rois, roi_labels, gt_boxes, gt_labels):
+        """Best same-class gt box of every RoI (cagroup_proposal_target_layer.py: a loop over the classes between the
+        smallest and the largest gt label, each with its own IoU call and three host read-backs).  Here: ONE IoU matrix of
+        all RoIs x all gt boxes, pairs of different labels masked out, one row maximum -- the same values (the IoU is
+        pairwise, torch.max returns the first maximum, and the gt boxes of a class keep their order), no host sync.  RoIs
+        without a gt box of their class keep overlap 0 and assignment 0, as the loop leaves them."""
         from . import ops
-        max_overlaps = rois.new_zeros(rois.shape[0])
-        assignment = roi_labels.new_zeros(roi_labels.shape[0])
-        for k in range(int(gt_labels.min()), int(gt_labels.max()) + 1):
-            rm, gm = roi_labels == k, gt_labels == k
-            if rm.sum() > 0 and gm.sum() > 0:
-                iou = ops.boxes_iou3d_gpu(rois[rm].contiguous(), gt_boxes[gm].contiguous())
-                best, arg = torch.max(iou, dim=1)
-                max_overlaps[rm] = best
-                assignment[rm] = gm.nonzero().view(-1)[arg]
-        return max_overlaps, assignment
+        if rois.shape[0] == 0 or gt_boxes.shape[0] == 0:
+            return rois.new_zeros(rois.shape[0]), roi_labels.new_zeros(roi_labels.shape[0])
+        iou = ops.boxes_iou3d_gpu(rois.contiguous(), gt_boxes.contiguous())
+        same = roi_labels.view(-1, 1) == gt_labels.view(1, -1)
+        best, arg = torch.max(torch.where(same, iou, iou.new_full((), -1.0)), dim=1)
+        has = best >= 0
+        return torch.where(has, best, best.new_zeros(())), torch.where(has, arg, arg.new_zeros(())).to(roi_labels.dtype)
 
 
 def reorder_rois(pred_boxes_3d, enlarge_ratio=False):

@@ -181,6 +181,39 @@ def cg3d_spconv_wgrad(**a):
         dW[k] = xin[src[hit]].T @ dy[rows[hit]]
 
 
+def _split_image(v: torch.Tensor) -> torch.Tensor:
+    """fp32 [n][C] -> int16 [n][2C]: per 32-channel chunk [hi 32 | lo 32] bf16 bit patterns (cg3d_split_bf16's layout)."""
+    n, C = v.shape
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    img = torch.stack([hi.view(n, C // 32, 32), lo.view(n, C // 32, 32)], dim=2)      # [n][C/32][2][32]
+    return img.reshape(n, 2 * C).view(torch.int16)
+
+
+def _unsplit_image(img: torch.Tensor, C: int) -> torch.Tensor:
+    n = img.shape[0]
+    parts = img[:, :2 * C].contiguous().view(torch.bfloat16).view(n, C // 32, 2, 32).float()
+    return (parts[:, :, 0] + parts[:, :, 1]).reshape(n, C)
+
+
+def cg3d_split_bf16(**a):
+    x, n, C = a["in"], a["n"], a["C"]
+    assert C % 32 == 0 and a["ld"] == x.stride(0) and a["out"].dtype == torch.int16 and a["out"].shape[1] == 2 * C
+    v = x[:n, :C].float()
+    if a["relu"]:
+        v = torch.relu(v)
+    a["out"][:n] = _split_image(v)
+
+
+def cg3d_spconv_wgrad_tc(**a):
+    """the tensor-core weight gradient: the same sums as cg3d_spconv_wgrad over the split-bf16 operands (hi + lo each)"""
+    K, Cin, Cout = a["K"], a["Cin"], a["Cout"]
+    assert Cin % 64 == 0 and Cout % 64 == 0 and a["dW"].shape == (K, Cin, Cout)
+    x, dy = _unsplit_image(a["x_split"], Cin), _unsplit_image(a["dy_split"], Cout)
+    cg3d_spconv_wgrad(x=x, dy=dy, dW=a["dW"], K=K, Cin=Cin, Cout=Cout, slabs=a["slabs"], in_act=0, col0=a["col0"], col1=a["col1"],
+                      out_rows=a["out_rows"], nbr=a["nbr"])
+
+
 def cg3d_bn_train_stats(**a):
     x, n = a["x"], a["n"]
     assert x.shape == (n, a["C"])
@@ -359,7 +392,8 @@ def cg3d_column_sum(**a):
 def cg3d_segment_mean(**a):
     assert a["ref"] is None and a["srcB"] is None, "only the plain (ref == NULL) form is emulated"
     src, inv, U, C = a["srcA"], a["inverse"].long(), a["n_unique"], a["C"]
-    assert src.shape == (a["n"], C) and a["ldA"] == src.stride(0) and a["workspace"].numel() >= U * C
+    assert src.shape == (a["n"], C) and a["ldA"] == src.stride(0)
+    assert a["workspace"].dtype == torch.int64 and a["workspace"].numel() >= (3 * (U + 1) + a["n"]) // 2   # counts | offsets | cursors | point list
     cnt = torch.bincount(inv, minlength=U).to(src.dtype)
     a["counts"][:U] = cnt
     a["out"].copy_(torch.zeros((U, C), dtype=src.dtype).index_add_(0, inv, src) / cnt[:, None])

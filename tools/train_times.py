@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--conv", default="tc")
     ap.add_argument("--p_sel", type=float, default=1 / 18)
     ap.add_argument("--top", type=int, default=30)
+    ap.add_argument("--host-profile", action="store_true", help="cProfile over the timed steps: where the HOST time of a step goes")
     a = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
     S.set_conv_impl(a.conv)
@@ -65,6 +66,18 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     print(f"training step {ms:.2f} ms -> {a.batch / ms * 1e3:.1f} scenes/s per GPU")
+    if a.host_profile:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(a.steps):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        st = pstats.Stats(pr)
+        st.sort_stats("tottime").print_stats(40)
+        st.sort_stats("cumulative").print_stats(60)
     S.Profile.active = []
     S.Profile.stage = "train"
     step()
