@@ -84,7 +84,12 @@ def knn(k: int, xyz: torch.Tensor, center_xyz: torch.Tensor = None, transposed: 
     B, npoint, _ = center_xyz.shape
     idx = torch.zeros((B, npoint, k), dtype=torch.int32, device=xyz.device)
     dist2 = torch.zeros((B, npoint, k), dtype=torch.float32, device=xyz.device)
-    S._call("cg3d_knn", xyz.float(), B, xyz.shape[1], center_xyz.float(), npoint, k, idx, dist2)
+    if k == 1 and xyz.shape[1] >= 4096:
+        # grid-bucketed nearest neighbour: the same indices and distances as the exhaustive scan (cg3d_knn_grid)
+        ws = torch.empty((S._lib.host("cg3d_knn_grid_workspace", xyz.shape[1]),), dtype=torch.int32, device=xyz.device)
+        S._call("cg3d_knn_grid", xyz.float(), B, xyz.shape[1], center_xyz.float(), npoint, idx, dist2, ws)
+    else:
+        S._call("cg3d_knn", xyz.float(), B, xyz.shape[1], center_xyz.float(), npoint, k, idx, dist2)
     return idx.transpose(2, 1).contiguous()
 
 

@@ -333,6 +333,13 @@ int cg3d_roi_decode(const float* rois, const float* reg, int n, int code_size, i
  * order with strict `<`, so ties resolve as in the reference (first index wins at k = 1). */
 int cg3d_knn(const float* xyz, int b, int n, const float* query, int m, int k, int* idx, float* dist2, void* stream);
 
+/* The k = 1 case on a uniform grid over the points (cells of >= 0.04 m, counting sort, ring search): idx / dist2
+ * ([b,m]) bit-identical to cg3d_knn / knn_cuda.cu -- the winner is the minimum of (dist2, index) with the same distance
+ * expression -- at O(m * points near a query) instead of O(m n).  workspace: cg3d_knn_grid_workspace(n) ints, 16-byte
+ * aligned.  Fewer than 4096 points per batch element: the exhaustive kernel. */
+int cg3d_knn_grid_workspace(int n);
+int cg3d_knn_grid(const float* xyz, int b, int n, const float* query, int m, int* idx, float* dist2, int* workspace, void* stream);
+
 /* sort_vertices_forward(vertices [b,n,m,2] f32, mask [b,n,m] bool, num_valid [b,n] i32) -> idx [b,n,9] i32
  * (sort_vert.cpp:6-33, sort_vert_kernel.cu:42-134): counter-clockwise order of the valid polygon vertices,
  * first index repeated, padded with an invalid intersection index.  The caller allocates idx (the reference

@@ -30,7 +30,7 @@ def test_every_stream_entry_point_ends_with_stream():
     assert _lib._host_only == {"cg3d_hash_capacity", "cg3d_scan_workspace_ints", "cg3d_sort_workspace_ints",
                                "cg3d_spconv_tc_ntile", "cg3d_spconv_tc_stacked", "cg3d_spconv_pairs_supported", "cg3d_spconv_pairs_tile_rows",
                                "cg3d_segment_mean_workspace", "cg3d_spconv_tc_splitk", "cg3d_spconv_wgrad_slabs",
-                               "cg3d_bn_train_workspace", "cg3d_focal_loss_workspace", "cg3d_loss_workspace"}
+                               "cg3d_bn_train_workspace", "cg3d_focal_loss_workspace", "cg3d_loss_workspace", "cg3d_knn_grid_workspace"}
 
 
 def test_host_only_helpers(lib):

