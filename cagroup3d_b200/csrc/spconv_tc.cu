@@ -32,14 +32,10 @@
 // Taps for which no row of the tile has a neighbour are skipped (prologue scan of the rule map); with rows ordered by
 // tap pattern (cg3d_table_mask_keys) that removes most of the padding.  No atomics; the accumulation order is fixed
 // (taps ascending), so results are deterministic.
-// Opt-in variants kept for the record (parity-tested, measured slower on B200, profiles/r1_conv_experiments.md):
-// STK (CG3D_TC_STACKED=1, two MMAs per k-step for Cout = 64) and TMAG (CG3D_TC_GATHER=tma, the gather as TMA
-// tile::gather4 instructions).
 //
 // Replaces MinkowskiConvolution / ConvolutionTranspose forward for every layer with Cin % 32 == 0 and Cout % 64 == 0
 // (SURVEY.md A4-A8, A12, A13, A19, A20); the Cin = 3 stem and the narrow prediction heads stay on the exact-fp32 SIMT
 // kernel (spconv_simt.cu).
-#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -47,12 +43,6 @@
 
 #include "common.cuh"
 #include "../../include/cagroup3d_b200.h"
-
-// persistent schedule of the same contraction (spconv_tc4.cu)
-int cg3d_spconv_tc4_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
-                           int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
-                           const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
-                           unsigned short* out_split, int out_split_relu, int NT, void* stream);
 
 // 64-column tiles with the gathered operand in tensor memory (spconv_ts.cu)
 int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
@@ -115,23 +105,6 @@ __device__ __forceinline__ void cp_async16_full(uint32_t dst, unsigned long long
 }
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
-}
-// TMA row gather: four rows (r0..r3; out-of-range, e.g. -1, gives a zero row) of the 2-D bf16 tensor behind `tmap`, 64
-// elements (128 bytes) from column `col`, written as four consecutive 128-byte rows of a 128B-swizzled tile at `dst`
-// (512-byte aligned inside a 1024-byte atom); 512 bytes are credited to the mbarrier (tools/probe/gather4_probe.cu).
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(dst), "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
-        : "memory");
-}
-// TMA tiled load: a box of the 2-D tensor behind `tmap` (here 64 bf16 columns x 128 rows, 128B swizzle = the UMMA K-major
-// A tile) starting at (col, row); rows past the end of the tensor arrive as zeros; the whole box is credited to the mbarrier.
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int col, int row, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(tmap), "r"(col), "r"(row), "r"(bar)
-        : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -209,35 +182,22 @@ struct TcArgs {
     int n_out, Cin, Cout, K, act, ldo;
     int ksplit;  // split-K: gridDim.z CTAs share a tile, CTA z runs the z-th slice of the active taps and writes its raw
     long long zstride;   // accumulator to out + z * zstride (a partial slab); cg3d_spconv_tc adds the slabs in order afterwards
-    int dense;   // 1: plain GEMM rows (K = 1, no rule map, no row permutation): the A tile is ONE tiled TMA load per stage
     int debug;   // timing experiments only (CG3D_TC_DEBUG): 1 = 16-byte weight copies, 2 = no feature loads, 4 = no gather
                  // copies at all, 8 = cycle counters, 16 = no MMAs, 64 = no rule-map loads in the K loop, 128 = no stash
 };
 
-// STK (Cout == 64 layers, NT = 64): a stage holds 64 channels -- A as a hi tile and a lo tile (128 rows x 128 bytes each),
-// B as ONE 128-row tile [W_hi (64 columns) ; W_lo (64 columns)] x 64 channels -- so that a 16-channel k-step takes two
-// MMAs instead of three: A_hi x [W_hi | W_lo] (N = 128: columns 0-63 collect hi*hi, columns 64-127 hi*lo) and
-// A_lo x W_hi (N = 64).  tcgen05.mma costs >= ~46 clk per instruction for any N <= 64 (profiles/r1_mma_probe.txt), so the
-// instruction count is what the 64-channel layers pay for.  The epilogue adds the two column halves.
-// TMAG: the A tile of a stage is fetched by the TMA engine (tile::gather4, one instruction per lane = 4 rows, one warp per
-// ring slot) instead of 1024 cp.async per stage: the gather warps were issue-bound (a handful of extra ALU instructions
-// per copy cost 10-15 % of the layer), the TMA path needs ~10 instructions per stage and no per-thread arrivals.
-// CPS (chunks per stage, plain variant only): a barrier phase carries CPS consecutive 32-channel sub-tiles [A | B], i.e. half
+// CPS (chunks per stage): a barrier phase carries CPS consecutive 32-channel sub-tiles [A | B], i.e. half
 // the producer -> MMA -> producer handshakes per tap at CPS = 2 for the same bytes in flight (the handshake costs 400-600 clk
 // per stage whatever the stage carries: profiles/r2_conv_skeleton_ablation.md).
-template <int NT, int STAGES, bool STASH, bool STK, bool TMAG, int CPS = 1>
-__global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap) {
-    static_assert(!STK || NT == 64, "the stacked-weights variant is the 64-column kernel");
-    static_assert(!(STK && TMAG), "the stacked variant keeps the cp.async gather");
-    static_assert(CPS == 1 || (!STK && !TMAG), "several sub-tiles per stage: plain variant only");
-    constexpr int KCH = STK ? 64 : KC * CPS;              // channels per stage
-    constexpr int A_TILE = STK ? 2 * A_BYTES : A_BYTES;   // STK: hi tile + lo tile
-    constexpr int B_BYTES = STK ? 128 * 128 : NT * 128;   // bytes of the B tile of a (sub-)stage
+template <int NT, int STAGES, bool STASH, int CPS = 1>
+__global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
+    constexpr int KCH = KC * CPS;                         // channels per stage
+    constexpr int A_TILE = A_BYTES;
+    constexpr int B_BYTES = NT * 128;                     // bytes of the B tile of a (sub-)stage
     constexpr int SUB_BYTES = A_TILE + B_BYTES;
     constexpr int STAGE_BYTES = CPS * SUB_BYTES;
-    constexpr int TCOLS = STK ? 128 : NT;                 // TMEM columns of the accumulator
+    constexpr int TCOLS = NT;                             // TMEM columns of the accumulator
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * NT) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     constexpr int KCAP = STASH ? 32 : MAX_TAPS + 3;
     constexpr int WPS = NGW / STAGES;                     // gather warps per ring slot
     constexpr int RW = TM / WPS;                          // rows of a stage one warp fills
@@ -278,9 +238,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
     // ---- prologue: barriers, TMEM, active-tap list ---------------------------------------------------
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            // TMAG: the gather warp's expect_tx arrival + the weight copy's; else one async arrival per lane of the slot's
-            // team + the weight copy's expect_tx
-            mbar_init(full0 + 8 * s, TMAG ? 2 : 32 * WPS + 1);
+            // one async arrival per lane of the slot's team + the weight copy's expect_tx
+            mbar_init(full0 + 8 * s, 32 * WPS + 1);
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(accum_bar, 1);
@@ -350,56 +309,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
-      if (TMAG && warp < STAGES) {
-        // ================= gather producer of ring slot `warp` (TMA) =================
-        // stage q = (active tap q / nchunks, channel chunk q % nchunks) lives in slot q % STAGES; lane l fetches rows
-        // 4 l .. 4 l + 3 of the tile with ONE tile::gather4 (rows without a neighbour: index -1 -> zero rows).
-        const int slot = warp;
-        const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
-        const uint32_t dst = base + (uint32_t)(slot * STAGE_BYTES + lane * 512);
-        auto fetch4 = [&](int q, int (&d)[4]) {
-            const int k = taps[a0 + q / nchunks];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = 4 * lane + j;
-                int v = -1;
-                if (r < nrows) {
-                    if (STASH) v = nbr_s[k * TM + r];
-                    else if (a.nbr) v = __ldg(a.nbr + (size_t)k * a.n_out + row0 + r);
-                    else v = a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r;
-                }
-                d[j] = (a.debug & 2) ? -1 : v;
-            }
-        };
-        uint32_t ph = 1u;
-        if (a.dense) {
-            // 1x1 convolution / linear layer: output row r reads input row r, so a stage's A tile is a contiguous
-            // 128-row x 64-column box of the split activation matrix -- one TMA instruction instead of 1024 cp.async
-#pragma unroll 1
-            for (int q = slot; q < n_iters; q += STAGES, ph ^= 1u) {
-                mbar_wait(empty_s, ph);
-                if (lane == 0) {
-                    mbar_expect_tx(full_s, (uint32_t)A_BYTES);
-                    tma_load_2d(base + (uint32_t)(slot * STAGE_BYTES), &tmap, (q % nchunks) * (2 * KC), row0, full_s);
-                }
-                __syncwarp();
-            }
-        }
-        int cur[4], nxt[4];
-        if (!a.dense && slot < n_iters) fetch4(slot, cur);
-#pragma unroll 1
-        for (int q = slot; !a.dense && q < n_iters; q += STAGES, ph ^= 1u) {
-            if (q + STAGES < n_iters) fetch4(q + STAGES, nxt);
-            const long long p1 = clock64();
-            mbar_wait(empty_s, ph);
-            if (t == 0) TC_PROF(8, clock64() - p1);
-            if (lane == 0) mbar_expect_tx(full_s, (uint32_t)A_BYTES);
-            __syncwarp();
-            tma_gather4(dst, &tmap, (q % nchunks) * (2 * KC), cur[0], cur[1], cur[2], cur[3], full_s);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
-        }
-      } else if (!TMAG && warp < WPS * STAGES) {
+      if (warp < WPS * STAGES) {
+
         // ================= gather producers =================
         // Ring slot s is filled by its own team of WPS warps (warp = s + STAGES * part), every time it comes round:
         // stage q = (active tap q / nchunks, channel chunk q % nchunks) lives in slot q % STAGES.  A warp therefore
@@ -412,11 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
         const uint32_t lane_off0 = (uint32_t)(rsub * 128 + ((piece ^ rsub) << 4));              // rows 8 m + rsub
         const uint32_t lane_off1 = (uint32_t)((4 + rsub) * 128 + ((piece ^ (4 + rsub)) << 4));  // rows 8 m + 4 + rsub
         const uint32_t row_bytes = 4u * (uint32_t)a.Cin;
-        // STK: piece p of the hi (lo) tile = channels 8 p .. 8 p + 7 of the 64-channel chunk, which the split layout keeps
-        // as [32-ch half p / 4][hi | lo][16-byte piece p % 4]
         // the source address of a copy is ONE 32 x 32 + 64-bit multiply-add (IMAD.WIDE.U32): base + row * row_bytes; the gather
         // warps are issue-bound, every instruction per copy counts (profiles/r1_conv_experiments.md)
-        const unsigned long long src0 = (unsigned long long)a.in_split + (unsigned)(STK ? (piece >> 2) * 128 + (piece & 3) * 16 : piece * 16);
+        const unsigned long long src0 = (unsigned long long)a.in_split + (unsigned)(piece * 16);
         const uint32_t dst0 = base + (uint32_t)(slot * STAGE_BYTES + (rbase >> 3) * 1024);
         const uint32_t full_s = full0 + 8 * slot, empty_s = empty0 + 8 * slot;
         auto fetch = [&](int q, int (&dst)[RW / 32]) {
@@ -462,19 +371,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
             if (!(a.debug & 4)) {
 #pragma unroll
               for (int u = 0; u < CPS; ++u) {
-                const unsigned long long src = src0 + (unsigned)(((q % nchunks) * CPS + u) * (STK ? 256 : 128));
+                const unsigned long long src = src0 + (unsigned)(((q % nchunks) * CPS + u) * 128);
 #pragma unroll
-                for (int i = 0; i < (STK ? RW / 2 : RW / 4); ++i) {
-                    const int m = STK ? (i >> 1) : i;             // 4-row group; STK: copy i fills tile i & 1 (hi, lo)
-                    const int tile = STK ? (i & 1) : 0;
+                for (int m = 0; m < RW / 4; ++m) {               // 4-row group
                     const int idx = __shfl_sync(0xffffffffu, cur[m >> 3], 4 * (m & 7) + rsub);
                     const bool ok = (okm[m >> 3] >> (4 * (m & 7))) & 1u;
                     const bool zero = (zm[m >> 3] >> (4 * (m & 7))) & 1u;
-                    const uint32_t dst = dst0 + (uint32_t)(u * SUB_BYTES + tile * A_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
+                    const uint32_t dst = dst0 + (uint32_t)(u * SUB_BYTES + (m >> 1) * 1024) + ((m & 1) ? lane_off1 : lane_off0);
                     // rows without a neighbour get zeros from a plain 16-byte shared store, not from a 0-byte cp.async:
                     // an LDGSTS that mixes copying and zero-filling lanes costs extra shared-memory wavefronts (ncu:
                     // half of the LSU wavefronts of the K = 729 layer were such conflicts, profiles/r1_ncu_spconv_tc.md)
-                    if (ok) cp_async16_full(dst, (src + (unsigned)(tile * 64)) + (unsigned long long)(unsigned)idx * row_bytes);
+                    if (ok) cp_async16_full(dst, src + (unsigned long long)(unsigned)idx * row_bytes);
                     else if (zero) st_shared_zero16(dst);
                 }
               }
@@ -524,15 +431,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, v);
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(c0 + 16), w);
-                if constexpr (STK) {                   // + the hi*lo products collected in columns 64 .. 127
-                    uint32_t v2[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(NT + c0), v2);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-                    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(NT + c0 + 16), v2);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(__uint_as_float(w[i]) + __uint_as_float(v2[i]));
-                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = w[i] = 0u;
@@ -632,15 +530,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
                             umma_bf16(tmem_base, dau + lo, dbu + hi, IDESC, 1u);
                         }
                     }
-                } else if constexpr (STK) {
-                    const uint64_t dal = make_desc(sa + A_BYTES);
-#pragma unroll
-                    for (int kk = 0; kk < KCH / 16; ++kk) {
-                        if (a.debug & 16) break;
-                        const uint64_t off = (uint64_t)(kk * 2);                             // in 16-byte units
-                        umma_bf16(tmem_base, da + off, db + off, IDESC2, (it | kk) ? 1u : 0u);   // A_hi x [W_hi | W_lo]
-                        umma_bf16(tmem_base, dal + off, db + off, IDESC, 1u);                    // A_lo x W_hi
-                    }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < KC / 16; ++kk) {
@@ -669,10 +558,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a, const 
 
 // fp32 W[G][K][Cin][Cout] -> per (g, k, 32-channel chunk, NT-column tile) block of NT * 128 bytes:
 // row n = [hi 32 bf16 along Cin | lo 32 bf16], 16-byte pieces XOR-swizzled by (n % 8) -- the exact smem image.
-// stacked = 1 (Cout == 64 layers): per (g, k, 64-channel chunk) ONE block of 128 rows x 128 bytes: row n = bf16 hi of
-// W[.][n] over the chunk's 64 channels, row 64 + n = bf16 lo, same swizzle.
 __global__ void weight_image_kernel(const float* __restrict__ W, long long total, int K, int Cin, int Cout, int NT,
-                                    int stacked, unsigned char* __restrict__ img) {
+                                    unsigned char* __restrict__ img) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         int co = (int)(i % Cout);
@@ -682,14 +569,6 @@ __global__ void weight_image_kernel(const float* __restrict__ W, long long total
         float w = W[i];
         __nv_bfloat16 hi = __float2bfloat16_rn(w);
         __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        if (stacked) {
-            const int c = ci / 64, p = (ci % 64) >> 3, slice = co / 64, m = co % 64;
-            unsigned char* b = img + (((size_t)gk * (Cin / 64) + c) * (Cout / 64) + slice) * (size_t)(128 * 128);
-            const int rh = m, rl = 64 + m;
-            *reinterpret_cast<__nv_bfloat16*>(b + (rh >> 3) * 1024 + (rh & 7) * 128 + ((p ^ (rh & 7)) << 4) + (ci & 7) * 2) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(b + (rl >> 3) * 1024 + (rl & 7) * 128 + ((p ^ (rl & 7)) << 4) + (ci & 7) * 2) = lo;
-            continue;
-        }
         int c = ci / KC, kk = ci % KC, tn = co / NT, n = co % NT;
         size_t blk = ((size_t)gk * (Cin / KC) + c) * (Cout / NT) + tn;
         size_t rowb = (size_t)(n >> 3) * 1024 + (size_t)(n & 7) * 128;
@@ -779,7 +658,7 @@ void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_ti
     // (stages x ~0.15 + 0.0016 NT us, measured per-stage cost) + slab traffic (written and read once, ~4 TB/s).
     const long long ctas = (long long)tiles * (Cout / NT);
     const long long stages = (long long)K * (Cin / KC);
-    if (splitk && !grouped && cg3d_spconv_tc_stacked(Cin, Cout) == 0 && stages >= 64 && ctas < 296) {
+    if (splitk && !grouped && stages >= 64 && ctas < 296) {
         const double t_cta = (double)stages * (0.15 + 0.0016 * NT);
         double best = 1e30;
         for (int c = 1; c <= 8 && c <= K && stages / c >= 24; ++c) {
@@ -790,18 +669,18 @@ void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_ti
     }
 }
 
-template <int NT, int STAGES, bool STASH, bool STK = false, bool TMAG = false, int CPS = 1>
-int launch_tc(const TcArgs& a, const CUtensorMap& tmap, int tiles, cudaStream_t s) {
-    constexpr int smem = STAGES * (STK ? 3 * A_BYTES : CPS * (A_BYTES + NT * 128)) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
+template <int NT, int STAGES, bool STASH, int CPS = 1>
+int launch_tc(const TcArgs& a, int tiles, cudaStream_t s) {
+    constexpr int smem = STAGES * CPS * (A_BYTES + NT * 128) + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(spconv_tc_kernel<NT, STAGES, STASH, CPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT, a.ksplit);
-    spconv_tc_kernel<NT, STAGES, STASH, STK, TMAG, CPS><<<grid, NTHREADS, smem, s>>>(a, tmap);
+    spconv_tc_kernel<NT, STAGES, STASH, CPS><<<grid, NTHREADS, smem, s>>>(a);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -819,22 +698,13 @@ int cg3d_spconv_tc_splitk(int n_out, int Cin, int Cout, int K, int grouped, int 
     return ks;
 }
 
-/* 1: the layer runs on the stacked-weights variant (two MMAs per k-step) and its weight image has that layout */
-int cg3d_spconv_tc_stacked(int Cin, int Cout) {
-    // opt-in (CG3D_TC_STACKED=1): measured equal to the three-MMA variant on B200 (profiles/r1_conv_experiments.md)
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("CG3D_TC_STACKED"); on = (e && e[0] == '1') ? 1 : 0; }
-    return (on && Cout == 64 && Cin % 64 == 0) ? 1 : 0;
-}
-
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream) {
     int NT = cg3d_spconv_tc_ntile(Cout);
     if (NT == 0 || Cin % KC != 0) return -1;
     long long total = (long long)G * K * Cin * Cout;
     if (total == 0) return 0;
     long long b = (total + 255) / 256;
-    weight_image_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 256, 0, (cudaStream_t)stream>>>(W, total, K, Cin, Cout, NT,
-                                                                                               cg3d_spconv_tc_stacked(Cin, Cout), img);
+    weight_image_kernel<<<(int)(b > 148 * 32 ? 148 * 32 : b), 256, 0, (cudaStream_t)stream>>>(W, total, K, Cin, Cout, NT, img);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -861,7 +731,7 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     if (ldo % 4 != 0 || ((size_t)out & 15) || ((size_t)wimg & 15) || ((size_t)in_split & 15)) return -3;
     if (out_split && (((size_t)out_split & 15) || Cout % 32 != 0)) return -3;
     TcArgs a{in_split, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, out_split,
-             out_split_relu, n_out, Cin, Cout, K, act, ldo, 1, 0, 0, 0};
+             out_split_relu, n_out, Cin, Cout, K, act, ldo, 1, 0, 0};
     if (ks > 1) {                                      // CTA z writes its raw accumulator into slab z of the workspace
         if ((size_t)splitk_ws & 15) return -3;
         a.out = splitk_ws; a.ldo = Cout; a.scale = a.shift = a.residual = nullptr; a.act = 0; a.out_split = nullptr;
@@ -874,81 +744,25 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     cudaStream_t s = (cudaStream_t)stream;
     // <= 96 KB of pipeline (+ 13.5 KB of stashed rule-map columns) per CTA so that two CTAs share an SM
     const bool stash = nbr && K <= STASH_K && !(dbg & 128);
-    // the split activation matrix as a 2-D bf16 tensor [n_in][2 Cin] for the TMA row gather: box = 64 elements x 1 row,
-    // 128B swizzle (the UMMA K-major tile layout); rows outside [0, n_in) read as zeros
-    static int use_tma = -1;
-    // "cpasync" (default) | "tma": on B200 the TMA row gather is parity-green but slower (a gather4 instruction costs the
-    // TMA unit ~25 clk whether its rows exist or not: K = 729 layer 11.2 ms vs 7.2 ms, backbone 10.3 vs 8.8 ms;
-    // profiles/r1_conv_experiments.md)
-    if (use_tma < 0) { const char* e = getenv("CG3D_TC_GATHER"); use_tma = (e && e[0] == 't') ? 1 : 0; }
-    const bool stacked = cg3d_spconv_tc_stacked(Cin, Cout) != 0;
-    // plain GEMM rows (1x1 convs, linear layers): tiled TMA loads of the A operand.  Opt-in (CG3D_TC_DENSE=1): parity-green,
-    // but the 1x1 layers are not gather-bound (they already run at 2-4.3 TB/s of algorithmic bytes): 1.64 vs 1.59 ms summed
-    static int use_dense = -1;
-    if (use_dense < 0) { const char* e = getenv("CG3D_TC_DENSE"); use_dense = (e && e[0] == '1') ? 1 : 0; }
-    const bool dense = use_dense && !stacked && !nbr && !out_rows && K == 1;
-    a.dense = dense ? 1 : 0;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if ((use_tma || dense) && !stacked) {
-        cuuint64_t gdim[2] = {(cuuint64_t)(2 * Cin), (cuuint64_t)(n_in > 0 ? n_in : 1)};
-        cuuint64_t gstride[1] = {(cuuint64_t)Cin * 4};
-        cuuint32_t box[2] = {2 * KC, dense ? (cuuint32_t)TM : 1u};
-        cuuint32_t estr[2] = {1, 1};
-        // the driver entry point is looked up through the runtime, so the library has no link-time dependency on
-        // libcuda.so.1 (it must load, and export its symbols, on a box without a driver)
-        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeTiled encode = nullptr;
-        if (!encode) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -4;
-            encode = (EncodeTiled)fn;
-        }
-        CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)in_split, gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return -4;
-    }
     static int cps2 = -1;
     if (cps2 < 0) { const char* e = getenv("CG3D_TC_CPS"); cps2 = (e ? atoi(e) : 2) == 2 ? 1 : 0; }
     int rc;
-    // CG3D_TC_V4=1: launches without split-K go to the persistent kernel (spconv_tc4.cu: one CTA per SM, overlapped epilogue;
-    // same bits).  Opt-in: measured 10-25 % SLOWER than two CTAs per SM of the kernel below, which overlap one tile's
-    // prologue / epilogue with the other's K loop already and have twice the gather warps (profiles/r2_conv_skeleton_ablation.md)
-    static int v4 = -1;
-    if (v4 < 0) { const char* e = getenv("CG3D_TC_V4"); v4 = e ? atoi(e) : 0; }
-    if (v4 && ks == 1 && !stacked && !use_tma && !dense && !dbg && (NT != 64 || Cin % 64 == 0)) {
-        return cg3d_spconv_tc4_launch(in_split, nbr, wimg, out, ldo, n_out, Cin, Cout, K, scale, shift, residual, act, tile_row0,
-                                      tile_rows, tile_group, tiles, out_rows, out_split, out_split_relu, NT, stream);
-    }
     // 64-column tiles: the gathered operand lives in TMEM (spconv_ts.cu), CG3D_TC_TS=0 restores the shared-memory kernel
-    const char* ts_env = getenv("CG3D_TC_TS");
     // (split-K launches stay on the shared-memory kernel: few tiles of dense taps, where the per-thread row loads of the
     // TMEM gather are L1-bound -- 7^3 RoI pooling contraction 0.31 vs 0.35 ms)
-    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && ks == 1 && !stacked && !use_tma && !dense;
+    const char* ts_env = getenv("CG3D_TC_TS");
+    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && ks == 1;
     if (ts)
         rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
                                    a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,
                                    a.ksplit, a.zstride, dbg, stream);
-    else if (stacked)
-        rc = stash ? launch_tc<64, 2, true, true>(a, tmap, tiles, s) : launch_tc<64, 2, false, true>(a, tmap, tiles, s);
-    else if (use_tma || dense) {
-        if (stash)
-            rc = NT == 256 ? launch_tc<256, 2, true, false, true>(a, tmap, tiles, s)
-                           : (NT == 128 ? launch_tc<128, 3, true, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, true, false, true>(a, tmap, tiles, s));
-        else
-            rc = NT == 256 ? launch_tc<256, 2, false, false, true>(a, tmap, tiles, s)
-                           : (NT == 128 ? launch_tc<128, 3, false, false, true>(a, tmap, tiles, s) : launch_tc<64, 4, false, false, true>(a, tmap, tiles, s));
-    } else if (NT == 64 && cps2 && Cin % 64 == 0) {
+    else if (NT == 64 && cps2 && Cin % 64 == 0) {
         // 64-column tiles: two 32-channel sub-tiles per barrier phase (2 stages of 48 KB instead of 4 of 24 KB)
-        rc = stash ? launch_tc<64, 2, true, false, false, 2>(a, tmap, tiles, s) : launch_tc<64, 2, false, false, false, 2>(a, tmap, tiles, s);
+        rc = stash ? launch_tc<64, 2, true, 2>(a, tiles, s) : launch_tc<64, 2, false, 2>(a, tiles, s);
     } else if (stash)
-        rc = NT == 256 ? launch_tc<256, 2, true>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tmap, tiles, s) : launch_tc<64, 4, true>(a, tmap, tiles, s));
+        rc = NT == 256 ? launch_tc<256, 2, true>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, true>(a, tiles, s) : launch_tc<64, 4, true>(a, tiles, s));
     else
-        rc = NT == 256 ? launch_tc<256, 2, false>(a, tmap, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tmap, tiles, s) : launch_tc<64, 4, false>(a, tmap, tiles, s));
+        rc = NT == 256 ? launch_tc<256, 2, false>(a, tiles, s) : (NT == 128 ? launch_tc<128, 3, false>(a, tiles, s) : launch_tc<64, 4, false>(a, tiles, s));
     if (rc == 0 && ks > 1) {
         const long long total = (long long)n_out * (Cout / 4);
         const long long b = (total + 255) / 256;

@@ -431,18 +431,10 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
         if split_out is not None and Cout % 32 == 0 and out.stride(0) == Cout:
             So = torch.empty((n_out, 2 * Cout), dtype=torch.int16, device=out.device)
             out._cg3d_split = {(out.data_ptr(), out._version, out.stride(0), 1 if split_out == "relu" else 0): So}
-        if pairs_route(nbr, Cin, Cout, K):
-            # a (row tile, tap) holds a fraction of the tile's rows: GEMM over compacted rule pairs (spconv_pairs.cu)
-            if tiles is not None:
-                pt = tiles.with_tile(pairs_tile_rows())
-                targs = (pt.row0, pt.rows, pt.group, pt.n, out_rows)
-            _call("cg3d_spconv_pairs", split_rows(Fin, in_act), nbr, weight_image(W, pairs=True), out, out.stride(0), n_out,
-                  Cin, Cout, K, scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, meta=meta)
-        else:
-            ks = _lib.host("cg3d_spconv_tc_splitk", n_out, Cin, Cout, K, 1 if tiles else 0, tiles.n if tiles else 0)
-            ws = torch.empty((ks * n_out * Cout,), dtype=torch.float32, device=out.device) if ks > 1 else None
-            _call("cg3d_spconv_tc", split_rows(Fin, in_act), Fin.shape[0], nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
-                  scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, ws, meta=meta)
+        ks = _lib.host("cg3d_spconv_tc_splitk", n_out, Cin, Cout, K, 1 if tiles else 0, tiles.n if tiles else 0)
+        ws = torch.empty((ks * n_out * Cout,), dtype=torch.float32, device=out.device) if ks > 1 else None
+        _call("cg3d_spconv_tc", split_rows(Fin, in_act), Fin.shape[0], nbr, weight_image(W), out, out.stride(0), n_out, Cin, Cout, K,
+              scale, shift, residual, ACT[act], *targs, So, 1 if split_out == "relu" else 0, ws, meta=meta)
     else:
         _call("cg3d_spconv_simt", Fin, Fin.stride(0), ACT[in_act], nbr, W, out, out.stride(0), n_out, Cin, Cout, K,
               scale, shift, residual, ACT[act], *targs, meta=meta)
@@ -472,43 +464,22 @@ def split_rows(F: torch.Tensor, in_act=None) -> torch.Tensor:
     return cache[key]
 
 
-# CG3D_PAIRS=1 sends the rule maps of 64 -> 64 channel layers with at least PAIRS_MIN_K taps to the pair-compacted kernel
-# (spconv_pairs.cu v2: 352-row tiles, <= 64 pairs per stage, weights as the M operand).  Parity-tested, OFF by default: on
-# B200 it is still behind the row-stationary kernel (9^3 class conv 7.7 vs 6.8 ms, 3^3 64-channel layers 0.25-0.45 vs
-# 0.17-0.20 ms): 12 MMAs per (tap, <= 64 pairs) at >= 52 clk each and ~1000 shared-memory wavefronts per stage
-# (profiles/r2_pairs_v2.md has the role-by-role numbers).
-PAIRS_MIN_K = int(os.environ.get("CG3D_PAIRS_MIN_K", "27"))
-PAIRS_MAX_COUT = int(os.environ.get("CG3D_PAIRS_MAX_COUT", "64"))
-_PAIRS = {"on": os.environ.get("CG3D_PAIRS", "0") == "1"}
-
-
-def pairs_route(nbr, Cin: int, Cout: int, K: int) -> bool:
-    return (nbr is not None and _PAIRS["on"] and K >= PAIRS_MIN_K and Cin == 64 and Cout % 64 == 0
-            and Cout <= PAIRS_MAX_COUT)
-
-
-def pairs_tile_rows() -> int:
-    return _lib.host("cg3d_spconv_pairs_tile_rows")
-
-
 def tc_supported(Cin: int, Cout: int, K: int = 1) -> bool:
     return Cin % 32 == 0 and Cout % 64 == 0 and K <= 729
 
 
-def weight_image(W: torch.Tensor, pairs: bool = False) -> torch.Tensor:
+def weight_image(W: torch.Tensor) -> torch.Tensor:
     """bf16 hi/lo split + UMMA-swizzled image of a weight tensor.  Built once and kept ON the tensor
-    object (so it dies with it); rebuilt when the tensor is modified in place or moved.
-    pairs=True: the stacked [W_hi ; W_lo] image of the pair-compacted kernel."""
-    attr = "_cg3d_wimg_pairs" if pairs else "_cg3d_wimg"
-    cached = getattr(W, attr, None)
+    object (so it dies with it); rebuilt when the tensor is modified in place or moved."""
+    cached = getattr(W, "_cg3d_wimg", None)
     if cached is not None and cached[0] == (W.data_ptr(), W._version):
         return cached[1]
     Cin, Cout = W.shape[-2], W.shape[-1]
     K = W.shape[-3] if W.dim() >= 3 else 1
     G = W.shape[0] if W.dim() == 4 else 1
     img = torch.empty((W.numel() * 4,), dtype=torch.uint8, device=W.device)
-    _call("cg3d_spconv_pairs_prepare" if pairs else "cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
-    setattr(W, attr, ((W.data_ptr(), W._version), img))
+    _call("cg3d_spconv_tc_prepare", W.detach(), G, K, Cin, Cout, img)
+    W._cg3d_wimg = ((W.data_ptr(), W._version), img)
     return img
 
 

@@ -143,15 +143,15 @@ int cg3d_spconv_simt(const float* in, int ldi, int in_act, const int* nbr, const
  *   cg3d_spconv_tc_prepare  weights: the pre-swizzled shared-memory image of W, made once per weight tensor (same
  *                           byte count as the fp32 weights), streamed by bulk async copies.
  * cg3d_spconv_tc_ntile(Cout) = NT (0: unsupported).  Grouped mode / out_rows as above with tiles of <= 128 rows.
- * n_in: rows of in_split (the gather is a TMA tile::gather4 over the [n_in][2 Cin] bf16 tensor; rule-map entries outside
- * [0, n_in), i.e. the -1 of a missing neighbour, read as zero rows).
+ * n_in: rows of in_split (rule-map entries must lie in [0, n_in) or be -1 = no neighbour: a zero row).  Launches whose
+ * column tile is 64 wide (Cout == 64 layers) keep the gathered operand in tensor memory (spconv_ts.cu: register gather ->
+ * tcgen05.st, tcgen05.mma with A from TMEM); wider tiles gather into shared memory with cp.async.
  * splitk_ws (may be NULL): launches with few row tiles and a long K loop (the 7^3 RoI pooling contraction) are split over
  * cg3d_spconv_tc_splitk(...) CTAs per tile; the partial slabs (that many x n_out x Cout floats) are added in a fixed order
  * by a second pass, so the result stays deterministic.
  * out_split (may be NULL): the epilogue also writes the result (ReLU'd when out_split_relu = 1) in the split layout
  * [n_out][2 * Cout], i.e. the operand of the next convolution, which then needs no cg3d_split_bf16 pass. */
 int cg3d_spconv_tc_ntile(int Cout);
-int cg3d_spconv_tc_stacked(int Cin, int Cout);   /* 1: Cout == 64 layer, weights stacked [hi ; lo] along N (2 MMAs per k-step) */
 int cg3d_spconv_tc_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
 int cg3d_split_bf16(const float* in, int ld, int n, int C, int relu, unsigned short* out, void* stream);
 int cg3d_spconv_tc_splitk(int n_out, int Cin, int Cout, int K, int grouped, int n_tiles);   /* split-K factor (1 = none) */
@@ -159,24 +159,6 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
                    int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
                    int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
                    const int* out_rows, unsigned short* out_split, int out_split_relu, float* splitk_ws, void* stream);
-
-/* Same contraction as a GEMM over the COMPACTED rule pairs (Cin == 64, Cout % 64 == 0, 1 < K <= 729): the 9^3 / 5^3
- * per-class convolutions of cagroup_head.py:255-266, the 64-channel 3^3 layers of biresnet.py:246-266 and
- * cagroup_head.py:166 -- layers where a (row tile, tap) holds only 3-25 % of the tile's rows, so the row-stationary
- * kernel spends its shared-memory and L2 -> SM bandwidth on zero rows and on re-streaming the tap's weights every 128
- * rows.  Operand roles swapped: the tap's weights are the M = 64 operand, the tap's compacted pairs of a
- * cg3d_spconv_pairs_tile_rows() = 448-row tile the N operand (8..64 per stage), results scattered into a shared-memory
- * accumulator with ONE owner thread per word.  MMA work is proportional to the number of pairs instead of rows x taps.
- * Same arguments, precision (bf16 hi/lo split, three products, fp32 accumulation) and determinism as cg3d_spconv_tc;
- * grouped launches pass tiles of at most cg3d_spconv_pairs_tile_rows() rows; the weight image has its own layout
- * (cg3d_spconv_pairs_prepare, same byte count as the fp32 weights). */
-int cg3d_spconv_pairs_supported(int Cin, int Cout, int K);
-int cg3d_spconv_pairs_tile_rows(void);
-int cg3d_spconv_pairs_prepare(const float* W, int G, int K, int Cin, int Cout, unsigned char* img, void* stream);
-int cg3d_spconv_pairs(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo,
-                      int n_out, int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual,
-                      int act, const int* tile_row0, const int* tile_rows, const int* tile_group, int n_tiles,
-                      const int* out_rows, unsigned short* out_split, int out_split_relu, void* stream);
 
 /* out = act(x * scale + shift + add) on an [n, C] matrix with row strides ldx / ldo; scale, shift, add
  * ([n, C] dense) may be NULL.  Pre-activation BatchNorm+ReLU of DAPPM (biresnet.py:109-174). */

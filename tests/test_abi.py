@@ -28,7 +28,7 @@ def test_every_stream_entry_point_ends_with_stream():
     from cagroup3d_b200 import _lib
     _lib.parse_header()
     assert _lib._host_only == {"cg3d_hash_capacity", "cg3d_scan_workspace_ints", "cg3d_sort_workspace_ints",
-                               "cg3d_spconv_tc_ntile", "cg3d_spconv_tc_stacked", "cg3d_spconv_pairs_supported", "cg3d_spconv_pairs_tile_rows",
+                               "cg3d_spconv_tc_ntile",
                                "cg3d_segment_mean_workspace", "cg3d_spconv_tc_splitk", "cg3d_spconv_wgrad_slabs",
                                "cg3d_bn_train_workspace", "cg3d_focal_loss_workspace", "cg3d_loss_workspace", "cg3d_knn_grid_workspace"}
 
@@ -40,8 +40,6 @@ def test_host_only_helpers(lib):
         assert _lib.scan_workspace_ints(n) >= 1
         assert _lib.sort_workspace_ints(n) >= 1
     assert [_lib.host("cg3d_spconv_tc_ntile", c) for c in (64, 128, 192, 256, 512, 18)] == [64, 128, 64, 256, 256, 0]
-    assert [_lib.host("cg3d_spconv_pairs_supported", *a) for a in ((64, 64, 729), (64, 128, 125), (128, 64, 27), (64, 64, 1))] == [1, 1, 0, 0]
-    assert _lib.host("cg3d_spconv_pairs_tile_rows") % 32 == 0
     assert 2 * _lib.host("cg3d_segment_mean_workspace", 1000, 1) >= 1000 + 6          # n points in a single segment
 
 

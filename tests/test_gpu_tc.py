@@ -95,59 +95,11 @@ def test_split_rows_layout(lib):
         assert ((hi + lo) - want).abs().max().item() <= 2 ** -16 * want.abs().max().item()
 
 
-@pytest.mark.parametrize("k,cout,grouped", [(5, 64, False), (5, 128, False), (9, 64, True), (7, 64, False), (3, 64, False)])
-def test_spconv_pairs_vs_simt_and_oracle(lib, monkeypatch, k, cout, grouped):
-    """pair-compacted tcgen05 kernel (wide kernels over thin maps) == exact fp32 SIMT kernel == CPU oracle, incl. grouped
-    per-class weights, a ragged last tile, residual + ELU epilogue, the split-bf16 second output and rows without any pair."""
+@pytest.mark.parametrize("cout", [128, 64])
+def test_conv_at_query_coordinates(lib, cout):
+    """conv evaluated at foreign query coordinates (RoI grid conv, A12): most queries have few or no neighbours.  Cout = 64
+    runs the TMEM-operand kernel (spconv_ts.cu, no stash: K = 125), Cout = 128 the shared-memory one."""
     from cagroup3d_b200 import sparse as S
-    g = torch.Generator().manual_seed(7)
-    # a ~30 % occupied volume (as the class maps of the head): many pairs per (tile, tap), the centre tap fills a tile
-    c = torch.cat([torch.randint(0, 2, (2600, 1), generator=g), torch.randint(0, 20, (2600, 2), generator=g),
-                   torch.randint(0, 9, (2600, 1), generator=g)], 1).float()
-    ox = me.from_points(c, torch.randn((2600, 64), generator=g))
-    n = ox.F.shape[0]
-    G = 3 if grouped else 1
-    W = torch.randn((G, k ** 3, 64, cout), generator=g) / np.sqrt(64 * 27)
-    scale, shift = torch.rand((G, cout), generator=g) + 0.5, torch.randn((G, cout), generator=g)
-    res = torch.randn((n, cout), generator=g)
-    x = to_gpu_sparse(ox.C, ox.F, 1)
-    nbr = S.neighbor_table(x.cmap, x.cmap, k, x.mgr)
-    offs = [0, n // 3, n // 3 + 77, n] if grouped else [0, n]
-    Wd = W.to(DEV) if grouped else W[0].to(DEV)
-    sc, sh = (scale.to(DEV), shift.to(DEV)) if grouped else (scale[0].to(DEV), shift[0].to(DEV))
-    kw = dict(scale=sc, shift=sh, residual=res.to(DEV), act="elu", in_act="relu")
-    assert lib.cg3d_spconv_pairs_supported(64, cout, k ** 3) == 1 and k ** 3 >= S.PAIRS_MIN_K
-    monkeypatch.setitem(S._PAIRS, "on", True)
-    monkeypatch.setattr(S, "PAIRS_MAX_COUT", 128)          # also the two-slice launch (not routed by default)
-    assert S.pairs_route(nbr, 64, cout, k ** 3)
-    got = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 128) if grouped else None, impl="tc",
-                      split_out="relu", **kw)
-    want = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 64) if grouped else None, impl="simt", **kw)
-    torch.cuda.synchronize()
-    mag = max(1.0, want.abs().max().item())
-    assert (got - want).abs().max().item() <= 2e-4 * mag
-    # split output = bf16 hi | lo of relu(result)
-    sp = got._cg3d_split[(got.data_ptr(), got._version, got.stride(0), 1)].view(torch.bfloat16).view(n, cout // 32, 2, 32).float()
-    assert ((sp[:, :, 0] + sp[:, :, 1]).reshape(n, cout) - torch.relu(got)).abs().max().item() <= 2 ** -15 * mag
-    # oracle (per group)
-    for i in range(G):
-        ref = me.conv(ox.with_F(torch.relu(ox.F)), W[i], k, 1).F[offs[i]:offs[i + 1]]
-        w = torch.nn.functional.elu(ref * scale[i] + shift[i] + res[offs[i]:offs[i + 1]])
-        assert (got[offs[i]:offs[i + 1]].cpu() - w).abs().max().item() <= 2e-4 * mag
-    # run-to-run deterministic
-    again = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 128) if grouped else None, impl="tc", **kw)
-    assert torch.equal(again, got)
-    # the default route for the same layer (row-stationary kernel) agrees as well
-    monkeypatch.setitem(S._PAIRS, "on", False)
-    rs = S.gemm_rows(x.F, nbr, Wd, n, k ** 3, tiles=S.make_tiles(offs, DEV, 128) if grouped else None, impl="tc", **kw)
-    assert (rs - want).abs().max().item() <= 2e-4 * mag
-
-
-def test_spconv_pairs_at_query_coordinates(lib, monkeypatch):
-    """conv evaluated at foreign query coordinates (RoI grid conv, A12): most queries have few or no neighbours."""
-    from cagroup3d_b200 import sparse as S
-    monkeypatch.setitem(S._PAIRS, "on", True)
-    monkeypatch.setattr(S, "PAIRS_MAX_COUT", 128)
     ox = oracle_tensor(33, 64, n=1500)
     x = to_gpu_sparse(ox.C, ox.F, 1)
     g = torch.Generator().manual_seed(8)
@@ -155,7 +107,7 @@ def test_spconv_pairs_at_query_coordinates(lib, monkeypatch):
     q = torch.unique(q, dim=0).to(DEV)
     qmap = S.build_map(q.contiguous(), 1, x.mgr)
     nbr = S.neighbor_table(x.cmap, qmap, 5, x.mgr)
-    W = (torch.randn((125, 64, 128), generator=g) / 40).to(DEV)
+    W = (torch.randn((125, 64, cout), generator=g) / 40).to(DEV)
     got = S.gemm_rows(x.F, nbr, W, qmap.n, 125, act="elu", impl="tc")
     want = S.gemm_rows(x.F, nbr, W, qmap.n, 125, act="elu", impl="simt")
     assert (got - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())

@@ -11,7 +11,7 @@ def main():
     rec = []
     orig = S._call
     def spy(name, *args, meta=None):
-        if name in ("cg3d_spconv_pairs", "cg3d_spconv_tc") and args[2 if name == "cg3d_spconv_pairs" else 2] is not None:
+        if name == "cg3d_spconv_tc" and args[2] is not None:
             rec.append((name, args))
         return orig(name, *args, meta=meta)
     S._call = spy
@@ -19,13 +19,11 @@ def main():
     S._call = orig
     torch.cuda.synchronize()
     for name, args in rec:
-        if name != ("cg3d_spconv_pairs" if os.environ.get("CG3D_PAIRS", "0") == "1" else "cg3d_spconv_tc"):
-            continue
-        K = args[8] if name == "cg3d_spconv_pairs" else args[9]
+        K = args[9]
         if K < int(os.environ.get("PROBE_MIN_K", "27")):
             continue
-        n_out = args[5] if name == "cg3d_spconv_pairs" else args[6]
-        line = f"{name} K={K} n_out={n_out} Cin={args[6] if name == 'cg3d_spconv_pairs' else args[7]}"
+        n_out = args[6]
+        line = f"{name} K={K} n_out={n_out} Cin={args[7]}"
         for dbg in os.environ.get("PROBE_DEBUGS", "0").split(","):
             os.environ["CG3D_TC_DEBUG"] = dbg                 # timing ablations of the SAME launch (results are garbage for dbg != 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
