@@ -73,25 +73,39 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 8000000000LL) __trap();     // ~4 s watchdog: a protocol bug must not hang the GPU
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)          // suspend-time hint: sleep in hardware until the phase flips
+        : "memory");
+    return ok != 0;
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;                   // the common case costs one instruction, no clock read
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 8000000000LL) __trap();     // ~4 s watchdog: a protocol bug must not hang the GPU
+}
+// bulk_copy_g2s / mbar_expect_tx_elect / umma_bf16 / umma_commit are called by ALL lanes of a converged warp; one elected lane
+// issues.  (From an `if (lane == 0)` branch ptxas wraps every such instruction in an ELECT / BRA.U.ANY loop over the active
+// lanes, ~70 clk per tcgen05.mma in the ncu source view: profiles/r2_spconv_ts.md.)
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -125,14 +139,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -164,6 +182,7 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, int rel
 // development aid (CG3D_TC_DEBUG & 8): per-role cycle counters summed over CTAs, printed by the host after the launch
 __device__ unsigned long long g_tc_prof[16];
 #define TC_PROF(i, v) do { if (a.debug & 8) atomicAdd(&g_tc_prof[i], (unsigned long long)(v)); } while (0)
+#define TC_CLK() ((a.debug & 8) ? clock64() : 0LL)      // the counters' clock reads cost issue slots: only when asked for
 
 struct TcArgs {
     const unsigned short* in_split;   // [rows][Cin/32][hi 32 | lo 32] bf16
@@ -215,7 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     __shared__ int n_active_s;
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const long long t_start = clock64();
+    const long long t_start = TC_CLK();
     int row0, nrows, g = 0;
     if (a.tile_row0) {
         row0 = a.tile_row0[blockIdx.x];
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
     const int n_iters = (a1 - a0) * nchunks;
     float* const outp = a.out + (size_t)blockIdx.z * a.zstride;
     const uint32_t tmem_base = tmem_slot;
-    const long long t_main = clock64();
+    const long long t_main = TC_CLK();
     if (t == 0) { TC_PROF(0, 1); TC_PROF(1, t_main - t_start); TC_PROF(10, n_iters); }
 
     if (warp < NPROD / 32) {
@@ -365,9 +384,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                 zm[j] = lazy_zero ? (dirty[j] & ~okm[j]) : ~okm[j];
                 dirty[j] = okm[j];
             }
-            const long long p1 = clock64();
+            const long long p1 = TC_CLK();
             mbar_wait(empty_s, ph);
-            if (t == 0) TC_PROF(8, clock64() - p1);
+            if (t == 0) TC_PROF(8, TC_CLK() - p1);
             if (!(a.debug & 4)) {
 #pragma unroll
               for (int u = 0; u < CPS; ++u) {
@@ -417,12 +436,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         constexpr int C_BEGIN_STEP = 32;
         const int c_begin = half * (NT / 2), c_end = (half + 1) * (NT / 2);
         load_residual(c_begin);
-        const long long e0 = clock64();
+        const long long e0 = TC_CLK();
         if (n_iters > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
         }
-        const long long e1 = clock64();
+        const long long e1 = TC_CLK();
         if (t == 0) { TC_PROF(5, e1 - t_main); TC_PROF(11, e1 - e0); }
 #pragma unroll 1
         for (int c0 = c_begin; c0 < c_end; c0 += C_BEGIN_STEP) {
@@ -478,10 +497,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
             if (c0 + C_BEGIN_STEP < c_end) load_residual(c0 + C_BEGIN_STEP);
         }
         tc_fence_before();
-        if (t == 0) TC_PROF(6, clock64() - e1);
+        if (t == 0) TC_PROF(6, TC_CLK() - e1);
     } else if (warp == NPROD / 32) {
-        // ================= weight-tile loader (bulk async copy) =================
-        if (lane == 0) {
+        // ================= weight-tile loader (bulk async copy): the whole warp runs the loop =================
+        {
             int it = 0;
             for (int ai = a0; ai < a1; ++ai) {
                 const int k = taps[ai];
@@ -490,7 +509,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     const uint32_t nbytes = (a.debug & 1) ? 16u : (uint32_t)B_BYTES;
-                    mbar_expect_tx(full0 + 8 * s, CPS * nbytes);
+                    mbar_expect_tx_elect(full0 + 8 * s, CPS * nbytes);
 #pragma unroll
                     for (int u = 0; u < CPS; ++u) {
                         const size_t blk = (((size_t)g * a.K + k) * (nchunks * CPS) + c * CPS + u) * ntn + blockIdx.y;
@@ -502,16 +521,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         }
         __syncwarp();
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the loop, one elected lane issues =================
+        {
             long long w_acc = 0, i_acc = 0;
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                const long long m0 = clock64();
+                const long long m0 = TC_CLK();
                 mbar_wait(full0 + 8 * s, ph);
-                const long long m1 = clock64();
-                if (it == 0) TC_PROF(4, m1 - m0); else w_acc += m1 - m0;
+                const long long m1 = TC_CLK();
+                if (it == 0) { if (lane == 0) TC_PROF(4, m1 - m0); } else w_acc += m1 - m0;
                 fence_async_smem();                   // cp.async wrote the A tile through the generic proxy
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)(s * STAGE_BYTES);
@@ -541,9 +560,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
                     }
                 }
                 umma_commit(empty0 + 8 * s);
-                i_acc += clock64() - m1;
+                i_acc += TC_CLK() - m1;
             }
-            TC_PROF(2, w_acc); TC_PROF(3, i_acc);
+            if (lane == 0) { TC_PROF(2, w_acc); TC_PROF(3, i_acc); }
             if (n_iters > 0) umma_commit(accum_bar);
         }
         __syncwarp();
@@ -553,7 +572,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_tc_kernel(TcArgs a) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
     }
-    if (t == 0) TC_PROF(7, clock64() - t_start);
+    if (t == 0) TC_PROF(7, TC_CLK() - t_start);
 }
 
 // fp32 W[G][K][Cin][Cout] -> per (g, k, 32-channel chunk, NT-column tile) block of NT * 128 bytes:
