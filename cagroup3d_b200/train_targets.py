@@ -141,16 +141,21 @@ class CrossEntropy(torch.nn.Module):
 
 
 class IoU3DLoss(torch.nn.Module):
-    """iou3d_loss.py:61-98 with with_yaw=False (ScanNet): axis-aligned (x, y, z, dx, dy, dz) boxes."""
+    """iou3d_loss.py:61-98.  with_yaw=False (ScanNet): axis-aligned (x, y, z, dx, dy, dz) boxes, loss and gradient in one
+    kernel (cg3d_iou_loss_aa).  with_yaw=True (SUN RGB-D): rot_iou_loss.RotatedIoU3DLoss."""
 
     def __init__(self, with_yaw=False, reduction="mean", loss_weight=1.0):
         super().__init__()
-        if with_yaw:
-            raise NotImplementedError("the rotated IoU loss (SUN RGB-D) is not on the CUDA training path yet")
         self.loss_weight = loss_weight
+        self.rotated = None
+        if with_yaw:                       # SUN RGB-D: differentiable rotated IoU around cg3d_sort_vertices
+            from .rot_iou_loss import RotatedIoU3DLoss
+            self.rotated = RotatedIoU3DLoss(reduction=reduction, loss_weight=loss_weight)
 
     def forward(self, pred, target, weight=None, avg_factor=None, **kw):
         _require_cuda(pred)
+        if self.rotated is not None:
+            return self.rotated(pred, target, weight=weight, avg_factor=avg_factor, **kw)
         assert weight is not None and avg_factor is not None
         if not bool(torch.any(weight > 0)):
             return pred.sum() * weight.sum()                      # iou3d_loss.py:75-76
