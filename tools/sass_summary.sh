@@ -2,12 +2,16 @@
 # SASS evidence of the Blackwell paths: per kernel of libcagroup3d_b200.so, the counts of the tcgen05 / TMEM /
 # bulk-copy mnemonics.   bash tools/sass_summary.sh > profiles/r2_sass_summary.txt
 LIB=cagroup3d_b200/libcagroup3d_b200.so
-echo "# cuobjdump -sass $LIB | per-function counts (sm_100a); UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit,"
-echo "# UBLKCP = cp.async.bulk, UTMALDG = cp.async.bulk.tensor (TMA), LDGSTS = cp.async, SYNCS = mbarrier"
-printf "%-78s %8s %6s %6s %7s %7s %8s %7s %6s\n" kernel UTCHMMA LDTM STTM UTCBAR UBLKCP UTMALDG LDGSTS SYNCS
+echo "# cuobjdump -sass $LIB | per-function instruction counts (sm_100a); UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st,"
+echo "# UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk, LDGSTS = cp.async, SYNCS = mbarrier ops; kernels without any of them omitted"
+printf "%8s %5s %5s %7s %7s %7s %6s  %s\n" UTCHMMA LDTM STTM UTCBAR UBLKCP LDGSTS SYNCS kernel
 cuobjdump -sass $LIB | awk '
 /Function :/ { if (name != "") emit(); name=$3; for (k in c) delete c[k]; next }
-/UTCHMMA/ {c["UTCHMMA"]++} /LDTM/ {c["LDTM"]++} /STTM/ {c["STTM"]++} /UTCBAR/ {c["UTCBAR"]++} /UBLKCP/ {c["UBLKCP"]++}
-/UTMALDG/ {c["UTMALDG"]++} /LDGSTS/ {c["LDGSTS"]++} /SYNCS/ {c["SYNCS"]++}
-function emit() { if (c["UTCHMMA"]+c["LDTM"]+c["STTM"]+c["UBLKCP"]+c["UTMALDG"] > 0) printf "%-78s %8d %6d %6d %7d %7d %8d %7d %6d\n", substr(name,1,78), c["UTCHMMA"], c["LDTM"], c["STTM"], c["UTCBAR"], c["UBLKCP"], c["UTMALDG"], c["LDGSTS"], c["SYNCS"] }
-END { emit() }' | while read -r line; do n=$(echo "$line" | awk '{print $1}'); d=$(echo "$n" | c++filt 2>/dev/null | sed 's/(anonymous namespace):://; s/<unnamed>:://; s/void //' | cut -c1-78); echo "$line" | awk -v d="$d" '{printf "%-78s %8s %6s %6s %7s %7s %8s %7s %6s\n", d, $2,$3,$4,$5,$6,$7,$8,$9}'; done
+/^ +\/\*[0-9a-f]+\*\/ / {
+  if ($0 ~ /UTCHMMA/) c["UTCHMMA"]++; if ($0 ~ / LDTM/) c["LDTM"]++; if ($0 ~ / STTM/) c["STTM"]++; if ($0 ~ /UTCBAR/) c["UTCBAR"]++;
+  if ($0 ~ /UBLKCP/) c["UBLKCP"]++; if ($0 ~ /LDGSTS/) c["LDGSTS"]++; if ($0 ~ /SYNCS/) c["SYNCS"]++ }
+function emit() { if (c["UTCHMMA"]+c["LDTM"]+c["STTM"]+c["UBLKCP"] > 0) printf "%8d %5d %5d %7d %7d %7d %6d  %s\n", c["UTCHMMA"], c["LDTM"], c["STTM"], c["UTCBAR"], c["UBLKCP"], c["LDGSTS"], c["SYNCS"], name }
+END { emit() }' | while read -r a b c d e f g name; do
+  dn=$(echo "$name" | cu++filt 2>/dev/null | python3 -c "import sys,re; t=sys.stdin.read().strip(); t=re.sub(r'\\(anonymous namespace\\)::|<unnamed>::|^void |\\((int|bool)\\)','',t); print(re.sub(r'\\((Tc|Ts|Wg)Args.*','',t))")
+  printf "%8s %5s %5s %7s %7s %7s %6s  %s\n" $a $b $c $d $e $f $g "$dn"
+done
