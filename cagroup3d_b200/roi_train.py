@@ -12,7 +12,9 @@ module and parameters.
     -> batch-statistics BatchNorm
     regression MLP (Linear + BatchNorm1d + ReLU [+ Dropout]) x 2 + Linear with bias, as 1x1 convs
 
-The proposal target layer and the RoI losses (cagroup_proposal_target_layer.py, cagroup_roi_head.py:512-615) are not built yet.
+Below it: the proposal target layer (cagroup_proposal_target_layer.py: ProposalTargetLayer, same-class IoU as one masked matrix),
+assign_targets / the residual coder and the smooth-L1 RoI regression loss (cagroup_roi_head.py:288-326,512-575) for code_size 6;
+the yaw / sin-cos codes and USE_IOU_LOSS of the SUN RGB-D config are not built.
 """
 from __future__ import annotations
 
