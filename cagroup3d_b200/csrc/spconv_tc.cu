@@ -48,7 +48,7 @@
 int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
                           int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
                           const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
-                          unsigned short* out_split, int out_split_relu, int ksplit, long long zstride, int debug, void* stream);
+                          unsigned short* out_split, int out_split_relu, int NT, int ksplit, long long zstride, int debug, void* stream);
 
 namespace {
 
@@ -769,12 +769,18 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     // 64-column tiles: the gathered operand lives in TMEM (spconv_ts.cu), CG3D_TC_TS=0 restores the shared-memory kernel
     // (split-K launches stay on the shared-memory kernel: few tiles of dense taps, where the per-thread row loads of the
     // TMEM gather are L1-bound -- 7^3 RoI pooling contraction 0.31 vs 0.35 ms)
+    // 128-column tiles too when the rule map is sparse in rows (K > 27: the RoI grid conv at query coordinates, 3.7 of 125
+    // taps per row: 0.93 -> 0.66 ms); on the dense 27-tap maps of the 128..512-channel layers the thread-per-row gather is
+    // L1-bound and loses 25 % to the shared-memory kernel.  CG3D_TC_TS: 0 = never, 64 = only 64-column tiles, 129 = every
+    // 64- / 128-column launch (timing experiments).
     const char* ts_env = getenv("CG3D_TC_TS");
-    const bool ts = !(ts_env && ts_env[0] == '0') && NT == 64 && Cin % 64 == 0 && ks == 1;
+    const int ts_max = ts_env ? atoi(ts_env) : 128;
+    const bool ts = Cin % 64 == 0 && ks == 1 &&
+                    ((NT == 64 && ts_max >= 64) || (NT == 128 && ts_max >= 128 && (K > STASH_K || ts_max > 128)));
     if (ts)
         rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
                                    a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,
-                                   a.ksplit, a.zstride, dbg, stream);
+                                   NT, a.ksplit, a.zstride, dbg, stream);
     else if (NT == 64 && cps2 && Cin % 64 == 0) {
         // 64-column tiles: two 32-channel sub-tiles per barrier phase (2 stages of 48 KB instead of 4 of 24 KB)
         rc = stash ? launch_tc<64, 2, true, 2>(a, tiles, s) : launch_tc<64, 2, false, 2>(a, tiles, s);

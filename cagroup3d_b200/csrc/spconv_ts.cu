@@ -1,8 +1,9 @@
 // 64-column sparse convolution tiles with the gathered operand in TENSOR MEMORY (tcgen05.mma with A from TMEM).
 //
 // spconv_tc.cu holds the description of the contraction, the bf16x3 precision scheme, the operand layouts and the
-// rule-map conventions; this file is the same math for the launches whose column tile is 64 wide (every Cout = 64 layer:
-// the 9^3 / 5^3 per-class convs of the head, the 64-channel stages of the backbone).
+// rule-map conventions; this file is the same math for the launches whose column tile is 64 or 128 wide (NT = 64: every
+// Cout = 64 layer -- the 9^3 / 5^3 per-class convs of the head, the 64-channel stages of the backbone; NT = 128: the
+// 128-channel stages and the RoI grid conv).
 //
 // Why.  With both operands in shared memory a 128 x 64 x 16 tcgen05.mma is bound by its operand fetch, not by the tensor
 // pipe: 4 KB of A + 2 KB of B per instruction at 128 B/clk = 48 clk (measured 52, profiles/r1_mma_probe.txt) against a
@@ -31,29 +32,30 @@
 namespace {
 
 constexpr int TM = 128;            // output rows per CTA (UMMA M) = TMEM lanes
-constexpr int NT = 64;             // output columns per CTA
 constexpr int KCH = 64;            // channels per stage
-constexpr int B_BYTES = NT * 128;  // one 32-channel weight sub-tile [n][hi 32 | lo 32]
-constexpr int STAGE_B = 2 * B_BYTES;
 constexpr int STASH_K = 27;
 constexpr int MAX_TAPS = 729;
-constexpr int NEPI = 8;            // epilogue warps (the first eight gather warps)
+constexpr int NEPI = 8;            // epilogue warps (the gather warps)
 constexpr int EPI_BYTES = NEPI * 32 * 36 * 4;
 // Shape: NG = 2 gather warp groups of four warps (group g fills the stages q = g (mod NG)), 10 warps, two CTAs per SM (256
-// TMEM columns each: accumulator + 3 A stages), so the prologue / epilogue of one tile overlaps the K loop of the other and
+// TMEM columns each: accumulator + A stages), so the prologue / epilogue of one tile overlaps the K loop of the other and
 // every SM has two MMA-issuing and two weight-loading warps.  (A one-CTA-per-SM shape with four groups, two MMA warps and two
 // accumulators was built and measured: equal on the 9^3 conv, 7 % faster on the 5^3 one, 35 % slower on K = 27 layers, and
 // its two accumulators make a row's sum depend on which taps its tile skips -- dropped.)
 // A group that waits for a slot's previous use to be consumed filled its last stage NG stages ago, after the MMAs of the
 // stage NG + SA back had completed; with SA >= NG that covers the slot's use before last, so a parity wait is unambiguous.
 constexpr int NG = 2;
-constexpr int SA = 3;              // A stages in TMEM
-constexpr int SB = 5;              // weight stages in shared memory (own ring, see the barriers)
 constexpr int NGW = 4 * NG;        // gather warps
 constexpr int NTHREADS = (NGW + 2) * 32;
-constexpr int TCOLS = NT + SA * KCH;   // 256
-constexpr int RING_BYTES = SB * STAGE_B > EPI_BYTES ? SB * STAGE_B : EPI_BYTES;
-constexpr int A_COL0 = NT;
+constexpr int TCOLS = 256;         // NT accumulator columns + SA A stages of 64 columns
+template <int NT> struct Tile {
+    static constexpr int B_BYTES = NT * 128;              // one 32-channel weight sub-tile [n][hi 32 | lo 32]
+    static constexpr int STAGE_B = 2 * B_BYTES;           // 16 KB (NT = 64) / 32 KB (NT = 128) per 64-channel stage
+    static constexpr int SA = (TCOLS - NT) / KCH;         // A stages in TMEM: 3 / 2
+    static constexpr int SB = NT == 64 ? 5 : 3;           // weight stages in shared memory (own ring, see the barriers)
+    static constexpr int RING_BYTES = SB * STAGE_B > EPI_BYTES ? SB * STAGE_B : EPI_BYTES;
+    static_assert(SA >= NG && SA * KCH + NT == TCOLS, "TMEM budget");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -127,9 +129,9 @@ __device__ __forceinline__ void umma_ts_bf16(uint32_t tmem_d, uint32_t tmem_a, u
 // by one from C++, every tcgen05.mma drags an ELECT, two VOTEU and 4 - 6 R2UR.BROADCAST along (~200 instructions per stage
 // on the issuing warp, which runs them in order: 75 % of its time in the ncu source view).
 //   a: TMEM column address of the stage's A tile ([hi 16 words | lo 16 words] per 32-channel half, a k-step = 8 words)
-//   b: shared-memory descriptor of the stage's first weight sub-tile (the second one B_BYTES further = +512 in 16-byte
-//      units; inside a 128-byte row: hi k-step kk at +2 kk, lo at +4 + 2 kk)
-__device__ __forceinline__ void umma_ts_stage(uint32_t tmem_d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t accum_first) {
+//   b / b2: shared-memory descriptors of the stage's two 32-channel weight sub-tiles (inside a 128-byte row: hi k-step kk
+//      at +2 kk, lo at +4 + 2 kk, in 16-byte units)
+__device__ __forceinline__ void umma_ts_stage(uint32_t tmem_d, uint32_t a, uint64_t b, uint64_t b2, uint32_t idesc, uint32_t accum_first) {
     asm volatile(
         "{\n\t"
         ".reg .pred q, p;\n\t"
@@ -157,25 +159,25 @@ __device__ __forceinline__ void umma_ts_stage(uint32_t tmem_d, uint32_t a, uint6
         "add.u64 tb, %2, 2;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 32;\n\t"
-        "add.u64 tb, %2, 512;\n\t"
+        "add.u64 tb, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 32;\n\t"
-        "add.u64 tb, %2, 516;\n\t"
+        "add.u64 tb, %5, 4;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 48;\n\t"
-        "add.u64 tb, %2, 512;\n\t"
+        "add.u64 tb, %5, 0;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 40;\n\t"
-        "add.u64 tb, %2, 514;\n\t"
+        "add.u64 tb, %5, 2;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 40;\n\t"
-        "add.u64 tb, %2, 518;\n\t"
+        "add.u64 tb, %5, 6;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "add.u32 ta, %1, 56;\n\t"
-        "add.u64 tb, %2, 514;\n\t"
+        "add.u64 tb, %5, 2;\n\t"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], tb, %3, p;\n\t"
         "}"
-        ::"r"(tmem_d), "r"(a), "l"(b), "r"(idesc), "r"(accum_first)
+        ::"r"(tmem_d), "r"(a), "l"(b), "r"(idesc), "r"(accum_first), "l"(b2)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -258,8 +260,10 @@ struct TsArgs {
                  // 16 = no MMAs, 64 = no rule-map loads in the K loop, 256 = no epilogue
 };
 
-template <bool STASH, bool PROF>
+template <int NT, bool STASH, bool PROF>
 __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
+    constexpr int B_BYTES = Tile<NT>::B_BYTES, STAGE_B = Tile<NT>::STAGE_B, SA = Tile<NT>::SA, SB = Tile<NT>::SB,
+                  RING_BYTES = Tile<NT>::RING_BYTES, A_COL0 = NT;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     constexpr int KCAP = STASH ? 32 : MAX_TAPS + 3;
 
@@ -471,21 +475,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
         int prs[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) prs[it] = __shfl_sync(0xffffffffu, prow, it * 4 + sub);
-        const int c0 = half * 32;
-        const int col = n0 + c0 + pc * 4;
+        // warp's columns: half * NT / 2 .. + NT / 2, in panels of 32
+        constexpr int PANELS = NT / 64;
         float4 rs[8];
+        auto load_residual = [&](int c0) {
+            const int col = n0 + c0 + pc * 4;
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-            rs[it] = (a.residual && prs[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)prs[it] * a.Cout + col))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
-        if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
+            for (int it = 0; it < 8; ++it)
+                rs[it] = (a.residual && prs[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(a.residual + (size_t)prs[it] * a.Cout + col))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        load_residual(half * (NT / 2));                   // everything that does not depend on the accumulator comes first
         if (n_iters > 0) {
             mbar_wait(accum_bar, 0);                      // every MMA has completed: the weight ring is idle as well
             tc_fence_after();
         }
-        if (!TS_DBG(256)) {
+#pragma unroll 1
+        for (int pnl = 0; pnl < PANELS; ++pnl) {
+            if (TS_DBG(256)) break;
+            const int c0 = half * (NT / 2) + pnl * 32;
+            const int col = n0 + c0 + pc * 4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.scale) sc = __ldg(reinterpret_cast<const float4*>(a.scale + (size_t)g * a.Cout + col));
+            if (a.shift) sh = __ldg(reinterpret_cast<const float4*>(a.shift + (size_t)g * a.Cout + col));
             uint32_t va[16], vb[16];
             if (n_iters > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, va);
@@ -503,6 +515,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
             float4 x[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + sub) * 36 + pc * 4);
+            __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int pr = prs[it];
@@ -529,6 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
                     }
                 }
             }
+            if (pnl + 1 < PANELS) load_residual(c0 + 32);
         }
       }
         tc_fence_before();
@@ -581,8 +595,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
                 tc_fence_after();
                 const long long m2 = TS_CLK();
                 if (!TS_DBG(16))
-                    umma_ts_stage(tmem_base, tmem_base + (uint32_t)(A_COL0 + sa * KCH), make_desc(base + (uint32_t)(sb * STAGE_B)), IDESC,
-                                  it ? 1u : 0u);
+                    umma_ts_stage(tmem_base, tmem_base + (uint32_t)(A_COL0 + sa * KCH), make_desc(base + (uint32_t)(sb * STAGE_B)),
+                                  make_desc(base + (uint32_t)(sb * STAGE_B + B_BYTES)), IDESC, it ? 1u : 0u);
                 umma_commit(empty0 + 8 * sa);
                 if (++sa == SA) { sa = 0; ph ^= 1u; }
                 if (++sb == SB) { sb = 0; phb ^= 1u; }
@@ -600,17 +614,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
     }
 }
 
-template <bool STASH, bool PROF>
+template <int NT, bool STASH, bool PROF>
 int launch_ts(const TsArgs& a, int tiles, cudaStream_t s) {
-    constexpr int smem = RING_BYTES + 1024 + (STASH ? STASH_K * TM * 4 : 0);
+    constexpr int smem = Tile<NT>::RING_BYTES + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_ts_kernel<STASH, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_ts_kernel<NT, STASH, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT, a.ksplit);
-    spconv_ts_kernel<STASH, PROF><<<grid, NTHREADS, smem, s>>>(a);
+    spconv_ts_kernel<NT, STASH, PROF><<<grid, NTHREADS, smem, s>>>(a);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -622,15 +636,20 @@ int launch_ts(const TsArgs& a, int tiles, cudaStream_t s) {
 int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const unsigned char* wimg, float* out, int ldo, int n_out,
                           int Cin, int Cout, int K, const float* scale, const float* shift, const float* residual, int act,
                           const int* tile_row0, const int* tile_rows, const int* tile_group, int tiles, const int* out_rows,
-                          unsigned short* out_split, int out_split_relu, int ksplit, long long zstride, int debug, void* stream) {
-    if (Cin % KCH != 0 || Cout % NT != 0 || K > MAX_TAPS) return -1;
+                          unsigned short* out_split, int out_split_relu, int NT, int ksplit, long long zstride, int debug, void* stream) {
+    if (Cin % KCH != 0 || (NT != 64 && NT != 128) || Cout % NT != 0 || K > MAX_TAPS) return -1;
     TsArgs a{in_split, nbr, wimg, out, scale, shift, residual, tile_row0, tile_rows, tile_group, out_rows, out_split,
              out_split_relu, n_out, Cin, Cout, K, act, ldo, ksplit, zstride, debug};
     const bool stash = nbr && K <= STASH_K;
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (debug) rc = stash ? launch_ts<true, true>(a, tiles, st) : launch_ts<false, true>(a, tiles, st);
-    else rc = stash ? launch_ts<true, false>(a, tiles, st) : launch_ts<false, false>(a, tiles, st);
+    if (NT == 64) {
+        if (debug) rc = stash ? launch_ts<64, true, true>(a, tiles, st) : launch_ts<64, false, true>(a, tiles, st);
+        else rc = stash ? launch_ts<64, true, false>(a, tiles, st) : launch_ts<64, false, false>(a, tiles, st);
+    } else {
+        if (debug) rc = stash ? launch_ts<128, true, true>(a, tiles, st) : launch_ts<128, false, true>(a, tiles, st);
+        else rc = stash ? launch_ts<128, true, false>(a, tiles, st) : launch_ts<128, false, false>(a, tiles, st);
+    }
     if (rc == 0 && (debug & 8)) {               // (any debug bit selects the instrumented build; 8 prints its counters)
         unsigned long long h[16], z[16] = {0};
         cudaStreamSynchronize((cudaStream_t)stream);
