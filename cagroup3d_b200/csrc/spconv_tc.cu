@@ -662,6 +662,13 @@ void tc_launch_shape(int n_out, int Cin, int Cout, int K, bool grouped, int n_ti
     if (adapt < 0) { const char* e = getenv("CG3D_TC_ADAPT_NT"); adapt = e ? atoi(e) : 1; }
     if (splitk < 0) { const char* e = getenv("CG3D_TC_SPLITK"); splitk = e ? atoi(e) : 1; }
     NT = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 0));
+    static int ntmax = -1;                                // CG3D_TC_NTMAX (timing experiments): cap the column tile
+    if (ntmax < 0) { const char* e = getenv("CG3D_TC_NTMAX"); ntmax = e ? atoi(e) : 256; }
+    while (NT > ntmax && NT > 64) NT >>= 1;
+    // 3^3-and-larger convs run 128-column tiles at most: two TMEM-operand CTAs per 256 columns beat one 256-column
+    // shared-memory CTA (256 -> 256 K = 27: 0.37 -> 0.31 ms, 128 -> 256: 0.18 -> 0.157); the 2^3 transposed conv
+    // (256 -> 256 at 307 k rows, one tap per row) does not (0.342 vs 0.324) and keeps 256 columns
+    if (K >= 27 && NT > 128) NT = 128;
     tiles = grouped ? n_tiles : cg3d_div_up(n_out, TM);
     ks = 1;
     if (NT == 0 || tiles == 0) return;
@@ -769,14 +776,11 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     // 64-column tiles: the gathered operand lives in TMEM (spconv_ts.cu), CG3D_TC_TS=0 restores the shared-memory kernel
     // (split-K launches stay on the shared-memory kernel: few tiles of dense taps, where the per-thread row loads of the
     // TMEM gather are L1-bound -- 7^3 RoI pooling contraction 0.31 vs 0.35 ms)
-    // 128-column tiles too when the rule map is sparse in rows (K > 27: the RoI grid conv at query coordinates, 3.7 of 125
-    // taps per row: 0.93 -> 0.66 ms); on the dense 27-tap maps of the 128..512-channel layers the thread-per-row gather is
-    // L1-bound and loses 25 % to the shared-memory kernel.  CG3D_TC_TS: 0 = never, 64 = only 64-column tiles, 129 = every
-    // 64- / 128-column launch (timing experiments).
+    // (with the 16x256b gather the TMEM-operand kernel is ahead on 128-column tiles too: 128 -> 128 K = 27 0.252 -> 0.229 ms,
+    // 512 -> 512 0.47 -> 0.39, RoI grid conv 0.93 -> 0.66.)  CG3D_TC_TS: 0 = never, 64 = only 64-column tiles.
     const char* ts_env = getenv("CG3D_TC_TS");
     const int ts_max = ts_env ? atoi(ts_env) : 128;
-    const bool ts = Cin % 64 == 0 && ks == 1 &&
-                    ((NT == 64 && ts_max >= 64) || (NT == 128 && ts_max >= 128 && (K > STASH_K || ts_max > 128)));
+    const bool ts = Cin % 64 == 0 && ks == 1 && (NT == 64 || NT == 128) && NT <= ts_max;
     if (ts)
         rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
                                    a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,

@@ -220,6 +220,24 @@ __device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint4 (&v)[16]) 
           "r"(v[14].x), "r"(v[14].y), "r"(v[14].z), "r"(v[14].w), "r"(v[15].x), "r"(v[15].y), "r"(v[15].z), "r"(v[15].w)
         : "memory");
 }
+// 16 TMEM lanes x 64 columns from one warp: repetition j = columns 8 j .. 8 j + 7; thread (rq = lane / 4, kq = lane % 4) holds
+// (row rq, columns 8 j + 2 kq, + 1) and (row rq + 8, same columns) -- the m16n8 accumulator fragment, eight times
+__device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint2 (&v)[8][2]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(v[0][0].x), "r"(v[0][0].y), "r"(v[0][1].x), "r"(v[0][1].y), "r"(v[1][0].x), "r"(v[1][0].y), "r"(v[1][1].x), "r"(v[1][1].y),
+          "r"(v[2][0].x), "r"(v[2][0].y), "r"(v[2][1].x), "r"(v[2][1].y), "r"(v[3][0].x), "r"(v[3][0].y), "r"(v[3][1].x), "r"(v[3][1].y),
+          "r"(v[4][0].x), "r"(v[4][0].y), "r"(v[4][1].x), "r"(v[4][1].y), "r"(v[5][0].x), "r"(v[5][0].y), "r"(v[5][1].x), "r"(v[5][1].y),
+          "r"(v[6][0].x), "r"(v[6][0].y), "r"(v[6][1].x), "r"(v[6][1].y), "r"(v[7][0].x), "r"(v[7][0].y), "r"(v[7][1].x), "r"(v[7][1].y)
+        : "memory");
+}
+__device__ __forceinline__ uint2 ldg_nc8(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -260,7 +278,9 @@ struct TsArgs {
                  // 16 = no MMAs, 64 = no rule-map loads in the K loop, 256 = no epilogue
 };
 
-template <int NT, bool STASH, bool PROF>
+// G16: the gather in the 16x256b shape -- four lanes share a row (32 bytes per L1 wavefront of a load instead of the 16 of a
+// thread-per-row load), each thread holds 8-byte pieces of four rows
+template <int NT, bool STASH, bool PROF, bool G16>
 __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
     constexpr int B_BYTES = Tile<NT>::B_BYTES, STAGE_B = Tile<NT>::STAGE_B, SA = Tile<NT>::SA, SB = Tile<NT>::SB,
                   RING_BYTES = Tile<NT>::RING_BYTES, A_COL0 = NT;
@@ -386,7 +406,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
         // A slot's empty barrier cannot run two phases ahead of a waiting group: the group filled stage q - 2 only after the
         // MMAs of stage q - 5 (hence q - 6, the slot's phase before last) had completed.
         const int grp = warp >> 2, lq = warp & 3;         // lq = the warp's TMEM lane quarter
-        const int r = lq * 32 + lane;
+        const int r_epi = lq * 32 + lane;                 // the row this thread writes in the epilogue
+        // the row whose rule-map entry this thread fetches: its own (32x32b), or -- G16 -- row (h, e) = (kq / 2, kq % 2) of the
+        // four rows 16 h + rq + 8 e its quad (rq = lane / 4) shares; the quad exchanges the four entries by shuffle
+        const int rq = lane >> 2, kq = lane & 3;
+        const int r = G16 ? lq * 32 + 16 * (kq >> 1) + rq + 8 * (kq & 1) : r_epi;
         const uint32_t row_bytes = 4u * (uint32_t)a.Cin;
         const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)A_COL0;
         // stage q = (active tap ai, 64-channel chunk c), A / B slot s, barrier phase parity ph: all advanced incrementally
@@ -433,13 +457,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
             request(ai_2, slot == 0 ? 2 : slot - 1, q + 2 * NG < n_iters);
             const long long i1 = TS_CLK();
             uint4 v[16];
-            if (cur >= 0 && !TS_DBG(2)) {
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.in_split) + (size_t)(unsigned)cur * row_bytes + (unsigned)(c * 256);
+            uint2 v2[2][8][2];
+            if constexpr (!G16) {
+                if (cur >= 0 && !TS_DBG(2)) {
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.in_split) + (size_t)(unsigned)cur * row_bytes + (unsigned)(c * 256);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = ldg_nc16(src + 16 * j);
+                    for (int j = 0; j < 16; ++j) v[j] = ldg_nc16(src + 16 * j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = make_uint4(0u, 0u, 0u, 0u);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = make_uint4(0u, 0u, 0u, 0u);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int idx = __shfl_sync(0xffffffffu, cur, (lane & ~3) | (2 * h + e));
+                        if (idx >= 0 && !TS_DBG(2)) {
+                            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.in_split) + (size_t)(unsigned)idx * row_bytes +
+                                                       (unsigned)(c * 256 + 8 * kq);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v2[h][j][e] = ldg_nc8(src + 32 * j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v2[h][j][e] = make_uint2(0u, 0u);
+                        }
+                    }
             }
             const long long w0 = TS_CLK();
             mbar_wait(empty0 + 8 * s, ph);
@@ -447,7 +490,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
             if (lq == 0 && lane == 0 && q >= SA) mbar_arrive(emptyB0 + 8 * sb_rel);      // stage q - SA has been consumed
             const long long w1 = TS_CLK();
             if (!TS_DBG(4)) {
-                tmem_st64(t_lane + (uint32_t)(s * KCH), v);
+                if constexpr (G16) {
+                    tmem_st_16x256b_x8(t_lane + (uint32_t)(s * KCH), v2[0]);
+                    tmem_st_16x256b_x8(t_lane + (16u << 16) + (uint32_t)(s * KCH), v2[1]);
+                } else {
+                    tmem_st64(t_lane + (uint32_t)(s * KCH), v);
+                }
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -469,7 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
         // (as spconv_tc.cu: 32-column panels transposed through a private shared-memory patch, 128-byte row segments out)
       if (warp < NEPI) {
         const int half = warp >> 2;
-        const int prow = (r < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r) : row0 + r) : -1;
+        const int prow = (r_epi < nrows) ? (a.out_rows ? __ldg(a.out_rows + row0 + r_epi) : row0 + r_epi) : -1;
         float* stg = reinterpret_cast<float*>(ring) + warp * (32 * 36);
         const int sub = lane >> 3, pc = lane & 7;
         int prs[8];
@@ -614,17 +662,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) spconv_ts_kernel(TsArgs a) {
     }
 }
 
-template <int NT, bool STASH, bool PROF>
+template <int NT, bool STASH, bool PROF, bool G16 = false>
 int launch_ts(const TsArgs& a, int tiles, cudaStream_t s) {
     constexpr int smem = Tile<NT>::RING_BYTES + 1024 + (STASH ? STASH_K * TM * 4 : 0);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_ts_kernel<NT, STASH, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_ts_kernel<NT, STASH, PROF, G16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid(tiles, a.Cout / NT, a.ksplit);
-    spconv_ts_kernel<NT, STASH, PROF><<<grid, NTHREADS, smem, s>>>(a);
+    spconv_ts_kernel<NT, STASH, PROF, G16><<<grid, NTHREADS, smem, s>>>(a);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
@@ -643,12 +691,18 @@ int cg3d_spconv_ts_launch(const unsigned short* in_split, const int* nbr, const 
     const bool stash = nbr && K <= STASH_K;
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (NT == 64) {
-        if (debug) rc = stash ? launch_ts<64, true, true>(a, tiles, st) : launch_ts<64, false, true>(a, tiles, st);
-        else rc = stash ? launch_ts<64, true, false>(a, tiles, st) : launch_ts<64, false, false>(a, tiles, st);
+    // CG3D_TS_G16=0: the thread-per-row 32x32b gather (kept for A/B timing; profiles/r2_spconv_ts.md)
+    const char* g16_env = getenv("CG3D_TS_G16");
+    const bool g16 = !(g16_env && g16_env[0] == '0');
+    if (debug) {                                   // instrumented build (cycle counters, ablation bits)
+        if (NT == 64) rc = stash ? launch_ts<64, true, true, true>(a, tiles, st) : launch_ts<64, false, true, true>(a, tiles, st);
+        else rc = stash ? launch_ts<128, true, true, true>(a, tiles, st) : launch_ts<128, false, true, true>(a, tiles, st);
+    } else if (g16) {
+        rc = NT == 64 ? (stash ? launch_ts<64, true, false, true>(a, tiles, st) : launch_ts<64, false, false, true>(a, tiles, st))
+                      : (stash ? launch_ts<128, true, false, true>(a, tiles, st) : launch_ts<128, false, false, true>(a, tiles, st));
     } else {
-        if (debug) rc = stash ? launch_ts<128, true, true>(a, tiles, st) : launch_ts<128, false, true>(a, tiles, st);
-        else rc = stash ? launch_ts<128, true, false>(a, tiles, st) : launch_ts<128, false, false>(a, tiles, st);
+        rc = NT == 64 ? (stash ? launch_ts<64, true, false, false>(a, tiles, st) : launch_ts<64, false, false, false>(a, tiles, st))
+                      : (stash ? launch_ts<128, true, false, false>(a, tiles, st) : launch_ts<128, false, false, false>(a, tiles, st));
     }
     if (rc == 0 && (debug & 8)) {               // (any debug bit selects the instrumented build; 8 prints its counters)
         unsigned long long h[16], z[16] = {0};
