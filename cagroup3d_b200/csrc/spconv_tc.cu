@@ -780,7 +780,8 @@ int cg3d_spconv_tc(const unsigned short* in_split, int n_in, const int* nbr, con
     // 512 -> 512 0.47 -> 0.39, RoI grid conv 0.93 -> 0.66.)  CG3D_TC_TS: 0 = never, 64 = only 64-column tiles.
     const char* ts_env = getenv("CG3D_TC_TS");
     const int ts_max = ts_env ? atoi(ts_env) : 128;
-    const bool ts = Cin % 64 == 0 && ks == 1 && (NT == 64 || NT == 128) && NT <= ts_max;
+    // (plain GEMM rows, K = 1 without a rule map, stay on the shared-memory kernel: equal or 5 - 8 % ahead there)
+    const bool ts = Cin % 64 == 0 && ks == 1 && nbr != nullptr && (NT == 64 || NT == 128) && NT <= ts_max;
     if (ts)
         rc = cg3d_spconv_ts_launch(a.in_split, a.nbr, a.wimg, a.out, a.ldo, a.n_out, a.Cin, a.Cout, a.K, a.scale, a.shift, a.residual,
                                    a.act, a.tile_row0, a.tile_rows, a.tile_group, tiles, a.out_rows, a.out_split, a.out_split_relu,

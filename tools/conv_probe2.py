@@ -11,7 +11,7 @@ def main():
     rec = []
     orig = S._call
     def spy(name, *args, meta=None):
-        if name == "cg3d_spconv_tc" and args[2] is not None:
+        if name == "cg3d_spconv_tc" and (args[2] is not None or os.environ.get("PROBE_ALL")):
             rec.append((name, args))
         return orig(name, *args, meta=meta)
     S._call = spy
@@ -23,7 +23,7 @@ def main():
         if K < int(os.environ.get("PROBE_MIN_K", "27")):
             continue
         n_out = args[6]
-        line = f"{name} K={K} n_out={n_out} Cin={args[7]}"
+        line = f"{name} K={K} n_out={n_out} Cin={args[7]} Cout={args[8]} {'map' if args[2] is not None else 'rows'}"
         for dbg in os.environ.get("PROBE_DEBUGS", "0").split(","):
             os.environ["CG3D_TC_DEBUG"] = dbg                 # timing ablations of the SAME launch (results are garbage for dbg != 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
