@@ -52,7 +52,7 @@ def conv_bn(x: S.SparseTensor, conv: MinkowskiConvolution, bn, fc: FoldCache, ac
         return x.with_F(F)
     omap = x.cmap if s == 1 else S.strided_map(x.cmap, x.mgr, s)
     nbr, order = S.neighbor_table(x.cmap, omap, k, x.mgr, ordered=True)
-    Fin = x.F
+    Fin, algo_cin = x.F, None
     if Fin.shape[1] < 32 and S.get_conv_impl() == "tc" and W.shape[-1] % 64 == 0:
         # the 3-channel stem on the tensor cores: input and weights zero-padded to 64 channels (bf16x3 like every other
         # layer; the zero channels add exact zeros).  0.39 ms of exact-fp32 FFMA -> 0.15 ms at 400 k voxels.
@@ -61,9 +61,9 @@ def conv_bn(x: S.SparseTensor, conv: MinkowskiConvolution, bn, fc: FoldCache, ac
                    lambda: torch.cat([W.detach(), W.new_zeros((W.shape[0], 64 - Cin, W.shape[2]))], 1).contiguous())
         Fp = Fin.new_zeros((Fin.shape[0], 64))
         Fp[:, :Cin] = Fin
-        Fin = Fp
+        Fin, algo_cin = Fp, Cin
     F = S.gemm_rows(Fin, nbr, W, omap.n, k ** 3, scale=scale, shift=shift, residual=residual, act=act,
-                    in_act=in_act, out=out, out_rows=order, split_out=split_out)
+                    in_act=in_act, out=out, out_rows=order, split_out=split_out, algo_cin=algo_cin)
     return S.SparseTensor(F, omap, x.mgr)
 
 

@@ -10,10 +10,13 @@
 // tensor floor of 128 * 64 / 256 = 32 clk, and bf16x3 reads the A tile three times per k-step.  On the 9^3 class conv
 // (87 % of the gathered rows are zero rows) the stage cost was the 72 KB of operand reads + 32 KB of A-tile writes.
 // Here the gather never touches shared memory:
-//   * every gather thread OWNS one output row of the tile = one TMEM lane.  It reads its neighbour's 64 channels of the
-//     stage (256 contiguous bytes of the split-bf16 matrix: [hi 32 | lo 32] x 2) straight into registers with 16
-//     ld.global.v4 -- or keeps zeros when the row has no neighbour for this tap -- and writes them to the stage's 64 TMEM
-//     columns with tcgen05.st (TMEM write 256 B/clk; no swizzle, no shuffles, no per-copy address arithmetic);
+//   * the gather threads of a warp own the warp's 32 output rows = 32 TMEM lanes.  In the 16x256b store shape four lanes
+//     share a row: a thread reads 8-byte pieces of four neighbour rows (8 x ld.global.v2 per row: 32 contiguous bytes per
+//     quad and instruction = one full sector per L1 wavefront) straight into registers -- zeros where the row has no
+//     neighbour for this tap -- and two tcgen05.st.16x256b.x8 write the stage's 64 TMEM columns (TMEM write 256 B/clk; no
+//     swizzle, no per-copy address arithmetic).  (First version: thread = row with 16 x ld.global.v4 and one 32x32b.x64
+//     store -- every lane of a load hits a different 128-byte line, 16 bytes per wavefront; the L1 data pipe sat at 72 %
+//     and dense 27-tap layers lost to the shared-memory kernel.  Kept as the G16 = false instantiation for A/B timing.)
 //   * the two gather warp groups (warps 0-3 / 4-7, one warp per TMEM lane quarter) take alternate stages, so each group
 //     has two stage times for its loads to land; three A stages live in TMEM next to the accumulator (64 + 3 * 64 = 256
 //     columns, two CTAs per SM);

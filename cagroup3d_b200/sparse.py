@@ -401,8 +401,11 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
 def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n_out: int, K: int,
               scale=None, shift=None, residual=None, act=None, tiles: Optional[Tiles] = None,
               impl: Optional[str] = None, in_act=None, out: Optional[torch.Tensor] = None,
-              out_rows: Optional[torch.Tensor] = None, split_out: Optional[str] = None) -> torch.Tensor:
+              out_rows: Optional[torch.Tensor] = None, split_out: Optional[str] = None,
+              algo_cin: Optional[int] = None) -> torch.Tensor:
     """out = act((sum_k in_act(Fin[nbr[k]]) @ W[k]) * scale + shift + residual); W: [(G,) K, Cin, Cout].
+    algo_cin: the layer's real input width when Fin / W are zero-padded (only the profiling record uses it: algorithmic
+    bytes and FLOPs are those of the unpadded layer).
 
     Fin / out may be column slices of wider row-major matrices (unit column stride).  out_rows: the table is
     positional (tile order); position j is output row out_rows[j].  split_out ("none" | "relu"): the tensor-core
@@ -422,7 +425,8 @@ def gemm_rows(Fin: torch.Tensor, nbr: Optional[torch.Tensor], W: torch.Tensor, n
               and out.stride(0) % 4 == 0)
     meta = None
     if Profile.active is not None and not Profile.conv_only:
-        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4,
+        ac = algo_cin or Cin
+        meta = dict(n_in=Fin.shape[0], n_out=n_out, Cin=ac, Cout=Cout, K=K, nbr=nbr, w_bytes=W.numel() * 4 * ac // Cin,
                     residual=residual is not None)
     targs = (tiles.row0 if tiles else None, tiles.rows if tiles else None, tiles.group if tiles else None,
              tiles.n if tiles else 0, out_rows)
