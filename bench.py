@@ -1,7 +1,7 @@
 """Benchmark of the CAGroup3D inference hot path (BASELINE.json: scenes/s at ~50k voxels/scene).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--conv simt|tc]
-                    [--workload scannet|sunrgbd|sweep|train] [--voxel-size 0.02]
+                    [--workload scannet|sunrgbd|sweep|train|train_sunrgbd] [--voxel-size 0.02]
 
 --workload (default scannet = BASELINE.json configs[1], the configuration the metric is quoted on):
     sunrgbd   configs[2]: SUN RGB-D-shaped inference, batch 16 per GPU, 10 classes, 100 000 points / scene, yaw boxes and
@@ -10,6 +10,7 @@
               64 scenes on 8 GPUs); the line's value is the 50k point, config.sweep holds every density
     train     configs[3]: ScanNet-shaped TRAINING step (forward, both stages' losses, backward, bucketed gradient
               all-reduce, AdamW), 4 scenes per GPU, fp32
+    train_sunrgbd   the same step for the SUN RGB-D model (WITH_YAW branches of both stages)
 
 One "step" = one forward of the whole detector (voxelise -> BiResNet -> class-aware grouping head ->
 RoI-Conv pooling -> NMS) over one batch of 8 synthetic ScanNet-shaped scenes (~50k active voxels each;
@@ -51,6 +52,9 @@ WORKLOADS = {
     "train": ("ScanNetV2-shaped CAGroup3D TRAINING step (forward + both stages' losses + backward + gradient all-reduce + AdamW), "
               "4 scenes per GPU, voxel 0.02 m, ~50k active voxels/scene, 18 classes, fp32 master weights",
               "train_scenes_per_sec_at_50k_voxels_per_scene", 18, False, 4, 50000, None, 4),
+    "train_sunrgbd": ("SUN RGB-D-shaped CAGroup3D TRAINING step (WITH_YAW: 3 votes per seed, yaw code + rotated IoU loss, RoI stage with "
+                      "(cos, sin) heading code and IoU loss), 4 scenes per GPU, voxel 0.02 m, ~50k active voxels/scene, 10 classes, fp32",
+                      "train_scenes_per_sec_sunrgbd_at_50k_voxels_per_scene", 10, True, 4, 50000, None, 6),
 }
 SWEEP_VOXELS = (10000, 20000, 50000, 100000, 200000)
 
@@ -378,12 +382,12 @@ def bench_train(args, rank, world, timed, conv, dist):
     """BASELINE configs[3]: one training step = train_step.training_step (tools/train_utils/train_utils.py:48-72)."""
     from cagroup3d_b200 import backbone_train as BT, dist as D, model_init, sparse as S, synthetic, train_step as TS
     from cagroup3d_b200.detector import voxelize
-    _, _, ncls, yaw, B, voxels, _, cfg = WORKLOADS["train"]
+    _, _, ncls, yaw, B, voxels, _, cfg = WORKLOADS[args.workload]
     B = args.batch or B
     voxels = args.voxels
     S.set_conv_impl(conv)
     dev = "cuda"
-    scenes = [synthetic.make_scene(1000 * cfg + rank * B + i, voxels, n_classes=ncls, return_masks=True) for i in range(B)]
+    scenes = [synthetic.make_scene(1000 * cfg + rank * B + i, voxels, n_classes=ncls, return_masks=True, sunrgbd=yaw) for i in range(B)]
     batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
     model = model_init.seeded_model(ncls, yaw, seed=0).to(dev).train()
     host_pts = torch.from_numpy(batch["points"]).pin_memory()
@@ -401,16 +405,17 @@ def bench_train(args, rank, world, timed, conv, dist):
     opt = torch.optim.AdamW(params, lr=1e-3)
     red = D.GradientAllReducer(params)
     gt = torch.from_numpy(batch["gt_boxes"]).float()
-    sem, ins = [s for _, _, s, _ in scenes], [m for _, _, _, m in scenes]
+    # SUN RGB-D items carry no per-point masks (its vote targets come from the boxes)
+    masks = {} if yaw else {"semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
     last = {}
 
     def step_resident():
-        bd = {"points": pts.clone(), "batch_size": B, "cur_epoch": 10, "gt_boxes": gt.to(dev), "semantic_mask": sem, "instance_mask": ins}
+        bd = {"points": pts.clone(), "batch_size": B, "cur_epoch": 10, "gt_boxes": gt.to(dev), **masks}
         last["tb"] = TS.training_step(model, bd, opt, red, grad_norm_clip=10.0)
 
     def step_e2e():
         bd = {"points": host_pts.to(dev, non_blocking=True), "batch_size": B, "cur_epoch": 10, "gt_boxes": gt.to(dev, non_blocking=True),
-              "semantic_mask": sem, "instance_mask": ins}
+              **masks}
         last["tb"] = TS.training_step(model, bd, opt, red, grad_norm_clip=10.0)      # tb_dict: python floats = D2H of the losses
 
     ms_total, launches, _ = timed(step_resident, args.steps, args.warmup)
@@ -509,7 +514,7 @@ def main():
     timed = Timer(dist, sampler)
 
     extra = {}
-    if wl == "train":
+    if wl.startswith("train"):
         r = bench_train(args, rank, world, timed, conv, dist)
     elif wl == "sweep":
         pts_ = []
@@ -539,7 +544,7 @@ def main():
 
     if rank == 0:
         cfg = {"workload": desc, **r["info"], "conv_impl": conv, "voxel_size_m": args.voxel_size, "p_sel": 1.0 / WORKLOADS[wl][2],
-               "p_box": P_BOX, "weights": "seed-0 random init (no checkpoint offline)" + ("" if wl == "train" else ", eval-mode BatchNorm"),
+               "p_box": P_BOX, "weights": "seed-0 random init (no checkpoint offline)" + ("" if wl.startswith("train") else ", eval-mode BatchNorm"),
                "l2": "working set > L2: ~0.5 GB of weights (+ images) and the activations are re-streamed every step, no flush needed",
                **extra}
         line = {

@@ -87,7 +87,7 @@ class CAGroup3D(nn.Module):
     def forward_train(self, batch_dict):
         """cagroup3d.py:41-47,99-158 in training mode: -> (ret_dict{'loss'}, tb_dict, disp_dict{..., 'cur_semantic_value'}),
         what tools/train_utils/train_utils.py:56-58 consumes: BiResNet and both heads with batch-statistics BatchNorm,
-        the five first-stage loss terms and the RoI regression loss (train_step.two_stage_loss).  WITH_YAW False only."""
+        the five first-stage loss terms and the RoI regression loss (train_step.two_stage_loss).  Both configurations (WITH_YAW: SUN RGB-D)."""
         from .train_step import two_stage_loss
         cur_epoch = batch_dict["cur_epoch"]
         assert cur_epoch is not None

@@ -82,9 +82,9 @@ def nms_and_pack(keys, src_row, n, boxes, box_dim, nseg, ncls, B, thr, with_yaw,
     counts[nseg:].zero_()
     S._call("cg3d_histogram_i32", seg, n, nseg, counts)
     seg_off, _ = S.exclusive_scan(counts)
-    max_len = n          # upper bound of any segment (avoids a sync for the true maximum)
+    max_len = n          # upper bound of any segment (avoids a sync for the true maximum; it only sizes a bitset)
     keep = _i32(n, device=dev)
-    S._call("cg3d_nms_segments", sorted_boxes, seg_off, nseg, max_len, float(thr), int(with_yaw), keep, None)
+    S._call("cg3d_nms_segments", sorted_boxes, n, seg_off, nseg, max_len, float(thr), int(with_yaw), keep, None)
     pos, total = S.exclusive_scan(keep)
     # per-sample kept counts = kept-prefix at the sample boundaries of seg_off
     m = int(total.item())

@@ -7,8 +7,8 @@ module / parameters, through the autograd bricks of autograd.py with batch-stati
 
 `semantic_and_vote_loss` evaluates the two terms per sample and averages them over the batch like CAGroup3DHead.loss
 (cagroup_head.py:374-398).  Together with backbone_train.run_train this is a complete, if partial, training step: it
-trains the backbone, the semantic branch and the vote branch (the per-class grouping branch -- centerness / box / class
-terms -- is not differentiable on the CUDA path yet).
+trains the backbone, the semantic branch and the vote branch; `first_stage_loss` below adds the per-class grouping branch
+(centerness / box / class terms) for both the ScanNet and the SUN RGB-D (WITH_YAW) configuration.
 """
 from __future__ import annotations
 
@@ -38,8 +38,8 @@ def semantic_and_vote_loss(head, out: S.SparseTensor, sem: torch.Tensor, offs: t
                            gt_bboxes: Sequence[torch.Tensor], gt_labels: Sequence[torch.Tensor],
                            scene_points: Sequence[torch.Tensor], pts_semantic_mask: Sequence[torch.Tensor],
                            pts_instance_mask: Sequence[torch.Tensor]):
-    """(loss_sem, loss_vote) averaged over the samples of the batch (WITH_YAW False)."""
-    assert not head.with_yaw, "the SUN RGB-D vote targets (3 votes per seed) are not on the CUDA training path yet"
+    """(loss_sem, loss_vote) averaged over the samples of the batch (both branches: per-point-mask votes for ScanNet, up to
+    three in-box votes per voxel for WITH_YAW, cagroup_head.py:418-451,505-517)."""
     from .dist import reduce_mean
     focal = TT.FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
     smooth = TT.SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0)
@@ -50,10 +50,18 @@ def semantic_and_vote_loss(head, out: S.SparseTensor, sem: torch.Tensor, offs: t
         vox = C[rows, 1:].float() * head.voxel_size
         with torch.no_grad():
             sem_labels, _ = TT.CAGroup3DAssigner.assign_semantic(vox, gt_bboxes[b], gt_labels[b], head.n_classes)
-            off_t, off_m = TT.vote_targets(scene_points[b], vox, gt_bboxes[b], pts_semantic_mask[b], pts_instance_mask[b],
-                                           head.n_classes)
-        w = (off_m / torch.ones_like(off_m).sum() + 1e-6).unsqueeze(1).repeat(1, 3)
-        votes.append(smooth(offs[rows], off_t, weight=w))
+            if head.with_yaw:
+                off_t, off_m = TT.vote_targets_yaw(vox, gt_bboxes[b], 3)
+            else:
+                off_t, off_m = TT.vote_targets(scene_points[b], vox, gt_bboxes[b], pts_semantic_mask[b], pts_instance_mask[b],
+                                               head.n_classes)
+        if head.with_yaw:
+            w = (off_m.float() / (off_m.float().sum() + 1e-6)).unsqueeze(1).repeat(1, 9)
+            base = vox.repeat(1, 3)
+            votes.append(smooth(base + offs[rows], base + off_t, weight=w))
+        else:
+            w = (off_m / torch.ones_like(off_m).sum() + 1e-6).unsqueeze(1).repeat(1, 3)
+            votes.append(smooth(offs[rows], off_t, weight=w))
         n_pos = max(float(reduce_mean((sem_labels >= 0).sum().float())), 1.)
         sems.append(focal(sem[rows], sem_labels, avg_factor=n_pos))
     return torch.mean(torch.stack(sems)), torch.mean(torch.stack(votes))
@@ -147,15 +155,15 @@ def first_stage_loss(head, out: S.SparseTensor, batch_size: int, gt_bboxes, gt_l
                      pts_instance_mask, impl: Optional[str] = None, art: Optional[dict] = None, return_branch: bool = False):
     """shared part -> coordinate phase -> per-class branch -> the five loss terms per sample -> batch means.
     Returns (loss, tb_dict) like the reference (`one_stage_loss` = the sum).  `art`: precomputed coordinate artifacts
-    (tests teacher-force them); WITH_YAW False only."""
-    assert not head.with_yaw
+    (tests teacher-force them).  WITH_YAW (SUN RGB-D): three votes per voxel, yaw code in the box prediction, rotated IoU
+    loss (train_targets.FirstStageLoss(with_yaw=True)); the per-point masks are not used there and may be None."""
     B = batch_size
     sem, offs, offF = shared_part(head, out, impl=impl)
     if art is None:
         with torch.no_grad():
             art = coordinate_phase(head, out, sem, offs, B)
     br = class_branch(head, out, offF, art, B, impl=impl)
-    crit = TT.FirstStageLoss(head.n_classes)
+    crit = TT.FirstStageLoss(head.n_classes, with_yaw=head.with_yaw, yaw_parametrization=head.yaw_parametrization)
     coords, vs = br["coords"], art["vsA"]
     C = out.C
     # Rows of the class-batched maps carry (class * B + sample) in column 0.  The reference walks samples and classes and

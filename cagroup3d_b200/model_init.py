@@ -24,7 +24,10 @@ def default_model_cfg(n_classes: int = 18, with_yaw: bool = False) -> dict:
                         NMS_CONFIG=dict(SCORE_THR=0.01, NMS_PRE=1000, IOU_THR=0.5)),
         ROI_HEAD=dict(NAME="CAGroup3DRoIHead", NUM_CLASSES=n_classes, MIDDLE_FEATURE_SOURCE=[3], GRID_SIZE=7,
                       VOXEL_SIZE=0.02, COORD_KEY=2, MLPS=[[64, 128, 128]], CODE_SIZE=7 if with_yaw else 6,
-                      ENCODE_SINCOS=with_yaw, ROI_CONV_KERNEL=5, USE_SIMPLE_POOLING=True, USE_CENTER_POOLING=True),
+                      ENCODE_SINCOS=with_yaw, ROI_CONV_KERNEL=5, USE_SIMPLE_POOLING=True, USE_CENTER_POOLING=True,
+                      ROI_PER_IMAGE=128, ROI_FG_RATIO=0.9, REG_FG_THRESH=0.3, USE_IOU_LOSS=with_yaw,
+                      LOSS_WEIGHTS=dict(RCNN_CLS_WEIGHT=1.0, RCNN_REG_WEIGHT=0.5 if with_yaw else 1.0, RCNN_IOU_WEIGHT=1.0,
+                                        CODE_WEIGHT=[1.0] * (8 if with_yaw else 6))),
         POST_PROCESSING=dict(RECALL_THRESH_LIST=[0.25, 0.5], EVAL_METRIC="scannet"),
     )
 

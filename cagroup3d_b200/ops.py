@@ -62,7 +62,7 @@ def _nms(boxes, scores, thresh, rotated, pre_maxsize=None):
         return order, None
     seg = torch.tensor([0, n], dtype=torch.int32, device=b.device)
     keep = torch.empty((n,), dtype=torch.int32, device=b.device)
-    S._call("cg3d_nms_segments", b, seg, 1, n, float(thresh), int(rotated), keep, None)
+    S._call("cg3d_nms_segments", b, n, seg, 1, n, float(thresh), int(rotated), keep, None)
     return order[keep.bool()].contiguous(), None
 
 

@@ -13,8 +13,9 @@ module and parameters.
     regression MLP (Linear + BatchNorm1d + ReLU [+ Dropout]) x 2 + Linear with bias, as 1x1 convs
 
 Below it: the proposal target layer (cagroup_proposal_target_layer.py: ProposalTargetLayer, same-class IoU as one masked matrix),
-assign_targets / the residual coder and the smooth-L1 RoI regression loss (cagroup_roi_head.py:288-326,512-575) for code_size 6;
-the yaw / sin-cos codes and USE_IOU_LOSS of the SUN RGB-D config are not built.
+assign_targets / the residual coder, the smooth-L1 RoI regression loss and the IoU loss on the decoded foreground boxes
+(cagroup_roi_head.py:288-326,512-615) for both configurations: ScanNet (code size 6) and SUN RGB-D (code size 7, heading coded
+as (cos, sin), USE_IOU_LOSS through the rotated IoU of rot_iou_loss.py).
 """
 from __future__ import annotations
 
@@ -245,34 +246,81 @@ def assign_targets(target_layer: ProposalTargetLayer, input_dict: dict, code_siz
     return t
 
 
-def encode_residuals(boxes: torch.Tensor, anchors: torch.Tensor) -> torch.Tensor:
-    """CAGroupResidualCoder.encode_torch for code_size 6 (cagroup_utils.py:99-145): centres by the anchor's BEV diagonal /
-    height, sizes as log ratios."""
+def encode_residuals(boxes: torch.Tensor, anchors: torch.Tensor, encode_sincos: bool = False) -> torch.Tensor:
+    """CAGroupResidualCoder.encode_torch (cagroup_utils.py:99-145): centres by the anchor's BEV diagonal / height, sizes as log
+    ratios; 7-column boxes add the heading -- as (cos, sin) of the target heading itself with encode_sincos ('directly encode
+    delta theta'), else as the difference to the anchor's."""
     a, g = anchors.clone(), boxes.clone()
     a[:, 3:6], g[:, 3:6] = torch.clamp_min(a[:, 3:6], min=1e-5), torch.clamp_min(g[:, 3:6], min=1e-5)
     diag = torch.sqrt(a[:, 3:4] ** 2 + a[:, 4:5] ** 2)
-    return torch.cat([(g[:, 0:1] - a[:, 0:1]) / diag, (g[:, 1:2] - a[:, 1:2]) / diag, (g[:, 2:3] - a[:, 2:3]) / a[:, 5:6],
-                      torch.log(g[:, 3:6] / a[:, 3:6])], dim=-1)
+    cols = [(g[:, 0:1] - a[:, 0:1]) / diag, (g[:, 1:2] - a[:, 1:2]) / diag, (g[:, 2:3] - a[:, 2:3]) / a[:, 5:6],
+            torch.log(g[:, 3:6] / a[:, 3:6])]
+    if boxes.shape[1] > 6:
+        cols += [torch.cos(g[:, 6:7]), torch.sin(g[:, 6:7])] if encode_sincos else [g[:, 6:7] - a[:, 6:7]]
+    return torch.cat(cols, dim=-1)
 
 
-def roi_reg_loss(rcnn_reg: torch.Tensor, targets: dict, code_size: int, code_weights, reg_weight: float = 1.0):
-    """get_box_reg_layer_loss (cagroup_roi_head.py:547-575), 'smooth-l1', code_size 6, no IoU loss: WeightedSmoothL1Loss
-    (beta 1/9, loss_utils.py:76-138) of the residual-coded targets, summed over the foreground RoIs / max(#foreground, 1).
-    The sum and its gradient are one cg3d_smooth_l1_loss call (the code weights scale prediction and target alike)."""
+def decode_residuals(codes: torch.Tensor, anchors: torch.Tensor, encode_sincos: bool = False) -> torch.Tensor:
+    """CAGroupResidualCoder.decode_torch (cagroup_utils.py:147-199), differentiable in `codes`: (n, 6 | 7 | 8) codes on
+    (n, 6 | 7) anchors -> boxes (n, 6 | 7)."""
+    diag = torch.sqrt(anchors[:, 3:4] ** 2 + anchors[:, 4:5] ** 2)
+    cols = [codes[:, 0:1] * diag + anchors[:, 0:1], codes[:, 1:2] * diag + anchors[:, 1:2], codes[:, 2:3] * anchors[:, 5:6] + anchors[:, 2:3],
+            torch.exp(codes[:, 3:6]) * anchors[:, 3:6]]
+    if anchors.shape[1] > 6:
+        r = torch.atan2(codes[:, 7:8], codes[:, 6:7]) if encode_sincos else codes[:, 6:7]
+        cols.append(r + anchors[:, 6:7])
+    return torch.cat(cols, dim=-1)
+
+
+def roi_reg_loss(rcnn_reg: torch.Tensor, targets: dict, code_size: int, code_weights, reg_weight: float = 1.0,
+                 encode_sincos: bool = False, use_iou_loss: bool = False, iou_weight: float = 1.0):
+    """get_box_reg_layer_loss + loss (cagroup_roi_head.py:512-529,547-615), 'smooth-l1':
+      * WeightedSmoothL1Loss (beta 1/9, loss_utils.py:76-138) of the residual-coded targets, summed over the foreground
+        RoIs / max(#foreground, 1), times RCNN_REG_WEIGHT.  The sum and its gradient are one cg3d_smooth_l1_loss call (the
+        code weights scale prediction and target alike).  code_size 7 (SUN RGB-D): the anchor's heading is zeroed, the
+        heading target is the (cos, sin) pair when encode_sincos.
+      * use_iou_loss (SUN RGB-D): the foreground regressions decoded on their RoIs (canonical frame -> rotate by the RoI's
+        heading -> shift to its centre) against the untransformed ground truth under the mean 3-D IoU loss (rotated when
+        code_size > 6: rot_iou_loss.py around cg3d_sort_vertices), times RCNN_IOU_WEIGHT.  The reference adds the smooth-L1
+        term only when RCNN_REG_WEIGHT > 0."""
     from . import train_targets as TT
-    assert code_size == 6, "the yaw / sin-cos codes of SUN RGB-D are not on the CUDA training path yet"
+    assert code_size in (6, 7)
     fg = targets["reg_valid_mask"].view(-1) > 0
     fg_sum = int(fg.long().sum())
     n = rcnn_reg.shape[0]
     anchors = targets["rois"][..., 0:code_size].clone().detach().view(-1, code_size)
     anchors[:, 0:3] = 0
-    tgt = encode_residuals(targets["gt_of_rois"][..., 0:code_size].reshape(n, code_size), anchors)
-    cw = torch.as_tensor(code_weights, dtype=torch.float32, device=rcnn_reg.device).view(1, -1)
+    if code_size > 6:
+        anchors[:, 6] = 0
+    tgt = encode_residuals(targets["gt_of_rois"][..., 0:code_size].reshape(n, code_size), anchors, encode_sincos)
+    n_code = tgt.shape[1]
+    cw = torch.as_tensor(code_weights, dtype=torch.float32, device=rcnn_reg.device).view(1, -1)[:, :n_code]
     pred = rcnn_reg.view(n, -1) * cw
     tgt = torch.where(torch.isnan(tgt), rcnn_reg.detach().view(n, -1), tgt) * cw
-    w = (fg.float() / max(fg_sum, 1)).unsqueeze(1).repeat(1, code_size)
-    loss = TT.SmoothL1Loss(beta=1.0 / 9.0, reduction="sum")(pred, tgt, weight=w) * reg_weight
-    return loss, {"rcnn_loss_reg": float(loss.detach()), "loss_two_stage": float(loss.detach())}
+    w = (fg.float() / max(fg_sum, 1)).unsqueeze(1).repeat(1, n_code)
+    loss_reg = TT.SmoothL1Loss(beta=1.0 / 9.0, reduction="sum")(pred, tgt, weight=w) * reg_weight
+    tb = {"rcnn_loss_reg": float(loss_reg.detach())}
+    if not use_iou_loss:
+        tb["loss_two_stage"] = tb["rcnn_loss_reg"]
+        return loss_reg, tb
+    loss_iou = torch.zeros((), device=rcnn_reg.device)
+    if fg_sum > 0:
+        rois_fg = targets["rois"][..., 0:code_size].reshape(-1, code_size)[fg].detach()
+        anc = rois_fg.clone()
+        anc[:, 0:3] = 0
+        boxes = decode_residuals(rcnn_reg.view(n, -1)[fg], anc, encode_sincos)
+        if code_size > 6:                               # rotate_points_along_z (common_utils.py:39-62) of the centre by the RoI heading
+            c, s_ = torch.cos(anc[:, 6]), torch.sin(anc[:, 6])
+            boxes = torch.cat([(boxes[:, 0] * c - boxes[:, 1] * s_).unsqueeze(1), (boxes[:, 0] * s_ + boxes[:, 1] * c).unsqueeze(1), boxes[:, 2:]], 1)
+        boxes = torch.cat([boxes[:, 0:3] + rois_fg[:, 0:3], boxes[:, 3:]], 1)
+        gt_src = targets["gt_of_rois_src"][..., 0:code_size].reshape(-1, code_size)[fg]
+        loss_iou = TT.IoU3DLoss(with_yaw=code_size > 6, loss_weight=1.0)(
+            boxes, gt_src, weight=None if code_size > 6 else torch.ones_like(boxes[:, 0]),
+            avg_factor=None if code_size > 6 else float(fg_sum)) * iou_weight
+        tb["rcnn_loss_iou"] = float(loss_iou.detach())
+    loss = loss_iou + loss_reg if reg_weight > 0 else loss_iou
+    tb["loss_two_stage"] = float(loss.detach())
+    return loss, tb
 
 
 def roi_stage_loss(roi_head, sp: S.SparseTensor, pred_bbox_list, gt_bboxes, gt_labels, impl: Optional[str] = None,
@@ -288,6 +336,8 @@ def roi_stage_loss(roi_head, sp: S.SparseTensor, pred_bbox_list, gt_bboxes, gt_l
     targets = assign_targets(layer, inp, roi_head.code_size)
     pooled, reg, _ = roi_branch(roi_head, sp, targets["rois"], B, layer.roi_per_image, impl=impl, dropout=dropout)
     lw = g("LOSS_WEIGHTS", {}) or {}
-    loss, tb = roi_reg_loss(reg, targets, roi_head.code_size, lw.get("CODE_WEIGHT", [1.0] * roi_head.code_size),
-                            lw.get("RCNN_REG_WEIGHT", 1.0))
+    sincos = bool(g("ENCODE_SINCOS", getattr(roi_head, "encode_angle_by_sincos", False)))
+    loss, tb = roi_reg_loss(reg, targets, roi_head.code_size, lw.get("CODE_WEIGHT", [1.0] * (roi_head.code_size + int(sincos))),
+                            lw.get("RCNN_REG_WEIGHT", 1.0), encode_sincos=sincos, use_iou_loss=bool(g("USE_IOU_LOSS", False)),
+                            iou_weight=lw.get("RCNN_IOU_WEIGHT", 1.0))
     return loss, tb, targets

@@ -2,13 +2,12 @@
 tools/train_utils/train_utils.py:42-75 (train_one_epoch's inner loop: forward, loss, backward, optimizer step), with
 the DDP gradient average done by dist.GradientAllReducer.
 
-  training_step               the reference's whole step for WITH_YAW False: both stages' losses (`loss_all`)
+  training_step               the reference's whole step: both stages' losses (`loss_all`), ScanNet and SUN RGB-D (WITH_YAW:
+                              3 votes per seed, yaw code + rotated IoU loss in the first stage; (cos, sin) residual code and
+                              IoU loss on the decoded RoIs in the second)
   first_stage_training_step   BiResNet in training mode + the whole CAGroup3DHead in training mode + all five terms of
                               CAGroup3DHead.loss (`one_stage_loss` of the reference's tb_dict)
   partial_training_step       the same restricted to the semantic and vote terms (no per-class branch)
-
-The SUN RGB-D branches (yaw: rotated IoU loss, sin-cos / yaw residual codes, 3 votes per seed) are not on the CUDA
-training path yet.
 """
 from __future__ import annotations
 
@@ -29,8 +28,9 @@ def _targets_of(batch_dict: dict, pts: torch.Tensor, B: int):
         gtb.append(g[:, :7].float().contiguous())
         gtl.append(g[:, 7].long())
         scene.append(pts[pts[:, 0] == b][:, 1:4].contiguous())
-        semm.append(torch.as_tensor(batch_dict["semantic_mask"][b], device=pts.device).long())
-        insm.append(torch.as_tensor(batch_dict["instance_mask"][b], device=pts.device).long())
+        has_masks = "semantic_mask" in batch_dict and "instance_mask" in batch_dict      # SUN RGB-D has none (sunrgbd_dataset.py)
+        semm.append(torch.as_tensor(batch_dict["semantic_mask"][b], device=pts.device).long() if has_masks else None)
+        insm.append(torch.as_tensor(batch_dict["instance_mask"][b], device=pts.device).long() if has_masks else None)
     return gtb, gtl, scene, semm, insm
 
 
@@ -61,7 +61,7 @@ def first_stage_training_step(model, batch_dict: dict, optimizer: Optional[torch
 
 
 def two_stage_loss(model, batch_dict: dict, impl: Optional[str] = None, dropout: bool = True):
-    """CAGroup3D.get_training_loss (cagroup3d.py:99-158): first-stage loss + RoI-stage loss of a batch, WITH_YAW False.
+    """CAGroup3D.get_training_loss (cagroup3d.py:99-158): first-stage loss + RoI-stage loss of a batch.
     -> (loss_all, tb_dict with the reference's keys).  batch_dict["points"] must already be normalised / on the device."""
     from . import roi_train as RT
     B = batch_dict["batch_size"]

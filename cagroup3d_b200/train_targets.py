@@ -206,24 +206,84 @@ def vote_targets(scene_points: torch.Tensor, voxel_points: torch.Tensor, gt_bbox
     return targets, mask
 
 
-def bbox_pred_to_bbox(points: torch.Tensor, bbox_pred: torch.Tensor) -> torch.Tensor:
-    """cagroup_head.py:654-670, 6 outputs (no yaw): face distances -> (x, y, z, dx, dy, dz).  Index glue on the positive
-    rows only (differentiable torch ops; the fused decode of the inference path, cg3d_head_decode, has no backward)."""
+def points_in_boxes(points: torch.Tensor, gt_bboxes: torch.Tensor) -> torch.Tensor:
+    """find_points_in_boxes (cagroup3d_assigner.py:9-36): (n, m) bool, point strictly inside the yawed box -- the six face
+    distances in the box frame (offset rotated by -yaw about z), all > 0.  Same operation order as the reference's tensors."""
+    b = gt_bboxes[:, :7].float()
+    d = points[:, None, :3].float() - b[None, :, :3]
+    c, s = torch.cos(-b[:, 6])[None], torch.sin(-b[:, 6])[None]
+    rx = d[..., 0] * c + d[..., 1] * s                     # [x, y] @ [[cos, -sin], [sin, cos]] with the angle -yaw
+    ry = -d[..., 0] * s + d[..., 1] * c
+    cx, cy, cz = b[None, :, 0] + rx, b[None, :, 1] + ry, b[None, :, 2] + d[..., 2]
+    faces = torch.stack([cx - b[None, :, 0] + b[None, :, 3] / 2, b[None, :, 0] + b[None, :, 3] / 2 - cx,
+                         cy - b[None, :, 1] + b[None, :, 4] / 2, b[None, :, 1] + b[None, :, 4] / 2 - cy,
+                         cz - b[None, :, 2] + b[None, :, 5] / 2, b[None, :, 2] + b[None, :, 5] / 2 - cz], -1)
+    return faces.min(-1)[0] > 0
+
+
+def vote_targets_yaw(voxel_points: torch.Tensor, gt_bboxes: torch.Tensor, gt_per_seed: int = 3):
+    """cagroup_head.py:418-451 (WITH_YAW / SUN RGB-D branch): every voxel inside a gt box votes for that box's centre, up to
+    gt_per_seed = 3 votes per voxel -> (targets (n, 9), mask (n,) long).  The reference walks the boxes in order and keeps a
+    per-point counter; its net effect, computed here without the loop (and without its 3 m host syncs): columns 0-2 = the
+    FIRST box that contains the point, columns 3-5 = the second (the first again if there is only one), columns 6-8 = the
+    LAST of the third and later ones (the counter is clamped at 2, so every later box overwrites the third slot; the first
+    box again if there are fewer than three)."""
+    assert gt_per_seed == 3
+    n, m = voxel_points.shape[0], gt_bboxes.shape[0]
+    dev = voxel_points.device
+    if m == 0 or n == 0:
+        return voxel_points.new_zeros((n, 9)), torch.zeros((n,), dtype=torch.long, device=dev)
+    inside = points_in_boxes(voxel_points, gt_bboxes)                                  # (n, m)
+    rank = torch.cumsum(inside.long(), 1)                                              # 1-based position among the containing boxes
+    ar = torch.arange(m, device=dev)[None]
+    big = m + 1
+    first = torch.where(inside & (rank == 1), ar, big).min(1)[0]
+    second = torch.where(inside & (rank == 2), ar, big).min(1)[0]
+    last3 = torch.where(inside & (rank >= 3), ar, -1).max(1)[0]
+    has1, has2, has3 = first < big, second < big, last3 >= 0
+    f = first.clamp(max=m - 1)
+    pick = torch.stack([f, torch.where(has2, second.clamp(max=m - 1), f), torch.where(has3, last3.clamp(min=0), f)], 1)   # (n, 3)
+    votes = gt_bboxes[:, :3].float()[pick] - voxel_points[:, None, :3].float()        # (n, 3, 3)
+    targets = torch.where(has1[:, None, None], votes, torch.zeros_like(votes)).reshape(n, 9)
+    return targets, has1.long()
+
+
+def bbox_pred_to_bbox(points: torch.Tensor, bbox_pred: torch.Tensor, yaw_parametrization: str = "fcaf3d") -> torch.Tensor:
+    """_bbox_pred_to_bbox (cagroup_head.py:654-703): face distances (+ yaw code) -> (x, y, z, dx, dy, dz [, yaw]).  6 outputs:
+    no yaw; 7 / 8 outputs: 'naive' (the angle itself), 'sin-cos' (atan2 of the normalised pair) or 'fcaf3d' (the pair codes
+    the double angle and, in its norm, the log aspect ratio q of the footprint whose perimeter share is the four planar
+    distances).  Index glue on the positive rows only (differentiable torch ops; the fused decode of the inference path,
+    cg3d_head_decode, has no backward)."""
     if bbox_pred.shape[0] == 0:
         return bbox_pred
     c = points[:, :3] + (bbox_pred[:, 1:6:2] - bbox_pred[:, 0:6:2]) / 2
-    return torch.cat([c, bbox_pred[:, 0:6:2] + bbox_pred[:, 1:6:2]], 1)
+    size = bbox_pred[:, 0:6:2] + bbox_pred[:, 1:6:2]
+    if bbox_pred.shape[1] == 6:
+        return torch.cat([c, size], 1)
+    if yaw_parametrization == "naive":
+        return torch.cat([c, size, bbox_pred[:, 6:7]], 1)
+    if yaw_parametrization == "sin-cos":
+        norm = torch.pow(torch.pow(bbox_pred[:, 6:7], 2) + torch.pow(bbox_pred[:, 7:8], 2), 0.5)
+        return torch.cat([c, size, torch.atan2(bbox_pred[:, 6:7] / norm, bbox_pred[:, 7:8] / norm)], 1)
+    scale = bbox_pred[:, 0] + bbox_pred[:, 1] + bbox_pred[:, 2] + bbox_pred[:, 3]
+    q = torch.exp(torch.sqrt(torch.pow(bbox_pred[:, 6], 2) + torch.pow(bbox_pred[:, 7], 2)))
+    alpha = 0.5 * torch.atan2(bbox_pred[:, 6], bbox_pred[:, 7])
+    return torch.stack([c[:, 0], c[:, 1], c[:, 2], scale / (1 + q), scale / (1 + q) * q, bbox_pred[:, 5] + bbox_pred[:, 4], alpha], -1)
 
 
 class FirstStageLoss:
-    """CAGroup3DHead._loss_single (cagroup_head.py:399-555) for WITH_YAW False, on the kernels above; the argument list
-    is the reference's.  `reduce_mean` is dist.reduce_mean (identity in a single process)."""
+    """CAGroup3DHead._loss_single (cagroup_head.py:399-555) on the kernels above; the argument list is the reference's.
+    with_yaw=False: ScanNet (vote targets from the per-point masks, axis-aligned IoU loss); with_yaw=True: SUN RGB-D (up to
+    three votes per voxel from the boxes that contain it, rotated IoU loss, yaw code in the box prediction).
+    `reduce_mean` is dist.reduce_mean (identity in a single process)."""
 
-    def __init__(self, n_classes: int, assigner_cfg=None):
+    def __init__(self, n_classes: int, assigner_cfg=None, with_yaw: bool = False, yaw_parametrization: str = "fcaf3d",
+                 gt_per_seed: int = 3):
         self.n_classes = n_classes
+        self.with_yaw, self.yaw_parametrization, self.gt_per_seed = with_yaw, yaw_parametrization, gt_per_seed
         self.assigner = CAGroup3DAssigner(assigner_cfg or {"LIMIT": 27, "TOPK": 18, "N_SCALES": 4})
         self.loss_centerness = CrossEntropy(use_sigmoid=True, loss_weight=1.0)
-        self.loss_bbox = IoU3DLoss(with_yaw=False, loss_weight=1.0)
+        self.loss_bbox = IoU3DLoss(with_yaw=with_yaw, loss_weight=1.0)
         self.loss_cls = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
         self.loss_sem = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0)
         self.loss_offset = SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0)
@@ -235,21 +295,31 @@ class FirstStageLoss:
         with torch.no_grad():
             semantic_labels, _ = self.assigner.assign_semantic(semantic_points, gt_bboxes, gt_labels, self.n_classes)
             centerness_targets, bbox_targets, labels = self.assigner.assign(points, gt_bboxes, gt_labels)
-            offset_targets, offset_masks = vote_targets(scene_points, original_points, gt_bboxes, pts_semantic_mask,
-                                                        pts_instance_mask, self.n_classes)
+            if self.with_yaw:
+                offset_targets, offset_masks = vote_targets_yaw(original_points, gt_bboxes, self.gt_per_seed)
+            else:
+                offset_targets, offset_masks = vote_targets(scene_points, original_points, gt_bboxes, pts_semantic_mask,
+                                                            pts_instance_mask, self.n_classes)
             pos = labels >= 0
             local = torch.stack([(semantic_labels >= 0).sum().float(), pos.sum().float(),
                                  centerness_targets[pos].sum()])            # (targets of unassigned locations may be NaN)
         return dict(semantic_labels=semantic_labels, centerness_targets=centerness_targets, bbox_targets=bbox_targets,
-                    labels=labels, offset_targets=offset_targets, offset_masks=offset_masks, local=local)
+                    labels=labels, offset_targets=offset_targets, offset_masks=offset_masks, local=local,
+                    original_points=original_points)
 
     def _terms(self, t, norm, centernesses, bbox_preds, cls_scores, points, voxel_offset_preds, semantic_scores):
         """the five loss terms of one sample given its targets and its (rank-averaged) normalisers (3 python floats)."""
         centerness, bbox_preds, cls_scores, points = (torch.cat(centernesses), torch.cat(bbox_preds), torch.cat(cls_scores),
                                                       torch.cat(points))
         offset_masks = t["offset_masks"]
-        w = (offset_masks.float() / torch.ones_like(offset_masks).float().sum() + 1e-6).unsqueeze(1).repeat(1, 3)
-        loss_offset = self.loss_offset(voxel_offset_preds, t["offset_targets"], weight=w)
+        if self.with_yaw:                                   # cagroup_head.py:512-516: the three votes against the three targets
+            k = self.gt_per_seed
+            w = (offset_masks.float() / (offset_masks.float().sum() + 1e-6)).unsqueeze(1).repeat(1, 3 * k)
+            base = t["original_points"][:, :3].repeat(1, k)
+            loss_offset = self.loss_offset(base + voxel_offset_preds, base + t["offset_targets"], weight=w)
+        else:
+            w = (offset_masks.float() / torch.ones_like(offset_masks).float().sum() + 1e-6).unsqueeze(1).repeat(1, 3)
+            loss_offset = self.loss_offset(voxel_offset_preds, t["offset_targets"], weight=w)
         sem_n_pos, n_pos, centerness_denorm = max(norm[0], 1.), max(norm[1], 1.), max(norm[2], 1e-6)
         loss_sem = self.loss_sem(semantic_scores, t["semantic_labels"], avg_factor=sem_n_pos)
         labels = t["labels"]
@@ -259,7 +329,7 @@ class FirstStageLoss:
         pos_centerness_targets = t["centerness_targets"][pos_inds].unsqueeze(1)
         if len(pos_inds) > 0:
             loss_centerness = self.loss_centerness(pos_centerness, pos_centerness_targets, avg_factor=n_pos)
-            loss_bbox = self.loss_bbox(bbox_pred_to_bbox(points[pos_inds], pos_bbox_preds), t["bbox_targets"][pos_inds],
+            loss_bbox = self.loss_bbox(bbox_pred_to_bbox(points[pos_inds], pos_bbox_preds, self.yaw_parametrization), t["bbox_targets"][pos_inds],
                                        weight=pos_centerness_targets.squeeze(1), avg_factor=centerness_denorm)
         else:
             loss_centerness, loss_bbox = pos_centerness.sum(), pos_bbox_preds.sum()

@@ -231,10 +231,14 @@ int cg3d_boxes_pairwise_bev(const float* boxes_a, int na, const float* boxes_b, 
 
 /* nms_gpu (rotated=1, iou3d_nms.cpp:90-136) / nms_normal_gpu (rotated=0, :139-186) for n_segments
  * independent instances in one launch.  Instance s owns rows [seg_offsets[s], seg_offsets[s+1]) of
- * sorted_boxes, already in descending-score order.  keep[i] in {0,1}; kept_count[s] (may be NULL).
- * The reference returns keep indices through a CPU tensor after a blocking D2H of an N x N/64 bitmask;
- * here the flags stay on the device and all (sample, class) instances run in one launch. */
-int cg3d_nms_segments(const float* sorted_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
+ * sorted_boxes [n_boxes, 7], already in descending-score order; max_segment_len >= the longest instance.
+ * keep[i] in {0,1}; kept_count[s] (may be NULL).
+ * The reference returns keep indices through a CPU tensor after a blocking D2H of an N x N/64 bitmask and a host
+ * loop (iou3d_nms.cpp:110-133); here the flags stay on the device and all (sample, class) instances run in one
+ * launch: the alive bitset in shared memory, instances walked in blocks of 64 boxes (pair tile of the block, keep
+ * bits of the block, then every later box against the block's kept boxes), a thread-block cluster of up to 8 CTAs
+ * per instance when the launch has fewer instances than SMs.  -2: max_segment_len too large for the bitset. */
+int cg3d_nms_segments(const float* sorted_boxes, int n_boxes, const int* seg_offsets, int n_segments, int max_segment_len,
                       float thr, int rotated, int* keep, int* kept_count, void* stream);
 
 /* ---- selection primitives (torch.sort / topk / nonzero / boolean masks on the path) ---- */

@@ -154,7 +154,76 @@ def parts():
     print("parts:", {k: round(out[k], 5) for k in ("loss_cls", "loss_sem", "loss_ctr", "loss_box", "loss_vote")}, "positives", len(pos), "of", N)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--yaw-parts" not in sys.argv:
     if "--parts-only" not in sys.argv:
         main()
     parts()
+
+
+def yaw_parts():
+    """tests/golden/train_yaw_parts.npz: the reference's CAGroup3DHead._loss_single with WITH_YAW = True (the SUN RGB-D branch:
+    find_points_in_boxes vote targets with 3 votes per seed, yaw-aware assigner, 'fcaf3d' box decode, rotated IoU loss) called
+    on seeded inputs through a stub `self`; the five loss terms and their gradients w.r.t. every prediction.  The CUDA op
+    sort_vertices is served by oracle/sort_vertices_oracle.py (see make_rotiou_golden.py)."""
+    import types
+    MG.install()
+    from oracle import sort_vertices_oracle as SVO
+    sv = types.ModuleType("sort_vertices")
+    sv.sort_vertices_forward = lambda v, m, nv: torch.from_numpy(SVO.sort_vertices(v.detach().numpy(), m.numpy(), nv.numpy())).int()
+    sys.modules["sort_vertices"] = sv
+    import pcdet.models.dense_heads.cagroup_head as H
+    from pcdet.models.dense_heads.target_assigner.cagroup3d_assigner import CAGroup3DAssigner
+    from pcdet.utils.loss_utils import CrossEntropy, FocalLoss, SmoothL1Loss
+    from pcdet.utils.iou3d_loss import IoU3DLoss
+    H.reduce_mean = lambda x: x                                # single process
+    g = torch.Generator().manual_seed(21)
+    ncls, m = 5, 12
+    boxes = torch.cat([(torch.rand((m, 3), generator=g) - 0.5) * 4, torch.rand((m, 3), generator=g) * 1.6 + 0.4,
+                       (torch.rand((m, 1), generator=g) - 0.5) * 3], 1)
+    boxes[6:9, :3] = boxes[0:3, :3] + 0.2                      # overlapping boxes: voxels with two and three votes
+    boxes[9:11, :3] = boxes[0:2, :3] - 0.15
+    labels = torch.randint(0, ncls, (m,), generator=g)
+    pts = [(torch.rand((int(n), 3), generator=g) - 0.5) * 5 for n in torch.randint(60, 300, (ncls,), generator=g)]
+    for c in range(ncls):
+        b = boxes[labels == c]
+        if len(b):
+            k = len(pts[c]) // 2
+            pts[c][:k] = b[torch.randint(0, len(b), (k,), generator=g), :3] + (torch.rand((k, 3), generator=g) - 0.5) * 0.7
+    nvox = 700
+    vox = (torch.rand((nvox, 3), generator=g) - 0.5) * 5
+    vox[:400] = boxes[torch.randint(0, m, (400,), generator=g), :3] + (torch.rand((400, 3), generator=g) - 0.5) * 0.9
+    N = sum(len(p) for p in pts)
+    leaf = lambda t: t.clone().requires_grad_(True)
+    ctr = leaf(torch.randn((N, 1), generator=g))
+    box = leaf(torch.cat([torch.rand((N, 6), generator=g) * 0.8 + 0.1, torch.randn((N, 2), generator=g) * 0.5], 1))
+    cls = leaf(torch.randn((N, ncls), generator=g) * 2)
+    off = leaf(torch.randn((nvox, 9), generator=g) * 0.1)
+    sem = leaf(torch.randn((nvox, ncls), generator=g) * 2)
+    stub = types.SimpleNamespace(
+        with_yaw=True, gt_per_seed=3, n_classes=ncls, yaw_parametrization="fcaf3d",
+        assigner=CAGroup3DAssigner(MG.EasyDict(LIMIT=27, TOPK=18, N_SCALES=4)),
+        loss_centerness=CrossEntropy(use_sigmoid=True, loss_weight=1.0), loss_bbox=IoU3DLoss(with_yaw=True, loss_weight=1.0),
+        loss_cls=FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+        loss_sem=FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+        loss_offset=SmoothL1Loss(beta=0.04, reduction="sum", loss_weight=1.0))
+    stub._bbox_pred_to_bbox = types.MethodType(H.CAGroup3DHead._bbox_pred_to_bbox, stub)
+    off_s = np.cumsum([0] + [len(p) for p in pts])
+    split = lambda t: [t[off_s[c]:off_s[c + 1]] for c in range(ncls)]
+    losses = H.CAGroup3DHead._loss_single(stub, split(ctr), split(box), split(cls), pts, off, vox, sem, vox, None, boxes, labels,
+                                          None, None, None)
+    sum(losses).backward()
+    out = {"boxes": MG.t2n(boxes), "labels": MG.t2n(labels), "n_per_class": np.array([len(p) for p in pts]), "points": MG.t2n(torch.cat(pts)),
+           "voxels": MG.t2n(vox), "ctr": MG.t2n(ctr), "box": MG.t2n(box), "cls": MG.t2n(cls), "off": MG.t2n(off), "sem": MG.t2n(sem),
+           "losses": np.array([float(l) for l in losses]),
+           "g_ctr": MG.t2n(ctr.grad), "g_box": MG.t2n(box.grad), "g_cls": MG.t2n(cls.grad), "g_off": MG.t2n(off.grad), "g_sem": MG.t2n(sem.grad)}
+    # the vote targets themselves (the reference's loop), for a direct comparison
+    from pcdet.models.dense_heads.target_assigner.cagroup3d_assigner import find_points_in_boxes
+    inside = find_points_in_boxes(vox, boxes)
+    out["inside"] = MG.t2n(inside)
+    np.savez_compressed(os.path.join(HERE, "train_yaw_parts.npz"), **out)
+    print("yaw parts:", dict(zip(("ctr", "bbox", "cls", "sem", "vote"), [round(float(l), 5) for l in losses])),
+          "votes per voxel histogram", np.bincount(inside.sum(1).numpy()))
+
+
+if __name__ == "__main__" and "--yaw-parts" in sys.argv:
+    yaw_parts()

@@ -137,7 +137,7 @@ def test_nms_properties_full_size(lib, rotated):
     counts = torch.bincount(seg.long(), minlength=nseg).int()
     seg_off = torch.cat([torch.zeros(1, dtype=torch.int32, device=DEV), torch.cumsum(counts, 0).int()]).contiguous()
     keep = torch.empty((n,), dtype=torch.int32, device=DEV)
-    S._call("cg3d_nms_segments", boxes, seg_off, nseg, n, 0.5, int(rotated), keep, None)
+    S._call("cg3d_nms_segments", boxes, n, seg_off, nseg, n, 0.5, int(rotated), keep, None)
     iou = lambda a, b: ops._pairwise(a, b, 1 if rotated else 2)       # the op NMS itself uses (rotated / axis-aligned BEV IoU)
     for s in (0, 17, nseg - 1):
         a, b = int(seg_off[s]), int(seg_off[s + 1])
@@ -154,7 +154,7 @@ def test_nms_properties_full_size(lib, rotated):
     kc = torch.bincount(seg[keep.bool()].long(), minlength=nseg).int()
     koff = torch.cat([torch.zeros(1, dtype=torch.int32, device=DEV), torch.cumsum(kc, 0).int()]).contiguous()
     keep2 = torch.empty((kept_boxes.shape[0],), dtype=torch.int32, device=DEV)
-    S._call("cg3d_nms_segments", kept_boxes, koff, nseg, kept_boxes.shape[0], 0.5, int(rotated), keep2, None)
+    S._call("cg3d_nms_segments", kept_boxes, kept_boxes.shape[0], koff, nseg, kept_boxes.shape[0], 0.5, int(rotated), keep2, None)
     assert bool(keep2.bool().all())
 
 

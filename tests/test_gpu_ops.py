@@ -242,9 +242,14 @@ def test_pairwise_iou_vs_oracle(lib):
     assert abs(out[0, 0].item() - 1) < 1e-6 and abs(out[0, 1].item() - 0.6) < 1e-6
 
 
+@pytest.mark.parametrize("path", ["auto", "serial", "blocked", "cluster"])
 @pytest.mark.parametrize("rotated", [0, 1])
-def test_nms_segments_vs_oracle(lib, rotated):
+def test_nms_segments_vs_oracle(lib, rotated, path, monkeypatch):
+    """path: the one-sweep-per-kept-box kernel, the blocked greedy kernel on one CTA or on a cluster of CTAs per segment, or
+    the library's own choice (cluster here: 1500 > 64, 5 segments)"""
     from cagroup3d_b200 import sparse as S
+    if path != "auto":
+        monkeypatch.setenv("CG3D_NMS", path)
     segs, boxes = [0], []
     want = []
     for s, n in enumerate((300, 0, 1, 1500, 64)):
@@ -261,6 +266,51 @@ def test_nms_segments_vs_oracle(lib, rotated):
     allb = torch.cat(boxes).to(DEV)
     keep = torch.empty((segs[-1],), dtype=torch.int32, device=DEV)
     cnt = torch.empty((5,), dtype=torch.int32, device=DEV)
-    S._call("cg3d_nms_segments", allb, torch.tensor(segs, dtype=torch.int32, device=DEV), 5, 1500, 0.5, rotated, keep, cnt)
+    S._call("cg3d_nms_segments", allb, allb.shape[0], torch.tensor(segs, dtype=torch.int32, device=DEV), 5, 1500, 0.5, rotated, keep, cnt)
     assert torch.equal(keep.cpu(), torch.cat(want))
     assert cnt.cpu().tolist() == [int(w.sum()) for w in want]
+
+
+def _clustered_boxes(n, seed, yaw):
+    """n candidates jittered around 12 objects (what a trained head hands to the NMS: heavy suppression)"""
+    g = torch.Generator().manual_seed(seed)
+    obj = random_boxes(12, seed + 1000, yaw=yaw)
+    b = obj[torch.randint(0, 12, (n,), generator=g)].clone()
+    b[:, :3] += torch.randn((n, 3), generator=g) * 0.08
+    b[:, 3:6] *= 1 + (torch.rand((n, 3), generator=g) - 0.5) * 0.3
+    if yaw:
+        b[:, 6] += torch.randn((n,), generator=g) * 0.1
+    return b
+
+
+@pytest.mark.parametrize("case", ["scattered-40x1000", "clustered-40x10000"])
+@pytest.mark.parametrize("rotated", [0, 1])
+def test_nms_long_segments_all_paths_agree(lib, rotated, case, monkeypatch):
+    """40 (sample, class) segments as a training step hands them to the NMS -- up to nms_pre = 1000 scattered candidates, or
+    up to n_classes * nms_pre = 10000 candidates clustered on 12 objects: the blocked greedy kernel (one CTA, and a cluster of
+    3 CTAs per segment) == the one-sweep-per-kept-box kernel, flag for flag; prints the device times."""
+    from cagroup3d_b200 import sparse as S
+    g = torch.Generator().manual_seed(3)
+    if case.startswith("scattered"):
+        lens = torch.randint(600, 1001, (40,), generator=g).tolist()
+        boxes = torch.cat([random_boxes(n, 50 + i, yaw=bool(rotated)) for i, n in enumerate(lens)]).to(DEV)
+    else:
+        lens = torch.randint(6000, 10001, (40,), generator=g).tolist()
+        boxes = torch.cat([_clustered_boxes(n, 50 + i, bool(rotated)) for i, n in enumerate(lens)]).to(DEV)
+    seg = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=DEV)
+    n = boxes.shape[0]
+    res, ms = {}, {}
+    for path in ("serial", "blocked", "cluster"):
+        monkeypatch.setenv("CG3D_NMS", path)
+        keep, cnt = torch.empty((n,), dtype=torch.int32, device=DEV), torch.empty((40,), dtype=torch.int32, device=DEV)
+        for it in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            S._call("cg3d_nms_segments", boxes, n, seg, 40, max(lens), 0.5, rotated, keep, cnt)
+            b.record()
+            torch.cuda.synchronize()
+        res[path], ms[path] = (keep.cpu(), cnt.cpu()), a.elapsed_time(b)
+    print(f"\nNMS {case} rotated={rotated}: " + ", ".join(f"{k} {v:.3f} ms" for k, v in ms.items()) + f", kept {int(res['serial'][0].sum())} of {n}")
+    for path in ("blocked", "cluster"):
+        assert torch.equal(res["serial"][0], res[path][0]) and torch.equal(res["serial"][1], res[path][1]), path
+    assert 0 < int(res["serial"][0].sum()) < n

@@ -56,7 +56,7 @@ def test_nms_vs_reference_cuda(lib, ref_iou, rotated, n):
     keep = torch.empty((n,), dtype=torch.int32, device=DEV)
     seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
     cnt = torch.empty((1,), dtype=torch.int32, device=DEV)
-    S._call("cg3d_nms_segments", b, seg, 1, n, 0.5, rotated, keep, cnt)
+    S._call("cg3d_nms_segments", b, n, seg, 1, n, 0.5, rotated, keep, cnt)
     assert torch.equal(keep.cpu(), want) and int(cnt.item()) == k
 
 

@@ -340,7 +340,8 @@ def _oracle_class_artifacts(res, thr, B, cfg, mgr):
     for cls in range(ncls):
         s = torch.sigmoid(hi["sem"][:, cls])
         sel = torch.cat([torch.nonzero(s > thr).squeeze(1), torch.from_numpy(pad_id)])
-        vc = Cf[sel].view(-1, 1, 4).repeat(1, 1, 1)
+        nv = hi["voted"].shape[1]                              # 3 votes per seed with yaw (SUN RGB-D), else 1
+        vc = Cf[sel].view(-1, 1, 4).repeat(1, nv, 1)
         vc[:, :, 1:4] = hi["voted"][sel]
         oc = Cf[sel].clone()
         oc[:, 1:4] *= vs
@@ -352,7 +353,8 @@ def _oracle_class_artifacts(res, thr, B, cfg, mgr):
         qa[:, 0] += cls * B
         qe[:, 0] += cls * B
         qa_all.append(qa.long().numpy()); qe_all.append(qe.long().numpy())
-        ref.append(torch.cat([torch.stack([sel, torch.zeros_like(sel)], 1), torch.stack([sel, -torch.ones_like(sel)], 1)]))
+        ref.append(torch.cat([torch.stack([sel.repeat_interleave(nv), torch.arange(nv).repeat(len(sel))], 1),
+                              torch.stack([sel, -torch.ones_like(sel)], 1)]))
     qa_all, qe_all, ref = np.concatenate(qa_all), np.concatenate(qe_all), torch.cat(ref).int()
     ua, inva, _ = me.unique_first(qa_all)
     ue, inve, _ = me.unique_first(qe_all)
@@ -471,15 +473,20 @@ def test_first_stage_loss_wiring_vs_training_oracle(monkeypatch):
     assert missing == [], missing
 
 
-def test_first_stage_training_step_driver(monkeypatch):
+@pytest.mark.parametrize("yaw", [False, True])
+def test_first_stage_training_step_driver(monkeypatch, yaw):
     """train_step.first_stage_training_step end to end on the emulated C ABI, with the coordinate phase served by the
-    oracle-backed artifact builder: tb_dict keys of the reference, gradients in the reducer's buckets, loss going down."""
+    oracle-backed artifact builder: tb_dict keys of the reference, gradients in the reducer's buckets, loss going down.
+    yaw: the SUN RGB-D configuration (10 classes, 3 votes per seed, yaw code + rotated IoU loss, no per-point masks; RoI stage
+    with code size 7, (cos, sin) heading code and the IoU loss)."""
     from cagroup3d_b200 import dist as D, head_train as HT, model_init, ops, sparse as S, synthetic, train_step as TS, train_targets as TT
+    from oracle import sort_vertices_oracle as SVO
     E.install(monkeypatch)
     monkeypatch.setattr(TT, "_require_cuda", lambda t: None)
     monkeypatch.setattr(ops, "_chk", lambda *ts: None)
-    B, ncls = 2, 18
-    cfg = O.default_cfg(ncls, False)
+    monkeypatch.setattr(ops, "sort_v", lambda v, m, nv: torch.from_numpy(SVO.sort_vertices(v.numpy(), m.numpy(), nv.numpy())).int())
+    B, ncls = 2, (10 if yaw else 18)
+    cfg = O.default_cfg(ncls, yaw)
 
     def voxelize_cpu(points, voxel_size):
         c = points[:, :4].clone()
@@ -495,23 +502,24 @@ def test_first_stage_training_step_driver(monkeypatch):
         ts, vs = out.cmap.stride, head.voxel_size
         mx = ((Cc[:, 1:].max(0)[0] + ts) * vs).float()
         mn = ((Cc[:, 1:].min(0)[0] - ts) * vs).float()
-        voted = (Cc[:, 1:].float() * vs).view(-1, 1, 3) + offs.detach().float().view(-1, 1, 3)
+        nv = offs.shape[1] // 3
+        voted = (Cc[:, 1:].float() * vs).view(-1, 1, 3) + offs.detach().float().view(-1, nv, 3)
         voted = torch.maximum(torch.minimum(voted, mx.view(1, 1, 3)), mn.view(1, 1, 3))
         res = dict(bb_coords=out.C.numpy().astype(np.int64), head=dict(sem=sem.detach(), voted=voted))
         return _oracle_class_artifacts(res, head.semantic_threshold, Bn, cfg, S.Manager())
     monkeypatch.setattr(TS, "voxelize", voxelize_cpu)
     monkeypatch.setattr(HT, "coordinate_phase", coordinate_phase_cpu)
-    scenes = [synthetic.make_scene(1000 * 7 + i, 150, n_classes=ncls, return_masks=True) for i in range(B)]
+    scenes = [synthetic.make_scene(1000 * 7 + i, 150, n_classes=ncls, return_masks=True, sunrgbd=yaw) for i in range(B)]
     batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
-    model = model_init.seeded_model(ncls, False, seed=3).train()
+    model = model_init.seeded_model(ncls, yaw, seed=3).train()
     with torch.no_grad():
         model.dense_head.semantic_conv.bias.fill_(-2.5)
     params = [p for n, p in model.named_parameters() if n.startswith(("backbone_3d.", "dense_head."))]
     opt = torch.optim.AdamW(params, lr=1e-3)
     red = D.GradientAllReducer(params, bucket_mb=64)
+    masks = {} if yaw else {"semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
     bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "cur_epoch": 3,
-          "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
-          "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+          "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(), **masks}
     tb = TS.first_stage_training_step(model, bd, opt, red, impl="simt")
     assert set(tb) == {"loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote", "one_stage_loss"}
     losses = [tb["one_stage_loss"]]
@@ -525,7 +533,7 @@ def test_first_stage_training_step_driver(monkeypatch):
 
     def proposals_cpu(head, br, Bn):                             # stage-1 detections near the gt boxes (the NMS kernels are not emulated)
         g = torch.Generator().manual_seed(0)
-        return [(torch.cat([gtb[b][:, :3] + torch.randn((len(gtb[b]), 3), generator=g) * 0.05, gtb[b][:, 3:6], torch.zeros((len(gtb[b]), 1))], 1),
+        return [(torch.cat([gtb[b][:, :3] + torch.randn((len(gtb[b]), 3), generator=g) * 0.05, gtb[b][:, 3:6], gtb[b][:, 6:7] + (0.1 if yaw else 0.0)], 1),
                  torch.rand((len(gtb[b]),), generator=g), gtl[b].clone()) for b in range(Bn)]
 
     def roi_coordinate_phase_cpu(roi_head, sp, rois, Bn, rmax):
@@ -538,11 +546,11 @@ def test_first_stage_training_step_driver(monkeypatch):
     monkeypatch.setattr(HT, "stage1_proposals", proposals_cpu)
     monkeypatch.setattr(RT, "coordinate_phase", roi_coordinate_phase_cpu)
     bd = {"points": torch.from_numpy(batch["points"]).clone(), "batch_size": B, "cur_epoch": 3,
-          "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(),
-          "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+          "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float(), **masks}
     np.random.seed(0)
     ret, tb, disp = model(dict(bd, points=bd["points"].clone()))
     assert {"loss_all", "one_stage_loss", "rcnn_loss_reg", "loss_two_stage"} <= set(tb) and tb["rcnn_loss_reg"] > 0
+    assert ("rcnn_loss_iou" in tb and 0 < tb["rcnn_loss_iou"] <= 1.0) if yaw else "rcnn_loss_iou" not in tb
     assert abs(tb["loss_all"] - tb["one_stage_loss"] - tb["loss_two_stage"]) < 1e-4
     losses.append(tb["one_stage_loss"])                          # after one AdamW step on the same batch
     assert np.isfinite(losses).all() and losses[1] < losses[0], losses

@@ -676,18 +676,21 @@ def test_roi_branch_training_on_device(lib):
     assert worst[0] < 2e-2, worst
 
 
-def test_two_stage_training_step_on_device(lib):
-    """The reference's whole training step for the ScanNet model on cuda:0: model.train(); model(batch_dict) ->
-    (ret_dict, tb_dict, disp_dict) with both stages' losses, every parameter reached by backward, and
-    train_step.training_step (bucketed gradient all-reduce, grad-norm clip, AdamW) lowering the loss on a fixed batch."""
+@pytest.mark.parametrize("yaw", [False, True])
+def test_two_stage_training_step_on_device(lib, yaw):
+    """The reference's whole training step on cuda:0 for the ScanNet model and (yaw) the SUN RGB-D model (10 classes, 3 votes
+    per seed, yaw code + rotated IoU loss in the first stage; code size 7, (cos, sin) heading code and IoU loss in the RoI
+    stage; no per-point masks): model.train(); model(batch_dict) -> (ret_dict, tb_dict, disp_dict) with both stages'
+    losses, every parameter reached by backward, and train_step.training_step (bucketed gradient all-reduce, grad-norm
+    clip, AdamW) lowering the loss on a fixed batch."""
     from cagroup3d_b200 import dist as D, model_init, synthetic, train_step as TS
     from cagroup3d_b200 import backbone_train as BT
     from cagroup3d_b200.detector import voxelize
-    B, ncls = 2, 18
-    scenes = [synthetic.make_scene(1000 * 7 + i, 2500, n_classes=ncls, return_masks=True) for i in range(B)]
+    B, ncls = 2, (10 if yaw else 18)
+    scenes = [synthetic.make_scene(1000 * 7 + i, 2500, n_classes=ncls, return_masks=True, sunrgbd=yaw) for i in range(B)]
     batch = synthetic.collate_batch([(p, b) for p, b, _, _ in scenes])
     pts = torch.from_numpy(batch["points"])
-    model = model_init.seeded_model(ncls, False, seed=3).to(DEV).train()
+    model = model_init.seeded_model(ncls, yaw, seed=3).to(DEV).train()
     p = pts.clone().to(DEV)
     p[:, -3:] /= 255.
     with torch.no_grad():
@@ -695,13 +698,15 @@ def test_two_stage_training_step_on_device(lib):
     model_init.calibrate_semantic_bias(model, feats, 0.10)
     with torch.no_grad():
         model.dense_head.cls_conv.bias.fill_(-2.0)            # enough stage-1 detections for the RoI stage to have work
+    masks = {} if yaw else {"semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
     mk = lambda: {"points": pts.clone().to(DEV), "batch_size": B, "cur_epoch": 10, "gt_boxes": torch.from_numpy(batch["gt_boxes"]).float().to(DEV),
-                  "semantic_mask": [s for _, _, s, _ in scenes], "instance_mask": [m for _, _, _, m in scenes]}
+                  **masks}
     np.random.seed(0)
     torch.manual_seed(0)
     ret, tb, disp = model(mk())
     assert {"loss_all", "one_stage_loss", "loss_centerness", "loss_bbox", "loss_cls", "loss_sem", "loss_vote", "rcnn_loss_reg",
             "loss_two_stage"} <= set(tb) and all(np.isfinite(v) for v in tb.values())
+    assert ("rcnn_loss_iou" in tb) == yaw
     assert abs(disp["cur_semantic_value"] - 0.05) < 1e-9
     ret["loss"].backward()
     torch.cuda.synchronize()
