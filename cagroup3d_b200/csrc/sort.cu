@@ -1,4 +1,4 @@
-// Selection primitives of the detection path: stable LSD radix sort of
+// Selection primitives of the detection path: stable one-sweep LSD radix sort of
 // (u64 key, i32 value) pairs, segment histograms and flag compaction.  They replace torch.sort /
 // Tensor.topk / torch.nonzero / boolean-mask gathers at cagroup_head.py:230,595-599,752-758,
 // iou3d_nms_utils.py:92,110 and cagroup_roi_head.py:440-446.  Integer, HBM/latency bound.
@@ -10,132 +10,115 @@
 
 namespace {
 
+// ---- one-sweep LSD radix sort (8-bit digits, chained look-back across tiles) ---------------------------------------------
+// One launch reads the keys once and builds the 256-bin histogram of EVERY digit position; then one launch per digit:
+// a CTA takes the next tile (4096 keys, ticket order), counts its digits, publishes the counts, sums the counts of the
+// tiles before it by looking back through their published (aggregate | inclusive-prefix) words -- no separate scan launch,
+// no per-CTA offset table in HBM -- and scatters its keys in index order (stable).  A 27-bit sort of 4 x 10^5 pairs is
+// 1 + 1 + 4 launches (memset, histograms, 4 digits) instead of 1 + 3 x 4 (histogram; scan, memset, scatter per digit).
 constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 8;
-constexpr int RS_ITEMS = RS_THREADS * RS_ROUNDS;   // elements per CTA
+constexpr int RS_ROUNDS = 16;
+constexpr int RS_ITEMS = RS_THREADS * RS_ROUNDS;   // keys per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MAX_PASSES = 8;
+constexpr unsigned RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE = (1u << 30) - 1u;
 
-// counts[d * nb + blk] = number of keys of CTA blk whose digit is d
+// ghist[p * 256 + d] = number of keys whose digit p (bits [begin_bit + 8 p, +8)) is d
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long long* __restrict__ keys, int n,
-                                                             int shift, int nb, int* __restrict__ counts) {
-    __shared__ int h[256];
-    h[threadIdx.x] = 0;
+                                                             int begin_bit, int passes, int* __restrict__ ghist) {
+    __shared__ int h[RS_MAX_PASSES][256];
+    for (int p = 0; p < passes; ++p) h[p][threadIdx.x] = 0;
     __syncthreads();
-    int base = blockIdx.x * RS_ITEMS;
-    for (int r = 0; r < RS_ROUNDS; ++r) {
-        int i = base + r * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xFF], 1);
+    for (int i = blockIdx.x * RS_THREADS + threadIdx.x; i < n; i += gridDim.x * RS_THREADS) {
+        const unsigned long long k = keys[i] >> begin_bit;
+        for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 0xFF], 1);
     }
     __syncthreads();
-    counts[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    for (int p = 0; p < passes; ++p)
+        if (h[p][threadIdx.x]) atomicAdd(ghist + p * 256 + threadIdx.x, h[p][threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const unsigned long long* __restrict__ keys,
-                                                                const int* __restrict__ vals, int n, int shift, int nb,
-                                                                const int* __restrict__ offsets,
-                                                                unsigned long long* __restrict__ keys_out,
-                                                                int* __restrict__ vals_out, int next_shift,
-                                                                int* __restrict__ counts_next) {
+// state: [tiles][256] words of this pass, zero before the launch: 0 = not yet known, RS_FLAG_AGG | count of the tile,
+// RS_FLAG_INC | count of the tile and of all tiles before it.  state_next (the other buffer, used by the pass after this
+// one) is zeroed here, ticket is this pass's tile counter.
+__global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const unsigned long long* __restrict__ keys,
+                                                                 const int* __restrict__ vals, int n, int shift,
+                                                                 const int* __restrict__ ghist, unsigned* state,
+                                                                 unsigned* __restrict__ state_next, int* ticket,
+                                                                 unsigned long long* __restrict__ keys_out,
+                                                                 int* __restrict__ vals_out) {
     __shared__ int base[256];
+    __shared__ int hist[256];
     __shared__ int wcnt[RS_WARPS][256];
+    __shared__ int wsum[RS_WARPS];
+    __shared__ int tile_s;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    base[t] = offsets[t * nb + blockIdx.x];
-    const int start = blockIdx.x * RS_ITEMS;
+    if (t == 0) tile_s = atomicAdd(ticket, 1);                       // a tile's predecessors have all started
+    hist[t] = 0;
+    __syncthreads();
+    const int tile = tile_s;
+    if (state_next) state_next[(size_t)tile * 256 + t] = 0u;
+    const int start = tile * RS_ITEMS;
+    unsigned long long key[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const int i = start + r * RS_THREADS + t;
+        key[r] = i < n ? keys[i] : 0ull;
+        if (i < n) atomicAdd(&hist[(key[r] >> shift) & 0xFF], 1);
+    }
+    // exclusive scan of the global digit histogram (bin t) while the tile's counts settle
+    const int g = ghist[t];
+    int x = g;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    int gex = x - g;
+    for (int j = 0; j < w; ++j) gex += wsum[j];
+    // publish this tile's count of digit t, then sum the tiles before it
+    const unsigned cnt = (unsigned)hist[t];
+    volatile unsigned* st = state;
+    unsigned excl = 0u;
+    if (tile == 0) {
+        st[t] = RS_FLAG_INC | cnt;
+    } else {
+        st[(size_t)tile * 256 + t] = RS_FLAG_AGG | cnt;
+        for (int p = tile - 1; p >= 0; --p) {
+            unsigned v;
+            do { v = st[(size_t)p * 256 + t]; } while ((v & ~RS_VALUE) == 0u);
+            excl += v & RS_VALUE;
+            if (v & RS_FLAG_INC) break;
+        }
+        st[(size_t)tile * 256 + t] = RS_FLAG_INC | (excl + cnt);
+    }
+    base[t] = gex + (int)excl;
+    // stable scatter: rounds in index order; within a round warps in order, within a warp lanes in order
+#pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
 #pragma unroll
         for (int j = 0; j < RS_WARPS; ++j) wcnt[j][t] = 0;
         __syncthreads();
-        int i = start + r * RS_THREADS + t;
-        bool valid = i < n;
-        unsigned long long key = valid ? keys[i] : 0ull;
-        int d = valid ? (int)((key >> shift) & 0xFF) : -1 - lane;    // invalid lanes match only themselves
-        unsigned m = __match_any_sync(0xffffffffu, d);
-        int rank = __popc(m & ((1u << lane) - 1));
+        const int i = start + r * RS_THREADS + t;
+        const bool valid = i < n;
+        const int d = valid ? (int)((key[r] >> shift) & 0xFF) : -1 - lane;   // invalid lanes match only themselves
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(m & ((1u << lane) - 1));
         if (valid && rank == 0) wcnt[w][d] = __popc(m);
         __syncthreads();
         if (valid) {
             int off = base[d] + rank;
             for (int j = 0; j < w; ++j) off += wcnt[j][d];
-            keys_out[off] = key;
+            keys_out[off] = key[r];
             vals_out[off] = vals[i];
-            // histogram of the NEXT digit, binned by the CTA that will own position `off` in the next pass
-            if (next_shift >= 0) atomicAdd(counts_next + (size_t)((key >> next_shift) & 0xFF) * nb + off / RS_ITEMS, 1);
         }
         __syncthreads();
         int add = 0;
 #pragma unroll
         for (int j = 0; j < RS_WARPS; ++j) add += wcnt[j][t];
         base[t] += add;
-        __syncthreads();
-    }
-}
-
-// exclusive scan of `n` ints by ONE CTA (16 ints per thread per round, coalesced int4 loads, a running carry); the
-// digit-offset tables of the radix sort are a few 10^4 entries, for which three launches of a multi-CTA scan cost more than
-// the scan itself.  16384 entries per round: the 50k-entry table of a 400k-key sort takes 4 rounds.
-__global__ void __launch_bounds__(1024) rs_scan_single(const int* __restrict__ in, int n, int* __restrict__ out) {
-    constexpr int PER = 16;
-    __shared__ int wsum[32];
-    __shared__ int carry_s;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) carry_s = 0;
-    __syncthreads();
-    const bool vec = ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) & 15) == 0;
-    for (int base = 0; base < n; base += 1024 * PER) {
-        const int i = base + t * PER;
-        int v[PER];
-        if (vec && i + PER <= n) {
-#pragma unroll
-            for (int j = 0; j < PER / 4; ++j) {
-                const int4 q = __ldg(reinterpret_cast<const int4*>(in + i) + j);
-                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < PER; ++j) v[j] = (i + j < n) ? in[i + j] : 0;
-        }
-        int local = 0;
-#pragma unroll
-        for (int j = 0; j < PER; ++j) local += v[j];
-        int x = local;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d) x += y;
-        }
-        if (lane == 31) wsum[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            int s2 = wsum[lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int y = __shfl_up_sync(0xffffffffu, s2, d);
-                if (lane >= d) s2 += y;
-            }
-            wsum[lane] = s2;
-        }
-        __syncthreads();
-        int excl = carry_s + (w ? wsum[w - 1] : 0) + x - local;
-        if (vec && i + PER <= n) {
-#pragma unroll
-            for (int j = 0; j < PER / 4; ++j) {
-                int4 q;
-                q.x = excl; excl += v[4 * j];
-                q.y = excl; excl += v[4 * j + 1];
-                q.z = excl; excl += v[4 * j + 2];
-                q.w = excl; excl += v[4 * j + 3];
-                reinterpret_cast<int4*>(out + i)[j] = q;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                if (i + j < n) out[i + j] = excl;
-                excl += v[j];
-            }
-        }
-        __syncthreads();
-        if (t == 1023) carry_s += wsum[31];
-        __syncthreads();
     }
 }
 
@@ -163,37 +146,30 @@ inline int flat_grid(long long n) {
 extern "C" {
 
 int cg3d_sort_workspace_ints(int n) {
-    int nb = cg3d_div_up(n > 0 ? n : 1, RS_ITEMS);
-    return 3 * 256 * nb + cg3d_scan_workspace_ints(256 * nb) + 8;
+    int tiles = cg3d_div_up(n > 0 ? n : 1, RS_ITEMS);
+    return RS_MAX_PASSES * 256 + 8 + 2 * 256 * tiles + 8;
 }
 
 int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, int end_bit,
                     unsigned long long* keys_tmp, int* vals_tmp, int* workspace, void* stream) {
     if (n <= 1) return 0;
     if (begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit) return -1;
+    if (n > (int)RS_VALUE) return -2;
     cudaStream_t s = (cudaStream_t)stream;
-    int nb = cg3d_div_up(n, RS_ITEMS);
-    const size_t tab = 256 * (size_t)nb;
-    int* counts[2] = {workspace, workspace + tab};
-    int* offsets = workspace + 2 * tab;
-    int* sums = workspace + 3 * tab;
-    int* total = sums + cg3d_scan_workspace_ints((int)tab);
+    const int tiles = cg3d_div_up(n, RS_ITEMS);
+    const int passes = (end_bit - begin_bit + 7) / 8;
+    // workspace: [digit histograms 8 x 256 | tile tickets 8 | look-back words A | look-back words B]
+    int* ghist = workspace;
+    int* tickets = workspace + RS_MAX_PASSES * 256;
+    unsigned* state[2] = {reinterpret_cast<unsigned*>(tickets + 8), reinterpret_cast<unsigned*>(tickets + 8) + (size_t)256 * tiles};
+    cudaMemsetAsync(workspace, 0, sizeof(int) * (size_t)(RS_MAX_PASSES * 256 + 8 + 256 * tiles), s);
+    const int hb = tiles * 2 < 148 * 4 ? tiles * 2 : 148 * 4;
+    rs_hist_kernel<<<hb, RS_THREADS, 0, s>>>(keys, n, begin_bit, passes, ghist);
     unsigned long long *kin = keys, *kout = keys_tmp;
     int *vin = vals, *vout = vals_tmp;
-    // per pass: ONE scan launch + ONE scatter launch; the scatter also builds the next digit's per-CTA histogram
-    rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(kin, n, begin_bit, nb, counts[0]);
-    int cur = 0;
-    for (int shift = begin_bit; shift < end_bit; shift += 8) {
-        const int next = shift + 8 < end_bit ? shift + 8 : -1;
-        if (tab <= (1u << 20)) {
-            rs_scan_single<<<1, 1024, 0, s>>>(counts[cur], (int)tab, offsets);
-        } else {
-            int rc = cg3d_exclusive_scan_i32(counts[cur], (int)tab, offsets, sums, total, stream);
-            if (rc) return rc;
-        }
-        if (next >= 0) cudaMemsetAsync(counts[cur ^ 1], 0, sizeof(int) * tab, s);
-        rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(kin, vin, n, shift, nb, offsets, kout, vout, next, counts[cur ^ 1]);
-        cur ^= 1;
+    for (int p = 0; p < passes; ++p) {
+        rs_onesweep_kernel<<<tiles, RS_THREADS, 0, s>>>(kin, vin, n, begin_bit + 8 * p, ghist + p * 256, state[p & 1],
+                                                         p + 1 < passes ? state[(p + 1) & 1] : nullptr, tickets + p, kout, vout);
         unsigned long long* tk = kin; kin = kout; kout = tk;
         int* tv = vin; vin = vout; vout = tv;
     }

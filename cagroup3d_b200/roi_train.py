@@ -317,7 +317,7 @@ def roi_reg_loss(rcnn_reg: torch.Tensor, targets: dict, code_size: int, code_wei
         loss_iou = TT.IoU3DLoss(with_yaw=code_size > 6, loss_weight=1.0)(
             boxes, gt_src, weight=None if code_size > 6 else torch.ones_like(boxes[:, 0]),
             avg_factor=None if code_size > 6 else float(fg_sum)) * iou_weight
-        tb["rcnn_loss_iou"] = float(loss_iou.detach())
+    tb["rcnn_loss_iou"] = float(loss_iou.detach())          # (loss() reports the term also when no RoI is foreground: 0)
     loss = loss_iou + loss_reg if reg_weight > 0 else loss_iou
     tb["loss_two_stage"] = float(loss.detach())
     return loss, tb

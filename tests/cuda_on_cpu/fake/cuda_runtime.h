@@ -131,6 +131,25 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     w.bar.wait();
     return r;
 }
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int delta) {
+    int lane = cpu_cuda::t_linear & 31;
+    T r = cpu_cuda::warp_read(v, lane >= delta ? lane - delta : lane);
+    return r;
+}
+template <class T>
+static inline unsigned __match_any_sync(unsigned, T v) {
+    cpu_cuda::Warp& w = (*cpu_cuda::warps)[cpu_cuda::t_linear >> 5];
+    w.buf[cpu_cuda::t_linear & 31] = cpu_cuda::to_bits(v);
+    w.bar.wait();
+    unsigned r = 0;
+    for (int l = 0; l < w.bar.n; ++l) r |= (unsigned)(w.buf[l] == cpu_cuda::to_bits(v)) << l;
+    w.bar.wait();
+    return r;
+}
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+enum { cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }

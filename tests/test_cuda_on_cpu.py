@@ -302,3 +302,26 @@ def test_nms_blocked_kernel_equals_the_sweep_kernel_and_the_oracle(K, rotated, m
     keep2 = np.full(n, -1, i32)
     K("cg3d_nms_segments", boxes, n, seg, len(lens), n, 0.5, rotated, keep2, None)
     assert np.array_equal(keep2, keep)
+
+
+@pytest.mark.parametrize("n,begin,end", [(2, 0, 8), (300, 0, 27), (4096, 6, 39), (4097, 0, 27), (20000, 0, 64), (13000, 32, 64)])
+def test_onesweep_radix_sort_is_a_stable_sort(K, n, begin, end):
+    """csrc/sort.cu cg3d_sort_pairs (digit histograms in one launch, then one chained-look-back launch per 8-bit digit) ==
+    numpy's stable argsort on the key bits [begin, end): keys with many duplicates, values = original index, so the
+    order of equal keys is checked; several tiles (4096 keys each), a partial last tile, odd and even numbers of digits."""
+    rng = np.random.default_rng(n + begin)
+    width = end - begin
+    base = rng.integers(0, 2 ** min(width, 62), n, dtype=np.uint64) if n > 300 else rng.integers(0, 7, n, dtype=np.uint64)
+    base[::3] = base[0]                                           # heavy duplication
+    noise = rng.integers(0, 2 ** 62, n, dtype=np.uint64)
+    lowmask = np.uint64((1 << begin) - 1)
+    keys = ((base << np.uint64(begin)) | (noise & lowmask)).astype(np.uint64)      # bits below begin_bit must be ignored
+    if end < 64:
+        keys &= np.uint64((1 << end) - 1)
+    vals = np.arange(n, dtype=i32)
+    k, v = keys.copy(), vals.copy()
+    ws = np.full(K("cg3d_sort_workspace_ints", n), -1, i32)         # (the sort clears what it needs itself)
+    K("cg3d_sort_pairs", k, v, n, begin, end, np.zeros(n, np.uint64), np.zeros(n, i32), ws)
+    digits = (keys >> np.uint64(begin)) & (np.uint64((1 << (8 * ((width + 7) // 8))) - 1) if 8 * ((width + 7) // 8) < 64 else np.uint64(2 ** 64 - 1))
+    order = np.argsort(digits, kind="stable")
+    assert np.array_equal(v, order.astype(i32)) and np.array_equal(k, keys[order])
