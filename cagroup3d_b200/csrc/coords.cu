@@ -101,73 +101,99 @@ __global__ void unique_emit_dev_kernel(const int4* __restrict__ coords, const in
         }
 }
 
-// ---- exclusive scan of int32 (three small kernels; n up to a few million) ---------------------
-constexpr int kScanBlock = 1024;
+// ---- exclusive scan of int32: ONE kernel, chained look-back across tiles (n up to a few million) ---------
+// A CTA takes the next tile of 4096 ints (ticket order), scans it, publishes the tile's sum, and its first warp sums the
+// published (aggregate | inclusive-prefix) words of the tiles before it, 32 at a time, until it meets an inclusive one.
+// State words: 2 flag bits | 30 value bits (sums < 2^30: the inputs are flags and counts of rows), zero before the launch.
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 16;
+constexpr int kScanTile = kScanThreads * kScanPer;
+constexpr unsigned kScanAgg = 1u << 30, kScanInc = 2u << 30, kScanVal = (1u << 30) - 1u;
 
-__global__ void scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ sums) {
-    __shared__ int warp_sum[32];
-    int i = blockIdx.x * kScanBlock + threadIdx.x;
-    int v = i < n ? in[i] : 0;
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = v;
+__global__ void __launch_bounds__(kScanThreads) scan_chained_kernel(const int* __restrict__ in, int n, int* __restrict__ out,
+                                                                    unsigned* state, int* ticket, int* __restrict__ total) {
+    __shared__ int wsum[kScanThreads / 32];
+    __shared__ int tile_s;
+    __shared__ int excl_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) tile_s = atomicAdd(ticket, 1);                       // a tile's predecessors have all started
     __syncthreads();
-    if (threadIdx.x < 32) {
-        int s = warp_sum[threadIdx.x];
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) sums[blockIdx.x] = s;
-    }
-}
-
-__global__ void scan_sums_inplace(int* sums, int nb, int* total) {
-    // single block: sequential over chunks of 1024 with a block-wide inclusive scan each
-    __shared__ int sh[kScanBlock];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < nb; base += kScanBlock) {
-        int i = base + threadIdx.x;
-        int v = i < nb ? sums[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < kScanBlock; o <<= 1) {
-            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+    const int tile = tile_s, tiles = gridDim.x;
+    const int i0 = tile * kScanTile + t * kScanPer;
+    int v[kScanPer];
+    const bool vec = (reinterpret_cast<size_t>(in) & 15) == 0 && i0 + kScanPer <= n;
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < kScanPer / 4; ++j) {
+            const int4 q = __ldg(reinterpret_cast<const int4*>(in + i0) + j);
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
         }
-        int incl = sh[threadIdx.x];
-        if (i < nb) sums[i] = carry + incl - v;
-        __syncthreads();
-        if (threadIdx.x == kScanBlock - 1) carry += incl;
-        __syncthreads();
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanPer; ++j) v[j] = i0 + j < n ? in[i0 + j] : 0;
     }
-    if (threadIdx.x == 0) *total = carry;
-}
-
-__global__ void scan_apply(const int* __restrict__ in, int n, const int* __restrict__ sums, int* __restrict__ out) {
-    __shared__ int warp_off[32];
-    int i = blockIdx.x * kScanBlock + threadIdx.x;
-    int v = i < n ? in[i] : 0;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int incl = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+    int local = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) local += v[j];
+    int x = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
     }
-    if (lane == 31) warp_off[w] = incl;
+    if (lane == 31) wsum[w] = x;
     __syncthreads();
+    int before = x - local, tile_total = 0;
+#pragma unroll
+    for (int j = 0; j < kScanThreads / 32; ++j) {
+        if (j < w) before += wsum[j];
+        tile_total += wsum[j];
+    }
     if (w == 0) {
-        int s = warp_off[lane];
-        int si = s;
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, si, o);
-            if (lane >= o) si += t;
+        volatile unsigned* st = state;
+        unsigned excl = 0u;
+        if (tile > 0) {
+            if (lane == 0) st[tile] = kScanAgg | (unsigned)tile_total;
+            for (int p = tile - 1;; p -= 32) {
+                const int idx = p - lane;
+                unsigned word = kScanInc;                            // before the first tile: an inclusive zero
+                if (idx >= 0) do { word = st[idx]; } while ((word & ~kScanVal) == 0u);
+                const unsigned inc = __ballot_sync(0xffffffffu, (word & kScanInc) != 0u);
+                const int first = __ffs(inc) - 1;                     // nearest predecessor with an inclusive prefix (-1: none)
+                unsigned part = (first < 0 || lane <= first) ? (word & kScanVal) : 0u;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                excl += part;
+                if (first >= 0) break;
+            }
         }
-        warp_off[lane] = si - s;
+        if (lane == 0) {
+            st[tile] = kScanInc | (excl + (unsigned)tile_total);
+            excl_s = (int)excl;
+            if (tile == tiles - 1 && total) *total = (int)excl + tile_total;
+        }
     }
     __syncthreads();
-    if (i < n) out[i] = sums[blockIdx.x] + warp_off[w] + incl - v;
+    int run = excl_s + before;
+    if (vec && (reinterpret_cast<size_t>(out) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < kScanPer / 4; ++j) {
+            int4 q;
+            q.x = run; run += v[4 * j];
+            q.y = run; run += v[4 * j + 1];
+            q.z = run; run += v[4 * j + 2];
+            q.w = run; run += v[4 * j + 3];
+            reinterpret_cast<int4*>(out + i0)[j] = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kScanPer; ++j) {
+            if (i0 + j < n) out[i0 + j] = run;
+            run += v[j];
+        }
+    }
 }
+
 
 __global__ void unique_emit_kernel(const int4* __restrict__ coords, const int* __restrict__ slot_of_row,
                                    const int* __restrict__ vals, const int* __restrict__ excl, int n,
@@ -379,15 +405,15 @@ int cg3d_stride_coords(const int* coords, int n, int ts, int* out, void* stream)
 
 int cg3d_exclusive_scan_i32(const int* in, int n, int* out, int* block_sums, int* total, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    int nb = cg3d_div_up(n > 0 ? n : 1, kScanBlock);
-    scan_block_sums<<<nb, kScanBlock, 0, s>>>(in, n, block_sums);
-    scan_sums_inplace<<<1, kScanBlock, 0, s>>>(block_sums, nb, total);
-    scan_apply<<<nb, kScanBlock, 0, s>>>(in, n, block_sums, out);
+    const int tiles = cg3d_div_up(n > 0 ? n : 1, kScanTile);
+    // block_sums: [tile ticket | look-back words], cleared here
+    cudaMemsetAsync(block_sums, 0, sizeof(int) * (size_t)(tiles + 1), s);
+    scan_chained_kernel<<<tiles, kScanThreads, 0, s>>>(in, n, out, reinterpret_cast<unsigned*>(block_sums + 1), block_sums, total);
     CG3D_LAUNCH_CHECK();
     return 0;
 }
 
-int cg3d_scan_workspace_ints(int n) { return cg3d_div_up(n > 0 ? n : 1, kScanBlock) + 8; }
+int cg3d_scan_workspace_ints(int n) { return cg3d_div_up(n > 0 ? n : 1, kScanTile) + 8; }
 
 int cg3d_unique_first(const int* coords, int n, unsigned long long* keys, int* vals, int capacity,
                       int* out_coords, int* first_row, int* inverse, int* n_unique, int* workspace, void* stream) {

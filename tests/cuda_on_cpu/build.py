@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cagroup3d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["spconv_bwd.cu", "train_bwd.cu", "train_assign.cu", "train_loss.cu", "nms.cu", "sort.cu"]
+SOURCES = ["spconv_bwd.cu", "train_bwd.cu", "train_assign.cu", "train_loss.cu", "nms.cu", "sort.cu", "coords.cu"]
 
 _DEFS = """
 #include <cuda_runtime.h>

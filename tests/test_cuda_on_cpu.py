@@ -325,3 +325,24 @@ def test_onesweep_radix_sort_is_a_stable_sort(K, n, begin, end):
     digits = (keys >> np.uint64(begin)) & (np.uint64((1 << (8 * ((width + 7) // 8))) - 1) if 8 * ((width + 7) // 8) < 64 else np.uint64(2 ** 64 - 1))
     order = np.argsort(digits, kind="stable")
     assert np.array_equal(v, order.astype(i32)) and np.array_equal(k, keys[order])
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 4096, 4097, 70001])
+def test_chained_exclusive_scan(K, n):
+    """csrc/coords.cu cg3d_exclusive_scan_i32 (one kernel: tiles of 4096 ints in ticket order, the offset of a tile from the
+    published sums of the tiles before it) == numpy cumsum; unaligned tails, one and many tiles, in place."""
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 5, max(n, 1)).astype(i32)
+    x[::7] = 0
+    out = np.full(max(n, 1), -7, i32)
+    ws = np.full(K("cg3d_scan_workspace_ints", n), -1, i32)
+    total = np.full(1, -1, i32)
+    K("cg3d_exclusive_scan_i32", x, n, out, ws, total)
+    want = np.concatenate([[0], np.cumsum(x[:n])]).astype(i32)
+    assert np.array_equal(out[:n], want[:n]) and total[0] == want[n]
+    if n:
+        y = x.copy()                                             # in place, and from an address that is not 16-byte aligned
+        buf = np.zeros(n + 1, i32)
+        buf[1:] = x[:n]
+        K("cg3d_exclusive_scan_i32", buf[1:], n, buf[1:], ws, total)
+        assert np.array_equal(buf[1:], want[:n]) and total[0] == want[n]
