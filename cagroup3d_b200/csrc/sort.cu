@@ -5,6 +5,8 @@
 //
 // The sort is stable, so "descending score, lower index first on ties" (the oracle's tie rule) is a
 // key of (segment << 32 | ~ordered(score)) sorted ascending.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/cagroup3d_b200.h"
 
@@ -12,13 +14,13 @@ namespace {
 
 // ---- one-sweep LSD radix sort (8-bit digits, chained look-back across tiles) ---------------------------------------------
 // One launch reads the keys once and builds the 256-bin histogram of EVERY digit position; then one launch per digit:
-// a CTA takes the next tile (4096 keys, ticket order), counts its digits, publishes the counts, sums the counts of the
+// a CTA takes the next tile (2048 or 4096 keys, ticket order), counts its digits, publishes the counts, sums the counts of the
 // tiles before it by looking back through their published (aggregate | inclusive-prefix) words -- no separate scan launch,
 // no per-CTA offset table in HBM -- and scatters its keys in index order (stable).  A 27-bit sort of 4 x 10^5 pairs is
 // 1 + 1 + 4 launches (memset, histograms, 4 digits) instead of 1 + 3 x 4 (histogram; scan, memset, scatter per digit).
 constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 16;
-constexpr int RS_ITEMS = RS_THREADS * RS_ROUNDS;   // keys per tile
+constexpr int RS_MIN_ROUNDS = 8;                    // keys per tile = 256 x rounds: 2048 (sorts that would not fill the SMs with
+constexpr int RS_MAX_ROUNDS = 16;                   // 4096-key tiles) or 4096
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_MAX_PASSES = 8;
 constexpr unsigned RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE = (1u << 30) - 1u;
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const unsigned long
 // state: [tiles][256] words of this pass, zero before the launch: 0 = not yet known, RS_FLAG_AGG | count of the tile,
 // RS_FLAG_INC | count of the tile and of all tiles before it.  state_next (the other buffer, used by the pass after this
 // one) is zeroed here, ticket is this pass's tile counter.
+template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const unsigned long long* __restrict__ keys,
                                                                  const int* __restrict__ vals, int n, int shift,
                                                                  const int* __restrict__ ghist, unsigned* state,
@@ -58,6 +61,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_onesweep_kernel(const unsigned 
     __syncthreads();
     const int tile = tile_s;
     if (state_next) state_next[(size_t)tile * 256 + t] = 0u;
+    constexpr int RS_ITEMS = RS_THREADS * RS_ROUNDS;
     const int start = tile * RS_ITEMS;
     unsigned long long key[RS_ROUNDS];
 #pragma unroll
@@ -146,7 +150,7 @@ inline int flat_grid(long long n) {
 extern "C" {
 
 int cg3d_sort_workspace_ints(int n) {
-    int tiles = cg3d_div_up(n > 0 ? n : 1, RS_ITEMS);
+    int tiles = cg3d_div_up(n > 0 ? n : 1, RS_THREADS * RS_MIN_ROUNDS);
     return RS_MAX_PASSES * 256 + 8 + 2 * 256 * tiles + 8;
 }
 
@@ -156,7 +160,10 @@ int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, i
     if (begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit) return -1;
     if (n > (int)RS_VALUE) return -2;
     cudaStream_t s = (cudaStream_t)stream;
-    const int tiles = cg3d_div_up(n, RS_ITEMS);
+    // 4096-key tiles once they fill two waves of SMs, 2048-key tiles below that (more CTAs, half the serial rounds each)
+    static const char* force_rounds = getenv("CG3D_SORT_ROUNDS");
+    const bool big = force_rounds ? atoi(force_rounds) == RS_MAX_ROUNDS : n >= 2 * 148 * RS_THREADS * RS_MAX_ROUNDS;
+    const int tiles = cg3d_div_up(n, RS_THREADS * (big ? RS_MAX_ROUNDS : RS_MIN_ROUNDS));
     const int passes = (end_bit - begin_bit + 7) / 8;
     // workspace: [digit histograms 8 x 256 | tile tickets 8 | look-back words A | look-back words B]
     int* ghist = workspace;
@@ -168,8 +175,13 @@ int cg3d_sort_pairs(unsigned long long* keys, int* vals, int n, int begin_bit, i
     unsigned long long *kin = keys, *kout = keys_tmp;
     int *vin = vals, *vout = vals_tmp;
     for (int p = 0; p < passes; ++p) {
-        rs_onesweep_kernel<<<tiles, RS_THREADS, 0, s>>>(kin, vin, n, begin_bit + 8 * p, ghist + p * 256, state[p & 1],
-                                                         p + 1 < passes ? state[(p + 1) & 1] : nullptr, tickets + p, kout, vout);
+        unsigned* nxt = p + 1 < passes ? state[(p + 1) & 1] : nullptr;
+        if (big)
+            rs_onesweep_kernel<RS_MAX_ROUNDS><<<tiles, RS_THREADS, 0, s>>>(kin, vin, n, begin_bit + 8 * p, ghist + p * 256, state[p & 1], nxt,
+                                                                            tickets + p, kout, vout);
+        else
+            rs_onesweep_kernel<RS_MIN_ROUNDS><<<tiles, RS_THREADS, 0, s>>>(kin, vin, n, begin_bit + 8 * p, ghist + p * 256, state[p & 1], nxt,
+                                                                            tickets + p, kout, vout);
         unsigned long long* tk = kin; kin = kout; kout = tk;
         int* tv = vin; vin = vout; vout = tv;
     }

@@ -248,7 +248,7 @@ int cg3d_sort_workspace_ints(int n);
 
 /* stable LSD radix sort of (u64 key, i32 value) pairs on key bits [begin_bit, end_bit) (rounded up to whole 8-bit
  * digits), ascending, in place (keys_tmp / vals_tmp: n elements of scratch each; workspace: cg3d_sort_workspace_ints(n)
- * ints, cleared by the call).  One launch builds the histograms of all digits, then one launch per digit: tiles of 4096
+ * ints, cleared by the call).  One launch builds the histograms of all digits, then one launch per digit: tiles of 2048 or 4096
  * keys in ticket order, the offsets of a tile from the published counts of the tiles before it (chained look-back).  Replaces scores.sort(descending=True)
  * (iou3d_nms_utils.py:92,110) and max_scores.topk (cagroup_head.py:596) with keys built by the
  * functions below: (segment << 32 | ~ordered(score)), ties keep the lower index first. */

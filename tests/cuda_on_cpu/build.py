@@ -69,6 +69,13 @@ def transform(src: str) -> str:
         if j < 0:
             return out + src[i:]
         k = j
+        if src[k - 1] == ">":                                 # kernel<template args><<<...>>>: include the argument list
+            depth = 0
+            while True:
+                k -= 1
+                depth += {">": 1, "<": -1}.get(src[k], 0)
+                if depth == 0:
+                    break
         while src[k - 1].isalnum() or src[k - 1] == "_":
             k -= 1
         kernel = src[k:j]

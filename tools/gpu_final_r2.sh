@@ -15,8 +15,10 @@ cut -c1-400 $O/final_bench.json
 timeout -k 5 300 python bench.py --workload sunrgbd --steps 5 --warmup 3 > $O/final_bench_sunrgbd.json 2>> $O/final_bench.err
 timeout -k 5 400 python bench.py --workload sweep --steps 5 --warmup 3 > $O/final_bench_sweep.json 2>> $O/final_bench.err
 timeout -k 5 300 python bench.py --workload train --steps 5 --warmup 3 > $O/final_bench_train.json 2>> $O/final_bench.err
+timeout -k 5 300 python bench.py --workload train_sunrgbd --steps 5 --warmup 3 --no-cpu-baseline > $O/final_bench_train_sunrgbd.json 2>> $O/final_bench.err
+timeout -k 5 120 python -m pytest tests/test_gpu_ops.py -m gpu -q -s -k "nms_long_segments" 2>&1 | grep "^NMS\|passed\|failed" > $O/final_nms_paths.log
 timeout -k 5 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/final_bench_reference.json 2>> $O/final_bench.err
-for f in sunrgbd sweep train reference; do cut -c1-200 $O/final_bench_$f.json; done
+for f in sunrgbd sweep train train_sunrgbd reference; do cut -c1-200 $O/final_bench_$f.json; done
 timeout -k 5 300 python tools/stage_times.py --conv tc > $O/final_stage_times.log 2>&1
 timeout -k 5 300 python tools/train_times.py --batch 4 --voxels 50000 --steps 3 > $O/final_train_times.log 2>&1
 timeout -k 5 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
@@ -29,4 +31,10 @@ python tools/ncu_summary.py /tmp/ncu/final_spconv_backbone.ncu-rep $O/final_ncu_
 timeout -k 5 900 ncu --profile-from-start off --set full --clock-control none -k regex:spconv_.*_kernel -s 56 -c 16 \
     -f -o /tmp/ncu/final_spconv_head python tools/ncu_step.py > $O/final_ncu_head.log 2>&1
 python tools/ncu_summary.py /tmp/ncu/final_spconv_head.ncu-rep $O/final_ncu_spconv_head
+ls -la /tmp/ncu $O | tail -40
+# the selection primitives rewritten at the end of round 2 (one-sweep sort, chained scan, blocked NMS)
+timeout -k 5 300 ncu --profile-from-start off --set full --clock-control none -k regex:"rs_onesweep_kernel|rs_hist_kernel|scan_chained_kernel|blocked_nms_kernel" -c 14 \
+    -f -o /tmp/ncu/final_select python tools/ncu_step.py > $O/final_ncu_select.log 2>&1
+python tools/ncu_summary.py /tmp/ncu/final_select.ncu-rep $O/final_ncu_select
+timeout -k 5 120 python tools/timeline.py > $O/final_timeline.log 2>&1
 ls -la /tmp/ncu $O | tail -40
