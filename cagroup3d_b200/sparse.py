@@ -394,7 +394,12 @@ def make_tiles(seg_offsets, device, tile=64) -> Tiles:
     first = np.cumsum(cnt) - cnt
     r0 = off[:-1][gg] + (np.arange(int(cnt.sum())) - first[gg]) * tile
     rn = np.minimum(tile, off[1:][gg] - r0)
-    t = torch.from_numpy(np.stack([r0, rn, gg]).astype(np.int32)).to(device, non_blocking=True)
+    t = torch.from_numpy(np.stack([r0, rn, gg]).astype(np.int32))
+    if torch.device(device).type == "cuda":
+        # pinned staging: a copy from pageable memory first waits for everything queued on the stream (the host would sit
+        # out the kernels launched just before and the GPU would idle after them while the next launches are prepared)
+        t = t.pin_memory()
+    t = t.to(device, non_blocking=True)
     return Tiles(t[0].contiguous(), t[1].contiguous(), t[2].contiguous(), int(cnt.sum()), list(seg_offsets), tile)
 
 
