@@ -7,8 +7,9 @@ Follows, for the ScanNet configuration (WITH_YAW False; the yaw handling of the 
   pcdet/utils/loss_utils.py:813-846  binary_cross_entropy (CrossEntropy, use_sigmoid)      :917-961, 1012-1032  FocalLoss
   pcdet/utils/loss_utils.py:1042-1074  smooth_l1_loss       pcdet/utils/iou3d_loss.py:31-58 + loss_utils.py:419-537  IoU loss
   pcdet/models/dense_heads/cagroup_head.py:505-554  the loss terms of _loss_single (no-yaw branch)
-Pinned by tests/golden/train_parts.npz (tests/golden/make_train_golden.py runs the reference's own classes on seeded
-random inputs) in tests/test_train_oracle.py.  torch CPU, fp32 like the reference.
+  pcdet/models/dense_heads/cagroup_head.py:418-451,681-703  WITH_YAW: in-box vote targets (3 per seed), 'fcaf3d' box decode
+Pinned by tests/golden/train_parts.npz and train_yaw_parts.npz (tests/golden/make_train_golden.py runs the reference's own
+classes on seeded random inputs) in tests/test_train_oracle.py / tests/test_train_yaw.py.  torch CPU, fp32 like the reference.
 """
 from __future__ import annotations
 
@@ -125,6 +126,46 @@ def head_loss_terms(centerness, bbox_decoded, cls_scores, centerness_targets, bb
     loss_ctr = bce_loss(centerness[pos], ct, n_pos)
     loss_box = axis_aligned_iou_loss(bbox_decoded[pos][:, :6], bbox_targets[pos][:, :6], ct.squeeze(1), max(float(ct.sum()), 1e-6))
     return loss_ctr, loss_box, loss_cls, loss_sem, loss_vote
+
+
+# ---- WITH_YAW (SUN RGB-D) pieces of _loss_single ------------------------------------------------------------------------------
+def points_in_boxes(points: torch.Tensor, gt_boxes: torch.Tensor) -> torch.Tensor:
+    """find_points_in_boxes (cagroup3d_assigner.py:9-36): (n, m) bool, all six face distances of the point in the box's own
+    frame > 0.  Pinned by the `inside` matrix of tests/golden/train_yaw_parts.npz (the reference's own function)."""
+    return face_distances(points, gt_boxes).min(-1)[0] > 0
+
+
+def vote_targets_in_boxes(voxel_points: torch.Tensor, gt_boxes: torch.Tensor, inside=None, gt_per_seed: int = 3):
+    """cagroup_head.py:418-451, statement by statement (the per-box loop and its per-point counter): every voxel inside a
+    gt box votes for that box's centre, up to gt_per_seed = 3 votes; the first containing box fills all three slots, the
+    second the second slot, every later one the third (the counter stops at 2).  -> (targets (n, 9), mask (n,) int64).
+    inside: the (n, m) containment matrix if it is already known (the golden's), else points_in_boxes."""
+    n = voxel_points.shape[0]
+    inside = points_in_boxes(voxel_points, gt_boxes) if inside is None else inside
+    votes = torch.zeros((n, 3 * gt_per_seed), dtype=voxel_points.dtype)
+    mask = torch.zeros((n,), dtype=torch.long)
+    cnt = torch.zeros((n,), dtype=torch.long)
+    for i in range(gt_boxes.shape[0]):
+        ind = torch.nonzero(inside[:, i]).squeeze(-1)
+        mask[ind] = 1
+        v = gt_boxes[i, :3].unsqueeze(0) - voxel_points[ind, :3]
+        for r, p in enumerate(ind.tolist()):
+            j = int(cnt[p])
+            votes[p, 3 * j:3 * j + 3] = v[r]
+            if j == 0:
+                votes[p] = v[r].repeat(gt_per_seed)
+        cnt[ind] = torch.clamp(cnt[ind] + 1, max=2)
+    return votes, mask
+
+
+def bbox_pred_to_bbox_fcaf3d(points: torch.Tensor, bbox_pred: torch.Tensor) -> torch.Tensor:
+    """_bbox_pred_to_bbox, 'fcaf3d' parametrisation (cagroup_head.py:681-703): (n, 8) face distances + (sin 2a, cos 2a)
+    scaled by the log aspect ratio -> (x, y, z, dx, dy, dz, alpha)."""
+    c = points[:, :3] + (bbox_pred[:, 1:6:2] - bbox_pred[:, 0:6:2]) / 2
+    scale = bbox_pred[:, 0] + bbox_pred[:, 1] + bbox_pred[:, 2] + bbox_pred[:, 3]
+    q = torch.exp(torch.sqrt(bbox_pred[:, 6] ** 2 + bbox_pred[:, 7] ** 2))
+    alpha = 0.5 * torch.atan2(bbox_pred[:, 6], bbox_pred[:, 7])
+    return torch.stack([c[:, 0], c[:, 1], c[:, 2], scale / (1 + q), scale / (1 + q) * q, bbox_pred[:, 5] + bbox_pred[:, 4], alpha], -1)
 
 
 # ---- first-stage training loss of a whole batch, on top of the inference oracle ---------------------------------------------

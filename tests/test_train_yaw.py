@@ -16,25 +16,9 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "train_yaw_parts.npz")
 TOL_LOSS, TOL_GRAD = 2e-5, 5e-5                       # fp32; gradients relative to the tensor's largest golden entry
 
 
-def _reference_vote_targets(vox, boxes, inside):
-    """the reference's loop (cagroup_head.py:424-451) restated on the golden's own `inside` matrix, for the direct check"""
-    n = len(vox)
-    votes, cnt, mask = np.zeros((n, 9), np.float32), np.zeros(n, np.int64), np.zeros(n, np.int64)
-    for i in range(len(boxes)):
-        ind = np.nonzero(inside[:, i])[0]
-        mask[ind] = 1
-        v = boxes[i, :3][None] - vox[ind]
-        for r, p in enumerate(ind):
-            j = int(cnt[p])
-            votes[p, 3 * j:3 * j + 3] = v[r]
-            if j == 0:
-                votes[p] = np.tile(v[r], 3)
-        cnt[ind] = np.minimum(2, cnt[ind] + 1)
-    return votes, mask
-
-
 def _run(dev, z):
     from cagroup3d_b200 import train_targets as TT
+    from oracle import train_oracle as T
     t = lambda k: torch.from_numpy(z[k]).to(dev)
     boxes, labels, vox = t("boxes"), t("labels"), t("voxels")
     sizes = z["n_per_class"].tolist()
@@ -43,10 +27,10 @@ def _run(dev, z):
     inside = TT.points_in_boxes(vox, boxes).cpu().numpy()
     assert (inside != z["inside"]).mean() <= 2e-3      # a voxel within an ulp of a face may fall on the other side
     if (inside == z["inside"]).all():
-        want_v, want_m = _reference_vote_targets(z["voxels"], z["boxes"], z["inside"])
+        want_v, want_m = T.vote_targets_in_boxes(torch.from_numpy(z["voxels"]), torch.from_numpy(z["boxes"]), torch.from_numpy(z["inside"]))
         got_v, got_m = TT.vote_targets_yaw(vox, boxes, 3)
-        assert np.array_equal(got_m.cpu().numpy(), want_m)
-        assert np.abs(got_v.cpu().numpy() - want_v).max() <= 1e-6
+        assert np.array_equal(got_m.cpu().numpy(), want_m.numpy())
+        assert np.abs(got_v.cpu().numpy() - want_v.numpy()).max() <= 1e-6
         assert (z["inside"].sum(1) >= 3).sum() > 5 and (z["inside"].sum(1) == 2).sum() > 5     # the golden exercises 2 and 3+ votes
     leaf = lambda k: t(k).requires_grad_(True)
     ctr, box, cls, off, sem = leaf("ctr"), leaf("box"), leaf("cls"), leaf("off"), leaf("sem")
@@ -142,3 +126,22 @@ def test_roi_targets_and_losses_with_yaw_equal_the_reference_cpu(monkeypatch, co
 @pytest.mark.gpu
 def test_roi_targets_and_losses_with_yaw_equal_the_reference_on_device(lib):
     _run_roi("cuda", np.load(ROI_GOLD))
+
+
+def test_yaw_oracle_pieces_equal_the_reference():
+    """oracle/train_oracle.py: points_in_boxes == the reference's find_points_in_boxes on the golden's voxels and yawed boxes
+    (its `inside` matrix); the 'fcaf3d' decode and the in-box vote targets feed the reference's loss values: the box loss
+    through the reference-pinned rotated IoU (rotiou_loss.npz) and the vote loss reproduce the golden's terms."""
+    from oracle import train_oracle as T
+    z = np.load(GOLD)
+    vox, boxes = torch.from_numpy(z["voxels"]), torch.from_numpy(z["boxes"])
+    assert np.array_equal(T.points_in_boxes(vox, boxes).numpy(), z["inside"])
+    tgt, mask = T.vote_targets_in_boxes(vox, boxes)
+    off = torch.from_numpy(z["off"])
+    w = (mask.float() / (mask.float().sum() + 1e-6)).unsqueeze(1).repeat(1, 9)
+    base = vox.repeat(1, 3)
+    vote = T.smooth_l1_sum(base + off, base + tgt, w)
+    assert abs(float(vote) - float(z["losses"][4])) <= 2e-5 * max(1.0, abs(float(z["losses"][4])))
+    dec = T.bbox_pred_to_bbox_fcaf3d(torch.from_numpy(z["points"]), torch.from_numpy(z["box"]))
+    assert dec.shape == (len(z["points"]), 7) and bool(torch.isfinite(dec).all()) and bool((dec[:, 3:6] > 0).all())
+    assert float(dec[:, 6].abs().max()) <= np.pi / 2 + 1e-6
