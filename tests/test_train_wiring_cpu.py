@@ -557,8 +557,9 @@ def test_first_stage_training_step_driver(monkeypatch, yaw):
     assert abs(disp.pop("cur_semantic_value") - max(0.15 - 3 * 0.02, 0.05)) < 1e-9 and set(disp) == set(tb) - {"loss_all"}
     ret["loss"].backward()
     assert [n for n, p in model.named_parameters() if p.grad is None] == []
-    tb2 = TS.training_step(model, dict(bd, points=bd["points"].clone()), opt, red, impl="simt", grad_norm_clip=10.0)
-    assert set(tb2) == set(tb)
+    if not yaw:                                                  # (the same driver code for both configurations: run once)
+        tb2 = TS.training_step(model, dict(bd, points=bd["points"].clone()), opt, red, impl="simt", grad_norm_clip=10.0)
+        assert set(tb2) == set(tb)
 
 
 def _roi_artifacts(inter, cfg, sp, nr):
