@@ -327,8 +327,8 @@ int cg3d_nms_segments(const float* sorted_boxes, int n_boxes, const int* seg_off
             cfg.attrs = at;
             cfg.numAttrs = 1;
             cudaError_t e = cudaLaunchKernelEx(&cfg, blocked_nms_kernel, sorted_boxes, seg_offsets, thr, rotated, cl, keep, kept_count);
-            if (e != cudaSuccess) return (int)e;
-            return 0;
+            if (e == cudaSuccess) return 0;
+            cudaGetLastError();                                       // a cluster that cannot be placed: one CTA per segment below
         }
 #endif
         blocked_nms_kernel<<<n_segments, NMS_BLOCKED_THREADS, smem, st>>>(sorted_boxes, seg_offsets, thr, rotated, 1, keep, kept_count);
