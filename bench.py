@@ -460,6 +460,26 @@ def bench_train(args, rank, world, timed, conv, dist):
                 "achieved": None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": None, "traffic": None,
                 "note": "training step: per-kernel device times below; the conv forward / dX launches are the inference kernel "
                         "(roofline in the scannet workload's line)"}
+    try:
+        # algorithmic bytes (SURVEY 8d formula) of the step's conv forward + dX launches over their own device time
+        cb, cms, cn = 0.0, 0.0, 0
+        for name, _, meta, a0, a1 in rec:
+            if meta is None or not name.startswith("cg3d_spconv"):
+                continue
+            P = int((meta["nbr"] >= 0).sum()) if meta["nbr"] is not None else 0
+            cb += conv_bytes(meta, P)
+            cms += a0.elapsed_time(a1)
+            cn += 1
+        if cn and cms > 0 and roofline["peak"]:
+            roofline.update(bound="hbm", kernel="cg3d_spconv_tc / cg3d_spconv_simt (conv forward + dX launches of one training step)",
+                            calls_per_step=cn, ms_per_step=cms, share_of_kernel_time=cms / max(kernel_ms, 1e-9),
+                            achieved=cb / (cms * 1e-3) / 1e9, frac=cb / (cms * 1e-3) / 1e9 / roofline["peak"],
+                            launch_bytes_avg=cb / cn,
+                            note="algorithmic bytes = SURVEY 8d formula per launch (dX = the same conv over the transposed rule map); "
+                                 "timed inside the instrumented step (events around every C-ABI call); these launches are "
+                                 "tensor-bound like the inference ones (scannet line: roofline.tensor), traffic not captured")
+    except Exception as e:                                      # the table above stays valid
+        roofline["note"] += f" [conv byte accounting failed: {type(e).__name__}: {e}]"
     table = [{"kernel": k, "calls": v[0], "ms": v[1], "share": v[1] / max(kernel_ms, 1e-9)} for k, v in top]
     info = {"batch_per_gpu": B, "stride2_voxels_per_scene": n_vox2 // B, "points_per_batch": int(host_pts.shape[0]),
             "iters_per_sec": 1e3 / ms_step, "parameters_M": sum(q.numel() for q in params) / 1e6,
