@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cagroup3d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["spconv_bwd.cu", "train_bwd.cu", "train_assign.cu", "train_loss.cu", "nms.cu", "sort.cu", "coords.cu"]
+SOURCES = ["spconv_bwd.cu", "train_bwd.cu", "train_assign.cu", "train_loss.cu", "nms.cu", "sort.cu", "coords.cu", "pool_interp.cu", "detect.cu", "proposal.cu", "train_ops.cu", "spconv_simt.cu"]
 
 _DEFS = """
 #include <cuda_runtime.h>
@@ -28,6 +28,7 @@ dim3 g_blockDim, g_gridDim;
 char* dyn_smem = nullptr;
 thread_local dim3 t_threadIdx, t_blockIdx;
 thread_local int t_linear = 0;
+int sync_or_acc[2] = {0, 0};
 }
 """
 

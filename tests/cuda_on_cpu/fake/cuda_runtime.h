@@ -5,6 +5,7 @@
 // nothing about performance and does not replace the run on hardware.  See tests/cuda_on_cpu/build.py.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -31,6 +32,8 @@ struct dim3 {
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct int4 { int x, y, z, w; };
 struct int2 { int x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
@@ -118,6 +121,18 @@ void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A... arg
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline void __syncthreads() { cpu_cuda::block_barrier.wait(); }
+namespace cpu_cuda { extern int sync_or_acc[2]; }
+static inline int __syncthreads_or(int pred) {                    // two alternating accumulators: a thread may enter the next
+    static thread_local int phase = 0;                            // call before the slowest one has read this call's result
+    int* acc = &cpu_cuda::sync_or_acc[phase & 1];
+    if (pred) __atomic_store_n(acc, 1, __ATOMIC_RELAXED);
+    cpu_cuda::block_barrier.wait();
+    int r = __atomic_load_n(acc, __ATOMIC_RELAXED);
+    cpu_cuda::block_barrier.wait();
+    if (cpu_cuda::t_linear == 0) __atomic_store_n(acc, 0, __ATOMIC_RELAXED);
+    ++phase;
+    return r;
+}
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int src) { return cpu_cuda::warp_read(v, src); }
 template <class T>
@@ -161,11 +176,18 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 enum { cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+// (no divergence tracking here: tests drive kernels that use it with whole warps, e.g. row counts that are multiples of 32)
+static inline unsigned __activemask() { return 0xffffffffu; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
+static inline long long __float2ll_rn(float f) { return (long long)nearbyintf(f); }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int atomicMin(int* p, int v) {
     int old = __atomic_load_n(p, __ATOMIC_RELAXED);

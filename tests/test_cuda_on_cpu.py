@@ -346,3 +346,315 @@ def test_chained_exclusive_scan(K, n):
         buf[1:] = x[:n]
         K("cg3d_exclusive_scan_i32", buf[1:], n, buf[1:], ws, total)
         assert np.array_equal(buf[1:], want[:n]) and total[0] == want[n]
+
+
+# ---- inference-side kernels (detect.cu, pool_interp.cu, proposal.cu) ------------------------------------------------------------
+@pytest.mark.parametrize("nreg", [6, 8])
+def test_head_decode_kernel_vs_oracle(K, nreg):
+    """csrc/detect.cu cg3d_head_decode == the oracle's forward_single tail (cagroup_head.py:636-649: Scale + exp on the six
+    face distances; :590-593: sigmoid(cls) * sigmoid(centerness); :654-703: _bbox_pred_to_bbox incl. the 'fcaf3d' yaw code) on
+    class-batched rows (batch index = class * B + sample, per-class voxel sizes and scales)."""
+    import torch
+    from oracle import cagroup3d_oracle as O
+    rng = np.random.default_rng(nreg)
+    n, ncls, B = 700, 5, 2
+    coords = np.concatenate([rng.integers(0, ncls * B, (n, 1)), rng.integers(-40, 40, (n, 3))], 1).astype(i32)
+    pred = rng.normal(0, 1.0, (n, 1 + ncls + nreg)).astype(f32)
+    vsA = rng.uniform(0.02, 0.2, (ncls, 3)).astype(f32)
+    scales = rng.uniform(0.5, 1.5, ncls).astype(f32)
+    scores, mx, boxes = np.zeros((n, ncls), f32), np.zeros(n, f32), np.full((n, 7), -9, f32)
+    K("cg3d_head_decode", pred, pred.shape[1], coords, n, ncls, nreg, B, vsA, scales, scores, mx, boxes, 7)
+    cls_of = coords[:, 0] // B
+    p = torch.from_numpy(pred).double()
+    pts = torch.from_numpy(coords[:, 1:].astype(np.float64) * vsA[cls_of].astype(np.float64))
+    reg = p[:, 1 + ncls:]
+    bp = torch.cat([torch.exp(reg[:, :6] * torch.from_numpy(scales[cls_of].astype(np.float64))[:, None]), reg[:, 6:]], 1)
+    want_boxes = O.bbox_pred_to_bbox(pts, bp).numpy()
+    want_scores = (torch.sigmoid(p[:, 1:1 + ncls]) * torch.sigmoid(p[:, :1])).numpy()
+    assert _rel(scores, want_scores) < 1e-6 and _rel(mx, want_scores.max(1)) < 1e-6
+    assert _rel(boxes[:, :want_boxes.shape[1]], want_boxes) < 2e-6
+    if nreg == 6:
+        assert np.all(boxes[:, 6] == 0)
+
+
+@pytest.mark.parametrize("code_size,sincos", [(6, 0), (7, 0), (7, 1)])
+def test_roi_decode_kernel_vs_oracle(K, code_size, sincos):
+    """csrc/detect.cu cg3d_roi_decode == CAGroupResidualCoder.decode_torch on the zero-centred RoI + rotation by the RoI heading +
+    shift to its centre (cagroup_roi_head.py:477-510; oracle: residual_decode + rotate_z)."""
+    import torch
+    from oracle import cagroup3d_oracle as O
+    rng = np.random.default_rng(10 * code_size + sincos)
+    n = 333
+    rois = np.concatenate([rng.uniform(-3, 3, (n, 3)), rng.uniform(0.3, 2, (n, 3)), rng.uniform(-3.1, 3.1, (n, 1)) * (code_size > 6)], 1).astype(f32)
+    reg = rng.normal(0, 0.3, (n, code_size + sincos)).astype(f32)
+    out = np.full((n, code_size), -9, f32)
+    K("cg3d_roi_decode", rois, reg, n, code_size, sincos, out)
+    r64 = torch.from_numpy(rois).double()
+    local = r64[:, :code_size].clone()
+    local[:, 0:3] = 0
+    dec = O.residual_decode(torch.from_numpy(reg).double(), local, code_size, bool(sincos)).view(-1, code_size)
+    if code_size > 6:
+        dec = torch.cat([O.rotate_z(dec[:, None, 0:3], r64[:, 6])[:, 0], dec[:, 3:]], 1)
+    dec[:, 0:3] += r64[:, 0:3]
+    assert _rel(out, dec.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("with_ref", [False, True])
+def test_segment_mean_kernel(K, with_ref):
+    """csrc/pool_interp.cu cg3d_segment_mean (histogram -> scan -> fill -> one warp per unique row, 2^-30 fixed-point sums) ==
+    the per-segment mean; with `ref`: point p reads slice `kind` of a wide source row or a row of the second source
+    (the head's voted / original copies, cagroup_head.py:257-271).  `inverse` comes from a unique pass in the product, so
+    every segment holds at least one point (as here); bit-repeatable."""
+    rng = np.random.default_rng(int(with_ref))
+    n, U, C, nv = 1500, 400, 64, 3
+    inv = rng.integers(0, U, n).astype(i32)
+    inv[:U] = np.arange(U)                                       # every segment occurs
+    inv[U:U + 50] = 7                                            # one long segment
+    out, cnt = np.full((U, C), -9, f32), np.full(U, -9, f32)
+    ws = np.zeros(K("cg3d_segment_mean_workspace", n, U), np.int64)
+    if with_ref:
+        rows = 300
+        A, Bm = rng.normal(0, 2, (rows, nv * C)).astype(f32), rng.normal(0, 2, (rows, C)).astype(f32)
+        ref = np.stack([rng.integers(0, rows, n), rng.integers(-1, nv, n)], 1).astype(i32)
+        K("cg3d_segment_mean", A, nv * C, Bm, C, ref, inv, n, U, C, out, cnt, ws)
+        feat = np.where((ref[:, 1] >= 0)[:, None], A.reshape(rows, nv, C)[ref[:, 0], np.maximum(ref[:, 1], 0)], Bm[ref[:, 0]])
+    else:
+        A = rng.normal(0, 2, (n, C)).astype(f32)
+        K("cg3d_segment_mean", A, C, None, 0, None, inv, n, U, C, out, cnt, ws)
+        feat = A
+    sums = np.zeros((U, C), np.float64)
+    np.add.at(sums, inv, feat.astype(np.float64))
+    m = np.bincount(inv, minlength=U)
+    want = sums / m[:, None]
+    assert m.min() >= 1 and np.array_equal(cnt, m.astype(f32)) and _rel(out, want) < 1e-6
+    out2 = np.zeros_like(out)
+    K("cg3d_segment_mean", *( (A, nv * C, Bm, C, ref) if with_ref else (A, C, None, 0, None) ), inv.copy(), n, U, C, out2, cnt, ws)
+    assert np.array_equal(out, out2)
+
+
+def test_topk_keys_and_rank_filter_kernels(K):
+    """csrc/proposal.cu cg3d_topk_keys -> cg3d_sort_pairs -> cg3d_rank_filter == `max_scores.topk(nms_pre)` per (sample, class
+    map) segment (cagroup_head.py:595-599): segments longer than nms_pre keep their nms_pre best rows (ties: lower row
+    first), shorter ones keep all rows in row order."""
+    rng = np.random.default_rng(3)
+    nseg, nms_pre = 6, 50
+    lens = [0, 20, 50, 51, 300, 120]
+    seg = np.repeat(np.arange(nseg), lens).astype(i32)
+    perm = rng.permutation(len(seg))
+    seg = seg[perm]                                              # rows of a segment are scattered over the array
+    n = len(seg)
+    score = rng.random(n).astype(f32)
+    score[::9] = score[0]                                        # ties
+    counts = np.bincount(seg, minlength=nseg).astype(i32)
+    keys, vals = np.zeros(n, np.uint64), np.zeros(n, i32)
+    K("cg3d_topk_keys", seg, score, n, counts, nms_pre, keys, vals)
+    ws = np.full(K("cg3d_sort_workspace_ints", n), -1, i32)
+    K("cg3d_sort_pairs", keys, vals, n, 0, 64, np.zeros(n, np.uint64), np.zeros(n, i32), ws)
+    seg_off = np.concatenate([[0], np.cumsum(counts)]).astype(i32)
+    flags = np.full(n, -1, i32)
+    K("cg3d_rank_filter", keys, n, seg_off, nms_pre, flags)
+    assert np.array_equal(seg[vals], np.sort(seg, kind="stable"))           # sorted by segment
+    for s in range(nseg):
+        rows = vals[seg_off[s]:seg_off[s + 1]]
+        kept = rows[flags[seg_off[s]:seg_off[s + 1]] == 1]
+        mine = np.nonzero(seg == s)[0]
+        if len(mine) <= nms_pre:
+            assert np.array_equal(kept, mine)                                # everything, in row order
+        else:
+            order = mine[np.argsort(-score[mine], kind="stable")][:nms_pre]  # best scores, lower row first on ties
+            assert np.array_equal(kept, order)
+
+
+def test_head_coordinate_kernels(K):
+    """csrc/detect.cu: cg3d_coord_bounds / cg3d_first_rows / cg3d_vote_points / cg3d_semantic_flags -> scan -> cg3d_compact_rows
+    == their numpy statements (cagroup_head.py:207-230: pad ids, scene bounds, clamped voted points, per-class selection in
+    row order)."""
+    rng = np.random.default_rng(8)
+    n, B, ncls, nv, ts, vs = 1024, 3, 4, 3, 2, 0.02                # whole warps (first_rows groups lanes with __activemask)
+    b = np.sort(rng.integers(0, B, n)).astype(i32)
+    coords = np.concatenate([b[:, None], rng.integers(-60, 90, (n, 3)) * ts], 1).astype(i32)
+    mm = np.zeros(6, i32)
+    K("cg3d_coord_bounds", coords, n, mm)
+    assert np.array_equal(mm, np.concatenate([coords[:, 1:].min(0), coords[:, 1:].max(0)]))
+    first = np.full(B, 0x7F7F7F7F, i32)
+    K("cg3d_first_rows", coords, n, B, first)
+    assert np.array_equal(first, [np.nonzero(b == k)[0][0] for k in range(B)])
+    off = rng.normal(0, 0.8, (n, nv, 3)).astype(f32)
+    voted = np.zeros((n, nv, 3), f32)
+    K("cg3d_vote_points", coords, off, n, nv, vs, ts, mm, voted)
+    lo, hi = ((mm[:3] - ts).astype(f32) * f32(vs)), ((mm[3:] + ts).astype(f32) * f32(vs))
+    want = np.maximum(np.minimum(coords[:, None, 1:].astype(f32) * f32(vs) + off, hi), lo)
+    assert np.array_equal(voted, want) and (voted == hi).any() and (voted == lo).any()
+    sem = rng.normal(-1.5, 1.5, (n, ncls)).astype(f32)
+    thr = 0.15
+    flags = np.zeros(ncls * n, i32)
+    K("cg3d_semantic_flags", sem, n, ncls, thr, flags)
+    sig = 1.0 / (1.0 + np.exp(-sem.astype(np.float64)))
+    want_f = (sig > thr).T.reshape(-1)
+    edge = np.abs(sig.T.reshape(-1) - thr) < 1e-6
+    assert np.array_equal(flags[~edge] == 1, want_f[~edge])
+    pos, total = np.zeros(ncls * n, i32), np.zeros(1, i32)
+    K("cg3d_exclusive_scan_i32", flags, ncls * n, pos, np.zeros(K("cg3d_scan_workspace_ints", ncls * n), i32), total)
+    sel = np.full(max(int(total[0]), 1), -1, i32)
+    K("cg3d_compact_rows", flags, pos, n, ncls, sel)
+    want_sel = np.concatenate([np.nonzero(flags[c * n:(c + 1) * n])[0] for c in range(ncls)])
+    assert total[0] == len(want_sel) > 0 and np.array_equal(sel[:total[0]], want_sel)
+
+
+def test_knn_kernels_vs_exhaustive_numpy(K):
+    """csrc/train_ops.cu: cg3d_knn (k = 1 and k = 3) == an exhaustive scan in index order with the kernel's distance
+    expression (knn_cuda.cu:58-94: strict `<`, first index wins); cg3d_knn_grid (counting sort into cells + ring search) ==
+    cg3d_knn bit for bit, incl. duplicated points, queries outside the box and a far cluster."""
+    rng = np.random.default_rng(4)
+    n, m = 4500, 320
+    xyz = rng.uniform(-2, 2, (1, n, 3)).astype(f32)
+    xyz[0, 100:110] = xyz[0, 90:100]                             # duplicated points: ties at distance 0 for a query on them
+    xyz[0, -40:] += 30.0                                         # a far cluster
+    q = rng.uniform(-2.2, 2.2, (1, m, 3)).astype(f32)
+    q[0, :10] = xyz[0, 100:110]
+    q[0, 10:14] = [[9, 9, 9], [-9, 0, 0], [31, 31, 31], [0, 0, -50]]
+    idx1, d1 = np.zeros((1, m, 1), i32), np.zeros((1, m, 1), f32)
+    K("cg3d_knn", xyz, 1, n, q, m, 1, idx1, d1)
+    # the kernel's expression (the reference binary's contraction): fmaf(dz, dz, fmaf(dx, dx, dy * dy)); an fp32 fma is the
+    # exactly formed product + addend rounded once: float64 holds the 48-bit product exactly
+    dx, dy, dz = ((q[0, :, None, a] - xyz[0, None, :, a]).astype(f32) for a in range(3))
+    f64 = np.float64
+    d = (dy * dy).astype(f32)
+    d = (dx.astype(f64) * dx.astype(f64) + d.astype(f64)).astype(f32)
+    d = (dz.astype(f64) * dz.astype(f64) + d.astype(f64)).astype(f32)
+    want = d.argmin(1)
+    assert np.array_equal(idx1[0, :, 0], want) and np.array_equal(d1[0, :, 0], d[np.arange(m), want])
+    assert np.array_equal(idx1[0, :10, 0], np.arange(90, 100))   # the first of two identical points wins
+    idx3, d3 = np.zeros((1, m, 3), i32), np.zeros((1, m, 3), f32)
+    K("cg3d_knn", xyz, 1, n, q, m, 3, idx3, d3)
+    order = np.argsort(d, 1, kind="stable")[:, :3]
+    assert np.array_equal(d3[0], np.take_along_axis(d, order, 1))
+    # equal distances (the duplicated points) leave the reference's heap in heap order: rows whose four smallest distances
+    # are distinct must match exactly; for the others every returned index must carry the returned distance
+    distinct = (np.diff(np.sort(d, 1)[:, :4], axis=1) > 0).all(1)
+    assert distinct.sum() > 290 and np.array_equal(idx3[0][distinct], order[distinct])
+    assert np.array_equal(np.take_along_axis(d, idx3[0].astype(np.int64), 1), d3[0])
+    assert all(len(set(r)) == 3 for r in idx3[0].tolist())
+    ig, dg = np.full((1, m), -1, i32), np.zeros((1, m), f32)
+    ws = np.zeros(K("cg3d_knn_grid_workspace", n) + 4, i32)
+    off = (-ws.ctypes.data // 4) % 4                             # 16-byte aligned start
+    K("cg3d_knn_grid", xyz, 1, n, q, m, ig, dg, ws[off:])
+    assert np.array_equal(ig[0], idx1[0, :, 0]) and np.array_equal(dg[0], d1[0, :, 0])
+
+
+def test_sort_vertices_kernel_vs_oracle(K):
+    """csrc/train_ops.cu cg3d_sort_vertices == oracle/sort_vertices_oracle.py (the numpy restatement of sort_vert_kernel.cu that
+    served the reference's Python when the rotated-IoU goldens were made) on random polygons with masked-out vertices."""
+    from oracle import sort_vertices_oracle as SVO
+    rng = np.random.default_rng(2)
+    b, n, m = 2, 96, 24
+    mask = np.zeros((b, n, m), bool)                             # 0 .. 8 valid vertices (a convex intersection has at most 8)
+    for bi in range(b):
+        for r in range(n):
+            mask[bi, r, rng.choice(m, rng.integers(0, 9), replace=False)] = True
+    mask[0, 0] = False
+    mask[0, 0, :3] = True                                        # a triangle
+    mask[0, 1] = False                                           # no valid vertex at all
+    nv = mask.sum(-1).astype(i32)
+    verts = rng.normal(0, 1, (b, n, m, 2)).astype(f32)
+    cen = (verts * mask[..., None]).sum(2, keepdims=True) / np.maximum(nv, 1)[..., None, None]
+    verts = (verts - cen).astype(f32)
+    idx = np.full((b, n, 9), -7, i32)
+    K("cg3d_sort_vertices", verts, mask.astype(np.uint8), nv, b, n, m, idx)
+    want = SVO.sort_vertices(verts, mask, nv)
+    assert np.array_equal(idx, want)
+
+
+@pytest.mark.parametrize("cin,cout,k,grouped", [(3, 16, 27, False), (20, 7, 8, False), (16, 24, 5, True)])
+def test_spconv_simt_kernel_vs_numpy(K, cin, cout, k, grouped):
+    """csrc/spconv_simt.cu cg3d_spconv_simt (exact-fp32 gather conv: the stem, the narrow heads, the training fallback) ==
+    out = act((sum_k in_act(in[nbr[k]]) @ W[g][k]) * scale + shift + residual) in fp64: missing neighbours (-1), input ReLU,
+    ELU, residual, column-sliced input / output, positional tables (out_rows) and the grouped (tile -> weight group) mode."""
+    rng = np.random.default_rng(cin * 100 + k)
+    n_in, n_out, G = 500, 300, (3 if grouped else 1)
+    ldi, ldo = cin + 5, cout + 3
+    X = rng.normal(0, 1, (n_in, ldi)).astype(f32)
+    nbr = rng.integers(-1, n_in, (k, n_out)).astype(i32)
+    nbr[rng.random((k, n_out)) < 0.5] = -1
+    W = rng.normal(0, 0.3, (G, k, cin, cout)).astype(f32)
+    scale, shift = rng.uniform(0.5, 1.5, (G, cout)).astype(f32), rng.normal(0, 0.2, (G, cout)).astype(f32)
+    res = rng.normal(0, 1, (n_out, cout)).astype(f32)
+    out = np.full((n_out, ldo), -9, f32)
+    perm = rng.permutation(n_out).astype(i32)                    # position j of the table is output row perm[j]
+    if grouped:
+        bounds = [0, 100, 100, 300]                              # an empty group in the middle
+        tiles = [(r0, min(64, bounds[g + 1] - r0), g) for g in range(G) for r0 in range(bounds[g], bounds[g + 1], 64)]
+        t0, tn, tg = (np.array(c, i32) for c in zip(*tiles))
+        K("cg3d_spconv_simt", X, ldi, 1, nbr, W, out, ldo, n_out, cin, cout, k, scale, shift, res, 2, t0, tn, tg, len(tiles), perm)
+        grp = np.repeat(np.arange(G), np.diff(bounds))
+    else:
+        K("cg3d_spconv_simt", X, ldi, 1, nbr, W, out, ldo, n_out, cin, cout, k, scale, shift, res, 2, None, None, None, 0, perm)
+        grp = np.zeros(n_out, np.int64)
+    Xr = np.maximum(X[:, :cin].astype(np.float64), 0)
+    acc = np.zeros((n_out, cout))
+    for j in range(n_out):
+        for t in range(k):
+            if nbr[t, j] >= 0:
+                acc[j] += Xr[nbr[t, j]] @ W[grp[j], t].astype(np.float64)
+    y = acc * scale[grp] + shift[grp] + res[perm]
+    y = np.where(y > 0, y, np.expm1(y))
+    want = np.zeros((n_out, cout))
+    want[perm] = y
+    assert _rel(out[:, :cout], want) < 1e-5
+    assert np.all(out[:, cout:] == -9)                           # the slice's neighbours are untouched
+
+
+def test_voxelise_and_rule_map_kernels_vs_me_oracle(K):
+    """csrc/coords.cu: cg3d_quantize -> cg3d_unique_first (hash insert with the min-row winner, scan, compact) == the oracle's
+    ME-CPU first-occurrence unique (unique rows, inverse, first rows, all exact); cg3d_stride_coords + a second unique = the
+    stride-2 map; cg3d_neighbor_table (3^3, strided 2^3 down-sampling map) and cg3d_neighbor_table_symmetric == the oracle's
+    kernel maps entry for entry; cg3d_hash_lookup finds every row and rejects absent coordinates."""
+    from oracle import me_cpu as me
+    rng = np.random.default_rng(6)
+    n = 3000
+    pts = np.concatenate([rng.integers(0, 2, (n, 1)).astype(f32), rng.uniform(-0.6, 0.6, (n, 3)).astype(f32)], 1)
+    pts[::11] = pts[5]                                           # many duplicates of one voxel
+    coords, err = np.zeros((n, 4), i32), np.zeros(1, i32)
+    K("cg3d_quantize", pts, 4, n, 0.02, 0.02, 0.02, 1, coords, err)
+    want_c = np.concatenate([pts[:, :1], np.floor(pts[:, 1:] / f32(0.02))], 1).astype(np.int64)
+    assert err[0] == 0 and np.array_equal(coords, want_c)
+
+    def unique(c):
+        m = len(c)
+        cap = K("cg3d_hash_capacity", m)
+        keys, vals = np.zeros(cap, np.uint64), np.zeros(cap, i32)
+        out, first, inv, nu = np.zeros((m, 4), i32), np.zeros(m, i32), np.zeros(m, i32), np.zeros(1, i32)
+        K("cg3d_unique_first", np.ascontiguousarray(c, i32), m, keys, vals, cap, out, first, inv, nu,
+          np.zeros(3 * m + K("cg3d_scan_workspace_ints", m), i32))
+        return out[:nu[0]].copy(), first[:nu[0]].copy(), inv, keys, vals, cap
+    u, first, inv, keys, vals, cap = unique(coords)
+    wu, winv, wfirst = me.unique_first(want_c)
+    assert np.array_equal(u, wu) and np.array_equal(inv, winv) and np.array_equal(first, wfirst) and len(u) < n
+    rows = np.zeros(len(u) + 3, i32)
+    query = np.concatenate([u, [[0, 500, 0, 0], [1, -31, 2, 900], [5, 0, 0, 0]]]).astype(i32)
+    K("cg3d_hash_lookup", query, len(query), keys, vals, cap, rows)
+    assert np.array_equal(rows[:len(u)], np.arange(len(u))) and np.all(rows[len(u):] == -1)
+    in_map = me.CoordMap(wu, 1)
+
+    def table(rules, n_out):
+        t = np.full((len(rules), n_out), -1, i32)
+        for k_, (i_, o_) in enumerate(rules):
+            t[k_, o_] = i_
+        return t
+    nbr = np.zeros((27, len(u)), i32)
+    K("cg3d_neighbor_table", u, len(u), keys, vals, cap, 3, 1, nbr)
+    want_t = table(me.kernel_map(in_map, wu, 3, 1), len(u))
+    assert np.array_equal(nbr, want_t) and (nbr >= 0).sum() > len(u)
+    nbr_s = np.full((27, len(u)), -5, i32)
+    K("cg3d_neighbor_table_symmetric", u, len(u), keys, vals, cap, 3, 1, nbr_s)
+    assert np.array_equal(nbr_s, want_t)
+    # stride-2 map (A6) and the 2^3 / stride-2 down-sampling rule map onto it
+    c2 = np.zeros((len(u), 4), i32)
+    K("cg3d_stride_coords", u, len(u), 2, c2)
+    assert np.array_equal(c2[:, 1:], (wu[:, 1:] // 2) * 2)
+    u2, _, _, _, _, _ = unique(c2)
+    assert np.array_equal(u2, me.unique_first(c2.astype(np.int64))[0])
+    nbr2 = np.zeros((8, len(u2)), i32)
+    K("cg3d_neighbor_table", u2, len(u2), keys, vals, cap, 2, 1, nbr2)
+    assert np.array_equal(nbr2, table(me.kernel_map(in_map, u2.astype(np.int64), 2, 1), len(u2)))
+    assert (nbr2 >= 0).sum() == len(u)                           # every fine voxel feeds exactly one coarse voxel
