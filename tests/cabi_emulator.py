@@ -445,15 +445,19 @@ class _Setter:
         setattr(obj, name, value)
 
 
-def install(monkeypatch=None, compiled: bool = False):
+def install(monkeypatch=None, compiled: bool = False, native_maps: bool = False):
     """route _lib.call to the emulation and the coordinate-map builders to the oracle (for the duration of a test;
     monkeypatch=None: for the rest of the process).
 
     compiled=True: the entry points of the training kernels are NOT emulated but served by their own CUDA sources compiled
     for the CPU (tests/cuda_on_cpu), called exactly as _lib.call calls the GPU library -- raw data pointers, sizes and
     strides as passed -- so a wrong stride / a non-contiguous view / a wrong dtype handed over by the Python side shows up
-    as a wrong result here instead of on the device."""
+    as a wrong result here instead of on the device.
+
+    native_maps=True (with compiled): the coordinate maps are the product's own too -- hash tables built, probed and uniqued
+    by csrc/coords.cu on the CPU; nothing of sparse.py is replaced (the inference-side tests, tests/test_inference_wiring_cpu.py)."""
     from cagroup3d_b200 import _lib, sparse as S
+    assert compiled or not native_maps
     monkeypatch = monkeypatch or _Setter
     native, protos = None, None
     if compiled:
@@ -468,8 +472,9 @@ def install(monkeypatch=None, compiled: bool = False):
         params = names[name]
         assert len(args) == len(params), (name, len(args), params)
         calls.append(name)
-        # (the interpolation backward probes the query map's REAL hash table, which cpu_map() does not build: stays emulated)
-        if native is not None and hasattr(native, name) and name != "cg3d_interp_trilinear_backward":
+        # (entry points that probe a coordinate map's REAL open-addressing table -- parameters `keys` / `capacity`, e.g. the
+        # interpolation and its backward -- stay emulated: cpu_map() keeps a sorted key list instead of a hash table)
+        if native is not None and hasattr(native, name) and (native_maps or not ("capacity" in params or "qcapacity" in params)):
             fn = getattr(native, name)
             fn.argtypes, fn.restype = protos[name], ctypes.c_int
             for a in args:
@@ -482,7 +487,8 @@ def install(monkeypatch=None, compiled: bool = False):
         table[name](**dict(zip(params, args)))
 
     monkeypatch.setattr(_lib, "call", call)
-    monkeypatch.setattr(S, "strided_map", _strided_map)
-    monkeypatch.setattr(S, "neighbor_table", _neighbor_table)
-    monkeypatch.setattr(S, "transpose_table", _transpose_table)
+    if not native_maps:
+        monkeypatch.setattr(S, "strided_map", _strided_map)
+        monkeypatch.setattr(S, "neighbor_table", _neighbor_table)
+        monkeypatch.setattr(S, "transpose_table", _transpose_table)
     return calls

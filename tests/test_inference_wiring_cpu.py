@@ -1,0 +1,108 @@
+"""Inference stages on the CPU: the product's own host code (cagroup3d_b200/head.py) driving the product's own CUDA sources
+compiled for the CPU (tests/cuda_on_cpu, routed by tests/cabi_emulator.install(compiled=True): raw pointers, sizes and strides
+exactly as _lib.call hands them to the GPU library), teacher-forced with the ORACLE's class maps like the GPU test
+tests/test_gpu_model.py::test_stage1_proposals_teacher_forced.  What it adds to the `-m "not gpu"` suite: the stage-1 proposal
+stage -- decode, per-(sample, class-map) top-k, per-(sample, class) score threshold, sort, NMS (axis-aligned and rotated),
+packing -- is checked against the oracle end to end without a GPU, 20 kernels and the Python between them; with
+CG3D_SLOW_TESTS=1 so is the whole RoI stage (hash-unique grid voxels, tap-pattern-ordered rule map, 5^3 conv, 7^3 pooling
+contraction, MLP, decode, NMS)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cagroup3d_oracle as O
+from tests import cabi_emulator as E
+
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("ncls,yaw", [pytest.param(18, False, marks=pytest.mark.slow), (10, True)], ids=["scannet18", "sunrgbd10"])
+def test_stage1_proposals_through_the_cuda_sources_on_cpu(monkeypatch, ncls, yaw):
+    from cagroup3d_b200 import model_init, synthetic
+    E.install(monkeypatch, compiled=True)
+    B = 2
+    batch = synthetic.make_batch(B, target_voxels=700, n_classes=ncls, sunrgbd=yaw, config=7)
+    model = model_init.seeded_model(ncls, yaw, seed=3)
+    pts = torch.from_numpy(batch["points"])
+    orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
+    model_init.calibrate_semantic_bias(model, orc.forward(pts, B, stages="backbone")["bb_feats"], 0.10)
+    orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+    pred = torch.cat([torch.cat([m["ctr"], m["cls"], m["reg"]], 1) for m in res["head"]["maps"]])
+    model_init.calibrate_cls_bias(model, pred, 0.05)             # enough boxes above the score threshold for the NMS to work on
+    orc = O.Oracle(model.state_dict(), O.default_cfg(ncls, yaw))
+    res = orc.forward(pts, B, cur_epoch=10)
+    coords, rows = [], []
+    for c, m in enumerate(res["head"]["maps"]):                  # class maps -> the `cm` dict `proposals` consumes
+        cc = m["coords"].copy()
+        cc[:, 0] += c * B
+        coords.append(cc)
+        rows.append(torch.cat([m["ctr"], m["cls"], m["reg"]], 1))
+    cm = dict(coords=torch.from_numpy(np.concatenate(coords).astype(np.int32)), pred=torch.cat(rows).float().contiguous())
+    db, ds, dl, off, _ = model.dense_head.proposals(cm, B)
+    assert off[-1] > 20
+    for b in range(B):
+        wb, ws, wl = res["stage1"][b]
+        gb, gs, gl = db[off[b]:off[b + 1]], ds[off[b]:off[b + 1]], dl[off[b]:off[b + 1]]
+        assert len(gb) == len(wb), (len(gb), len(wb))
+        assert torch.equal(gl.long(), wl.long())
+        assert (gs - ws.float()).abs().max().item() <= TOL and (gb - wb.float()).abs().max().item() <= TOL
+
+
+# (one minute each on CPU threads, both pass: CG3D_SLOW_TESTS=1)
+@pytest.mark.slow
+@pytest.mark.parametrize("ncls,yaw", [(18, False), (10, True)], ids=["scannet18", "sunrgbd10"])
+def test_roi_stage_through_the_cuda_sources_on_cpu(monkeypatch, ncls, yaw):
+    """roi_head.CAGroup3DRoIHead.run -- pad the detections, 7^3 grid points per RoI -> hash-unique voxels, the 5^3 conv at
+    those voxels over a rule map with the tap-pattern tile order, the 7^3 pooling contraction, the regression MLP, the box
+    decode and the per-class NMS -- with coordinate maps, rule maps, sorts and the exact-fp32 conv all served by the product's
+    CUDA sources on the CPU, against the oracle's RoI head on the same (oracle) stage-1 detections and backbone features:
+    RoI grid voxels exact, pooled features / regression / decoded boxes <= 1e-3, the same final detections."""
+    from cagroup3d_b200 import model_init, synthetic, sparse as S
+    from tests.util import assert_same_coord_set
+    E.install(monkeypatch, compiled=True, native_maps=True)
+    monkeypatch.setitem(S._CONV_IMPL, "name", "simt")
+    monkeypatch.setattr(S, "MASK_MIN_ROWS", 256)                 # small scene: still take the tap-pattern tile order
+    B = 2
+    batch = synthetic.make_batch(B, target_voxels=300, n_classes=ncls, sunrgbd=yaw, config=7)
+    model = model_init.seeded_model(ncls, yaw, seed=3)
+    pts = torch.from_numpy(batch["points"])
+    cfg = O.default_cfg(ncls, yaw)
+    orc = O.Oracle(model.state_dict(), cfg)
+    bb = orc.forward(pts, B, stages="backbone")
+    # two stage-1 detections per sample (jittered ground-truth boxes): the RoI stage's input
+    g = torch.Generator().manual_seed(1)
+    st1 = []
+    for b in range(B):
+        gt = torch.from_numpy(batch["gt_boxes"][b][:2, :7]).float()
+        bx = gt.clone()
+        bx[:, :3] += torch.randn((len(gt), 3), generator=g) * 0.05
+        if not yaw:
+            bx[:, 6] = 0
+        st1.append((bx, torch.rand((len(gt),), generator=g) * 0.5 + 0.3, torch.from_numpy(batch["gt_boxes"][b][:2, 7]).long() % ncls))
+    omgr, ocm = O.me.Manager(), O.me.CoordMap(bb["bb_coords"], 2)
+    omgr.by_stride[2] = ocm
+    want_final, inter_o = orc.roi_head(O.me.SparseTensor(bb["bb_feats"], ocm, omgr), st1, B)
+    # product side, everything on CPU tensors
+    mgr = S.Manager()
+    cmap = S.build_map(torch.from_numpy(np.ascontiguousarray(bb["bb_coords"], dtype=np.int32)), 2, mgr)
+    mgr.by_stride[2] = cmap
+    sp = S.SparseTensor(bb["bb_feats"].detach().float().contiguous(), cmap, mgr)
+    db = torch.cat([x[0] for x in st1]).float().contiguous()
+    ds = torch.cat([x[1] for x in st1]).float().contiguous()
+    dl = torch.cat([x[2] for x in st1]).int().contiguous()
+    off = np.cumsum([0] + [len(x[0]) for x in st1]).tolist()
+    fb, fs, fl, foff, inter = model.roi_head.run(sp, db, ds, dl, off, B)
+    assert (inter["rois"] - inter_o["rois"].float()).abs().max().item() == 0
+    want_gc = inter_o["grid_coords"].copy()
+    want_gc[:, 1:] *= 2
+    assert (inter["grid_coords"].numpy().astype(np.int64) == want_gc).all()
+    assert_same_coord_set(inter["uniq"].numpy(), inter_o["uniq"])
+    assert (inter["pooled"] - inter_o["pooled"]).abs().max().item() <= TOL
+    assert (inter["rcnn_reg"] - inter_o["rcnn_reg"]).abs().max().item() <= TOL
+    assert (inter["decoded"] - inter_o["decoded"].float()).abs().max().item() <= TOL
+    for b in range(B):
+        wb, ws, wl = want_final[b]
+        gb, gs, gl = fb[foff[b]:foff[b + 1]], fs[foff[b]:foff[b + 1]], fl[foff[b]:foff[b + 1]]
+        assert len(gb) == len(wb) > 0 and torch.equal(gl.long(), wl.long())
+        assert (gs - ws.float()).abs().max().item() <= TOL and (gb - wb.float()).abs().max().item() <= TOL
