@@ -106,3 +106,35 @@ def test_roi_stage_through_the_cuda_sources_on_cpu(monkeypatch, ncls, yaw):
         gb, gs, gl = fb[foff[b]:foff[b + 1]], fs[foff[b]:foff[b + 1]], fl[foff[b]:foff[b + 1]]
         assert len(gb) == len(wb) > 0 and torch.equal(gl.long(), wl.long())
         assert (gs - ws.float()).abs().max().item() <= TOL and (gb - wb.float()).abs().max().item() <= TOL
+
+
+def test_voxelise_and_coordinate_pyramid_on_cpu(monkeypatch):
+    """sparse.quantize + sparse.voxel_pyramid (the stride-1 map and the nine strided maps of BiResNet / DAPPM built with
+    DEVICE-side row counts and one size read-back, cg3d_unique_first_dev) over the CUDA sources on the CPU == the oracle's
+    ME-CPU maps: the same rows in the same (first-occurrence) order at every stride, each derived from the rows of the level
+    the plan names; the first-point colours of the voxels equal the oracle's RANDOM_SUBSAMPLE-made-deterministic features."""
+    from cagroup3d_b200 import sparse as S, synthetic
+    from oracle import me_cpu as me
+    E.install(monkeypatch, compiled=True, native_maps=True)
+    batch = synthetic.make_batch(2, target_voxels=1500, n_classes=18, config=7)
+    pts = torch.from_numpy(batch["points"]).float().contiguous()
+    pts[:, 4:] /= 255.
+    n, ld = pts.shape
+    coords, err = S.quantize(pts, ld, n, (0.02,) * 3)
+    mgr = S.Manager()
+    cmap, first, n_err = S.voxel_pyramid(coords, mgr, err=err)
+    assert n_err == 0 and sorted(mgr.by_stride) == [1] + [p[0] for p in S.BACKBONE_PYRAMID]
+    c = pts[:, :4].clone()
+    c[:, 1:] /= 0.02
+    ox = me.from_points(c, pts[:, 4:])
+    assert np.array_equal(cmap.coords.numpy(), ox.C) and cmap.n == len(ox.C) < n
+    F = S.gather_rows(pts, 4, first, cmap.n, ld - 4)
+    assert torch.equal(F, ox.F.float())
+    omaps = {1: ox.cmap}
+    for ts, src in S.BACKBONE_PYRAMID:
+        cc = omaps[src].coords.copy()
+        cc[:, 1:] = np.floor_divide(cc[:, 1:], ts) * ts
+        omaps[ts] = me.CoordMap(me.unique_first(cc)[0], ts)
+        got = mgr.by_stride[ts]
+        assert got.stride == ts and got.n == len(omaps[ts]) and np.array_equal(got.coords.numpy()[:got.n], omaps[ts].coords), ts
+    assert mgr.by_stride[512].n <= mgr.by_stride[64].n <= mgr.by_stride[2].n < cmap.n
