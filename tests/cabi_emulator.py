@@ -399,6 +399,16 @@ def cg3d_segment_mean(**a):
     a["out"].copy_(torch.zeros((U, C), dtype=src.dtype).index_add_(0, inv, src) / cnt[:, None])
 
 
+def cg3d_first_rows(**a):
+    """first[b] = first row of sample b.  (Always served from here: the kernel groups the lanes of a warp with
+    __match_any_sync(__activemask(), ...) inside its row loop, which the CPU harness can only run for whole warps -- it is
+    checked natively in tests/test_cuda_on_cpu.py::test_head_coordinate_kernels with a row count that is a multiple of 32.)"""
+    b = a["coords"][:a["n"], 0].long()
+    for k in range(a["B"]):
+        r = torch.nonzero(b == k).flatten()
+        a["first"][k] = int(r[0]) if len(r) else 0x7F7F7F7F
+
+
 def cg3d_sort_pairs(**a):
     n, b0, b1 = a["n"], a["begin_bit"], a["end_bit"]
     k = a["keys"][:n]
@@ -474,7 +484,8 @@ def install(monkeypatch=None, compiled: bool = False, native_maps: bool = False)
         calls.append(name)
         # (entry points that probe a coordinate map's REAL open-addressing table -- parameters `keys` / `capacity`, e.g. the
         # interpolation and its backward -- stay emulated: cpu_map() keeps a sorted key list instead of a hash table)
-        if native is not None and hasattr(native, name) and (native_maps or not ("capacity" in params or "qcapacity" in params)):
+        if native is not None and hasattr(native, name) and name != "cg3d_first_rows" \
+                and (native_maps or not ("capacity" in params or "qcapacity" in params)):
             fn = getattr(native, name)
             fn.argtypes, fn.restype = protos[name], ctypes.c_int
             for a in args:

@@ -138,3 +138,44 @@ def test_voxelise_and_coordinate_pyramid_on_cpu(monkeypatch):
         got = mgr.by_stride[ts]
         assert got.stride == ts and got.n == len(omaps[ts]) and np.array_equal(got.coords.numpy()[:got.n], omaps[ts].coords), ts
     assert mgr.by_stride[512].n <= mgr.by_stride[64].n <= mgr.by_stride[2].n < cmap.n
+
+
+@pytest.mark.parametrize("ncls,yaw", [pytest.param(18, False, marks=pytest.mark.slow), (10, True)], ids=["scannet18", "sunrgbd10"])
+def test_class_grouping_coordinate_phase_on_cpu(monkeypatch, ncls, yaw):
+    """head_train.coordinate_phase -- the coordinate half of the class-aware grouping (cagroup_head.py:227-271: per-class
+    threshold selection, voted points clamped to the scene, fused voted + original points quantised at the class's voxel
+    size and at 3 x that, hash-unique class maps with the point -> voxel inverse; the same kernels and class-batched layout
+    as the inference plan, 1 or 3 votes per seed) over the CUDA sources on the CPU == the oracle's per-class loop: the same
+    class voxels in the same order, the same inverse maps, the same per-class row ranges."""
+    from cagroup3d_b200 import head_train as HT, model_init, sparse as S, synthetic
+    from tests.test_train_wiring_cpu import _oracle_class_artifacts
+    E.install(monkeypatch, compiled=True, native_maps=True)
+    B = 2
+    batch = synthetic.make_batch(B, target_voxels=600, n_classes=ncls, sunrgbd=yaw, config=7)
+    model = model_init.seeded_model(ncls, yaw, seed=3)
+    pts = torch.from_numpy(batch["points"])
+    cfg = O.default_cfg(ncls, yaw)
+    orc = O.Oracle(model.state_dict(), cfg)
+    model_init.calibrate_semantic_bias(model, orc.forward(pts, B, stages="backbone")["bb_feats"], 0.10)
+    orc = O.Oracle(model.state_dict(), cfg)
+    res = orc.forward(pts, B, cur_epoch=10, stages="head")
+    hi = res["head"]
+    head = model.dense_head
+    head.semantic_threshold = 0.05
+    mgr = S.Manager()
+    cmap = S.build_map(torch.from_numpy(np.ascontiguousarray(res["bb_coords"], dtype=np.int32)), 2, mgr)
+    mgr.by_stride[2] = cmap
+    out = S.SparseTensor(res["bb_feats"].detach().float().contiguous(), cmap, mgr)
+    art = HT.coordinate_phase(head, out, hi["sem"].float().contiguous(), hi["offsets"].float().contiguous(), B)
+    # the oracle-backed builder the training wiring tests use (itself == the oracle's per-class maps)
+    E.install(monkeypatch)                                       # (its coordinate maps are oracle objects)
+    want = _oracle_class_artifacts(res, 0.05, B, cfg, S.Manager())
+    assert art["offA"] == want["offA"] and art["offE"] == want["offE"] and art["offA"][-1] > 50
+    assert np.array_equal(art["mapA"].coords.numpy(), want["mapA"].coords.numpy())
+    assert np.array_equal(art["mapE"].coords.numpy(), want["mapE"].coords.numpy())
+    assert torch.equal(art["invA"].int(), want["invA"]) and torch.equal(art["invE"].int(), want["invE"])
+    assert torch.equal(art["ref"].int(), want["ref"])
+    for c, m in enumerate(hi["maps"]):                           # and directly: the oracle's class voxels
+        rows = art["mapA"].coords[art["offA"][c]:art["offA"][c + 1]].numpy().astype(np.int64)
+        rows[:, 0] -= c * B
+        assert np.array_equal(rows, m["coords"]), c
