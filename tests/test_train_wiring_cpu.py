@@ -183,6 +183,7 @@ def test_first_stage_loss_single_wiring(monkeypatch, compiled):
         assert t.grad is not None and _rel(t.grad, d[k].grad) < 1e-4, k
 
 
+@pytest.mark.slow       # (40 s; the semantic + vote terms it checks are two of the five of test_first_stage_loss_wiring_vs_training_oracle)
 def test_partial_training_step_wiring_vs_oracle(monkeypatch):
     """backbone (training mode) -> shared part of the head -> semantic + vote loss -> backward, on the emulated C ABI,
     against the same two terms computed from the oracle's training-mode forward: loss values and the gradient of every
@@ -473,7 +474,8 @@ def test_first_stage_loss_wiring_vs_training_oracle(monkeypatch):
     assert missing == [], missing
 
 
-@pytest.mark.parametrize("yaw", [False, True])
+# (the ScanNet variant runs the same driver code as the SUN RGB-D one, whose branches are a superset: CG3D_SLOW_TESTS=1)
+@pytest.mark.parametrize("yaw", [pytest.param(False, marks=pytest.mark.slow), True])
 def test_first_stage_training_step_driver(monkeypatch, yaw):
     """train_step.first_stage_training_step end to end on the emulated C ABI, with the coordinate phase served by the
     oracle-backed artifact builder: tb_dict keys of the reference, gradients in the reducer's buckets, loss going down.
